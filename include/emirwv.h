@@ -1,0 +1,194 @@
+/*
+ * emirwv — C ABI of the B200-native rectification + wavelength-calibration path.
+ *
+ * This is the drop-in boundary for ONE hot path of guaix-ucm/pyemir:
+ *   emirdrp.processing.wavecal.apply_rectwv_coeff
+ *   (reference: src/emirdrp/processing/wavecal/apply_rectwv_coeff.py:35-287).
+ * The reference is pure Python; the arithmetic it delegates to numina
+ * (apply_integer_offsets :74-78, Slitlet2D.rectify -> rectify2d slitlet2d.py:421-423,
+ * resample_image2d_flux :152-159, find_pix_borders :190) is what this library
+ * replaces.  A Python caller binds it with ctypes (pyemir_b200/_cabi.py); the
+ * reference-side stub is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, POD structs; no C++ or torch types cross the boundary;
+ *  - every function returns 0 on success or a negative EMIRWV_E_* code;
+ *    emirwv_last_error() gives the message of the calling thread's last failure;
+ *  - "d_" arguments are device pointers on the CUDA device that was current when the
+ *    plan was created, "h_" arguments are host pointers; the caller owns all of them;
+ *  - emirwv_run is asynchronous on the given stream and may be called concurrently
+ *    on different streams (a plan is immutable after creation);
+ *  - there is no CPU fallback: without a CUDA device every compute entry point
+ *    fails with EMIRWV_E_CUDA.
+ */
+#ifndef EMIRWV_H
+#define EMIRWV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMIRWV_VERSION 100          /* 0.1.0 */
+
+#define EMIRWV_MAX_SLITLETS 55      /* EMIR_NBARS, core/__init__.py:39 */
+#define EMIRWV_MAX_COEF 21          /* 2-D polynomial of order 5 */
+#define EMIRWV_MAX_WPOLY 16         /* wavelength polynomial coefficients */
+#define EMIRWV_ROWS_SCANNED 39      /* 38 pasted rows + 1 (apply_rectwv_coeff.py:189) */
+
+/* error codes; the Python shim maps them to the exceptions of the reference */
+#define EMIRWV_OK 0
+#define EMIRWV_E_VALUE (-1)         /* invalid argument            -> ValueError  */
+#define EMIRWV_E_INDEX (-2)         /* row outside the bounding box -> IndexError */
+#define EMIRWV_E_CUDA (-3)          /* CUDA runtime failure         -> RuntimeError */
+#define EMIRWV_E_NOMEM (-4)         /* allocation failure           -> MemoryError */
+#define EMIRWV_E_LIMIT (-5)         /* geometry exceeds kernel limits -> RuntimeError */
+
+/* element type of the frames, of the arithmetic and of the output */
+#define EMIRWV_F32 0                /* float32 in, float32 arithmetic, float32 out */
+#define EMIRWV_F64 1                /* float64 in, float64 arithmetic, float64 out */
+
+/* resampling: the reference's args_resampling (slitlet2d.py:388-389) */
+#define EMIRWV_NEAREST 1            /* nearest neighbour                          */
+#define EMIRWV_AREA 2               /* flux preserving (exact pixel-overlap area) */
+#define EMIRWV_BILINEAR 3           /* extension, not in the reference: bilinear  */
+
+/* One slitlet of RectWaveCoeff.contents (slitlet2d.py:149-215). */
+typedef struct emirwv_slitlet_desc {
+    int32_t valid;                  /* 0: listed in missing_slitlets (rows stay 0) */
+    int32_t bb_nc1_orig;            /* bounding box, 1-based inclusive             */
+    int32_t bb_nc2_orig;
+    int32_t bb_ns1_orig;
+    int32_t bb_ns2_orig;
+    int32_t min_row_rectified;      /* 0-based row of the rectified slitlet        */
+    int32_t max_row_rectified;
+    int32_t ncoef;                  /* len(ttd_aij) = (order+1)(order+2)/2         */
+    int32_t nwpoly;                 /* len(wpoly_coeff)                            */
+    int32_t reserved;
+    double aij[EMIRWV_MAX_COEF];    /* ttd_aij (tti_aij for the inverse map)       */
+    double bij[EMIRWV_MAX_COEF];    /* ttd_bij                                     */
+    double wpoly[EMIRWV_MAX_WPOLY]; /* wavelength vs 1-based pixel, ascending powers */
+} emirwv_slitlet_desc;
+
+/* Everything apply_rectwv_coeff reads from RectWaveCoeff + set_wv_parameters. */
+typedef struct emirwv_plan_desc {
+    int32_t naxis1;                 /* frame columns (EMIR_NAXIS1 = 2048)          */
+    int32_t naxis2;                 /* frame rows    (EMIR_NAXIS2 = 2048)          */
+    int32_t nslitlets;              /* EMIR_NBARS = 55                             */
+    int32_t rows_per_slitlet;       /* EMIR_NPIXPERSLIT_RECTIFIED = 38             */
+    int32_t offx;                   /* global_integer_offset_x_pix                 */
+    int32_t offy;                   /* global_integer_offset_y_pix                 */
+    int32_t resampling;             /* EMIRWV_NEAREST / _AREA / _BILINEAR          */
+    int32_t dtype;                  /* EMIRWV_F32 / EMIRWV_F64                     */
+    int32_t max_order;              /* numina's cap is 4; 5 is accepted on request */
+    int32_t naxis1_out;             /* naxis1_enlarged                             */
+    double crpix1;                  /* crpix1_enlarged (1.0)                       */
+    double crval1;                  /* crval1_enlarged                             */
+    double cdelt1;                  /* cdelt1_enlarged                             */
+    int32_t tile_k;                 /* tuning, 0 = default: output columns per tile */
+    int32_t tile_rows;              /* tuning, 0 = default: rectified rows per tile */
+    emirwv_slitlet_desc slitlet[EMIRWV_MAX_SLITLETS];
+} emirwv_plan_desc;
+
+typedef struct emirwv_plan emirwv_plan;   /* opaque */
+
+typedef struct emirwv_plan_info {
+    int32_t dtype;
+    int32_t resampling;
+    int32_t footprint;              /* K: every output pixel reads K x K source pixels */
+    int32_t naxis1_out;
+    int32_t naxis2_out;             /* nslitlets * rows_per_slitlet                */
+    int32_t ntiles;                 /* work items per frame group                  */
+    int32_t ntiles_empty;           /* tiles outside the wavelength coverage       */
+    int32_t tile_k;
+    int32_t tile_rows;
+    int32_t window_rows;            /* staged source window (max over tiles)       */
+    int32_t window_cols;
+    int32_t max_span;               /* max whole source pixels inside one output pixel */
+    int32_t frames_per_cta;         /* G chosen for the next launch                */
+    int32_t smem_bytes;             /* dynamic shared memory of that launch        */
+    int64_t table_bytes;            /* device memory held by the plan              */
+    int64_t in_frame_bytes;
+    int64_t out_frame_bytes;
+} emirwv_plan_info;
+
+int emirwv_version(void);
+const char *emirwv_last_error(void);
+
+/* Number of CUDA devices visible, or a negative error code. */
+int emirwv_device_count(void);
+
+/* Select the CUDA device used by subsequent emirwv_plan_create calls of this thread
+ * (one process per GPU: pass LOCAL_RANK). */
+int emirwv_set_device(int device);
+
+/*
+ * Build the frame-independent tables of a RectWaveCoeff on the current device.
+ * Replaces the per-frame work of Slitlet2D.__init__ (slitlet2d.py:145-218), fmap /
+ * the corner mapping and polygon clipping inside rectify2d, and the wavelength
+ * border bookkeeping inside resample_image2d_flux.
+ */
+int emirwv_plan_create(const emirwv_plan_desc *desc, emirwv_plan **plan);
+void emirwv_plan_destroy(emirwv_plan *plan);
+int emirwv_plan_get_info(const emirwv_plan *plan, emirwv_plan_info *info);
+
+/* Launch tuning for subsequent runs (0 keeps the default): frames per CTA
+ * (1, 2 or 4), rectified rows per pass, threads per CTA (multiple of 32). */
+int emirwv_plan_set_tuning(emirwv_plan *plan, int frames_per_cta, int rows_per_pass,
+                           int threads);
+
+/*
+ * Rectify + wavelength-calibrate nframes device-resident frames.
+ *   d_in      [nframes][naxis2][naxis1]            plan dtype
+ *   d_out     [nframes][naxis2_out][naxis1_out]    plan dtype (every element written)
+ *   d_jminmax [nframes][nslitlets][2] int32: 0-based first / last channel with a
+ *             non-zero value over the 39 scanned rows of each slitlet, or
+ *             (INT32_MAX, -1) when there is none; may be NULL.
+ * Replaces the slitlet loop of apply_rectwv_coeff.py:136-204.
+ */
+int emirwv_run(const emirwv_plan *plan, const void *d_in, void *d_out, int nframes,
+               int32_t *d_jminmax, void *cuda_stream);
+
+/*
+ * Same from host buffers: host->device copies, kernels and device->host copies are
+ * pipelined over internal streams; returns when h_out / h_jminmax are complete.
+ * Pinned buffers (emirwv_host_alloc, cudaHostAlloc, torch pin_memory) copy
+ * asynchronously; pageable buffers work but serialise.
+ */
+int emirwv_run_host(emirwv_plan *plan, const void *h_in, void *h_out, int nframes,
+                    int32_t *h_jminmax);
+
+void *emirwv_host_alloc(int64_t nbytes);   /* pinned host memory, NULL on failure */
+void emirwv_host_free(void *ptr);
+
+/*
+ * Kernel 1 alone: the rectified slitlet rows before the wavelength rebin,
+ * d_rect [39][bbw] for rows min_row_rectified .. max_row_rectified+1 of slitlet
+ * islitlet (1-based).  Serves Slitlet2D.rectify (slitlet2d.py:381-431).
+ */
+int emirwv_rectify_slitlet(const emirwv_plan *plan, const void *d_frame, int islitlet,
+                           void *d_rect, void *cuda_stream);
+
+/*
+ * Parity hooks (tests): the plan's geometry for one slitlet, copied to the host.
+ *   h_row, h_col [39][bbw]       source pixel of tap (0,0) in bounding-box array
+ *                                coordinates (for EMIRWV_NEAREST: the index maps
+ *                                iyyy, ixxx of rectify2d)
+ *   h_ok         [39][bbw]       EMIRWV_NEAREST: 1 when the source pixel exists
+ *   h_weights    [39][bbw][K][K] float64 weights as used by the kernels (NULL ok)
+ */
+int emirwv_debug_geometry(const emirwv_plan *plan, int islitlet, int32_t *h_row,
+                          int32_t *h_col, uint8_t *h_ok, double *h_weights);
+
+/*
+ *   h_idx [naxis1_out+1] source interval of every output border
+ *   h_t   [naxis1_out+1] offset inside that interval (wavelength units)
+ */
+int emirwv_debug_borders(const emirwv_plan *plan, int islitlet, int32_t *h_idx,
+                         double *h_t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMIRWV_H */

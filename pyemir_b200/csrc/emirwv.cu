@@ -1,0 +1,1172 @@
+// emirwv.cu — sm_100a implementation of the apply_rectwv_coeff hot path.
+//
+// Reference path: emirdrp/processing/wavecal/apply_rectwv_coeff.py:35-287 and the
+// numina routines it calls.  Design:
+//
+//   plan  (once per RectWaveCoeff, float64, on the GPU + a little host code)
+//     k_extent / k_build_geometry : 2-D polynomial map of every output pixel
+//         (its centre, or its four corners) and the exact overlap areas with the
+//         source pixels  ->  frame-independent tables  base[s][y][j], w[s][y][tap][j]
+//     build_border_tables (host)  : for every border of the linear wavelength grid
+//         the source interval it falls in and the offset inside it
+//     build_tiles (host)          : work items (slitlet, row block, column block)
+//         with the source window each one needs
+//
+//   run   (per batch of frames; one fused kernel, nothing intermediate touches HBM)
+//     k_rectwv<T,K,G>:  stage the source window of G frames in shared memory ->
+//         A: rectified flux = K*K weighted gather            (kernel 1 of the spec)
+//         C: Steffen slopes of the cumulative flux per knot   (kernel 2)
+//         D: cumulative-flux difference at the output borders (kernel 2), store,
+//            first/last non-zero channel per slitlet          (kernel 3)
+//
+// No tensor cores (there is no dense contraction), no CPU fallback.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "emirwv.h"
+#include "geom.cuh"
+
+namespace {
+
+using namespace emirwv;
+
+constexpr int NROWS = EMIRWV_ROWS_SCANNED;   // 39 rectified rows per slitlet
+constexpr int MAXK = 4;                      // largest supported footprint
+constexpr int HOST_SLOTS = 3;                // pipeline depth of emirwv_run_host
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+thread_local std::string g_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(call)                                                              \
+    do {                                                                            \
+        cudaError_t err_ = (call);                                                  \
+        if (err_ != cudaSuccess)                                                    \
+            return fail(EMIRWV_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(err_)); \
+    } while (0)
+
+// ------------------------------------------------------------------ device structs
+struct SlitDev {
+    int valid;
+    int ns1, nc1;       // 1-based origin of the bounding box in the frame
+    int bbh, bbw;
+    int min_row;
+    int order;
+    int pad;
+    double a[EMIRWV_MAX_COEF];
+    double b[EMIRWV_MAX_COEF];
+};
+
+struct Tile {
+    int slit;           // 0-based slitlet
+    int y0, ny;         // rows (of the 39 scanned) handled by this tile
+    int k0, nk;         // output columns [k0, k0+nk)
+    int jlo, npx;       // rectified columns needed: [jlo, jlo+npx)
+    int r0, c0;         // frame coordinates of the staged source window origin
+    int wrows, wcols;
+    int empty;          // no wavelength coverage: the tile is exactly zero
+    int nchan;          // bbw of the slitlet
+    int pad[3];
+};
+
+struct GeomParams {
+    const SlitDev *slit;
+    int nsl, W;             // W: table pitch (= naxis1 of the frame)
+    int naxis1, naxis2;
+    int offx, offy;
+    int mode, K;
+    int32_t *base;
+    int *kmax;              // k_extent result
+};
+
+template <typename T>
+struct alignas(4 * sizeof(T)) Knot {
+    T rect;   // flux of the source pixel (= y_{i+1} - y_i of the cumulative flux)
+    T s;      // secant slope rect / h_i
+    T yp0;    // limited slope at the left knot
+    T yp1;    // limited slope at the right knot
+};
+
+template <typename T>
+struct RunParams {
+    const T *in;
+    T *out;
+    int32_t *jmm;
+    int nframes;
+    const Tile *tiles;
+    const int32_t *base;
+    const T *w;
+    const int32_t *idx;
+    const T *t;
+    const T *tau;
+    const T *invh;
+    const T *rr;
+    int W, naxis1, naxis2;
+    int nout, NB;           // naxis1_out, naxis1_out + 1
+    int rps, nrows_out;     // 38, 55*38
+    int nsl;
+    int wpitch, wsz;        // shared window: row pitch and elements per frame
+    int npxp;               // scratch pitch (>= max npx)
+    int RB;                 // rectified rows per pass
+};
+
+__host__ __device__ inline int32_t pack_base(int r, int c) {
+    r = max(-30000, min(30000, r));
+    c = max(-30000, min(30000, c));
+    return (int32_t)(((uint32_t)(r & 0xffff) << 16) | (uint32_t)(c & 0xffff));
+}
+__host__ __device__ inline int base_row(int32_t p) { return (int)(int16_t)((uint32_t)p >> 16); }
+__host__ __device__ inline int base_col(int32_t p) { return (int)(int16_t)((uint32_t)p & 0xffffu); }
+
+__device__ inline double clampd(double v) { return fmin(fmax(v, -1.0e6), 1.0e6); }
+
+// corners of output pixel (j, i) in numina's order:
+// (j-.5,i-.5) (j-.5,i+.5) (j+.5,i+.5) (j+.5,i-.5)
+__device__ inline void map_corners(const SlitDev &sd, int j, int row, double *qu, double *qv) {
+    const double dj[4] = {-0.5, -0.5, 0.5, 0.5};
+    const double di[4] = {-0.5, 0.5, 0.5, -0.5};
+    for (int c = 0; c < 4; ++c) {
+        double u, v;
+        fmap(sd.order, sd.a, sd.b, (double)j + dj[c], (double)row + di[c], u, v);
+        qu[c] = clampd(u);
+        qv[c] = clampd(v);
+    }
+}
+
+// ---------------------------------------------------------------- plan kernels
+// Largest footprint (in source pixels) of any mapped output pixel, mode 2.
+__global__ void k_extent(GeomParams p) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int s = blockIdx.z;
+    const SlitDev &sd = p.slit[s];
+    int need = 1;
+    if (sd.valid && j < sd.bbw) {
+        double qu[4], qv[4];
+        map_corners(sd, j, sd.min_row + y, qu, qv);
+        int lo, hi;
+        quad_extent(qu, lo, hi);
+        need = hi - lo + 1;
+        quad_extent(qv, lo, hi);
+        need = max(need, hi - lo + 1);
+    }
+    need = __reduce_max_sync(0xffffffffu, need);
+    if ((threadIdx.x & 31) == 0) atomicMax(p.kmax, need);
+}
+
+// base[s][y][j] (frame coordinates of tap (0,0)) and w[s][y][tap][j].
+template <typename T>
+__global__ void k_build_geometry(GeomParams p, T *w) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int s = blockIdx.z;
+    const SlitDev &sd = p.slit[s];
+    if (j >= p.W) return;
+    const int K = p.K, KK = K * K;
+    const size_t rowtab = (size_t)s * NROWS + y;
+    T *wp = w + rowtab * KK * p.W + j;
+    if (!sd.valid || j >= sd.bbw) {
+        p.base[rowtab * p.W + j] = pack_base(0, 0);
+        for (int tap = 0; tap < KK; ++tap) wp[(size_t)tap * p.W] = T(0);
+        return;
+    }
+    const int row = sd.min_row + y;
+    double wt[MAXK * MAXK];
+    int br, bc;
+    if (p.mode == EMIRWV_AREA) {
+        double qu[4], qv[4];
+        map_corners(sd, j, row, qu, qv);
+        int hr, hc;
+        quad_extent(qu, bc, hc);
+        quad_extent(qv, br, hr);
+        for (int a = 0; a < K; ++a)
+            for (int b = 0; b < K; ++b) {
+                double area = 0.0;
+                if (br + a <= hr && bc + b <= hc)
+                    area = quad_box_area(qu, qv, (double)(bc + b) - 0.5, (double)(bc + b) + 0.5,
+                                         (double)(br + a) - 0.5, (double)(br + a) + 0.5);
+                wt[a * K + b] = area;
+            }
+    } else {
+        double u, v;
+        fmap(sd.order, sd.a, sd.b, (double)j, (double)row, u, v);
+        u = clampd(u);
+        v = clampd(v);
+        if (p.mode == EMIRWV_NEAREST) {
+            bc = (int)rint(u);     // round half to even, like numpy.rint
+            br = (int)rint(v);
+            wt[0] = 1.0;
+        } else {                   // bilinear extension
+            const double fu0 = floor(u), fv0 = floor(v);
+            bc = (int)fu0;
+            br = (int)fv0;
+            const double fu = u - fu0, fv = v - fv0;
+            wt[0] = (1.0 - fv) * (1.0 - fu);
+            wt[1] = (1.0 - fv) * fu;
+            wt[2] = fv * (1.0 - fu);
+            wt[3] = fv * fu;
+        }
+    }
+    // frame coordinates: bounding-box crop (slitlet2d.py:366-369) and the global
+    // integer offsets (apply_rectwv_coeff.py:74-78) folded into the address
+    const int fr0 = br + sd.ns1 - 1 - p.offy;
+    const int fc0 = bc + sd.nc1 - 1 - p.offx;
+    for (int a = 0; a < K; ++a)
+        for (int b = 0; b < K; ++b) {
+            const int r = br + a, c = bc + b;
+            const int fr = fr0 + a, fc = fc0 + b;
+            const bool inside = r >= 0 && r < sd.bbh && c >= 0 && c < sd.bbw && fr >= 0 &&
+                                fr < p.naxis2 && fc >= 0 && fc < p.naxis1;
+            wp[(size_t)(a * K + b) * p.W] = inside ? (T)wt[a * K + b] : T(0);
+        }
+    p.base[rowtab * p.W + j] = pack_base(fr0, fc0);
+}
+
+__global__ void k_init_jmm(int32_t *jmm, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) jmm[i] = (i & 1) ? -1 : INT_MAX;
+}
+
+// Kernel 1 alone, straight from global memory (parity hook / Slitlet2D.rectify).
+template <typename T>
+__global__ void k_rectify_only(const T *frame, T *rect, const int32_t *base, const T *w,
+                               int s, int K, int W, int bbw, int naxis1, int naxis2) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (j >= bbw) return;
+    const size_t rowtab = (size_t)s * NROWS + y;
+    const int32_t pk = base[rowtab * W + j];
+    const int r0 = base_row(pk), c0 = base_col(pk);
+    const T *wp = w + rowtab * (K * K) * W + j;
+    T acc = T(0);
+    for (int a = 0; a < K; ++a)
+        for (int b = 0; b < K; ++b) {
+            const T wt = wp[(size_t)(a * K + b) * W];
+            const int r = min(max(r0 + a, 0), naxis2 - 1);
+            const int c = min(max(c0 + b, 0), naxis1 - 1);
+            acc = fma(wt, frame[(size_t)r * naxis1 + c], acc);
+        }
+    rect[(size_t)y * bbw + j] = acc;
+}
+
+// ---------------------------------------------------------------- the hot kernel
+template <typename T, int K, int G>
+__global__ void __launch_bounds__(256) k_rectwv(const RunParams<T> p) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const Tile tile = p.tiles[blockIdx.y];
+    const int g0 = blockIdx.x * G;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int s = tile.slit;
+    const size_t frame_in = (size_t)p.naxis1 * p.naxis2;
+    const size_t frame_out = (size_t)p.nrows_out * p.nout;
+
+    if (tile.empty) {
+        // outside the wavelength coverage (or a missing slitlet): exact zeros
+        const int ylast = min(tile.y0 + tile.ny, p.rps);
+        for (int g = 0; g < G && g0 + g < p.nframes; ++g)
+            for (int y = tile.y0 + warp; y < ylast; y += nwarps) {
+                T *orow = p.out + (size_t)(g0 + g) * frame_out +
+                          (size_t)(s * p.rps + y) * p.nout + tile.k0;
+                for (int k = lane; k < tile.nk; k += 32) orow[k] = T(0);
+            }
+        return;
+    }
+
+    Knot<T> *knots = reinterpret_cast<Knot<T> *>(smem_raw);
+    T *win = reinterpret_cast<T *>(knots + (size_t)G * p.RB * p.npxp);
+    T *rect = win + (size_t)G * p.wsz;
+
+    // ---- stage the source window of each frame (zero outside the detector)
+    for (int g = 0; g < G; ++g) {
+        const bool live = g0 + g < p.nframes;
+        const T *fr = p.in + (size_t)(live ? g0 + g : 0) * frame_in;
+        T *wg = win + (size_t)g * p.wsz;
+        for (int rr = warp; rr < tile.wrows; rr += nwarps) {
+            const int r = tile.r0 + rr;
+            const bool rok = live && r >= 0 && r < p.naxis2;
+            const T *src = fr + (size_t)(rok ? r : 0) * p.naxis1;
+            for (int cc = lane; cc < tile.wcols; cc += 32) {
+                const int c = tile.c0 + cc;
+                wg[rr * p.wpitch + cc] = (rok && c >= 0 && c < p.naxis1) ? __ldg(src + c) : T(0);
+            }
+        }
+    }
+    __syncthreads();
+
+    int jmin[G], jmax[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        jmin[g] = INT_MAX;
+        jmax[g] = -1;
+    }
+
+    const int npx = tile.npx;
+    const int ncg = (tile.nk + 30) / 31;     // a warp evaluates 32 borders = 31 pixels
+    const int kend = tile.k0 + tile.nk;
+    const T *invh = p.invh + (size_t)s * p.W;
+    const T *rrt = p.rr + (size_t)s * (p.W + 1);
+    const size_t btab = (size_t)s * p.NB;
+
+    for (int yb = 0; yb < tile.ny; yb += p.RB) {
+        const int nyy = min(p.RB, tile.ny - yb);
+
+        // ---- A: rectified flux, K*K weighted gather from the staged window
+        for (int item = tid; item < nyy * npx; item += blockDim.x) {
+            const int yy = item / npx;
+            const int pp = item - yy * npx;
+            const int j = tile.jlo + pp;
+            const size_t rowtab = (size_t)s * NROWS + (tile.y0 + yb + yy);
+            const int32_t pk = __ldg(p.base + rowtab * p.W + j);
+            const T *wp = p.w + rowtab * (K * K) * p.W + j;
+            T wt[K * K];
+#pragma unroll
+            for (int tap = 0; tap < K * K; ++tap) wt[tap] = __ldg(wp + (size_t)tap * p.W);
+            const T *src = win + (base_row(pk) - tile.r0) * p.wpitch + (base_col(pk) - tile.c0);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                T acc = T(0);
+#pragma unroll
+                for (int a = 0; a < K; ++a)
+#pragma unroll
+                    for (int b = 0; b < K; ++b)
+                        acc = fma(wt[a * K + b], src[(size_t)g * p.wsz + a * p.wpitch + b], acc);
+                rect[(g * p.RB + yy) * p.npxp + pp] = acc;
+            }
+        }
+        __syncthreads();
+
+        // ---- C: secant slope of every source interval and Steffen's limited
+        //         slopes at its two knots (end knots of the spectrum have slope 0)
+        for (int item = tid; item < nyy * npx; item += blockDim.x) {
+            const int yy = item / npx;
+            const int pp = item - yy * npx;
+            const int i = tile.jlo + pp;
+            const bool has_l = pp > 0, has_r = pp < npx - 1;
+            const T ih0 = __ldg(invh + i);
+            const T ihm = has_l ? __ldg(invh + i - 1) : T(0);
+            const T ihp = has_r ? __ldg(invh + i + 1) : T(0);
+            const T r0 = __ldg(rrt + i);
+            const T r1 = __ldg(rrt + i + 1);
+            const bool knot0 = has_l && i > 0;
+            const bool knot1 = has_r && i + 1 < tile.nchan;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const T *rv = rect + (g * p.RB + yy) * p.npxp;
+                const T c = rv[pp];
+                const T sm = has_l ? rv[pp - 1] * ihm : T(0);
+                const T s0 = c * ih0;
+                const T sp = has_r ? rv[pp + 1] * ihp : T(0);
+                Knot<T> kn;
+                kn.rect = c;
+                kn.s = s0;
+                kn.yp0 = knot0 ? steffen_slope(sm, s0, r0) : T(0);
+                kn.yp1 = knot1 ? steffen_slope(s0, sp, r1) : T(0);
+                knots[(g * p.RB + yy) * p.npxp + pp] = kn;
+            }
+        }
+        __syncthreads();
+
+        // ---- D: cumulative flux at the output borders, difference, store
+        for (int task = warp; task < nyy * ncg; task += nwarps) {
+            const int yy = task / ncg;
+            const int cg = task - yy * ncg;
+            const int kb = tile.k0 + cg * 31 + lane;          // border index
+            const int kbc = min(kb, kend);
+            const int ib = __ldg(p.idx + btab + kbc);
+            const T tt = __ldg(p.t + btab + kbc);
+            const T ta = __ldg(p.tau + btab + kbc);
+            const int ibn = __shfl_down_sync(0xffffffffu, ib, 1);
+            const int y = tile.y0 + yb + yy;
+            const bool col_ok = lane < 31 && kb < kend;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const Knot<T> *kr = knots + (g * p.RB + yy) * p.npxp - tile.jlo;
+                const Knot<T> kn = kr[ib];
+                const T P = steffen_partial(kn.s, kn.yp0, kn.yp1, tt, ta);
+                const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
+                T whole = T(0);
+                if (col_ok && ibn > ib) {
+                    whole = kn.rect;
+                    for (int i = ib + 1; i < ibn; ++i) whole += kr[i].rect;
+                }
+                const T o = whole + (Pn - P);
+                if (col_ok && g0 + g < p.nframes) {
+                    if (y < p.rps)
+                        p.out[(size_t)(g0 + g) * frame_out + (size_t)(s * p.rps + y) * p.nout + kb] = o;
+                    if (o != T(0)) {
+                        jmin[g] = min(jmin[g], kb);
+                        jmax[g] = max(jmax[g], kb);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
+    if (p.jmm != nullptr) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int lo = __reduce_min_sync(0xffffffffu, jmin[g]);
+            const int hi = __reduce_max_sync(0xffffffffu, jmax[g]);
+            if (lane == 0 && hi >= 0 && g0 + g < p.nframes) {
+                int32_t *dst = p.jmm + ((size_t)(g0 + g) * p.nsl + s) * 2;
+                atomicMin(dst, lo);
+                atomicMax(dst + 1, hi);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// =================================================================== plan object
+struct emirwv_plan {
+    emirwv_plan_desc desc;
+    int device = 0;
+    int dtype = 0, mode = 0, K = 1;
+    int nsl = 0, rps = 0, W = 0, nout = 0, NB = 0;
+    size_t esize = 4;
+
+    SlitDev *d_slit = nullptr;
+    int32_t *d_base = nullptr;
+    void *d_w = nullptr;
+    int32_t *d_idx = nullptr;
+    void *d_t = nullptr, *d_tau = nullptr, *d_invh = nullptr, *d_rr = nullptr;
+    Tile *d_tiles = nullptr;
+
+    std::vector<SlitDev> h_slit;
+    std::vector<int32_t> h_base;
+    std::vector<int32_t> h_idx;
+    std::vector<double> h_t;
+    std::vector<Tile> h_tiles;
+
+    int ntiles = 0, ntiles_empty = 0;
+    int tile_k = 0, tile_rows = 0;
+    int wrows_max = 0, wcols_max = 0, wpitch = 0, npxp = 0, max_span = 0;
+    int tune_G = 0, tune_RB = 0, tune_threads = 0;
+    int64_t table_bytes = 0;
+
+    std::mutex mu;
+    struct Slot {
+        void *d_in = nullptr;
+        void *d_out = nullptr;
+        int32_t *d_jmm = nullptr;
+        cudaStream_t stream = nullptr;
+    } slots[HOST_SLOTS];
+    int ws_chunk = 0;
+};
+
+namespace {
+
+template <typename T>
+int upload(const std::vector<double> &src, void **dst, int64_t &bytes) {
+    std::vector<T> tmp(src.size());
+    for (size_t i = 0; i < src.size(); ++i) tmp[i] = (T)src[i];
+    CUDA_TRY(cudaMalloc(dst, tmp.size() * sizeof(T)));
+    CUDA_TRY(cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
+    bytes += (int64_t)(tmp.size() * sizeof(T));
+    return EMIRWV_OK;
+}
+
+int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : fallback;
+}
+
+// launch configuration for a given number of frames per CTA
+struct LaunchCfg {
+    int G, RB, threads;
+    size_t smem;
+};
+
+size_t smem_bytes(const emirwv_plan *pl, int G, int RB) {
+    const size_t knots = (size_t)G * RB * pl->npxp * 4 * pl->esize;
+    const size_t win = (size_t)G * pl->wrows_max * pl->wpitch * pl->esize;
+    const size_t rect = (size_t)G * RB * pl->npxp * pl->esize;
+    return knots + win + rect;
+}
+
+LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
+    LaunchCfg cfg;
+    cfg.threads = pl->tune_threads > 0 ? pl->tune_threads : env_int("EMIRWV_THREADS", 256);
+    cfg.threads = std::max(32, std::min(256, (cfg.threads / 32) * 32));
+    cfg.RB = pl->tune_RB > 0 ? pl->tune_RB : env_int("EMIRWV_RB", 4);
+    cfg.RB = std::max(1, std::min(NROWS, cfg.RB));
+    int G = pl->tune_G > 0 ? pl->tune_G : env_int("EMIRWV_G", 2);
+    G = (G >= 4) ? 4 : (G >= 2 ? 2 : 1);
+    while (G > 1 && (G > nframes || smem_bytes(pl, G, cfg.RB) > (size_t)SMEM_LIMIT)) G >>= 1;
+    while (cfg.RB > 1 && smem_bytes(pl, G, cfg.RB) > (size_t)SMEM_LIMIT) --cfg.RB;
+    cfg.G = G;
+    cfg.smem = smem_bytes(pl, G, cfg.RB);
+    return cfg;
+}
+
+template <typename T, int K, int G>
+int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
+               cudaStream_t st) {
+    auto kern = k_rectwv<T, K, G>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)cfg.smem));
+    const dim3 grid((rp.nframes + G - 1) / G, pl->ntiles);
+    kern<<<grid, cfg.threads, cfg.smem, st>>>(rp);
+    CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+template <typename T, int K>
+int launch_k(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
+             cudaStream_t st) {
+    switch (cfg.G) {
+        case 4: return launch_one<T, K, 4>(pl, rp, cfg, st);
+        case 2: return launch_one<T, K, 2>(pl, rp, cfg, st);
+        default: return launch_one<T, K, 1>(pl, rp, cfg, st);
+    }
+}
+
+template <typename T>
+int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
+             int32_t *d_jmm, cudaStream_t st) {
+    const LaunchCfg cfg = choose_cfg(pl, nframes);
+    if (cfg.smem > (size_t)SMEM_LIMIT)
+        return fail(EMIRWV_E_LIMIT, "tile needs %zu bytes of shared memory", cfg.smem);
+    RunParams<T> rp;
+    rp.in = static_cast<const T *>(d_in);
+    rp.out = static_cast<T *>(d_out);
+    rp.jmm = d_jmm;
+    rp.nframes = nframes;
+    rp.tiles = pl->d_tiles;
+    rp.base = pl->d_base;
+    rp.w = static_cast<const T *>(pl->d_w);
+    rp.idx = pl->d_idx;
+    rp.t = static_cast<const T *>(pl->d_t);
+    rp.tau = static_cast<const T *>(pl->d_tau);
+    rp.invh = static_cast<const T *>(pl->d_invh);
+    rp.rr = static_cast<const T *>(pl->d_rr);
+    rp.W = pl->W;
+    rp.naxis1 = pl->desc.naxis1;
+    rp.naxis2 = pl->desc.naxis2;
+    rp.nout = pl->nout;
+    rp.NB = pl->NB;
+    rp.rps = pl->rps;
+    rp.nrows_out = pl->nsl * pl->rps;
+    rp.nsl = pl->nsl;
+    rp.wpitch = pl->wpitch;
+    rp.wsz = pl->wrows_max * pl->wpitch;
+    rp.npxp = pl->npxp;
+    rp.RB = cfg.RB;
+    if (d_jmm != nullptr) {
+        const int n = nframes * pl->nsl * 2;
+        k_init_jmm<<<(n + 255) / 256, 256, 0, st>>>(d_jmm, n);
+        CUDA_TRY(cudaGetLastError());
+    }
+    switch (pl->K) {
+        case 1: return launch_k<T, 1>(pl, rp, cfg, st);
+        case 2: return launch_k<T, 2>(pl, rp, cfg, st);
+        case 3: return launch_k<T, 3>(pl, rp, cfg, st);
+        case 4: return launch_k<T, 4>(pl, rp, cfg, st);
+    }
+    return fail(EMIRWV_E_LIMIT, "unsupported footprint %d", pl->K);
+}
+
+// numpy.polynomial.polynomial.polyval: Horner, one rounding per operation
+double polyval_np(double x, const double *c, int n) {
+    double c0 = c[n - 1];
+    for (int m = n - 2; m >= 0; --m) c0 = add_rn(c[m], mul_rn(c0, x));
+    return c0;
+}
+
+// Border tables of every slitlet; float64 with numpy's operation order so that the
+// interval of every border is the one numpy.searchsorted finds in the reference's
+// resample_image2d_flux / SteffenInterpolator (apply_rectwv_coeff.py:152-159).
+int build_border_tables(emirwv_plan *pl, std::vector<uint8_t> &covered) {
+    const emirwv_plan_desc &d = pl->desc;
+    const int nout = pl->nout, NB = pl->NB, W = pl->W, nsl = pl->nsl;
+    std::vector<double> nb(NB), wl(nout);
+    for (int k = 0; k < nout; ++k) wl[k] = add_rn(d.crval1, mul_rn(d.cdelt1, (double)k));
+    for (int k = 1; k < nout; ++k) nb[k] = mul_rn(0.5, add_rn(wl[k], wl[k - 1]));
+    nb[0] = add_rn(mul_rn(2.0, wl[0]), -nb[1]);
+    nb[nout] = add_rn(mul_rn(2.0, wl[nout - 1]), -nb[nout - 1]);
+
+    pl->h_idx.assign((size_t)nsl * NB, 0);
+    pl->h_t.assign((size_t)nsl * NB, 0.0);
+    std::vector<double> h_tau((size_t)nsl * NB, 0.0);
+    std::vector<double> h_invh((size_t)nsl * W, 0.0), h_rr((size_t)nsl * (W + 1), 0.0);
+    covered.assign((size_t)nsl * NB, 0);
+    pl->max_span = 0;
+
+    std::vector<double> xw(W + 1), h(W);
+    for (int s = 0; s < nsl; ++s) {
+        const emirwv_slitlet_desc &sl = d.slitlet[s];
+        if (!sl.valid) continue;
+        const int nchan = sl.bb_nc2_orig - sl.bb_nc1_orig + 1;
+        for (int i = 0; i <= nchan; ++i) {
+            const double xb = add_rn(add_rn(-0.5, (double)i), d.crpix1);
+            xw[i] = polyval_np(xb, sl.wpoly, sl.nwpoly);
+        }
+        for (int i = 0; i < nchan; ++i) {
+            h[i] = xw[i + 1] - xw[i];
+            if (!(h[i] > 0.0))
+                return fail(EMIRWV_E_VALUE,
+                            "slitlet %d: wavelength polynomial is not increasing at pixel %d",
+                            s + 1, i + 1);
+            h_invh[(size_t)s * W + i] = 1.0 / h[i];
+        }
+        for (int i = 1; i < nchan; ++i) h_rr[(size_t)s * (W + 1) + i] = h[i] / (h[i - 1] + h[i]);
+        int prev = 0;
+        for (int k = 0; k < NB; ++k) {
+            const double x = nb[k];
+            int idx;
+            double t;
+            uint8_t cov = 1;
+            if (x < xw[0]) {                       // extrapolate='border': y_0
+                idx = 0;
+                t = 0.0;
+                cov = 0;
+            } else if (x > xw[nchan]) {            // extrapolate='border': y_N
+                idx = nchan - 1;
+                t = h[nchan - 1];
+                cov = 0;
+            } else {                               // searchsorted(side='left').clip(1, N) - 1
+                const int pos = (int)(std::lower_bound(xw.begin(), xw.begin() + nchan + 1, x) -
+                                      xw.begin());
+                idx = std::min(std::max(pos, 1), nchan) - 1;
+                t = x - xw[idx];
+            }
+            pl->h_idx[(size_t)s * NB + k] = idx;
+            pl->h_t[(size_t)s * NB + k] = t;
+            h_tau[(size_t)s * NB + k] = t * h_invh[(size_t)s * W + idx];
+            covered[(size_t)s * NB + k] = cov;
+            if (k > 0) pl->max_span = std::max(pl->max_span, idx - prev);
+            prev = idx;
+        }
+    }
+    CUDA_TRY(cudaMalloc(&pl->d_idx, pl->h_idx.size() * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpy(pl->d_idx, pl->h_idx.data(), pl->h_idx.size() * sizeof(int32_t),
+                        cudaMemcpyHostToDevice));
+    pl->table_bytes += (int64_t)(pl->h_idx.size() * sizeof(int32_t));
+    int rc;
+    if (pl->dtype == EMIRWV_F32) {
+        if ((rc = upload<float>(pl->h_t, &pl->d_t, pl->table_bytes))) return rc;
+        if ((rc = upload<float>(h_tau, &pl->d_tau, pl->table_bytes))) return rc;
+        if ((rc = upload<float>(h_invh, &pl->d_invh, pl->table_bytes))) return rc;
+        if ((rc = upload<float>(h_rr, &pl->d_rr, pl->table_bytes))) return rc;
+    } else {
+        if ((rc = upload<double>(pl->h_t, &pl->d_t, pl->table_bytes))) return rc;
+        if ((rc = upload<double>(h_tau, &pl->d_tau, pl->table_bytes))) return rc;
+        if ((rc = upload<double>(h_invh, &pl->d_invh, pl->table_bytes))) return rc;
+        if ((rc = upload<double>(h_rr, &pl->d_rr, pl->table_bytes))) return rc;
+    }
+    return EMIRWV_OK;
+}
+
+// Work items: (slitlet, block of rectified rows, block of output columns).
+int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
+    const emirwv_plan_desc &d = pl->desc;
+    const int nout = pl->nout, NB = pl->NB, W = pl->W, K = pl->K;
+    const int TK = pl->tile_k, TR = pl->tile_rows;
+    std::vector<Tile> live, dead;
+    pl->wrows_max = pl->wcols_max = 1;
+    int npx_max = 1;
+    for (int s = 0; s < pl->nsl; ++s) {
+        const emirwv_slitlet_desc &sl = d.slitlet[s];
+        const int nchan = sl.valid ? sl.bb_nc2_orig - sl.bb_nc1_orig + 1 : 0;
+        for (int y0 = 0; y0 < NROWS; y0 += TR) {
+            const int ny = std::min(TR, NROWS - y0);
+            for (int k0 = 0; k0 < nout; k0 += TK) {
+                Tile t;
+                memset(&t, 0, sizeof(t));
+                t.slit = s;
+                t.y0 = y0;
+                t.ny = ny;
+                t.k0 = k0;
+                t.nk = std::min(TK, nout - k0);
+                t.nchan = nchan;
+                bool any = false;
+                if (sl.valid)
+                    for (int k = k0; k <= k0 + t.nk; ++k) any |= covered[(size_t)s * NB + k] != 0;
+                // a pixel whose two borders lie on either side of the spectrum also counts
+                if (sl.valid && !any)
+                    any = pl->h_idx[(size_t)s * NB + k0] != pl->h_idx[(size_t)s * NB + k0 + t.nk];
+                if (!any) {
+                    t.empty = 1;
+                    if (y0 < pl->rps) dead.push_back(t);   // the ghost row stores nothing
+                    continue;
+                }
+                const int ilo = pl->h_idx[(size_t)s * NB + k0];
+                const int ihi = pl->h_idx[(size_t)s * NB + k0 + t.nk];
+                t.jlo = std::max(0, ilo - 1);
+                const int jhi = std::min(nchan - 1, ihi + 1);
+                t.npx = jhi - t.jlo + 1;
+                int r0 = INT_MAX, r1 = INT_MIN, c0 = INT_MAX, c1 = INT_MIN;
+                for (int y = y0; y < y0 + ny; ++y) {
+                    const int32_t *row = pl->h_base.data() + ((size_t)s * NROWS + y) * W;
+                    for (int j = t.jlo; j <= jhi; ++j) {
+                        const int br = base_row(row[j]), bc = base_col(row[j]);
+                        r0 = std::min(r0, br);
+                        r1 = std::max(r1, br + K - 1);
+                        c0 = std::min(c0, bc);
+                        c1 = std::max(c1, bc + K - 1);
+                    }
+                }
+                t.r0 = r0;
+                t.c0 = c0;
+                t.wrows = r1 - r0 + 1;
+                t.wcols = c1 - c0 + 1;
+                pl->wrows_max = std::max(pl->wrows_max, t.wrows);
+                pl->wcols_max = std::max(pl->wcols_max, t.wcols);
+                npx_max = std::max(npx_max, t.npx);
+                live.push_back(t);
+            }
+        }
+    }
+    pl->ntiles_empty = (int)dead.size();
+    pl->h_tiles = live;
+    pl->h_tiles.insert(pl->h_tiles.end(), dead.begin(), dead.end());
+    pl->ntiles = (int)pl->h_tiles.size();
+    pl->wpitch = (pl->wcols_max + 3) & ~3;
+    pl->npxp = (npx_max + 3) & ~3;
+    if (pl->ntiles > 65535) return fail(EMIRWV_E_LIMIT, "too many tiles (%d)", pl->ntiles);
+    if (smem_bytes(pl, 1, 1) > (size_t)SMEM_LIMIT)
+        return fail(EMIRWV_E_LIMIT,
+                    "distortion too strong: a %d x %d source window does not fit in shared memory",
+                    pl->wrows_max, pl->wcols_max);
+    CUDA_TRY(cudaMalloc(&pl->d_tiles, pl->h_tiles.size() * sizeof(Tile)));
+    CUDA_TRY(cudaMemcpy(pl->d_tiles, pl->h_tiles.data(), pl->h_tiles.size() * sizeof(Tile),
+                        cudaMemcpyHostToDevice));
+    pl->table_bytes += (int64_t)(pl->h_tiles.size() * sizeof(Tile));
+    return EMIRWV_OK;
+}
+
+int validate(const emirwv_plan_desc *d) {
+    if (d->naxis1 < 2 || d->naxis2 < 2 || d->naxis1 > 16384 || d->naxis2 > 16384)
+        return fail(EMIRWV_E_VALUE, "unsupported frame size %d x %d", d->naxis1, d->naxis2);
+    if (d->nslitlets < 1 || d->nslitlets > EMIRWV_MAX_SLITLETS)
+        return fail(EMIRWV_E_VALUE, "nslitlets=%d out of range", d->nslitlets);
+    if (d->rows_per_slitlet != NROWS - 1)
+        return fail(EMIRWV_E_VALUE, "rows_per_slitlet must be %d", NROWS - 1);
+    if (d->resampling < 1 || d->resampling > 3)
+        return fail(EMIRWV_E_VALUE, "Unexpected resampling value=%d", d->resampling);
+    if (d->dtype != EMIRWV_F32 && d->dtype != EMIRWV_F64)
+        return fail(EMIRWV_E_VALUE, "unknown dtype %d", d->dtype);
+    if (d->naxis1_out < 2 || d->naxis1_out > 65536)
+        return fail(EMIRWV_E_VALUE, "naxis1_out=%d out of range", d->naxis1_out);
+    if (!(d->cdelt1 > 0.0)) return fail(EMIRWV_E_VALUE, "cdelt1 must be positive");
+    const int cap = d->max_order > 0 ? d->max_order : 4;
+    for (int s = 0; s < d->nslitlets; ++s) {
+        const emirwv_slitlet_desc &sl = d->slitlet[s];
+        if (!sl.valid) continue;
+        const int order = order_from_ncoef(sl.ncoef);
+        if (order < 0 || order > cap)
+            return fail(EMIRWV_E_VALUE, "order > %d not implemented", cap);
+        if (sl.nwpoly < 1 || sl.nwpoly > EMIRWV_MAX_WPOLY)
+            return fail(EMIRWV_E_VALUE, "slitlet %d: %d wavelength coefficients", s + 1, sl.nwpoly);
+        if (sl.bb_nc1_orig < 1 || sl.bb_nc2_orig > d->naxis1 || sl.bb_nc2_orig < sl.bb_nc1_orig + 1 ||
+            sl.bb_ns1_orig < 1 || sl.bb_ns2_orig > d->naxis2 || sl.bb_ns2_orig < sl.bb_ns1_orig)
+            return fail(EMIRWV_E_VALUE, "slitlet %d: bounding box outside the frame", s + 1);
+        const int bbh = sl.bb_ns2_orig - sl.bb_ns1_orig + 1;
+        if (sl.max_row_rectified - sl.min_row_rectified + 1 != d->rows_per_slitlet)
+            return fail(EMIRWV_E_VALUE,
+                        "could not broadcast input array from shape (%d,%d) into shape (%d,%d)",
+                        sl.max_row_rectified - sl.min_row_rectified + 1, d->naxis1_out,
+                        d->rows_per_slitlet, d->naxis1_out);
+        if (sl.min_row_rectified < 0)
+            return fail(EMIRWV_E_VALUE, "slitlet %d: negative min_row_rectified", s + 1);
+        if (sl.max_row_rectified + 1 >= bbh)
+            return fail(EMIRWV_E_INDEX, "index %d is out of bounds for axis 0 with size %d",
+                        sl.max_row_rectified + 1, bbh);
+    }
+    return EMIRWV_OK;
+}
+
+int build_plan(emirwv_plan *pl) {
+    const emirwv_plan_desc &d = pl->desc;
+    CUDA_TRY(cudaGetDevice(&pl->device));
+    pl->dtype = d.dtype;
+    pl->mode = d.resampling;
+    pl->esize = d.dtype == EMIRWV_F32 ? 4 : 8;
+    pl->nsl = d.nslitlets;
+    pl->rps = d.rows_per_slitlet;
+    pl->W = d.naxis1;
+    pl->nout = d.naxis1_out;
+    pl->NB = d.naxis1_out + 1;
+    pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", 124);
+    pl->tile_rows = d.tile_rows > 0 ? d.tile_rows : env_int("EMIRWV_TILE_ROWS", NROWS);
+    pl->tile_k = std::max(31, std::min(pl->tile_k, 1024));
+    pl->tile_rows = std::max(1, std::min(pl->tile_rows, NROWS));
+
+    pl->h_slit.resize(pl->nsl);
+    for (int s = 0; s < pl->nsl; ++s) {
+        const emirwv_slitlet_desc &sl = d.slitlet[s];
+        SlitDev &sd = pl->h_slit[s];
+        memset(&sd, 0, sizeof(sd));
+        sd.valid = sl.valid ? 1 : 0;
+        if (!sl.valid) continue;
+        sd.ns1 = sl.bb_ns1_orig;
+        sd.nc1 = sl.bb_nc1_orig;
+        sd.bbh = sl.bb_ns2_orig - sl.bb_ns1_orig + 1;
+        sd.bbw = sl.bb_nc2_orig - sl.bb_nc1_orig + 1;
+        sd.min_row = sl.min_row_rectified;
+        sd.order = order_from_ncoef(sl.ncoef);
+        memcpy(sd.a, sl.aij, sizeof(double) * sl.ncoef);
+        memcpy(sd.b, sl.bij, sizeof(double) * sl.ncoef);
+    }
+    CUDA_TRY(cudaMalloc(&pl->d_slit, pl->nsl * sizeof(SlitDev)));
+    CUDA_TRY(cudaMemcpy(pl->d_slit, pl->h_slit.data(), pl->nsl * sizeof(SlitDev),
+                        cudaMemcpyHostToDevice));
+
+    GeomParams gp;
+    gp.slit = pl->d_slit;
+    gp.nsl = pl->nsl;
+    gp.W = pl->W;
+    gp.naxis1 = d.naxis1;
+    gp.naxis2 = d.naxis2;
+    gp.offx = d.offx;
+    gp.offy = d.offy;
+    gp.mode = pl->mode;
+    gp.kmax = nullptr;
+    const dim3 block(128);
+    const dim3 grid((pl->W + 127) / 128, NROWS, pl->nsl);
+
+    if (pl->mode == EMIRWV_AREA) {
+        int *d_kmax = nullptr;
+        int kmax = 1;
+        CUDA_TRY(cudaMalloc(&d_kmax, sizeof(int)));
+        CUDA_TRY(cudaMemcpy(d_kmax, &kmax, sizeof(int), cudaMemcpyHostToDevice));
+        gp.kmax = d_kmax;
+        gp.K = 0;
+        gp.base = nullptr;
+        k_extent<<<grid, block>>>(gp);
+        cudaError_t err = cudaGetLastError();
+        if (err == cudaSuccess)
+            err = cudaMemcpy(&kmax, d_kmax, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaFree(d_kmax);
+        if (err != cudaSuccess)
+            return fail(EMIRWV_E_CUDA, "k_extent failed: %s", cudaGetErrorString(err));
+        if (kmax > MAXK)
+            return fail(EMIRWV_E_LIMIT,
+                        "distortion too strong: an output pixel covers %d source pixels "
+                        "along one axis (limit %d)", kmax, MAXK);
+        pl->K = kmax;
+    } else {
+        pl->K = pl->mode == EMIRWV_NEAREST ? 1 : 2;
+    }
+
+    const size_t nrowtab = (size_t)pl->nsl * NROWS;
+    CUDA_TRY(cudaMalloc(&pl->d_base, nrowtab * pl->W * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&pl->d_w, nrowtab * pl->K * pl->K * pl->W * pl->esize));
+    pl->table_bytes += (int64_t)(nrowtab * pl->W * sizeof(int32_t));
+    pl->table_bytes += (int64_t)(nrowtab * pl->K * pl->K * pl->W * pl->esize);
+    gp.K = pl->K;
+    gp.base = pl->d_base;
+    gp.kmax = nullptr;
+    if (pl->dtype == EMIRWV_F32)
+        k_build_geometry<float><<<grid, block>>>(gp, static_cast<float *>(pl->d_w));
+    else
+        k_build_geometry<double><<<grid, block>>>(gp, static_cast<double *>(pl->d_w));
+    CUDA_TRY(cudaGetLastError());
+    pl->h_base.resize(nrowtab * pl->W);
+    CUDA_TRY(cudaMemcpy(pl->h_base.data(), pl->d_base, pl->h_base.size() * sizeof(int32_t),
+                        cudaMemcpyDeviceToHost));
+
+    std::vector<uint8_t> covered;
+    int rc = build_border_tables(pl, covered);
+    if (rc) return rc;
+    return build_tiles(pl, covered);
+}
+
+void release_workspace(emirwv_plan *pl) {
+    for (auto &sl : pl->slots) {
+        if (sl.d_in) cudaFree(sl.d_in);
+        if (sl.d_out) cudaFree(sl.d_out);
+        if (sl.d_jmm) cudaFree(sl.d_jmm);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+        sl = emirwv_plan::Slot();
+    }
+    pl->ws_chunk = 0;
+}
+
+int ensure_workspace(emirwv_plan *pl, int chunk) {
+    if (pl->ws_chunk >= chunk) return EMIRWV_OK;
+    release_workspace(pl);
+    const size_t in_b = (size_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
+    const size_t out_b = (size_t)pl->nsl * pl->rps * pl->nout * pl->esize;
+    for (auto &sl : pl->slots) {
+        CUDA_TRY(cudaMalloc(&sl.d_in, in_b * chunk));
+        CUDA_TRY(cudaMalloc(&sl.d_out, out_b * chunk));
+        CUDA_TRY(cudaMalloc(&sl.d_jmm, (size_t)chunk * pl->nsl * 2 * sizeof(int32_t)));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    }
+    pl->ws_chunk = chunk;
+    return EMIRWV_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int emirwv_version(void) { return EMIRWV_VERSION; }
+
+const char *emirwv_last_error(void) { return g_error.c_str(); }
+
+int emirwv_device_count(void) {
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess)
+        return fail(EMIRWV_E_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(err));
+    return n;
+}
+
+int emirwv_set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return EMIRWV_OK;
+}
+
+int emirwv_plan_create(const emirwv_plan_desc *desc, emirwv_plan **out) {
+    if (desc == nullptr || out == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    *out = nullptr;
+    int rc = validate(desc);
+    if (rc) return rc;
+    emirwv_plan *pl = new (std::nothrow) emirwv_plan();
+    if (pl == nullptr) return fail(EMIRWV_E_NOMEM, "out of host memory");
+    pl->desc = *desc;
+    rc = build_plan(pl);
+    if (rc == EMIRWV_OK) {
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess)
+            rc = fail(EMIRWV_E_CUDA, "plan build failed: %s", cudaGetErrorString(err));
+    }
+    if (rc) {
+        const std::string keep = g_error;
+        emirwv_plan_destroy(pl);
+        g_error = keep;
+        return rc;
+    }
+    *out = pl;
+    return EMIRWV_OK;
+}
+
+void emirwv_plan_destroy(emirwv_plan *pl) {
+    if (pl == nullptr) return;
+    DeviceGuard guard(pl->device);
+    release_workspace(pl);
+    cudaFree(pl->d_slit);
+    cudaFree(pl->d_base);
+    cudaFree(pl->d_w);
+    cudaFree(pl->d_idx);
+    cudaFree(pl->d_t);
+    cudaFree(pl->d_tau);
+    cudaFree(pl->d_invh);
+    cudaFree(pl->d_rr);
+    cudaFree(pl->d_tiles);
+    delete pl;
+}
+
+int emirwv_plan_get_info(const emirwv_plan *pl, emirwv_plan_info *info) {
+    if (pl == nullptr || info == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    memset(info, 0, sizeof(*info));
+    const LaunchCfg cfg = choose_cfg(pl, 1 << 20);
+    info->dtype = pl->dtype;
+    info->resampling = pl->mode;
+    info->footprint = pl->K;
+    info->naxis1_out = pl->nout;
+    info->naxis2_out = pl->nsl * pl->rps;
+    info->ntiles = pl->ntiles;
+    info->ntiles_empty = pl->ntiles_empty;
+    info->tile_k = pl->tile_k;
+    info->tile_rows = pl->tile_rows;
+    info->window_rows = pl->wrows_max;
+    info->window_cols = pl->wcols_max;
+    info->max_span = pl->max_span;
+    info->frames_per_cta = cfg.G;
+    info->smem_bytes = (int32_t)cfg.smem;
+    info->table_bytes = pl->table_bytes;
+    info->in_frame_bytes = (int64_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
+    info->out_frame_bytes = (int64_t)pl->nsl * pl->rps * pl->nout * pl->esize;
+    return EMIRWV_OK;
+}
+
+int emirwv_plan_set_tuning(emirwv_plan *pl, int frames_per_cta, int rows_per_pass, int threads) {
+    if (pl == nullptr) return fail(EMIRWV_E_VALUE, "null plan");
+    pl->tune_G = frames_per_cta;
+    pl->tune_RB = rows_per_pass;
+    pl->tune_threads = threads;
+    return EMIRWV_OK;
+}
+
+int emirwv_run(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
+               int32_t *d_jminmax, void *cuda_stream) {
+    if (pl == nullptr || d_in == nullptr || d_out == nullptr)
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (nframes < 0) return fail(EMIRWV_E_VALUE, "negative frame count");
+    if (nframes == 0) return EMIRWV_OK;
+    DeviceGuard guard(pl->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (pl->dtype == EMIRWV_F32) return launch_t<float>(pl, d_in, d_out, nframes, d_jminmax, st);
+    return launch_t<double>(pl, d_in, d_out, nframes, d_jminmax, st);
+}
+
+int emirwv_run_host(emirwv_plan *pl, const void *h_in, void *h_out, int nframes,
+                    int32_t *h_jminmax) {
+    if (pl == nullptr || h_in == nullptr || h_out == nullptr)
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (nframes < 0) return fail(EMIRWV_E_VALUE, "negative frame count");
+    if (nframes == 0) return EMIRWV_OK;
+    DeviceGuard guard(pl->device);
+    std::lock_guard<std::mutex> lock(pl->mu);
+    const int chunk = std::max(1, std::min(nframes, env_int("EMIRWV_HOST_CHUNK", 8)));
+    int rc = ensure_workspace(pl, chunk);
+    if (rc) return rc;
+    const size_t in_b = (size_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
+    const size_t out_b = (size_t)pl->nsl * pl->rps * pl->nout * pl->esize;
+    const size_t jmm_b = (size_t)pl->nsl * 2 * sizeof(int32_t);
+    int slot = 0;
+    for (int f0 = 0; f0 < nframes; f0 += chunk, slot = (slot + 1) % HOST_SLOTS) {
+        const int n = std::min(chunk, nframes - f0);
+        emirwv_plan::Slot &sl = pl->slots[slot];
+        CUDA_TRY(cudaMemcpyAsync(sl.d_in, static_cast<const char *>(h_in) + (size_t)f0 * in_b,
+                                 in_b * n, cudaMemcpyHostToDevice, sl.stream));
+        if (pl->dtype == EMIRWV_F32)
+            rc = launch_t<float>(pl, sl.d_in, sl.d_out, n, sl.d_jmm, sl.stream);
+        else
+            rc = launch_t<double>(pl, sl.d_in, sl.d_out, n, sl.d_jmm, sl.stream);
+        if (rc) break;
+        CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(h_out) + (size_t)f0 * out_b, sl.d_out,
+                                 out_b * n, cudaMemcpyDeviceToHost, sl.stream));
+        if (h_jminmax != nullptr)
+            CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char *>(h_jminmax) + (size_t)f0 * jmm_b,
+                                     sl.d_jmm, jmm_b * n, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    for (auto &sl : pl->slots) {
+        cudaError_t err = cudaStreamSynchronize(sl.stream);
+        if (err != cudaSuccess && rc == EMIRWV_OK)
+            rc = fail(EMIRWV_E_CUDA, "stream failed: %s", cudaGetErrorString(err));
+    }
+    return rc;
+}
+
+void *emirwv_host_alloc(int64_t nbytes) {
+    void *ptr = nullptr;
+    if (nbytes <= 0) return nullptr;
+    if (cudaHostAlloc(&ptr, (size_t)nbytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail(EMIRWV_E_NOMEM, "cudaHostAlloc(%lld) failed", (long long)nbytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return ptr;
+}
+
+void emirwv_host_free(void *ptr) {
+    if (ptr != nullptr) cudaFreeHost(ptr);
+}
+
+int emirwv_rectify_slitlet(const emirwv_plan *pl, const void *d_frame, int islitlet,
+                           void *d_rect, void *cuda_stream) {
+    if (pl == nullptr || d_frame == nullptr || d_rect == nullptr)
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (islitlet < 1 || islitlet > pl->nsl || !pl->h_slit[islitlet - 1].valid)
+        return fail(EMIRWV_E_VALUE, "slitlet %d is not available", islitlet);
+    DeviceGuard guard(pl->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int s = islitlet - 1;
+    const int bbw = pl->h_slit[s].bbw;
+    const dim3 grid((bbw + 127) / 128, NROWS);
+    if (pl->dtype == EMIRWV_F32)
+        k_rectify_only<float><<<grid, 128, 0, st>>>(
+            static_cast<const float *>(d_frame), static_cast<float *>(d_rect), pl->d_base,
+            static_cast<const float *>(pl->d_w), s, pl->K, pl->W, bbw, pl->desc.naxis1,
+            pl->desc.naxis2);
+    else
+        k_rectify_only<double><<<grid, 128, 0, st>>>(
+            static_cast<const double *>(d_frame), static_cast<double *>(d_rect), pl->d_base,
+            static_cast<const double *>(pl->d_w), s, pl->K, pl->W, bbw, pl->desc.naxis1,
+            pl->desc.naxis2);
+    CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+int emirwv_debug_geometry(const emirwv_plan *pl, int islitlet, int32_t *h_row, int32_t *h_col,
+                          uint8_t *h_ok, double *h_weights) {
+    if (pl == nullptr) return fail(EMIRWV_E_VALUE, "null plan");
+    if (islitlet < 1 || islitlet > pl->nsl || !pl->h_slit[islitlet - 1].valid)
+        return fail(EMIRWV_E_VALUE, "slitlet %d is not available", islitlet);
+    DeviceGuard guard(pl->device);
+    const int s = islitlet - 1;
+    const SlitDev &sd = pl->h_slit[s];
+    const int W = pl->W, KK = pl->K * pl->K;
+    for (int y = 0; y < NROWS; ++y)
+        for (int j = 0; j < sd.bbw; ++j) {
+            const int32_t pk = pl->h_base[((size_t)s * NROWS + y) * W + j];
+            const int r = base_row(pk) - (sd.ns1 - 1 - pl->desc.offy);
+            const int c = base_col(pk) - (sd.nc1 - 1 - pl->desc.offx);
+            if (h_row) h_row[(size_t)y * sd.bbw + j] = r;
+            if (h_col) h_col[(size_t)y * sd.bbw + j] = c;
+            if (h_ok) h_ok[(size_t)y * sd.bbw + j] = (r >= 0 && r < sd.bbh && c >= 0 && c < sd.bbw);
+        }
+    if (h_weights) {
+        const size_t n = (size_t)NROWS * KK * W;
+        std::vector<unsigned char> raw(n * pl->esize);
+        CUDA_TRY(cudaMemcpy(raw.data(),
+                            static_cast<const char *>(pl->d_w) + (size_t)s * n * pl->esize,
+                            n * pl->esize, cudaMemcpyDeviceToHost));
+        for (int y = 0; y < NROWS; ++y)
+            for (int tap = 0; tap < KK; ++tap)
+                for (int j = 0; j < sd.bbw; ++j) {
+                    const size_t src = ((size_t)y * KK + tap) * W + j;
+                    const double v = pl->dtype == EMIRWV_F32
+                                         ? (double)reinterpret_cast<const float *>(raw.data())[src]
+                                         : reinterpret_cast<const double *>(raw.data())[src];
+                    h_weights[((size_t)y * sd.bbw + j) * KK + tap] = v;
+                }
+    }
+    return EMIRWV_OK;
+}
+
+int emirwv_debug_borders(const emirwv_plan *pl, int islitlet, int32_t *h_idx, double *h_t) {
+    if (pl == nullptr) return fail(EMIRWV_E_VALUE, "null plan");
+    if (islitlet < 1 || islitlet > pl->nsl || !pl->h_slit[islitlet - 1].valid)
+        return fail(EMIRWV_E_VALUE, "slitlet %d is not available", islitlet);
+    const size_t off = (size_t)(islitlet - 1) * pl->NB;
+    for (int k = 0; k < pl->NB; ++k) {
+        if (h_idx) h_idx[k] = pl->h_idx[off + k];
+        if (h_t) h_t[k] = pl->h_t[off + k];
+    }
+    return EMIRWV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,357 @@
+"""CUDA path vs oracle, through the C ABI (needs a B200: ``-m gpu``).
+
+Tolerances (BASELINE.json north_star): bit-exact for index maps, interval indices,
+slitlet masks / zero patterns and header integers; 1e-12 relative for float64
+flux; 1e-5 relative for float32 flux.  "Relative" is applied per pixel with an
+absolute floor tied to the frame's flux scale (stated next to each assert),
+because pixels at the edge of the wavelength coverage are differences of nearly
+equal numbers in the oracle itself.
+"""
+
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import numina_restated as nr
+from oracle.pipeline import apply_rectwv_coeff as oracle_apply
+from pyemir_b200 import synthetic
+from pyemir_b200.apply_rectwv_coeff import (apply_rectwv_coeff, apply_rectwv_coeff_batch,
+                                            rectify_frames)
+from pyemir_b200.plan import RectWavePlan, clear_plan_cache, get_plan
+from pyemir_b200.set_wv_parameters import set_wv_parameters
+
+import proto_tables as proto
+
+pytestmark = pytest.mark.gpu
+
+
+def grid_of(coeff):
+    p = set_wv_parameters(coeff.tags["filter"], coeff.tags["grism"])
+    return dict(naxis1=p["naxis1_enlarged"], cdelt1=p["cdelt1_enlarged"],
+                crval1=p["crval1_enlarged"], crpix1=p["crpix1_enlarged"])
+
+
+def only_slitlets(coeff, keep):
+    c = copy.deepcopy(coeff)
+    c.missing_slitlets = [i for i in range(1, 56) if i not in keep]
+    return c
+
+
+def header_cards(hdul):
+    """All cards except the time-stamped last HISTORY (apply_rectwv_coeff.py:277-279)."""
+    cards = list(hdul[0].header.cards)
+    assert cards[-1][0] == "HISTORY" and "calibration time" in cards[-1][1]
+    return cards[:-1]
+
+
+def assert_flux_close(got, want, rtol, floor, what=""):
+    scale = np.abs(want).max()
+    err = np.abs(got.astype(np.float64) - want)
+    bound = rtol * np.abs(want) + floor * scale
+    worst = np.argmax(err - bound)
+    assert np.all(err <= bound), (what, float(err.ravel()[worst]), float(want.ravel()[worst]),
+                                  float(scale))
+
+
+@pytest.fixture(scope="module")
+def oracle_j(coeff_j, frame_j):
+    """Oracle output of BASELINE config 1 (one J+J frame), modes 1 and 2, float64."""
+    hdul = synthetic.make_hdulist(frame_j, coeff_j, with_mecs=True)
+    res = {}
+    for mode in (1, 2):
+        res[mode] = oracle_apply(hdul, coeff_j, args_resampling=mode,
+                                 only_needed_rows=True, return_float64=True)
+    return hdul, res
+
+
+# ------------------------------------------------------------------ plan geometry
+def test_nearest_index_maps_bit_exact_all_slitlets(coeff_j):
+    plan = get_plan(coeff_j, 1, "float64")
+    assert plan.info()["footprint"] == 1
+    for islitlet in range(1, 56):
+        entry = coeff_j.contents[islitlet - 1]
+        bbh, bbw = plan.bbox[islitlet]
+        rows = list(range(entry["min_row_rectified"], entry["max_row_rectified"] + 2))
+        _, iv, ju, ok = nr.rectify2d(np.zeros((bbh, bbw)), entry["ttd_aij"], entry["ttd_bij"],
+                                     1, rows=rows, return_maps=True)
+        g_row, g_col, g_ok, _ = plan.debug_geometry(islitlet, weights=False)
+        assert np.array_equal(g_row, iv), islitlet
+        assert np.array_equal(g_col, ju), islitlet
+        assert np.array_equal(g_ok, ok), islitlet
+
+
+def test_nearest_index_maps_bit_exact_order5():
+    coeff = synthetic.make_config(3)
+    plan = RectWavePlan(coeff, 1, "float64", max_order=5)
+    for islitlet in (1, 20, 55):
+        entry = coeff.contents[islitlet - 1]
+        bbh, bbw = plan.bbox[islitlet]
+        rows = list(range(entry["min_row_rectified"], entry["max_row_rectified"] + 2))
+        _, iv, ju, ok = nr.rectify2d(np.zeros((bbh, bbw)), entry["ttd_aij"], entry["ttd_bij"],
+                                     1, nmax_order=5, rows=rows, return_maps=True)
+        g_row, g_col, g_ok, _ = plan.debug_geometry(islitlet, weights=False)
+        assert np.array_equal(g_row, iv) and np.array_equal(g_col, ju)
+        assert np.array_equal(g_ok, ok)
+    plan.close()
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_weight_tables_match_independent_statement(coeff_j, mode):
+    plan = get_plan(coeff_j, mode, "float64")
+    for islitlet in (1, 33):
+        entry = coeff_j.contents[islitlet - 1]
+        br, bc, w, K = proto.rectify_tables(entry, mode)
+        g_row, g_col, _, g_w = plan.debug_geometry(islitlet)
+        assert plan.info()["footprint"] >= K
+        Kp = g_w.shape[-1]
+        ns1, nc1 = entry["bb_ns1_orig"], entry["bb_nc1_orig"]
+        assert np.array_equal(g_row + ns1 - 1, br) and np.array_equal(g_col + nc1 - 1, bc)
+        assert np.allclose(g_w[..., :K, :K], w, rtol=0, atol=1e-13)
+        if Kp > K:
+            assert np.all(g_w[..., K:, :] == 0) and np.all(g_w[..., :, K:] == 0)
+        # mode 2: weights of an interior pixel add up to the mapped pixel's area (≈ Jacobian)
+        if mode == 2:
+            total = g_w.sum(axis=(-1, -2))[5:30, 100:1900]
+            assert np.all((total > 0.8) & (total < 1.2))
+
+
+def test_border_tables_bit_exact(coeff_j):
+    plan = get_plan(coeff_j, 2, "float64")
+    for islitlet in (1, 28, 55):
+        tb = proto.rebin_tables(coeff_j.contents[islitlet - 1], **grid_of(coeff_j))
+        idx, t = plan.debug_borders(islitlet)
+        assert np.array_equal(idx, tb["idx"])
+        assert np.array_equal(t, tb["t"])
+
+
+def test_kernel1_alone_matches_oracle_rectify(coeff_j, frame_j):
+    import torch
+    plan = get_plan(coeff_j, 2, "float64")
+    frame = torch.from_numpy(frame_j.astype(np.float64)).cuda()
+    for islitlet in (2, 40):
+        entry = coeff_j.contents[islitlet - 1]
+        ns1, ns2 = entry["bb_ns1_orig"], entry["bb_ns2_orig"]
+        rows = list(range(entry["min_row_rectified"], entry["max_row_rectified"] + 2))
+        want = nr.rectify2d(frame_j[ns1 - 1:ns2].astype(float), entry["ttd_aij"],
+                            entry["ttd_bij"], 2, rows=rows)[rows]
+        got = plan.rectify_slitlet_torch(frame, islitlet).cpu().numpy()
+        assert np.allclose(got, want, rtol=1e-13, atol=1e-13 * np.abs(want).max())
+
+
+# ------------------------------------------------------------------ full path parity
+@pytest.mark.parametrize("mode", [1, 2])
+def test_float64_parity_full_frame(coeff_j, frame_j, oracle_j, mode):
+    _, res = oracle_j
+    ref_hdul, ref64 = res[mode]
+    out, keywords = rectify_frames(frame_j.astype(np.float64), coeff_j, mode, dtype="float64")
+    got = out[0]
+    assert got.dtype == np.float64 and got.shape == (2090, 3400)
+    # float64: 1e-12 relative; floor 1e-12 x frame scale (the oracle differences a
+    # running sum ~1e4 x larger than a pixel, i.e. carries ~1e-12 relative noise itself)
+    assert_flux_close(got, ref64, 1e-12, 1e-12, f"mode {mode}")
+    assert np.array_equal(got == 0, ref64 == 0)           # coverage mask, bit-exact
+    hdr = ref_hdul[0].header
+    for islitlet, (imn, imx, jmn, jmx) in enumerate(keywords[0], start=1):
+        assert (imn, imx, jmn, jmx) == tuple(
+            hdr[f"{k}{islitlet:02d}"] for k in ("IMNSLT", "IMXSLT", "JMNSLT", "JMXSLT"))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_float32_parity_full_frame(coeff_j, frame_j, oracle_j, mode):
+    _, res = oracle_j
+    ref_hdul, ref64 = res[mode]
+    out, keywords = rectify_frames(frame_j, coeff_j, mode, dtype="float32")
+    got = out[0]
+    assert got.dtype == np.float32
+    # float32: 1e-5 relative, floor 2e-7 x frame scale (a few float32 ulps of the
+    # brightest pixel) for pixels that are small differences of large ones
+    assert_flux_close(got, ref64, 1e-5, 2e-7, f"mode {mode}")
+    assert np.array_equal(got == 0, ref64 == 0)
+    hdr = ref_hdul[0].header
+    for islitlet, (imn, imx, jmn, jmx) in enumerate(keywords[0], start=1):
+        assert (jmn, jmx) == (hdr[f"JMNSLT{islitlet:02d}"], hdr[f"JMXSLT{islitlet:02d}"])
+
+
+def test_dropin_hdulist_matches_oracle(coeff_j, frame_j, oracle_j):
+    hdul, res = oracle_j
+    ref_hdul, _ = res[2]
+    before = copy.deepcopy(hdul[0].header.cards)
+    got = apply_rectwv_coeff(hdul, coeff_j)                   # default kwargs, like the recipes
+    assert hdul[0].header.cards == before and hdul[0].data is frame_j   # input untouched
+    assert got[0].data.dtype == np.float32 and got[0].data.shape == (2090, 3400)
+    assert "MECS" in got and got["MECS"].header["XDTU"] == hdul["MECS"].header["XDTU"]
+    assert header_cards(got) == header_cards(ref_hdul)       # keywords, values, comments, order
+    assert_flux_close(got[0].data, ref_hdul[0].data.astype(np.float64), 1e-5, 2e-7)
+    for key in ("CD1_1", "PCD1_1", "PCRPIX1"):
+        assert key not in got[0].header
+    assert got[0].header["CRVAL1"] == 11200.0 and got[0].header["CTYPE1"] == "WAVE"
+
+
+def test_dropin_float64_input_uses_float64_kernels(coeff_j, frame_j, oracle_j):
+    hdul, res = oracle_j
+    ref_hdul, _ = res[2]
+    h64 = synthetic.make_hdulist(frame_j.astype(np.float64), coeff_j)
+    got = apply_rectwv_coeff(h64, coeff_j)
+    # float64 arithmetic then the same float32 cast as the reference: equal to 1 ulp
+    a, b = got[0].data, ref_hdul[0].data
+    assert a.dtype == np.float32
+    assert np.all(np.abs(a - b) <= np.spacing(np.abs(b)) + 1e-12 * np.abs(b).max())
+
+
+def test_error_behaviour(coeff_j, frame_j):
+    hdul = synthetic.make_hdulist(frame_j, coeff_j)
+    bad = copy.deepcopy(hdul)
+    bad[0].header["FILTER"] = "H"
+    with pytest.raises(ValueError, match="Filter name does not match!"):
+        apply_rectwv_coeff(bad, coeff_j)
+    bad = copy.deepcopy(hdul)
+    bad[0].header["GRISM"] = "K"
+    with pytest.raises(ValueError, match="Grism name does not match!"):
+        apply_rectwv_coeff(bad, coeff_j)
+    bad = copy.deepcopy(hdul)
+    bad[0].header["XDTU"] = 1.0
+    apply_rectwv_coeff(bad, coeff_j)                                   # warning only
+    with pytest.raises(ValueError, match="DTU configurations do not match!"):
+        apply_rectwv_coeff(bad, coeff_j, args_ignore_dtu_configuration=False)
+    with pytest.raises(ValueError, match="Unexpected resampling value=7"):
+        apply_rectwv_coeff(hdul, coeff_j, args_resampling=7)
+    small = synthetic.make_hdulist(frame_j[:100], coeff_j)
+    with pytest.raises(ValueError, match="Unexpected naxis2"):
+        apply_rectwv_coeff(small, coeff_j)
+    c5 = synthetic.make_config(3)
+    h5 = synthetic.make_hdulist(frame_j, c5)
+    with pytest.raises(ValueError, match="order > 4 not implemented"):
+        apply_rectwv_coeff(h5, c5)
+    cbad = copy.deepcopy(coeff_j)
+    cbad.global_integer_offset_x_pix = 1.0
+    with pytest.raises(ValueError, match="non-integer offsets"):
+        apply_rectwv_coeff(hdul, cbad)
+    cbad = copy.deepcopy(coeff_j)
+    cbad.contents[9]["max_row_rectified"] = (cbad.contents[9]["bb_ns2_orig"]
+                                             - cbad.contents[9]["bb_ns1_orig"])
+    cbad.contents[9]["min_row_rectified"] = cbad.contents[9]["max_row_rectified"] - 37
+    with pytest.raises(IndexError):
+        apply_rectwv_coeff(hdul, cbad)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_missing_slitlets_and_offsets(frame_j):
+    coeff = synthetic.make_config(1, missing_slitlets=[1, 55, 17], offx=3, offy=-2)
+    hdul = synthetic.make_hdulist(frame_j, coeff)
+    ref, ref64 = oracle_apply(hdul, coeff, only_needed_rows=True, return_float64=True)
+    got = apply_rectwv_coeff(hdul, coeff, dtype="float64")
+    assert header_cards(got) == header_cards(ref)
+    for islitlet in (1, 17, 55):
+        assert np.all(got[0].data[(islitlet - 1) * 38: islitlet * 38] == 0)
+        assert got[0].header[f"IMNSLT{islitlet:02d}"] == 0
+    out, _ = rectify_frames(frame_j.astype(np.float64), coeff, 2, dtype="float64")
+    assert_flux_close(out[0], ref64, 1e-12, 1e-12)
+    assert np.array_equal(out[0] == 0, ref64 == 0)
+
+
+def test_order5_distortion(frame_j):
+    coeff = only_slitlets(synthetic.make_config(3), [3, 30, 53])
+    hdul = synthetic.make_hdulist(frame_j, coeff)
+    ref, ref64 = oracle_apply(hdul, coeff, only_needed_rows=True, return_float64=True,
+                              nmax_order=5)
+    out, kw = rectify_frames(frame_j.astype(np.float64), coeff, 2, dtype="float64", max_order=5)
+    assert_flux_close(out[0], ref64, 1e-12, 1e-12)
+    assert np.array_equal(out[0] == 0, ref64 == 0)
+    out32, _ = rectify_frames(frame_j, coeff, 2, dtype="float32", max_order=5)
+    assert_flux_close(out32[0], ref64, 1e-5, 2e-7)
+
+
+@pytest.mark.parametrize("number", [4, "4b"])
+def test_lr_grisms_float64(frame_j, number):
+    coeff = only_slitlets(synthetic.make_config(number), [4, 29, 55])
+    hdul = synthetic.make_hdulist(frame_j, coeff)
+    ref, ref64 = oracle_apply(hdul, coeff, only_needed_rows=True, return_float64=True)
+    out, kw = rectify_frames(frame_j.astype(np.float64), coeff, 2, dtype="float64")
+    assert out.shape[1:] == ref64.shape and ref64.shape[1] in (1270, 1435)
+    assert_flux_close(out[0], ref64, 1e-12, 1e-12)
+    assert np.array_equal(out[0] == 0, ref64 == 0)
+    got = apply_rectwv_coeff(hdul, coeff, dtype="float64")
+    assert header_cards(got) == header_cards(ref)
+
+
+def test_bilinear_extension(coeff_j, frame_j):
+    coeff = only_slitlets(coeff_j, [12, 44])
+    hdul = synthetic.make_hdulist(frame_j, coeff)
+    _, ref64 = oracle_apply(hdul, coeff, args_resampling=3, only_needed_rows=True,
+                            allow_extensions=True, return_float64=True)
+    out, _ = rectify_frames(frame_j.astype(np.float64), coeff, 3, dtype="float64")
+    assert_flux_close(out[0], ref64, 1e-12, 1e-12)
+
+
+def test_integer_input(coeff_j, frame_j):
+    coeff = only_slitlets(coeff_j, [8])
+    data = np.clip(frame_j, 0, 60000).astype(np.uint16)
+    hdul = synthetic.make_hdulist(data, coeff)
+    ref = oracle_apply(hdul, coeff, only_needed_rows=True)
+    got = apply_rectwv_coeff(hdul, coeff)
+    assert header_cards(got) == header_cards(ref)
+    assert_flux_close(got[0].data, ref[0].data.astype(np.float64), 1e-5, 2e-7)
+
+
+# ------------------------------------------------------------------ size-independent properties
+@pytest.fixture(scope="module")
+def batch64(coeff_j, scene_j):
+    """BASELINE config-2 sized batch: 64 frames (float32)."""
+    return synthetic.make_frames(coeff_j, 64, seed=77, scene=scene_j)
+
+
+def test_batch_properties_64_frames(coeff_j, batch64):
+    import torch
+    plan = get_plan(coeff_j, 2, "float32")
+    frames = torch.from_numpy(batch64).cuda()
+    out, jmm = plan.run_torch(frames)
+    torch.cuda.synchronize()
+    # determinism and independence of the frame grouping inside a CTA
+    for g, rb, threads in ((1, 1, 128), (2, 4, 256), (4, 2, 192)):
+        plan.set_tuning(g, rb, threads)
+        out2, jmm2 = plan.run_torch(frames[:7])
+        torch.cuda.synchronize()
+        assert torch.equal(out2, out[:7]) and torch.equal(jmm2, jmm[:7]), (g, rb, threads)
+    plan.set_tuning(0, 0, 0)
+    # homogeneity: every stage is positively homogeneous, scaling by 2 is exact in binary
+    out3, _ = plan.run_torch(frames[:4] * 2.0)
+    assert torch.equal(out3, out[:4] * 2.0)
+    # zero frames -> exact zeros and no useful channel
+    outz, jmmz = plan.run_torch(torch.zeros_like(frames[:2]))
+    assert not outz.any()
+    assert bool((jmmz[..., 1] == -1).all()) and bool((jmmz[..., 0] == 2**31 - 1).all())
+    # flux conservation of the rebin: sum over wavelength of a slitlet row equals the
+    # rectified row's flux inside the output grid (float64 sums of float32 data)
+    islitlet = 28
+    entry = coeff_j.contents[islitlet - 1]
+    tb = proto.rebin_tables(entry, **grid_of(coeff_j))
+    rect = plan.rectify_slitlet_torch(frames[5], islitlet).double().cpu().numpy()
+    rows = out[5, (islitlet - 1) * 38: islitlet * 38].double().cpu().numpy()
+    starts_before = tb["idx"][0] == 0 and tb["t"][0] == 0
+    ends_after = tb["idx"][-1] == tb["nchan"] - 1 and np.isclose(tb["tau"][-1], 1.0)
+    assert starts_before and ends_after          # J slitlet 28 lies inside the grid
+    assert np.allclose(rows.sum(axis=1), rect[:38].sum(axis=1), rtol=2e-6)
+    # host-buffer entry point agrees bit for bit with the device entry point
+    host_out, host_jmm = plan.run_host(batch64[:11])
+    assert np.array_equal(host_out, out[:11].cpu().numpy())
+    assert np.array_equal(host_jmm, jmm[:11].cpu().numpy())
+
+
+def test_batch_api_equals_single_calls(coeff_j, batch64):
+    hduls = [synthetic.make_hdulist(batch64[i], coeff_j) for i in range(3)]
+    batch = apply_rectwv_coeff_batch(hduls, coeff_j)
+    for hdul, got in zip(hduls, batch):
+        single = apply_rectwv_coeff(hdul, coeff_j)
+        assert np.array_equal(single[0].data, got[0].data)
+        assert header_cards(single) == header_cards(got)
+
+
+def test_plan_cache_reuse(coeff_j):
+    clear_plan_cache()
+    a = get_plan(coeff_j, 2, "float32")
+    b = get_plan(copy.deepcopy(coeff_j), 2, "float32")
+    assert a is b
+    c = copy.deepcopy(coeff_j)
+    c.global_integer_offset_x_pix += 1
+    assert get_plan(c, 2, "float32") is not a
