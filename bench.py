@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the apply_rectwv_coeff hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle)
+
+A "step" is one pass of the hot path over one batch of synthetic frames per GPU
+(default: BASELINE config 2 — 64 float32 2048x2048 frames, grism H + filter H,
+resampling 2, one shared RectWaveCoeff).  Ranks own independent batches (weak
+scaling, no collective on the data path).  Rank 0 prints ONE JSON line.
+"""
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rectified+wavecal 2048x2048 frames/sec"
+UNIT = "frames/s"
+FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="2", help="BASELINE config number (1,2,3,4,4b,5)")
+    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--resampling", type=int, default=2)
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--g", type=int, default=0, help="frames per CTA (tuning)")
+    ap.add_argument("--rb", type=int, default=0, help="rectified rows per pass (tuning)")
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--tile-k", type=int, default=0)
+    ap.add_argument("--tile-rows", type=int, default=0)
+    ap.add_argument("--combine", default="none", choices=["none", "mean", "gather"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=3,
+                    help="frames of the CPU-baseline sample (0 disables it)")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0)
+    return ap.parse_args()
+
+
+def config_key(text):
+    return int(text) if text.isdigit() else text
+
+
+# --------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1 + 0.15] or [l for _, l in self.lines]
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for row in rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------- CPU arms
+def _oracle_one(args):
+    """Worker: the oracle on one frame restricted to some slitlets (faithful rows)."""
+    seed, config, resampling, keep = args
+    import copy
+
+    from oracle.pipeline import apply_rectwv_coeff as oracle_apply
+    from pyemir_b200 import synthetic
+    coeff = _cached_coeff(config)
+    frame = _cached_frames(config, seed)
+    c = copy.copy(coeff)
+    c.missing_slitlets = sorted(set(coeff.missing_slitlets)
+                                | {i for i in range(1, 56) if i not in keep})
+    hdul = synthetic.make_hdulist(frame, c)
+    t0 = time.perf_counter()
+    oracle_apply(hdul, c, args_resampling=resampling,
+                 nmax_order=5 if config == 3 else 4)
+    return time.perf_counter() - t0
+
+
+_COEFF = {}
+_FRAMES = {}
+
+
+def _cached_coeff(config):
+    from pyemir_b200 import synthetic
+    if config not in _COEFF:
+        _COEFF[config] = synthetic.make_config(config)
+    return _COEFF[config]
+
+
+def _cached_frames(config, seed):
+    from pyemir_b200 import synthetic
+    key = (config, seed)
+    if key not in _FRAMES:
+        _FRAMES[key] = synthetic.make_frames(_cached_coeff(config), 1, seed=seed)[0]
+    return _FRAMES[key]
+
+
+def cpu_baseline_single(config, resampling, nframes):
+    """Oracle, one process, one thread, whole frames (mirrors how the reference runs)."""
+    times = [_oracle_one((1000 + i, config, resampling, tuple(range(1, 56))))
+             for i in range(nframes)]
+    total = sum(times)
+    return {"value": nframes / total, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{nframes} whole frames of this workload through the float64 CPU "
+                      f"oracle (restatement of pyemir+numina, all bounding-box rows), "
+                      f"1 process / 1 thread, {total:.1f} s"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU oracle on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    config = config_key(args.config)
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    per_slitlet_s = 0.11
+    nsl = int(args.ref_budget_s / ((args.steps + args.warmup) * per_slitlet_s))
+    nsl = max(5, min(55, nsl))
+    _cached_coeff(config)
+    for w in range(workers):
+        _cached_frames(config, 2000 + w)        # generated before the fork, shared
+    ctx = mp.get_context("fork")
+    step_times = []
+    with ctx.Pool(workers) as pool:
+        for step in range(args.warmup + args.steps):
+            first = (step * nsl) % 55
+            keep = tuple(((first + k) % 55) + 1 for k in range(nsl))
+            jobs = [(2000 + w, config, args.resampling, keep) for w in range(workers)]
+            t0 = time.perf_counter()
+            pool.map(_oracle_one, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                step_times.append(dt)
+    total = sum(step_times)
+    frames_equiv = workers * (nsl / 55.0) * len(step_times)
+    value = frames_equiv / total
+    sample = (f"each step: {workers} worker processes x 1 frame x {nsl} of 55 slitlets "
+              f"through the float64 CPU oracle (restatement of pyemir+numina; the real "
+              f"reference needs numina+astropy, absent here)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(step_times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, config, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, config, info):
+    from pyemir_b200 import synthetic
+    cfg = synthetic.BASELINE_CONFIGS[config]
+    out = {
+        "workload": (f"BASELINE config {config}: {args.frames} synthetic 2048x2048 float32 "
+                     f"frames per GPU per step, grism {cfg['grism']} + filter "
+                     f"{cfg['filter_name']}, 55 slitlets, ttd order {cfg['order']}, "
+                     f"resampling {args.resampling} (flux-preserving area overlap), one "
+                     f"shared RectWaveCoeff"),
+        "frames_per_gpu_per_step": args.frames,
+        "resampling": args.resampling,
+        "l2_policy": "inputs larger than L2 (batch in+out = %.2f GB per step vs 126 MB L2)"
+                     % (args.frames * (16.78 + 28.42) / 1e3),
+        "combine": args.combine,
+    }
+    if info:
+        out.update({"frames_per_cta": info["frames_per_cta"], "tile_k": info["tile_k"],
+                    "tile_rows": info["tile_rows"], "footprint": info["footprint"],
+                    "smem_bytes": info["smem_bytes"], "table_MB": info["table_bytes"] / 1e6})
+    return out
+
+
+# --------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pyemir_b200 import synthetic
+    from pyemir_b200.distributed import gather_frames, init_from_env, reduce_mean
+    from pyemir_b200.plan import RectWavePlan
+
+    rank, world, local_rank = init_from_env("nccl")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pyemir_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    config = config_key(args.config)
+    cfg = synthetic.BASELINE_CONFIGS[config]
+
+    coeff = synthetic.make_config(config)
+    plan = RectWavePlan(coeff, args.resampling, args.dtype, max_order=5,
+                        tile_k=args.tile_k, tile_rows=args.tile_rows, device=local_rank)
+    plan.set_tuning(args.g, args.rb, args.threads)
+    info = plan.info()
+    F = args.frames
+    npdt = np.float32 if args.dtype == "float32" else np.float64
+    frames_np = synthetic.make_frames(coeff, F, seed=cfg["seed"] + 31 * rank, dtype=npdt)
+
+    h_in = torch.empty(frames_np.shape, dtype=torch.from_numpy(frames_np[:1]).dtype,
+                       pin_memory=True)
+    h_in.copy_(torch.from_numpy(frames_np))
+    del frames_np
+    d_in = h_in.to(dev, non_blocking=True)
+    d_out = torch.empty((F,) + plan.out_shape, dtype=d_in.dtype, device=dev)
+    d_jmm = torch.empty((F, 55, 2), dtype=torch.int32, device=dev)
+    counts = [F] * world
+
+    def step():
+        plan.run_torch(d_in, d_out, d_jmm)
+        if args.combine == "mean":
+            reduce_mean(d_out, F * world, 0)
+        elif args.combine == "gather":
+            gather_frames(d_out, counts, 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    t0 = time.perf_counter()
+    events[0].record()
+    for i in range(args.steps):
+        step()
+        events[i + 1].record()
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    elapsed_ms = events[0].elapsed_time(events[-1])
+    launch_ms = [events[i].elapsed_time(events[i + 1]) for i in range(args.steps)]
+    el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(el.item())
+    value = world * F * args.steps / (elapsed_ms / 1e3)
+
+    # ---- end to end through the host-buffer C-ABI entry (pinned host in/out)
+    e2e = None
+    if args.e2e_steps > 0:
+        h_out = torch.empty((F,) + plan.out_shape, dtype=h_in.dtype, pin_memory=True)
+        h_jmm = torch.empty((F, 55, 2), dtype=torch.int32, pin_memory=True)
+        a_in, a_out, a_jmm = h_in.numpy(), h_out.numpy(), h_jmm.numpy()
+        plan.run_host(a_in, a_out, a_jmm)                    # warm-up (allocates staging)
+        barrier()
+        t0e = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            plan.run_host(a_in, a_out, a_jmm)
+        barrier()
+        dte = time.perf_counter() - t0e
+        te = torch.tensor([dte], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * F * args.e2e_steps / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(a_in.nbytes),
+               "d2h_bytes_per_step": int(a_out.nbytes + a_jmm.nbytes),
+               "steps": args.e2e_steps,
+               "checksum": float(a_out[0, 1000:1038].sum())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_rectwv): algorithmic bytes / launch time
+    bytes_per_launch = F * (info["in_frame_bytes"] + info["out_frame_bytes"])
+    avg_launch_s = statistics.mean(launch_ms) / 1e3
+    achieved = bytes_per_launch / avg_launch_s / 1e9
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fd:
+            peak = float(json.load(fd)["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fd:
+            rec = json.load(fd).get(f"config{config}_{args.dtype}_r{args.resampling}")
+            if rec and rec.get("frames"):
+                traffic = rec["dram_bytes_per_launch"] * F / rec["frames"]
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel": "k_rectwv", "bytes_per_launch": bytes_per_launch,
+                "launch_ms": statistics.mean(launch_ms)}
+
+    cpu = None
+    if world == 1 and args.cpu_frames > 0:
+        cpu = cpu_baseline_single(config, args.resampling, args.cpu_frames)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+        "config": workload_config(args, config, info),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": 2 * args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -200,6 +200,7 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
         int hr, hc;
         quad_extent(qu, bc, hc);
         quad_extent(qv, br, hr);
+        // absolute bounding-box coordinates, like the reference's clipping
         for (int a = 0; a < K; ++a)
             for (int b = 0; b < K; ++b) {
                 double area = 0.0;

@@ -35,6 +35,17 @@ EMIRWV_HD double add_rn(double a, double b) {
 #endif
 }
 
+EMIRWV_HD double sub_rn(double a, double b) { return add_rn(a, -b); }
+
+EMIRWV_HD double div_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    volatile double r = a / b;
+    return r;
+#endif
+}
+
 // order from the number of coefficients, -1 when ncoef is not triangular
 EMIRWV_HD int order_from_ncoef(int ncoef) {
     for (int order = 1; order <= 5; ++order)
@@ -78,15 +89,18 @@ struct Poly {
     int n;
 };
 
-// keep the part of `in` where sgn * (coord - bound) >= 0; axis 0 = x, 1 = y
+// keep the part of `in` where sgn * (coord - bound) >= 0; axis 0 = x, 1 = y.
+// Individually rounded operations in the reference's order (absolute image
+// coordinates, no fused multiply-add): the float64 areas then agree with the CPU
+// restatement of numina's clipping to the last bit instead of to ~ulp(2048).
 EMIRWV_HD void clip_edge(const Poly &in, int axis, double bound, double sgn, Poly &out) {
     out.n = 0;
     for (int i = 0; i < in.n; ++i) {
         const int j = (i + 1 == in.n) ? 0 : i + 1;
         const double ci = axis == 0 ? in.x[i] : in.y[i];
         const double cj = axis == 0 ? in.x[j] : in.y[j];
-        const double di = sgn * (ci - bound);
-        const double dj = sgn * (cj - bound);
+        const double di = mul_rn(sgn, sub_rn(ci, bound));
+        const double dj = mul_rn(sgn, sub_rn(cj, bound));
         const bool keep_i = di >= 0.0;
         const bool keep_j = dj >= 0.0;
         if (keep_i) {
@@ -95,9 +109,9 @@ EMIRWV_HD void clip_edge(const Poly &in, int axis, double bound, double sgn, Pol
             ++out.n;
         }
         if (keep_i != keep_j) {
-            const double f = di / (di - dj);
-            double nx = in.x[i] + f * (in.x[j] - in.x[i]);
-            double ny = in.y[i] + f * (in.y[j] - in.y[i]);
+            const double f = div_rn(di, sub_rn(di, dj));
+            double nx = add_rn(in.x[i], mul_rn(f, sub_rn(in.x[j], in.x[i])));
+            double ny = add_rn(in.y[i], mul_rn(f, sub_rn(in.y[j], in.y[i])));
             if (axis == 0) nx = bound; else ny = bound;
             out.x[out.n] = nx;
             out.y[out.n] = ny;
@@ -125,7 +139,7 @@ EMIRWV_HD double quad_box_area(const double *qx, const double *qy, double x0, do
     double twice = 0.0;
     for (int i = 0; i < p.n; ++i) {
         const int j = (i + 1 == p.n) ? 0 : i + 1;
-        twice += p.x[i] * p.y[j] - p.x[j] * p.y[i];
+        twice = add_rn(twice, sub_rn(mul_rn(p.x[i], p.y[j]), mul_rn(p.x[j], p.y[i])));
     }
     return 0.5 * fabs(twice);
 }

@@ -107,11 +107,13 @@ def test_weight_tables_match_independent_statement(coeff_j, mode):
         Kp = g_w.shape[-1]
         ns1, nc1 = entry["bb_ns1_orig"], entry["bb_nc1_orig"]
         assert np.array_equal(g_row + ns1 - 1, br) and np.array_equal(g_col + nc1 - 1, bc)
-        assert np.allclose(g_w[..., :K, :K], w, rtol=0, atol=1e-13)
+        # same clipping order and individually rounded operations as the oracle:
+        # the float64 weight tables are bit-identical
+        assert np.array_equal(g_w[..., :K, :K], w), np.abs(g_w[..., :K, :K] - w).max()
         if Kp > K:
             assert np.all(g_w[..., K:, :] == 0) and np.all(g_w[..., :, K:] == 0)
         # mode 2: weights of an interior pixel add up to the mapped pixel's area (≈ Jacobian)
-        if mode == 2:
+        if mode == 2 and islitlet == 33:      # slitlet 1 is cut by the detector edge
             total = g_w.sum(axis=(-1, -2))[5:30, 100:1900]
             assert np.all((total > 0.8) & (total < 1.2))
 
