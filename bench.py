@@ -40,7 +40,6 @@ def parse_args():
     ap.add_argument("--resampling", type=int, default=2)
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--g", type=int, default=0, help="frames per CTA (tuning)")
-    ap.add_argument("--rb", type=int, default=0, help="rectified rows per pass (tuning)")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--tile-k", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=0)
@@ -229,7 +228,8 @@ def workload_config(args, config, info):
         "combine": args.combine,
     }
     if info:
-        out.update({"frames_per_cta": info["frames_per_cta"], "tile_k": info["tile_k"],
+        out.update({"frames_per_cta": info["frames_per_cta"], "threads": info["threads"],
+                    "tile_k": info["tile_k"],
                     "tile_rows": info["tile_rows"], "footprint": info["footprint"],
                     "smem_bytes": info["smem_bytes"], "table_MB": info["table_bytes"] / 1e6})
     return out
@@ -256,7 +256,7 @@ def run_ours(args):
     coeff = synthetic.make_config(config)
     plan = RectWavePlan(coeff, args.resampling, args.dtype, max_order=5,
                         tile_k=args.tile_k, tile_rows=args.tile_rows, device=local_rank)
-    plan.set_tuning(args.g, args.rb, args.threads)
+    plan.set_tuning(args.g, args.threads)
     info = plan.info()
     F = args.frames
     npdt = np.float32 if args.dtype == "float32" else np.float64

@@ -107,7 +107,9 @@ typedef struct emirwv_plan_info {
     int32_t window_cols;
     int32_t max_span;               /* max whole source pixels inside one output pixel */
     int32_t frames_per_cta;         /* G chosen for the next launch                */
+    int32_t threads;                /* threads per CTA of that launch              */
     int32_t smem_bytes;             /* dynamic shared memory of that launch        */
+    int32_t reserved;
     int64_t table_bytes;            /* device memory held by the plan              */
     int64_t in_frame_bytes;
     int64_t out_frame_bytes;
@@ -134,9 +136,8 @@ void emirwv_plan_destroy(emirwv_plan *plan);
 int emirwv_plan_get_info(const emirwv_plan *plan, emirwv_plan_info *info);
 
 /* Launch tuning for subsequent runs (0 keeps the default): frames per CTA
- * (1, 2 or 4), rectified rows per pass, threads per CTA (multiple of 32). */
-int emirwv_plan_set_tuning(emirwv_plan *plan, int frames_per_cta, int rows_per_pass,
-                           int threads);
+ * (1, 2 or 4) and threads per CTA (multiple of 32, at most 512). */
+int emirwv_plan_set_tuning(emirwv_plan *plan, int frames_per_cta, int threads);
 
 /*
  * Rectify + wavelength-calibrate nframes device-resident frames.

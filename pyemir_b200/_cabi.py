@@ -84,7 +84,9 @@ class PlanInfo(ctypes.Structure):
         ("window_cols", ctypes.c_int32),
         ("max_span", ctypes.c_int32),
         ("frames_per_cta", ctypes.c_int32),
+        ("threads", ctypes.c_int32),
         ("smem_bytes", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
         ("table_bytes", ctypes.c_int64),
         ("in_frame_bytes", ctypes.c_int64),
         ("out_frame_bytes", ctypes.c_int64),
@@ -132,7 +134,7 @@ def load():
     lib.emirwv_plan_get_info.restype = i32
     lib.emirwv_plan_get_info.argtypes = [vp, ctypes.POINTER(PlanInfo)]
     lib.emirwv_plan_set_tuning.restype = i32
-    lib.emirwv_plan_set_tuning.argtypes = [vp, i32, i32, i32]
+    lib.emirwv_plan_set_tuning.argtypes = [vp, i32, i32]
     lib.emirwv_run.restype = i32
     lib.emirwv_run.argtypes = [vp, vp, vp, i32, vp, vp]
     lib.emirwv_run_host.restype = i32

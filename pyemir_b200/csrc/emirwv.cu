@@ -8,16 +8,17 @@
 //         (its centre, or its four corners) and the exact overlap areas with the
 //         source pixels  ->  frame-independent tables  base[s][y][j], w[s][y][tap][j]
 //     build_border_tables (host)  : for every border of the linear wavelength grid
-//         the source interval it falls in and the offset inside it
+//         the source interval it falls in and the fractional position inside it
 //     build_tiles (host)          : work items (slitlet, row block, column block)
 //         with the source window each one needs
 //
 //   run   (per batch of frames; one fused kernel, nothing intermediate touches HBM)
-//     k_rectwv<T,K,G>:  stage the source window of G frames in shared memory ->
+//     k_rectwv<T,K,G>: stage the source window of G frames in shared memory, then
+//       every warp owns whole rectified rows of the tile:
 //         A: rectified flux = K*K weighted gather            (kernel 1 of the spec)
-//         C: Steffen slopes of the cumulative flux per knot   (kernel 2)
-//         D: cumulative-flux difference at the output borders (kernel 2), store,
-//            first/last non-zero channel per slitlet          (kernel 3)
+//         C: Steffen-limited end slopes of every source pixel (kernel 2)
+//         D: cumulative-flux difference at the output borders (kernel 2), coalesced
+//            store, first/last non-zero channel per slitlet   (kernel 3)
 //
 // No tensor cores (there is no dense contraction), no CPU fallback.
 
@@ -43,7 +44,9 @@ namespace {
 using namespace emirwv;
 
 constexpr int NROWS = EMIRWV_ROWS_SCANNED;   // 39 rectified rows per slitlet
+constexpr int W = 2048;                      // EMIR_NAXIS1: pitch of per-column tables
 constexpr int MAXK = 4;                      // largest supported footprint
+constexpr int MAXTHREADS = 512;
 constexpr int HOST_SLOTS = 3;                // pipeline depth of emirwv_run_host
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -84,7 +87,7 @@ struct Tile {
     int k0, nk;         // output columns [k0, k0+nk)
     int jlo, npx;       // rectified columns needed: [jlo, jlo+npx)
     int r0, c0;         // frame coordinates of the staged source window origin
-    int wrows, wcols;
+    int wrows, wcols;   // c0 and wcols are multiples of 4 (16-byte vector loads)
     int empty;          // no wavelength coverage: the tile is exactly zero
     int nchan;          // bbw of the slitlet
     int pad[3];
@@ -92,7 +95,7 @@ struct Tile {
 
 struct GeomParams {
     const SlitDev *slit;
-    int nsl, W;             // W: table pitch (= naxis1 of the frame)
+    int nsl;
     int naxis1, naxis2;
     int offx, offy;
     int mode, K;
@@ -100,12 +103,29 @@ struct GeomParams {
     int *kmax;              // k_extent result
 };
 
+// Per source pixel i of a slitlet (frame independent), one 16/32-byte load:
+//   qm = h_i / h_{i-1},  qp = h_i / h_{i+1}   (h: width of the pixel in wavelength)
+//   r0 = h_i / (h_{i-1} + h_i),  r1 = h_{i+1} / (h_i + h_{i+1})
+template <typename T>
+struct alignas(4 * sizeof(T)) PixGeom {
+    T qm, qp, r0, r1;
+};
+
+// Per output border k of a slitlet: fractional position tau in source pixel idx.
+template <typename T>
+struct alignas(2 * sizeof(T)) Border {
+    T tau;
+    int32_t idx;
+};
+
+// Per source pixel and frame (shared memory): its flux and the Steffen-limited
+// slopes of the cumulative flux at its two ends, in flux-per-pixel units.
 template <typename T>
 struct alignas(4 * sizeof(T)) Knot {
-    T rect;   // flux of the source pixel (= y_{i+1} - y_i of the cumulative flux)
-    T s;      // secant slope rect / h_i
-    T yp0;    // limited slope at the left knot
-    T yp1;    // limited slope at the right knot
+    T rect;   // flux of the pixel = y_{i+1} - y_i of the cumulative flux
+    T ya;     // h_i * y'(left knot)
+    T yb;     // h_i * y'(right knot)
+    T pad;
 };
 
 template <typename T>
@@ -117,18 +137,16 @@ struct RunParams {
     const Tile *tiles;
     const int32_t *base;
     const T *w;
-    const int32_t *idx;
-    const T *t;
-    const T *tau;
-    const T *invh;
-    const T *rr;
-    int W, naxis1, naxis2;
+    const Border<T> *border;
+    const PixGeom<T> *pix;
+    int naxis2;
     int nout, NB;           // naxis1_out, naxis1_out + 1
     int rps, nrows_out;     // 38, 55*38
     int nsl;
-    int wpitch, wsz;        // shared window: row pitch and elements per frame
+    int wpitch, wrows;      // shared window: row pitch and rows per frame
     int npxp;               // scratch pitch (>= max npx)
-    int RB;                 // rectified rows per pass
+    int max_span;           // max whole source pixels inside one output pixel
+    int vec_ok;             // rows of the output are 16-byte aligned
 };
 
 __host__ __device__ inline int32_t pack_base(int r, int c) {
@@ -182,13 +200,13 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
     const int y = blockIdx.y;
     const int s = blockIdx.z;
     const SlitDev &sd = p.slit[s];
-    if (j >= p.W) return;
+    if (j >= W) return;
     const int K = p.K, KK = K * K;
     const size_t rowtab = (size_t)s * NROWS + y;
-    T *wp = w + rowtab * KK * p.W + j;
+    T *wp = w + rowtab * KK * W + j;
     if (!sd.valid || j >= sd.bbw) {
-        p.base[rowtab * p.W + j] = pack_base(0, 0);
-        for (int tap = 0; tap < KK; ++tap) wp[(size_t)tap * p.W] = T(0);
+        p.base[rowtab * W + j] = pack_base(0, 0);
+        for (int tap = 0; tap < KK; ++tap) wp[(size_t)tap * W] = T(0);
         return;
     }
     const int row = sd.min_row + y;
@@ -239,9 +257,9 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
             const int fr = fr0 + a, fc = fc0 + b;
             const bool inside = r >= 0 && r < sd.bbh && c >= 0 && c < sd.bbw && fr >= 0 &&
                                 fr < p.naxis2 && fc >= 0 && fc < p.naxis1;
-            wp[(size_t)(a * K + b) * p.W] = inside ? (T)wt[a * K + b] : T(0);
+            wp[(size_t)(a * K + b) * W] = inside ? (T)wt[a * K + b] : T(0);
         }
-    p.base[rowtab * p.W + j] = pack_base(fr0, fc0);
+    p.base[rowtab * W + j] = pack_base(fr0, fc0);
 }
 
 __global__ void k_init_jmm(int32_t *jmm, int n) {
@@ -252,7 +270,7 @@ __global__ void k_init_jmm(int32_t *jmm, int n) {
 // Kernel 1 alone, straight from global memory (parity hook / Slitlet2D.rectify).
 template <typename T>
 __global__ void k_rectify_only(const T *frame, T *rect, const int32_t *base, const T *w,
-                               int s, int K, int W, int bbw, int naxis1, int naxis2) {
+                               int s, int K, int bbw, int naxis1, int naxis2) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (j >= bbw) return;
@@ -272,48 +290,137 @@ __global__ void k_rectify_only(const T *frame, T *rect, const int32_t *base, con
 }
 
 // ---------------------------------------------------------------- the hot kernel
-template <typename T, int K, int G>
-__global__ void __launch_bounds__(256) k_rectwv(const RunParams<T> p) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+    using type = float4;
+    static constexpr int N = 4;
+};
+template <>
+struct Vec16<double> {
+    using type = double2;
+    static constexpr int N = 2;
+};
+
+// 16-byte asynchronous global -> shared copy (LDGSTS); zero fill when !valid
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int src_bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+// 8/16/32-byte table records through the read-only path (ld.global.nc)
+__device__ __forceinline__ PixGeom<float> ldg_struct(const PixGeom<float> *p) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    return PixGeom<float>{v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ PixGeom<double> ldg_struct(const PixGeom<double> *p) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return PixGeom<double>{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ Border<float> ldg_struct(const Border<float> *p) {
+    const int2 v = __ldg(reinterpret_cast<const int2 *>(p));
+    Border<float> b;
+    b.tau = __int_as_float(v.x);
+    b.idx = v.y;
+    return b;
+}
+__device__ __forceinline__ Border<double> ldg_struct(const Border<double> *p) {
+    const int4 v = __ldg(reinterpret_cast<const int4 *>(p));
+    Border<double> b;
+    b.tau = __hiloint2double(v.y, v.x);
+    b.idx = v.z;
+    return b;
+}
+
+// Make a loop-invariant value opaque so that the compiler keeps it in a register
+// instead of recomputing it from kernel parameters inside the hot loops.
+__device__ __forceinline__ void pin(int &x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
+template <typename P>
+__device__ __forceinline__ void pin(P *&x) { asm volatile("" : "+l"(x)); }
+
+// NPXP_C / WP_C: compile-time scratch pitch and window pitch (0 = take them from the
+// plan at run time).  With constants the gather taps and the per-frame scratch rows
+// are addressed with immediate offsets.
+template <typename T, int K, int G, int NPXP_C, int WP_C>
+__global__ void __launch_bounds__(MAXTHREADS) k_rectwv(const RunParams<T> p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using V = typename Vec16<T>::type;
+    constexpr int VN = Vec16<T>::N;
+
     const Tile tile = p.tiles[blockIdx.y];
     const int g0 = blockIdx.x * G;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int s = tile.slit;
-    const size_t frame_in = (size_t)p.naxis1 * p.naxis2;
+    const size_t frame_in = (size_t)W * p.naxis2;
     const size_t frame_out = (size_t)p.nrows_out * p.nout;
 
     if (tile.empty) {
         // outside the wavelength coverage (or a missing slitlet): exact zeros
         const int ylast = min(tile.y0 + tile.ny, p.rps);
+        const bool vec = p.vec_ok && ((tile.k0 | tile.nk) % VN) == 0;
         for (int g = 0; g < G && g0 + g < p.nframes; ++g)
             for (int y = tile.y0 + warp; y < ylast; y += nwarps) {
                 T *orow = p.out + (size_t)(g0 + g) * frame_out +
                           (size_t)(s * p.rps + y) * p.nout + tile.k0;
-                for (int k = lane; k < tile.nk; k += 32) orow[k] = T(0);
+                if (vec) {
+                    V zero;
+                    memset(&zero, 0, sizeof(zero));
+                    for (int k = lane; k < tile.nk / VN; k += 32) reinterpret_cast<V *>(orow)[k] = zero;
+                } else {
+                    for (int k = lane; k < tile.nk; k += 32) orow[k] = T(0);
+                }
             }
         return;
     }
 
-    Knot<T> *knots = reinterpret_cast<Knot<T> *>(smem_raw);
-    T *win = reinterpret_cast<T *>(knots + (size_t)G * p.RB * p.npxp);
-    T *rect = win + (size_t)G * p.wsz;
+    // shared memory: [G windows][per warp: G x (Knot[npxp], rect[npxp + 4])]
+    // (rect rows carry one zero element before and after the npx live ones)
+    const int npxp = NPXP_C ? NPXP_C : p.npxp;
+    const int wp1 = WP_C ? WP_C : p.wpitch;
+    const int wsz = p.wrows * wp1;
+    const int rpitch = npxp + 4;
+    T *win = reinterpret_cast<T *>(smem_raw);
+    int woff = G * wsz + warp * (G * (npxp * 4 + rpitch));     // this warp's scratch
+    pin(woff);                                                 // (kept in a register)
+    Knot<T> *knots = reinterpret_cast<Knot<T> *>(win + woff);  // [G][npxp]
+    T *rect = win + woff + G * npxp * 4 + 1;                   // [G][rpitch], halo at -1
 
-    // ---- stage the source window of each frame (zero outside the detector)
-    for (int g = 0; g < G; ++g) {
-        const bool live = g0 + g < p.nframes;
-        const T *fr = p.in + (size_t)(live ? g0 + g : 0) * frame_in;
-        T *wg = win + (size_t)g * p.wsz;
-        for (int rr = warp; rr < tile.wrows; rr += nwarps) {
-            const int r = tile.r0 + rr;
-            const bool rok = live && r >= 0 && r < p.naxis2;
-            const T *src = fr + (size_t)(rok ? r : 0) * p.naxis1;
-            for (int cc = lane; cc < tile.wcols; cc += 32) {
-                const int c = tile.c0 + cc;
-                wg[rr * p.wpitch + cc] = (rok && c >= 0 && c < p.naxis1) ? __ldg(src + c) : T(0);
+    // ---- stage the source window of each frame with cp.async (16-byte chunks, zero
+    //      fill outside the detector): c0, wcols and the frame width are multiples of 4.
+    //      One chunk index per thread; the row / column split uses the reciprocal trick.
+    {
+        const int vcols = tile.wcols / VN;
+        const int nvec = tile.wrows * vcols;
+        const float inv = 1.0f / (float)vcols;
+        for (int g = 0; g < G; ++g) {
+            if (g0 + g >= p.nframes) break;
+            const T *fr = p.in + (size_t)(g0 + g) * frame_in;
+            T *wg = win + (size_t)g * wsz;
+            for (int e = tid; e < nvec; e += blockDim.x) {
+                const int rr = (int)(((float)e + 0.5f) * inv);
+                const int vc = e - rr * vcols;
+                const int r = tile.r0 + rr, c = tile.c0 + vc * VN;
+                const bool ok = r >= 0 && r < p.naxis2 && c >= 0 && c < W;
+                cp_async_16(wg + rr * wp1 + vc * VN, fr + (ok ? (size_t)r * W + c : 0), ok);
             }
         }
     }
+    const int npx = tile.npx;
+    if (lane < G) {
+        rect[lane * rpitch - 1] = T(0);
+        rect[lane * rpitch + npx] = T(0);
+    }
+    cp_async_wait_all();
     __syncthreads();
 
     int jmin[G], jmax[G];
@@ -323,107 +430,117 @@ __global__ void __launch_bounds__(256) k_rectwv(const RunParams<T> p) {
         jmax[g] = -1;
     }
 
-    const int npx = tile.npx;
-    const int ncg = (tile.nk + 30) / 31;     // a warp evaluates 32 borders = 31 pixels
     const int kend = tile.k0 + tile.nk;
-    const T *invh = p.invh + (size_t)s * p.W;
-    const T *rrt = p.rr + (size_t)s * (p.W + 1);
-    const size_t btab = (size_t)s * p.NB;
+    const int max_span = p.max_span;
+    const int nlive = min(G, p.nframes - g0);
+    const PixGeom<T> *pix = p.pix + (size_t)s * W + tile.jlo + lane;
+    const Border<T> *border = p.border + (size_t)s * p.NB;
+    const Knot<T> *kread = knots - tile.jlo;                   // indexed by source pixel
+    T *obase = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
+    unsigned fo = (unsigned)frame_out;                         // < 2^32 elements per frame
+    int wb = -(tile.r0 * wp1 + tile.c0);                       // window addressed by frame coords
+    pin(pix);
+    pin(border);
+    pin(fo);
+    pin(wb);
 
-    for (int yb = 0; yb < tile.ny; yb += p.RB) {
-        const int nyy = min(p.RB, tile.ny - yb);
+    // every warp owns whole rows of the tile: no block-level barrier below
+    for (int yy = warp; yy < tile.ny; yy += nwarps) {
+        const int y = tile.y0 + yy;
+        const size_t rowtab = (size_t)s * NROWS + y;
+        const int32_t *brow = p.base + rowtab * W + tile.jlo + lane;
+        const T *wrow = p.w + rowtab * (K * K) * W + tile.jlo + lane;
+        T *orow = obase + (size_t)y * p.nout;
+        pin(orow);
 
         // ---- A: rectified flux, K*K weighted gather from the staged window
-        for (int item = tid; item < nyy * npx; item += blockDim.x) {
-            const int yy = item / npx;
-            const int pp = item - yy * npx;
-            const int j = tile.jlo + pp;
-            const size_t rowtab = (size_t)s * NROWS + (tile.y0 + yb + yy);
-            const int32_t pk = __ldg(p.base + rowtab * p.W + j);
-            const T *wp = p.w + rowtab * (K * K) * p.W + j;
-            T wt[K * K];
+        for (int p0 = 0; p0 < npx; p0 += 32) {
+            if (p0 + lane < npx) {
+                const int32_t pk = __ldg(brow + p0);
+                T wt[K * K];
 #pragma unroll
-            for (int tap = 0; tap < K * K; ++tap) wt[tap] = __ldg(wp + (size_t)tap * p.W);
-            const T *src = win + (base_row(pk) - tile.r0) * p.wpitch + (base_col(pk) - tile.c0);
+                for (int tap = 0; tap < K * K; ++tap) wt[tap] = __ldg(wrow + p0 + tap * W);
+                const T *src = win + (wb + base_row(pk) * wp1 + base_col(pk));
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                T acc = T(0);
+                for (int g = 0; g < G; ++g) {
+                    const T *sg = src + g * wsz;
+                    T acc = T(0);
 #pragma unroll
-                for (int a = 0; a < K; ++a)
+                    for (int a = 0; a < K; ++a)
 #pragma unroll
-                    for (int b = 0; b < K; ++b)
-                        acc = fma(wt[a * K + b], src[(size_t)g * p.wsz + a * p.wpitch + b], acc);
-                rect[(g * p.RB + yy) * p.npxp + pp] = acc;
-            }
-        }
-        __syncthreads();
-
-        // ---- C: secant slope of every source interval and Steffen's limited
-        //         slopes at its two knots (end knots of the spectrum have slope 0)
-        for (int item = tid; item < nyy * npx; item += blockDim.x) {
-            const int yy = item / npx;
-            const int pp = item - yy * npx;
-            const int i = tile.jlo + pp;
-            const bool has_l = pp > 0, has_r = pp < npx - 1;
-            const T ih0 = __ldg(invh + i);
-            const T ihm = has_l ? __ldg(invh + i - 1) : T(0);
-            const T ihp = has_r ? __ldg(invh + i + 1) : T(0);
-            const T r0 = __ldg(rrt + i);
-            const T r1 = __ldg(rrt + i + 1);
-            const bool knot0 = has_l && i > 0;
-            const bool knot1 = has_r && i + 1 < tile.nchan;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const T *rv = rect + (g * p.RB + yy) * p.npxp;
-                const T c = rv[pp];
-                const T sm = has_l ? rv[pp - 1] * ihm : T(0);
-                const T s0 = c * ih0;
-                const T sp = has_r ? rv[pp + 1] * ihp : T(0);
-                Knot<T> kn;
-                kn.rect = c;
-                kn.s = s0;
-                kn.yp0 = knot0 ? steffen_slope(sm, s0, r0) : T(0);
-                kn.yp1 = knot1 ? steffen_slope(s0, sp, r1) : T(0);
-                knots[(g * p.RB + yy) * p.npxp + pp] = kn;
-            }
-        }
-        __syncthreads();
-
-        // ---- D: cumulative flux at the output borders, difference, store
-        for (int task = warp; task < nyy * ncg; task += nwarps) {
-            const int yy = task / ncg;
-            const int cg = task - yy * ncg;
-            const int kb = tile.k0 + cg * 31 + lane;          // border index
-            const int kbc = min(kb, kend);
-            const int ib = __ldg(p.idx + btab + kbc);
-            const T tt = __ldg(p.t + btab + kbc);
-            const T ta = __ldg(p.tau + btab + kbc);
-            const int ibn = __shfl_down_sync(0xffffffffu, ib, 1);
-            const int y = tile.y0 + yb + yy;
-            const bool col_ok = lane < 31 && kb < kend;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const Knot<T> *kr = knots + (g * p.RB + yy) * p.npxp - tile.jlo;
-                const Knot<T> kn = kr[ib];
-                const T P = steffen_partial(kn.s, kn.yp0, kn.yp1, tt, ta);
-                const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
-                T whole = T(0);
-                if (col_ok && ibn > ib) {
-                    whole = kn.rect;
-                    for (int i = ib + 1; i < ibn; ++i) whole += kr[i].rect;
+                        for (int b = 0; b < K; ++b) acc = fma(wt[a * K + b], sg[a * wp1 + b], acc);
+                    rect[g * rpitch + p0 + lane] = acc;
                 }
-                const T o = whole + (Pn - P);
-                if (col_ok && g0 + g < p.nframes) {
-                    if (y < p.rps)
-                        p.out[(size_t)(g0 + g) * frame_out + (size_t)(s * p.rps + y) * p.nout + kb] = o;
-                    if (o != T(0)) {
+            }
+        }
+        __syncwarp();
+
+        // ---- C: Steffen-limited slopes at both ends of every source pixel, scaled by
+        //         the pixel width (flux units).  Branch-free: the table holds qm = 0 for
+        //         the first pixel of the spectrum and qp = 0 for the last one, which
+        //         gives the zero end slopes; the halo of `rect` is zero.  The table row
+        //         of the next pass is requested before this pass is computed.
+        {
+            PixGeom<T> next = ldg_struct(pix);
+            for (int p0 = 0; p0 < npx; p0 += 32) {
+                const PixGeom<T> pg = next;
+                next = ldg_struct(pix + p0 + 32);              // table is padded
+                if (p0 + lane < npx) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const T *rv = rect + g * rpitch + p0 + lane;
+                        const T c = rv[0];
+                        const T cl = rv[-1] * pg.qm;
+                        const T cr = rv[1] * pg.qp;
+                        Knot<T> kn;
+                        kn.rect = c;
+                        kn.ya = steffen_slope(cl, c, pg.r0);
+                        kn.yb = steffen_slope(c, cr, pg.r1);
+                        kn.pad = T(0);
+                        knots[g * npxp + p0 + lane] = kn;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- D: cumulative flux at the output borders (32 borders = 31 pixels per
+        //         warp pass), difference, coalesced store, non-zero channel range.
+        //         Lanes past the tile's last border re-read that border: their source
+        //         pixel stays inside this warp's scratch and their result is dropped.
+        {
+            const bool store = y < p.rps;
+            Border<T> next = ldg_struct(border + min(tile.k0 + lane, kend));
+            for (int kb0 = tile.k0; kb0 < kend; kb0 += 31) {
+                const int kb = kb0 + lane;
+                const Border<T> bd = next;
+                next = ldg_struct(border + min(kb + 31, kend));
+                const int ib = bd.idx;
+                const int ibn = __shfl_down_sync(0xffffffffu, ib, 1);
+                const bool col_ok = lane < 31 && kb < kend;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const Knot<T> *kr = kread + g * npxp;
+                    const Knot<T> kn = kr[ib];
+                    const T P = steffen_partial_flux(kn.rect, kn.ya, kn.yb, bd.tau);
+                    const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
+                    T whole = (ibn > ib) ? kn.rect : T(0);
+                    if (max_span > 1) {                        // warp-uniform
+                        if (ibn > ib + 1) whole += kr[ib + 1].rect;
+                        if (max_span > 2)
+                            for (int i = ib + 2; i < ibn; ++i) whole += kr[i].rect;
+                    }
+                    const T o = whole + (Pn - P);
+                    const bool okg = col_ok && g < nlive;
+                    if (okg && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o);
+                    if (okg && o != T(0)) {
                         jmin[g] = min(jmin[g], kb);
                         jmax[g] = max(jmax[g], kb);
                     }
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 
     // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
@@ -448,14 +565,13 @@ struct emirwv_plan {
     emirwv_plan_desc desc;
     int device = 0;
     int dtype = 0, mode = 0, K = 1;
-    int nsl = 0, rps = 0, W = 0, nout = 0, NB = 0;
+    int nsl = 0, rps = 0, nout = 0, NB = 0;
     size_t esize = 4;
 
     SlitDev *d_slit = nullptr;
     int32_t *d_base = nullptr;
     void *d_w = nullptr;
-    int32_t *d_idx = nullptr;
-    void *d_t = nullptr, *d_tau = nullptr, *d_invh = nullptr, *d_rr = nullptr;
+    void *d_border = nullptr, *d_pix = nullptr;
     Tile *d_tiles = nullptr;
 
     std::vector<SlitDev> h_slit;
@@ -467,7 +583,8 @@ struct emirwv_plan {
     int ntiles = 0, ntiles_empty = 0;
     int tile_k = 0, tile_rows = 0;
     int wrows_max = 0, wcols_max = 0, wpitch = 0, npxp = 0, max_span = 0;
-    int tune_G = 0, tune_RB = 0, tune_threads = 0;
+    int tune_G = 0, tune_threads = 0;
+    bool fast_pitch = false;     // npxp / wpitch equal the compile-time constants
     int64_t table_bytes = 0;
 
     std::mutex mu;
@@ -482,16 +599,6 @@ struct emirwv_plan {
 
 namespace {
 
-template <typename T>
-int upload(const std::vector<double> &src, void **dst, int64_t &bytes) {
-    std::vector<T> tmp(src.size());
-    for (size_t i = 0; i < src.size(); ++i) tmp[i] = (T)src[i];
-    CUDA_TRY(cudaMalloc(dst, tmp.size() * sizeof(T)));
-    CUDA_TRY(cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
-    bytes += (int64_t)(tmp.size() * sizeof(T));
-    return EMIRWV_OK;
-}
-
 int env_int(const char *name, int fallback) {
     const char *v = getenv(name);
     return (v && *v) ? atoi(v) : fallback;
@@ -499,42 +606,50 @@ int env_int(const char *name, int fallback) {
 
 // launch configuration for a given number of frames per CTA
 struct LaunchCfg {
-    int G, RB, threads;
+    int G, threads;
     size_t smem;
 };
 
-size_t smem_bytes(const emirwv_plan *pl, int G, int RB) {
-    const size_t knots = (size_t)G * RB * pl->npxp * 4 * pl->esize;
+size_t smem_bytes(const emirwv_plan *pl, int G, int threads) {
     const size_t win = (size_t)G * pl->wrows_max * pl->wpitch * pl->esize;
-    const size_t rect = (size_t)G * RB * pl->npxp * pl->esize;
-    return knots + win + rect;
+    const size_t scratch = (size_t)(threads / 32) * G * (pl->npxp * 5 + 4) * pl->esize;
+    return win + scratch;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
     LaunchCfg cfg;
     cfg.threads = pl->tune_threads > 0 ? pl->tune_threads : env_int("EMIRWV_THREADS", 256);
-    cfg.threads = std::max(32, std::min(256, (cfg.threads / 32) * 32));
-    cfg.RB = pl->tune_RB > 0 ? pl->tune_RB : env_int("EMIRWV_RB", 4);
-    cfg.RB = std::max(1, std::min(NROWS, cfg.RB));
+    cfg.threads = std::max(32, std::min(MAXTHREADS, (cfg.threads / 32) * 32));
     int G = pl->tune_G > 0 ? pl->tune_G : env_int("EMIRWV_G", 2);
     G = (G >= 4) ? 4 : (G >= 2 ? 2 : 1);
-    while (G > 1 && (G > nframes || smem_bytes(pl, G, cfg.RB) > (size_t)SMEM_LIMIT)) G >>= 1;
-    while (cfg.RB > 1 && smem_bytes(pl, G, cfg.RB) > (size_t)SMEM_LIMIT) --cfg.RB;
+    while (G > 1 && (G > nframes || smem_bytes(pl, G, cfg.threads) > (size_t)SMEM_LIMIT)) G >>= 1;
+    while (cfg.threads > 32 && smem_bytes(pl, G, cfg.threads) > (size_t)SMEM_LIMIT)
+        cfg.threads -= 32;
     cfg.G = G;
-    cfg.smem = smem_bytes(pl, G, cfg.RB);
+    cfg.smem = smem_bytes(pl, G, cfg.threads);
     return cfg;
 }
 
-template <typename T, int K, int G>
-int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
-               cudaStream_t st) {
-    auto kern = k_rectwv<T, K, G>;
+constexpr int FAST_NPXP = 144;   // scratch pitch of the specialised kernels
+constexpr int FAST_WP = 160;     // window pitch of the specialised kernels
+
+template <typename T, int K, int G, int NPXP_C, int WP_C>
+int launch_pitch(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
+                 cudaStream_t st) {
+    auto kern = k_rectwv<T, K, G, NPXP_C, WP_C>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)cfg.smem));
     const dim3 grid((rp.nframes + G - 1) / G, pl->ntiles);
     kern<<<grid, cfg.threads, cfg.smem, st>>>(rp);
     CUDA_TRY(cudaGetLastError());
     return EMIRWV_OK;
+}
+
+template <typename T, int K, int G>
+int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
+               cudaStream_t st) {
+    if (pl->fast_pitch) return launch_pitch<T, K, G, FAST_NPXP, FAST_WP>(pl, rp, cfg, st);
+    return launch_pitch<T, K, G, 0, 0>(pl, rp, cfg, st);
 }
 
 template <typename T, int K>
@@ -553,6 +668,8 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     const LaunchCfg cfg = choose_cfg(pl, nframes);
     if (cfg.smem > (size_t)SMEM_LIMIT)
         return fail(EMIRWV_E_LIMIT, "tile needs %zu bytes of shared memory", cfg.smem);
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
+        return fail(EMIRWV_E_VALUE, "device buffers must be 16-byte aligned");
     RunParams<T> rp;
     rp.in = static_cast<const T *>(d_in);
     rp.out = static_cast<T *>(d_out);
@@ -561,13 +678,8 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     rp.tiles = pl->d_tiles;
     rp.base = pl->d_base;
     rp.w = static_cast<const T *>(pl->d_w);
-    rp.idx = pl->d_idx;
-    rp.t = static_cast<const T *>(pl->d_t);
-    rp.tau = static_cast<const T *>(pl->d_tau);
-    rp.invh = static_cast<const T *>(pl->d_invh);
-    rp.rr = static_cast<const T *>(pl->d_rr);
-    rp.W = pl->W;
-    rp.naxis1 = pl->desc.naxis1;
+    rp.border = static_cast<const Border<T> *>(pl->d_border);
+    rp.pix = static_cast<const PixGeom<T> *>(pl->d_pix);
     rp.naxis2 = pl->desc.naxis2;
     rp.nout = pl->nout;
     rp.NB = pl->NB;
@@ -575,9 +687,10 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     rp.nrows_out = pl->nsl * pl->rps;
     rp.nsl = pl->nsl;
     rp.wpitch = pl->wpitch;
-    rp.wsz = pl->wrows_max * pl->wpitch;
+    rp.wrows = pl->wrows_max;
     rp.npxp = pl->npxp;
-    rp.RB = cfg.RB;
+    rp.max_span = pl->max_span;
+    rp.vec_ok = ((size_t)pl->nout * sizeof(T)) % 16 == 0;
     if (d_jmm != nullptr) {
         const int n = nframes * pl->nsl * 2;
         k_init_jmm<<<(n + 255) / 256, 256, 0, st>>>(d_jmm, n);
@@ -599,12 +712,48 @@ double polyval_np(double x, const double *c, int n) {
     return c0;
 }
 
+template <typename T>
+int upload_tables(emirwv_plan *pl, const std::vector<double> &tau, const std::vector<double> &h) {
+    const int nsl = pl->nsl, NB = pl->NB;
+    // both tables carry 64 extra entries: the kernel requests the row of its next
+    // pass before it knows whether there is one
+    std::vector<Border<T>> border((size_t)nsl * NB + 64);
+    memset(border.data(), 0, border.size() * sizeof(Border<T>));
+    for (size_t k = 0; k < (size_t)nsl * NB; ++k) {
+        border[k].tau = (T)tau[k];
+        border[k].idx = pl->h_idx[k];
+    }
+    std::vector<PixGeom<T>> pix((size_t)nsl * W + 64);
+    memset(pix.data(), 0, pix.size() * sizeof(PixGeom<T>));
+    for (int s = 0; s < nsl; ++s) {
+        const emirwv_slitlet_desc &sl = pl->desc.slitlet[s];
+        if (!sl.valid) continue;
+        const int nchan = sl.bb_nc2_orig - sl.bb_nc1_orig + 1;
+        const double *hs = h.data() + (size_t)s * W;
+        for (int i = 0; i < nchan; ++i) {
+            PixGeom<T> &pg = pix[(size_t)s * W + i];
+            pg.qm = i > 0 ? (T)(hs[i] / hs[i - 1]) : T(0);
+            pg.qp = i + 1 < nchan ? (T)(hs[i] / hs[i + 1]) : T(0);
+            pg.r0 = i > 0 ? (T)(hs[i] / (hs[i - 1] + hs[i])) : T(0);
+            pg.r1 = i + 1 < nchan ? (T)(hs[i + 1] / (hs[i] + hs[i + 1])) : T(0);
+        }
+    }
+    CUDA_TRY(cudaMalloc(&pl->d_border, border.size() * sizeof(Border<T>)));
+    CUDA_TRY(cudaMemcpy(pl->d_border, border.data(), border.size() * sizeof(Border<T>),
+                        cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&pl->d_pix, pix.size() * sizeof(PixGeom<T>)));
+    CUDA_TRY(cudaMemcpy(pl->d_pix, pix.data(), pix.size() * sizeof(PixGeom<T>),
+                        cudaMemcpyHostToDevice));
+    pl->table_bytes += (int64_t)(border.size() * sizeof(Border<T>) + pix.size() * sizeof(PixGeom<T>));
+    return EMIRWV_OK;
+}
+
 // Border tables of every slitlet; float64 with numpy's operation order so that the
 // interval of every border is the one numpy.searchsorted finds in the reference's
 // resample_image2d_flux / SteffenInterpolator (apply_rectwv_coeff.py:152-159).
 int build_border_tables(emirwv_plan *pl, std::vector<uint8_t> &covered) {
     const emirwv_plan_desc &d = pl->desc;
-    const int nout = pl->nout, NB = pl->NB, W = pl->W, nsl = pl->nsl;
+    const int nout = pl->nout, NB = pl->NB, nsl = pl->nsl;
     std::vector<double> nb(NB), wl(nout);
     for (int k = 0; k < nout; ++k) wl[k] = add_rn(d.crval1, mul_rn(d.cdelt1, (double)k));
     for (int k = 1; k < nout; ++k) nb[k] = mul_rn(0.5, add_rn(wl[k], wl[k - 1]));
@@ -614,15 +763,16 @@ int build_border_tables(emirwv_plan *pl, std::vector<uint8_t> &covered) {
     pl->h_idx.assign((size_t)nsl * NB, 0);
     pl->h_t.assign((size_t)nsl * NB, 0.0);
     std::vector<double> h_tau((size_t)nsl * NB, 0.0);
-    std::vector<double> h_invh((size_t)nsl * W, 0.0), h_rr((size_t)nsl * (W + 1), 0.0);
+    std::vector<double> h_h((size_t)nsl * W, 0.0);
     covered.assign((size_t)nsl * NB, 0);
     pl->max_span = 0;
 
-    std::vector<double> xw(W + 1), h(W);
+    std::vector<double> xw(W + 1);
     for (int s = 0; s < nsl; ++s) {
         const emirwv_slitlet_desc &sl = d.slitlet[s];
         if (!sl.valid) continue;
         const int nchan = sl.bb_nc2_orig - sl.bb_nc1_orig + 1;
+        double *h = h_h.data() + (size_t)s * W;
         for (int i = 0; i <= nchan; ++i) {
             const double xb = add_rn(add_rn(-0.5, (double)i), d.crpix1);
             xw[i] = polyval_np(xb, sl.wpoly, sl.nwpoly);
@@ -633,60 +783,46 @@ int build_border_tables(emirwv_plan *pl, std::vector<uint8_t> &covered) {
                 return fail(EMIRWV_E_VALUE,
                             "slitlet %d: wavelength polynomial is not increasing at pixel %d",
                             s + 1, i + 1);
-            h_invh[(size_t)s * W + i] = 1.0 / h[i];
         }
-        for (int i = 1; i < nchan; ++i) h_rr[(size_t)s * (W + 1) + i] = h[i] / (h[i - 1] + h[i]);
         int prev = 0;
         for (int k = 0; k < NB; ++k) {
             const double x = nb[k];
             int idx;
-            double t;
+            double t, tau;
             uint8_t cov = 1;
             if (x < xw[0]) {                       // extrapolate='border': y_0
                 idx = 0;
                 t = 0.0;
+                tau = 0.0;
                 cov = 0;
             } else if (x > xw[nchan]) {            // extrapolate='border': y_N
                 idx = nchan - 1;
                 t = h[nchan - 1];
+                tau = 1.0;
                 cov = 0;
             } else {                               // searchsorted(side='left').clip(1, N) - 1
                 const int pos = (int)(std::lower_bound(xw.begin(), xw.begin() + nchan + 1, x) -
                                       xw.begin());
                 idx = std::min(std::max(pos, 1), nchan) - 1;
                 t = x - xw[idx];
+                tau = t / h[idx];
             }
             pl->h_idx[(size_t)s * NB + k] = idx;
             pl->h_t[(size_t)s * NB + k] = t;
-            h_tau[(size_t)s * NB + k] = t * h_invh[(size_t)s * W + idx];
+            h_tau[(size_t)s * NB + k] = tau;
             covered[(size_t)s * NB + k] = cov;
             if (k > 0) pl->max_span = std::max(pl->max_span, idx - prev);
             prev = idx;
         }
     }
-    CUDA_TRY(cudaMalloc(&pl->d_idx, pl->h_idx.size() * sizeof(int32_t)));
-    CUDA_TRY(cudaMemcpy(pl->d_idx, pl->h_idx.data(), pl->h_idx.size() * sizeof(int32_t),
-                        cudaMemcpyHostToDevice));
-    pl->table_bytes += (int64_t)(pl->h_idx.size() * sizeof(int32_t));
-    int rc;
-    if (pl->dtype == EMIRWV_F32) {
-        if ((rc = upload<float>(pl->h_t, &pl->d_t, pl->table_bytes))) return rc;
-        if ((rc = upload<float>(h_tau, &pl->d_tau, pl->table_bytes))) return rc;
-        if ((rc = upload<float>(h_invh, &pl->d_invh, pl->table_bytes))) return rc;
-        if ((rc = upload<float>(h_rr, &pl->d_rr, pl->table_bytes))) return rc;
-    } else {
-        if ((rc = upload<double>(pl->h_t, &pl->d_t, pl->table_bytes))) return rc;
-        if ((rc = upload<double>(h_tau, &pl->d_tau, pl->table_bytes))) return rc;
-        if ((rc = upload<double>(h_invh, &pl->d_invh, pl->table_bytes))) return rc;
-        if ((rc = upload<double>(h_rr, &pl->d_rr, pl->table_bytes))) return rc;
-    }
-    return EMIRWV_OK;
+    if (pl->dtype == EMIRWV_F32) return upload_tables<float>(pl, h_tau, h_h);
+    return upload_tables<double>(pl, h_tau, h_h);
 }
 
 // Work items: (slitlet, block of rectified rows, block of output columns).
 int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
     const emirwv_plan_desc &d = pl->desc;
-    const int nout = pl->nout, NB = pl->NB, W = pl->W, K = pl->K;
+    const int nout = pl->nout, NB = pl->NB, K = pl->K;
     const int TK = pl->tile_k, TR = pl->tile_rows;
     std::vector<Tile> live, dead;
     pl->wrows_max = pl->wcols_max = 1;
@@ -713,7 +849,13 @@ int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
                     any = pl->h_idx[(size_t)s * NB + k0] != pl->h_idx[(size_t)s * NB + k0 + t.nk];
                 if (!any) {
                     t.empty = 1;
-                    if (y0 < pl->rps) dead.push_back(t);   // the ghost row stores nothing
+                    if (y0 >= pl->rps) continue;           // the ghost row stores nothing
+                    // neighbouring empty tiles become one wide run of zeros
+                    if (!dead.empty() && dead.back().slit == s && dead.back().y0 == y0 &&
+                        dead.back().k0 + dead.back().nk == k0 && dead.back().nk + t.nk <= 1024)
+                        dead.back().nk += t.nk;
+                    else
+                        dead.push_back(t);
                     continue;
                 }
                 const int ilo = pl->h_idx[(size_t)s * NB + k0];
@@ -732,10 +874,11 @@ int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
                         c1 = std::max(c1, bc + K - 1);
                     }
                 }
+                c0 = (int)(std::floor(c0 / 4.0) * 4.0);    // 16-byte aligned window rows
                 t.r0 = r0;
                 t.c0 = c0;
                 t.wrows = r1 - r0 + 1;
-                t.wcols = c1 - c0 + 1;
+                t.wcols = ((c1 - c0 + 1) + 3) & ~3;
                 pl->wrows_max = std::max(pl->wrows_max, t.wrows);
                 pl->wcols_max = std::max(pl->wcols_max, t.wcols);
                 npx_max = std::max(npx_max, t.npx);
@@ -747,10 +890,16 @@ int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
     pl->h_tiles = live;
     pl->h_tiles.insert(pl->h_tiles.end(), dead.begin(), dead.end());
     pl->ntiles = (int)pl->h_tiles.size();
-    pl->wpitch = (pl->wcols_max + 3) & ~3;
+    pl->wpitch = pl->wcols_max;                       // multiple of 4
+    if ((pl->wpitch & 31) == 0) pl->wpitch += 4;      // rows start in different banks
     pl->npxp = (npx_max + 3) & ~3;
+    pl->fast_pitch = pl->npxp <= FAST_NPXP && pl->wcols_max <= FAST_WP;
+    if (pl->fast_pitch) {
+        pl->npxp = FAST_NPXP;
+        pl->wpitch = FAST_WP;
+    }
     if (pl->ntiles > 65535) return fail(EMIRWV_E_LIMIT, "too many tiles (%d)", pl->ntiles);
-    if (smem_bytes(pl, 1, 1) > (size_t)SMEM_LIMIT)
+    if (smem_bytes(pl, 1, 32) > (size_t)SMEM_LIMIT)
         return fail(EMIRWV_E_LIMIT,
                     "distortion too strong: a %d x %d source window does not fit in shared memory",
                     pl->wrows_max, pl->wcols_max);
@@ -762,8 +911,9 @@ int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
 }
 
 int validate(const emirwv_plan_desc *d) {
-    if (d->naxis1 < 2 || d->naxis2 < 2 || d->naxis1 > 16384 || d->naxis2 > 16384)
-        return fail(EMIRWV_E_VALUE, "unsupported frame size %d x %d", d->naxis1, d->naxis2);
+    // Slitlet2D.extract_slitlet2d accepts 2048 x 2048 frames only (slitlet2d.py:359-363)
+    if (d->naxis1 != W) return fail(EMIRWV_E_VALUE, "Unexpected naxis1");
+    if (d->naxis2 < 2 || d->naxis2 > 16384) return fail(EMIRWV_E_VALUE, "Unexpected naxis2");
     if (d->nslitlets < 1 || d->nslitlets > EMIRWV_MAX_SLITLETS)
         return fail(EMIRWV_E_VALUE, "nslitlets=%d out of range", d->nslitlets);
     if (d->rows_per_slitlet != NROWS - 1)
@@ -810,7 +960,6 @@ int build_plan(emirwv_plan *pl) {
     pl->esize = d.dtype == EMIRWV_F32 ? 4 : 8;
     pl->nsl = d.nslitlets;
     pl->rps = d.rows_per_slitlet;
-    pl->W = d.naxis1;
     pl->nout = d.naxis1_out;
     pl->NB = d.naxis1_out + 1;
     pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", 124);
@@ -841,7 +990,6 @@ int build_plan(emirwv_plan *pl) {
     GeomParams gp;
     gp.slit = pl->d_slit;
     gp.nsl = pl->nsl;
-    gp.W = pl->W;
     gp.naxis1 = d.naxis1;
     gp.naxis2 = d.naxis2;
     gp.offx = d.offx;
@@ -849,7 +997,7 @@ int build_plan(emirwv_plan *pl) {
     gp.mode = pl->mode;
     gp.kmax = nullptr;
     const dim3 block(128);
-    const dim3 grid((pl->W + 127) / 128, NROWS, pl->nsl);
+    const dim3 grid((W + 127) / 128, NROWS, pl->nsl);
 
     if (pl->mode == EMIRWV_AREA) {
         int *d_kmax = nullptr;
@@ -876,10 +1024,10 @@ int build_plan(emirwv_plan *pl) {
     }
 
     const size_t nrowtab = (size_t)pl->nsl * NROWS;
-    CUDA_TRY(cudaMalloc(&pl->d_base, nrowtab * pl->W * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&pl->d_w, nrowtab * pl->K * pl->K * pl->W * pl->esize));
-    pl->table_bytes += (int64_t)(nrowtab * pl->W * sizeof(int32_t));
-    pl->table_bytes += (int64_t)(nrowtab * pl->K * pl->K * pl->W * pl->esize);
+    CUDA_TRY(cudaMalloc(&pl->d_base, nrowtab * W * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&pl->d_w, nrowtab * pl->K * pl->K * W * pl->esize));
+    pl->table_bytes += (int64_t)(nrowtab * W * sizeof(int32_t));
+    pl->table_bytes += (int64_t)(nrowtab * pl->K * pl->K * W * pl->esize);
     gp.K = pl->K;
     gp.base = pl->d_base;
     gp.kmax = nullptr;
@@ -888,7 +1036,7 @@ int build_plan(emirwv_plan *pl) {
     else
         k_build_geometry<double><<<grid, block>>>(gp, static_cast<double *>(pl->d_w));
     CUDA_TRY(cudaGetLastError());
-    pl->h_base.resize(nrowtab * pl->W);
+    pl->h_base.resize(nrowtab * W);
     CUDA_TRY(cudaMemcpy(pl->h_base.data(), pl->d_base, pl->h_base.size() * sizeof(int32_t),
                         cudaMemcpyDeviceToHost));
 
@@ -989,11 +1137,8 @@ void emirwv_plan_destroy(emirwv_plan *pl) {
     cudaFree(pl->d_slit);
     cudaFree(pl->d_base);
     cudaFree(pl->d_w);
-    cudaFree(pl->d_idx);
-    cudaFree(pl->d_t);
-    cudaFree(pl->d_tau);
-    cudaFree(pl->d_invh);
-    cudaFree(pl->d_rr);
+    cudaFree(pl->d_border);
+    cudaFree(pl->d_pix);
     cudaFree(pl->d_tiles);
     delete pl;
 }
@@ -1015,6 +1160,7 @@ int emirwv_plan_get_info(const emirwv_plan *pl, emirwv_plan_info *info) {
     info->window_cols = pl->wcols_max;
     info->max_span = pl->max_span;
     info->frames_per_cta = cfg.G;
+    info->threads = cfg.threads;
     info->smem_bytes = (int32_t)cfg.smem;
     info->table_bytes = pl->table_bytes;
     info->in_frame_bytes = (int64_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
@@ -1022,10 +1168,9 @@ int emirwv_plan_get_info(const emirwv_plan *pl, emirwv_plan_info *info) {
     return EMIRWV_OK;
 }
 
-int emirwv_plan_set_tuning(emirwv_plan *pl, int frames_per_cta, int rows_per_pass, int threads) {
+int emirwv_plan_set_tuning(emirwv_plan *pl, int frames_per_cta, int threads) {
     if (pl == nullptr) return fail(EMIRWV_E_VALUE, "null plan");
     pl->tune_G = frames_per_cta;
-    pl->tune_RB = rows_per_pass;
     pl->tune_threads = threads;
     return EMIRWV_OK;
 }
@@ -1110,12 +1255,12 @@ int emirwv_rectify_slitlet(const emirwv_plan *pl, const void *d_frame, int islit
     if (pl->dtype == EMIRWV_F32)
         k_rectify_only<float><<<grid, 128, 0, st>>>(
             static_cast<const float *>(d_frame), static_cast<float *>(d_rect), pl->d_base,
-            static_cast<const float *>(pl->d_w), s, pl->K, pl->W, bbw, pl->desc.naxis1,
+            static_cast<const float *>(pl->d_w), s, pl->K, bbw, pl->desc.naxis1,
             pl->desc.naxis2);
     else
         k_rectify_only<double><<<grid, 128, 0, st>>>(
             static_cast<const double *>(d_frame), static_cast<double *>(d_rect), pl->d_base,
-            static_cast<const double *>(pl->d_w), s, pl->K, pl->W, bbw, pl->desc.naxis1,
+            static_cast<const double *>(pl->d_w), s, pl->K, bbw, pl->desc.naxis1,
             pl->desc.naxis2);
     CUDA_TRY(cudaGetLastError());
     return EMIRWV_OK;
@@ -1129,7 +1274,7 @@ int emirwv_debug_geometry(const emirwv_plan *pl, int islitlet, int32_t *h_row, i
     DeviceGuard guard(pl->device);
     const int s = islitlet - 1;
     const SlitDev &sd = pl->h_slit[s];
-    const int W = pl->W, KK = pl->K * pl->K;
+    const int KK = pl->K * pl->K;
     for (int y = 0; y < NROWS; ++y)
         for (int j = 0; j < sd.bbw; ++j) {
             const int32_t pk = pl->h_base[((size_t)s * NROWS + y) * W + j];

@@ -158,13 +158,17 @@ EMIRWV_HD void quad_extent(const double *q, int &lo, int &hi) {
 }
 
 // Steffen (1990) limited slope at an interior knot from the two adjacent secant
-// slopes; r = h_right / (h_left + h_right) weights the left slope.
+// slopes; r = h_right / (h_left + h_right) weights the left slope:
+//   p = sl*r + sr*(1-r);  y' = (sign(sl)+sign(sr)) * min(|sl|, |sr|, |p|/2)
+// Branch-free: when the signs differ the result is 0; when either slope is 0 the
+// minimum is 0.  Positively homogeneous in (sl, sr).
 template <typename T>
 EMIRWV_HD T steffen_slope(T sl, T sr, T r) {
-    const T p = sl * r + sr * (T(1) - r);
+    const T p = sr + r * (sl - sr);
     const T m = fmin(fmin(fabs(sl), fabs(sr)), T(0.5) * fabs(p));
-    const bool same = (sl > T(0) && sr > T(0)) || (sl < T(0) && sr < T(0));
-    return same ? (sl > T(0) ? T(2) * m : -T(2) * m) : T(0);
+    const T twice = copysign(m + m, sr);
+    const bool opposite = (sl < T(0)) != (sr < T(0));
+    return opposite ? T(0) : twice;
 }
 
 // Cumulative flux inside one source interval, measured from its left knot:
@@ -175,6 +179,18 @@ EMIRWV_HD T steffen_partial(T s, T yp0, T yp1, T t, T tau) {
     const T A = yp0 + yp1 - T(2) * s;
     const T B = s - yp0 - A;
     return t * (yp0 + tau * (B + tau * A));
+}
+
+// Same piece in flux units, as the kernels use it: rect = s*h is the flux of the
+// source pixel, ya = h*yp0 and yb = h*yp1 its end slopes scaled by its width; only
+// the fractional position tau = t/h is needed.  P(0) = 0, P(1) = rect.
+// (Steffen's limiter is positively homogeneous, so ya, yb come from steffen_slope
+// applied to fluxes scaled by ratios of neighbouring pixel widths.)
+template <typename T>
+EMIRWV_HD T steffen_partial_flux(T rect, T ya, T yb, T tau) {
+    const T A = ya + yb - T(2) * rect;
+    const T B = rect - ya - A;
+    return tau * (ya + tau * (B + tau * A));
 }
 
 }  // namespace emirwv

@@ -37,3 +37,7 @@ double hostcheck_steffen_partial(double s, double yp0, double yp1, double t, dou
 int hostcheck_order_from_ncoef(int ncoef) { return emirwv::order_from_ncoef(ncoef); }
 
 }  // extern "C"
+
+extern "C" double hostcheck_steffen_partial_flux(double rect, double ya, double yb, double tau) {
+    return emirwv::steffen_partial_flux<double>(rect, ya, yb, tau);
+}

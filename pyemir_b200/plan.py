@@ -172,9 +172,9 @@ class RectWavePlan:
         _cabi.check(self._lib.emirwv_plan_get_info(self._handle, ctypes.byref(info)))
         return info.asdict()
 
-    def set_tuning(self, frames_per_cta=0, rows_per_pass=0, threads=0):
+    def set_tuning(self, frames_per_cta=0, threads=0):
         _cabi.check(self._lib.emirwv_plan_set_tuning(self._handle, int(frames_per_cta),
-                                                     int(rows_per_pass), int(threads)))
+                                                     int(threads)))
 
     # -- execution -----------------------------------------------------------
     def run_host(self, frames, out=None, jminmax=None):

@@ -310,12 +310,12 @@ def test_batch_properties_64_frames(coeff_j, batch64):
     out, jmm = plan.run_torch(frames)
     torch.cuda.synchronize()
     # determinism and independence of the frame grouping inside a CTA
-    for g, rb, threads in ((1, 1, 128), (2, 4, 256), (4, 2, 192)):
-        plan.set_tuning(g, rb, threads)
+    for g, threads in ((1, 128), (2, 256), (4, 192), (1, 512)):
+        plan.set_tuning(g, threads)
         out2, jmm2 = plan.run_torch(frames[:7])
         torch.cuda.synchronize()
-        assert torch.equal(out2, out[:7]) and torch.equal(jmm2, jmm[:7]), (g, rb, threads)
-    plan.set_tuning(0, 0, 0)
+        assert torch.equal(out2, out[:7]) and torch.equal(jmm2, jmm[:7]), (g, threads)
+    plan.set_tuning(0, 0)
     # homogeneity: every stage is positively homogeneous, scaling by 2 is exact in binary
     out3, _ = plan.run_torch(frames[:4] * 2.0)
     assert torch.equal(out3, out[:4] * 2.0)

@@ -97,3 +97,26 @@ def test_steffen_pieces_match_interpolator(hc, rng):
         t = rng.uniform(0, h[i])
         got = y[i] + hc.hostcheck_steffen_partial(s[i], yp[i], yp[i + 1], t, t / h[i])
         assert got == pytest.approx(float(interp(np.array([x[i] + t]))[0]), rel=1e-12, abs=1e-12)
+
+
+def test_flux_unit_form_equals_slope_form(hc, rng):
+    """The kernels' flux-unit Steffen piece (only tau needed) is the slope form."""
+    hc.hostcheck_steffen_partial_flux.restype = ctypes.c_double
+    hc.hostcheck_steffen_partial_flux.argtypes = [ctypes.c_double] * 4
+    h = rng.uniform(0.5, 1.5, 3)                       # widths of pixels i-1, i, i+1
+    for _ in range(500):
+        flux = rng.normal(3.0, 5.0, 3)
+        s = flux / h
+        yp0 = hc.hostcheck_steffen_slope(s[0], s[1], h[1] / (h[0] + h[1]))
+        yp1 = hc.hostcheck_steffen_slope(s[1], s[2], h[2] / (h[1] + h[2]))
+        # homogeneity: h_i * steffen(s_l, s_r) = steffen(h_i s_l, h_i s_r)
+        ya = hc.hostcheck_steffen_slope(flux[0] * (h[1] / h[0]), flux[1], h[1] / (h[0] + h[1]))
+        yb = hc.hostcheck_steffen_slope(flux[1], flux[2] * (h[1] / h[2]), h[2] / (h[1] + h[2]))
+        assert ya == pytest.approx(h[1] * yp0, rel=1e-13, abs=1e-13)
+        assert yb == pytest.approx(h[1] * yp1, rel=1e-13, abs=1e-13)
+        tau = rng.uniform(0, 1)
+        want = hc.hostcheck_steffen_partial(s[1], yp0, yp1, tau * h[1], tau)
+        got = hc.hostcheck_steffen_partial_flux(flux[1], ya, yb, tau)
+        assert got == pytest.approx(want, rel=1e-12, abs=1e-12)
+    assert hc.hostcheck_steffen_partial_flux(7.0, 1.0, 2.0, 0.0) == 0.0
+    assert hc.hostcheck_steffen_partial_flux(7.0, 1.0, 2.0, 1.0) == pytest.approx(7.0, rel=1e-15)
