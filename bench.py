@@ -372,7 +372,8 @@ def run_ours(args):
         "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
         "config": workload_config(args, config, info),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": 2 * args.steps, "clocks": clocks,
+        # per step: k_init_jmm + k_zero_fill + k_rectwv (persistent)
+        "gpu_launches": 3 * args.steps, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -147,6 +147,10 @@ struct RunParams {
     int npxp;               // scratch pitch (>= max npx)
     int max_span;           // max whole source pixels inside one output pixel
     int vec_ok;             // rows of the output are 16-byte aligned
+    int nlive_tiles;        // tiles [0, nlive_tiles) have wavelength coverage
+    int ngroups;            // ceil(nframes / G)
+    int stage_bytes;        // one pipeline stage in shared memory
+    int off_border, off_pix;  // byte offsets of the tables inside a stage
 };
 
 __host__ __device__ inline int32_t pack_base(int r, int c) {
@@ -311,6 +315,15 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src
                  "r"(src_bytes)
                  : "memory");
 }
+// 8- or 16-byte asynchronous copy of one table record
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void *smem_dst, const void *gmem_src) {
+    static_assert(BYTES == 8 || BYTES == 16, "record size");
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(dst), "l"(gmem_src),
+                 "n"(BYTES)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
@@ -347,145 +360,209 @@ __device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
 template <typename P>
 __device__ __forceinline__ void pin(P *&x) { asm volatile("" : "+l"(x)); }
 
-// NPXP_C / WP_C: compile-time scratch pitch and window pitch (0 = take them from the
-// plan at run time).  With constants the gather taps and the per-frame scratch rows
-// are addressed with immediate offsets.
-template <typename T, int K, int G, int NPXP_C, int WP_C>
-__global__ void __launch_bounds__(MAXTHREADS) k_rectwv(const RunParams<T> p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// Zero-coverage tiles (outside the wavelength range of a slitlet, or a missing
+// slitlet): exact zeros, written with 16-byte stores where the row alignment allows.
+template <typename T>
+__global__ void __launch_bounds__(256) k_zero_fill(const RunParams<T> p, int first_tile) {
     using V = typename Vec16<T>::type;
     constexpr int VN = Vec16<T>::N;
-
-    const Tile tile = p.tiles[blockIdx.y];
-    const int g0 = blockIdx.x * G;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int s = tile.slit;
-    const size_t frame_in = (size_t)W * p.naxis2;
+    const Tile tile = p.tiles[first_tile + blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const size_t frame_out = (size_t)p.nrows_out * p.nout;
-
-    if (tile.empty) {
-        // outside the wavelength coverage (or a missing slitlet): exact zeros
-        const int ylast = min(tile.y0 + tile.ny, p.rps);
-        const bool vec = p.vec_ok && ((tile.k0 | tile.nk) % VN) == 0;
-        for (int g = 0; g < G && g0 + g < p.nframes; ++g)
-            for (int y = tile.y0 + warp; y < ylast; y += nwarps) {
-                T *orow = p.out + (size_t)(g0 + g) * frame_out +
-                          (size_t)(s * p.rps + y) * p.nout + tile.k0;
-                if (vec) {
-                    V zero;
-                    memset(&zero, 0, sizeof(zero));
-                    for (int k = lane; k < tile.nk / VN; k += 32) reinterpret_cast<V *>(orow)[k] = zero;
-                } else {
-                    for (int k = lane; k < tile.nk; k += 32) orow[k] = T(0);
-                }
+    const int ylast = min(tile.y0 + tile.ny, p.rps);
+    const bool vec = p.vec_ok && ((tile.k0 | tile.nk) % VN) == 0;
+    for (int f = blockIdx.y; f < p.nframes; f += gridDim.y)
+        for (int y = tile.y0 + warp; y < ylast; y += nwarps) {
+            T *orow = p.out + (size_t)f * frame_out + (size_t)(tile.slit * p.rps + y) * p.nout + tile.k0;
+            if (vec) {
+                V zero;
+                memset(&zero, 0, sizeof(zero));
+                for (int k = lane; k < tile.nk / VN; k += 32) __stcs(reinterpret_cast<V *>(orow) + k, zero);
+            } else {
+                for (int k = lane; k < tile.nk; k += 32) __stcs(orow + k, T(0));
             }
-        return;
-    }
+        }
+}
 
-    // shared memory: [G windows][per warp: G x (Knot[npxp], rect[npxp + 4])]
-    // (rect rows carry one zero element before and after the npx live ones)
+// One pipeline stage in shared memory: everything a work item (tile x frame group)
+// needs that does not depend on the rectified row.
+//   [G source windows][Border table of the tile][PixGeom table of the tile]
+// Copied with cp.async while the previous item is being computed.
+template <typename T, int G>
+__device__ __forceinline__ void issue_stage(const RunParams<T> &p, const Tile &t, int grp,
+                                            unsigned char *stage, int wp1, int tid, int nthr) {
+    constexpr int VN = Vec16<T>::N;
+    T *win = reinterpret_cast<T *>(stage);
+    const int wsz = p.wrows * wp1;
+    const int vcols = t.wcols / VN;
+    const int nvec = t.wrows * vcols;
+    const float inv = 1.0f / (float)vcols;
+    const size_t frame_in = (size_t)W * p.naxis2;
+    const int nlive = min(G, p.nframes - grp * G);
+    for (int g = 0; g < nlive; ++g) {
+        const T *fr = p.in + (size_t)(grp * G + g) * frame_in;
+        T *wg = win + (size_t)g * wsz;
+        for (int e = tid; e < nvec; e += nthr) {
+            const int rr = (int)(((float)e + 0.5f) * inv);     // e / vcols, exact here
+            const int vc = e - rr * vcols;
+            const int r = t.r0 + rr, c = t.c0 + vc * VN;
+            const bool ok = r >= 0 && r < p.naxis2 && c >= 0 && c < W;
+            cp_async_16(wg + rr * wp1 + vc * VN, fr + (ok ? (size_t)r * W + c : 0), ok);
+        }
+    }
+    Border<T> *bs = reinterpret_cast<Border<T> *>(stage + p.off_border);
+    const Border<T> *bsrc = p.border + (size_t)t.slit * p.NB + t.k0;
+    for (int e = tid; e <= t.nk; e += nthr) cp_async_small<sizeof(Border<T>)>(bs + e, bsrc + e);
+    PixGeom<T> *ps = reinterpret_cast<PixGeom<T> *>(stage + p.off_pix);
+    const PixGeom<T> *psrc = p.pix + (size_t)t.slit * W + t.jlo;
+    for (int e = tid; e < t.npx * (int)(sizeof(PixGeom<T>) / 16); e += nthr)
+        cp_async_16(reinterpret_cast<char *>(ps) + e * 16,
+                    reinterpret_cast<const char *>(psrc) + e * 16, true);
+}
+
+// NPXP_C / WP_C: compile-time scratch pitch and window pitch (0 = take them from the
+// plan at run time).  SPANLOOP: an output pixel may contain more than one whole
+// source pixel (coarse output grids); the EMIR grids need at most one.
+//
+// Persistent kernel: CTA b processes work items b, b + gridDim.x, ...; item =
+// (live tile, frame group), frame group fastest so that CTAs running at the same
+// time share the tile's tables in L2.  Shared memory:
+//   [tile descriptor ring: 3][stage 0][stage 1][per warp: G x (Knot[npxp], rect[npxp+4])]
+template <typename T, int K, int G, int NPXP_C, int WP_C, bool SPANLOOP>
+__global__ void __launch_bounds__(MAXTHREADS) k_rectwv(const RunParams<T> p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     const int npxp = NPXP_C ? NPXP_C : p.npxp;
     const int wp1 = WP_C ? WP_C : p.wpitch;
     const int wsz = p.wrows * wp1;
     const int rpitch = npxp + 4;
-    T *win = reinterpret_cast<T *>(smem_raw);
-    int woff = G * wsz + warp * (G * (npxp * 4 + rpitch));     // this warp's scratch
-    pin(woff);                                                 // (kept in a register)
-    Knot<T> *knots = reinterpret_cast<Knot<T> *>(win + woff);  // [G][npxp]
-    T *rect = win + woff + G * npxp * 4 + 1;                   // [G][rpitch], halo at -1
+    const size_t frame_out = (size_t)p.nrows_out * p.nout;
+    const int nwork = p.nlive_tiles * p.ngroups;
 
-    // ---- stage the source window of each frame with cp.async (16-byte chunks, zero
-    //      fill outside the detector): c0, wcols and the frame width are multiples of 4.
-    //      One chunk index per thread; the row / column split uses the reciprocal trick.
+    Tile *ring = reinterpret_cast<Tile *>(smem_raw);                       // [3]
+    unsigned char *stage0 = smem_raw + 3 * sizeof(Tile);
+    T *scr = reinterpret_cast<T *>(stage0 + 2 * (size_t)p.stage_bytes);
+    int woff = warp * (G * (npxp * 4 + rpitch));                // this warp's scratch
+    pin(woff);
+    Knot<T> *knots = reinterpret_cast<Knot<T> *>(scr + woff);   // [G][npxp]
+    T *rect = scr + woff + G * npxp * 4 + 1;                    // [G][rpitch], halo at -1
+
+    int w = blockIdx.x;
+    if (w >= nwork) return;
+
+    // prologue: stage of the first item, descriptors of the first two
     {
-        const int vcols = tile.wcols / VN;
-        const int nvec = tile.wrows * vcols;
-        const float inv = 1.0f / (float)vcols;
-        for (int g = 0; g < G; ++g) {
-            if (g0 + g >= p.nframes) break;
-            const T *fr = p.in + (size_t)(g0 + g) * frame_in;
-            T *wg = win + (size_t)g * wsz;
-            for (int e = tid; e < nvec; e += blockDim.x) {
-                const int rr = (int)(((float)e + 0.5f) * inv);
-                const int vc = e - rr * vcols;
-                const int r = tile.r0 + rr, c = tile.c0 + vc * VN;
-                const bool ok = r >= 0 && r < p.naxis2 && c >= 0 && c < W;
-                cp_async_16(wg + rr * wp1 + vc * VN, fr + (ok ? (size_t)r * W + c : 0), ok);
-            }
-        }
-    }
-    const int npx = tile.npx;
-    if (lane < G) {
-        rect[lane * rpitch - 1] = T(0);
-        rect[lane * rpitch + npx] = T(0);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-
-    int jmin[G], jmax[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        jmin[g] = INT_MAX;
-        jmax[g] = -1;
+        const Tile t0 = p.tiles[w / p.ngroups];
+        issue_stage<T, G>(p, t0, w % p.ngroups, stage0, wp1, tid, nthr);
+        if (tid < 4) cp_async_16(reinterpret_cast<char *>(&ring[0]) + tid * 16,
+                                 reinterpret_cast<const char *>(p.tiles + w / p.ngroups) + tid * 16, true);
+        const int w1 = w + gridDim.x;
+        if (w1 < nwork && tid >= 4 && tid < 8)
+            cp_async_16(reinterpret_cast<char *>(&ring[1]) + (tid - 4) * 16,
+                        reinterpret_cast<const char *>(p.tiles + w1 / p.ngroups) + (tid - 4) * 16, true);
     }
 
-    const int kend = tile.k0 + tile.nk;
-    const int max_span = p.max_span;
-    const int nlive = min(G, p.nframes - g0);
-    const PixGeom<T> *pix = p.pix + (size_t)s * W + tile.jlo + lane;
-    const Border<T> *border = p.border + (size_t)s * p.NB;
-    const Knot<T> *kread = knots - tile.jlo;                   // indexed by source pixel
-    T *obase = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
     unsigned fo = (unsigned)frame_out;                         // < 2^32 elements per frame
-    int wb = -(tile.r0 * wp1 + tile.c0);                       // window addressed by frame coords
-    pin(pix);
-    pin(border);
     pin(fo);
-    pin(wb);
 
-    // every warp owns whole rows of the tile: no block-level barrier below
-    for (int yy = warp; yy < tile.ny; yy += nwarps) {
-        const int y = tile.y0 + yy;
-        const size_t rowtab = (size_t)s * NROWS + y;
-        const int32_t *brow = p.base + rowtab * W + tile.jlo + lane;
-        const T *wrow = p.w + rowtab * (K * K) * W + tile.jlo + lane;
-        T *orow = obase + (size_t)y * p.nout;
-        pin(orow);
+    for (int it = 0;; ++it) {
+        cp_async_wait_all();
+        __syncthreads();                     // stage(it), descriptors it and it+1 have landed
 
-        // ---- A: rectified flux, K*K weighted gather from the staged window
-        for (int p0 = 0; p0 < npx; p0 += 32) {
-            if (p0 + lane < npx) {
-                const int32_t pk = __ldg(brow + p0);
-                T wt[K * K];
+        unsigned char *stage = stage0 + (size_t)(it & 1) * p.stage_bytes;
+        const int wnext = w + gridDim.x;
+        if (wnext < nwork) {
+            // prefetch the next item's stage; its descriptor arrived one iteration ago
+            const Tile tn = ring[(it + 1) % 3];
+            issue_stage<T, G>(p, tn, wnext % p.ngroups,
+                              stage0 + (size_t)((it + 1) & 1) * p.stage_bytes, wp1, tid, nthr);
+            const int w2 = wnext + gridDim.x;
+            if (w2 < nwork && tid < 4)
+                cp_async_16(reinterpret_cast<char *>(&ring[(it + 2) % 3]) + tid * 16,
+                            reinterpret_cast<const char *>(p.tiles + w2 / p.ngroups) + tid * 16, true);
+        }
+
+        // ---------------------------------------------------------------- item `w`
+        const Tile tile = ring[it % 3];
+        const int grp = w % p.ngroups;
+        const int g0 = grp * G;
+        const int s = tile.slit;
+        const int npx = tile.npx;
+        const int nlive = min(G, p.nframes - g0);
+        const T *win = reinterpret_cast<const T *>(stage);
+        const Border<T> *border = reinterpret_cast<const Border<T> *>(stage + p.off_border);
+        const PixGeom<T> *pix = reinterpret_cast<const PixGeom<T> *>(stage + p.off_pix);
+        const Knot<T> *kread = knots - tile.jlo;               // indexed by source pixel
+        T *obase = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
+        int wb = -(tile.r0 * wp1 + tile.c0);                   // window addressed by frame coords
+        pin(wb);
+
+        if (lane < G) {
+            rect[lane * rpitch - 1] = T(0);
+            rect[lane * rpitch + npx] = T(0);
+        }
+        int jmin[G], jmax[G];
 #pragma unroll
-                for (int tap = 0; tap < K * K; ++tap) wt[tap] = __ldg(wrow + p0 + tap * W);
-                const T *src = win + (wb + base_row(pk) * wp1 + base_col(pk));
+        for (int g = 0; g < G; ++g) {
+            jmin[g] = INT_MAX;
+            jmax[g] = -1;
+        }
+
+        // every warp owns whole rows of the tile: no block-level barrier inside
+        for (int yy = warp; yy < tile.ny; yy += nwarps) {
+            const int y = tile.y0 + yy;
+            const size_t rowtab = (size_t)s * NROWS + y;
+            const int32_t *brow = p.base + rowtab * W + tile.jlo + lane;
+            const T *wrow = p.w + rowtab * (K * K) * W + tile.jlo + lane;
+            T *orow = obase + (size_t)y * p.nout;
+            pin(orow);
+
+            // ---- A: rectified flux, K*K weighted gather from the staged window.
+            //         The table entries of the next 32 pixels are requested before the
+            //         current ones are used (the tables are padded past their end).
+            {
+                int32_t npk = __ldg(brow);
+                T nwt[K * K];
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const T *sg = src + g * wsz;
-                    T acc = T(0);
+                for (int tap = 0; tap < K * K; ++tap) nwt[tap] = __ldg(wrow + tap * W);
+                for (int p0 = 0; p0 < npx; p0 += 32) {
+                    const int32_t pk = npk;
+                    T wt[K * K];
 #pragma unroll
-                    for (int a = 0; a < K; ++a)
+                    for (int tap = 0; tap < K * K; ++tap) wt[tap] = nwt[tap];
+                    if (p0 + 32 < npx) {
+                        npk = __ldg(brow + p0 + 32);
 #pragma unroll
-                        for (int b = 0; b < K; ++b) acc = fma(wt[a * K + b], sg[a * wp1 + b], acc);
-                    rect[g * rpitch + p0 + lane] = acc;
+                        for (int tap = 0; tap < K * K; ++tap)
+                            nwt[tap] = __ldg(wrow + p0 + 32 + tap * W);
+                    }
+                    if (p0 + lane < npx) {
+                        const T *src = win + (wb + base_row(pk) * wp1 + base_col(pk));
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            const T *sg = src + g * wsz;
+                            T acc = T(0);
+#pragma unroll
+                            for (int a = 0; a < K; ++a)
+#pragma unroll
+                                for (int b = 0; b < K; ++b)
+                                    acc = fma(wt[a * K + b], sg[a * wp1 + b], acc);
+                            rect[g * rpitch + p0 + lane] = acc;
+                        }
+                    }
                 }
             }
-        }
-        __syncwarp();
+            __syncwarp();
 
-        // ---- C: Steffen-limited slopes at both ends of every source pixel, scaled by
-        //         the pixel width (flux units).  Branch-free: the table holds qm = 0 for
-        //         the first pixel of the spectrum and qp = 0 for the last one, which
-        //         gives the zero end slopes; the halo of `rect` is zero.  The table row
-        //         of the next pass is requested before this pass is computed.
-        {
-            PixGeom<T> next = ldg_struct(pix);
+            // ---- C: Steffen-limited slopes at both ends of every source pixel, scaled
+            //         by the pixel width (flux units).  Branch-free: the table holds
+            //         qm = 0 for the first pixel of the spectrum and qp = 0 for the last
+            //         one, which gives the zero end slopes; the halo of `rect` is zero.
             for (int p0 = 0; p0 < npx; p0 += 32) {
-                const PixGeom<T> pg = next;
-                next = ldg_struct(pix + p0 + 32);              // table is padded
                 if (p0 + lane < npx) {
+                    const PixGeom<T> pg = pix[p0 + lane];
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const T *rv = rect + g * rpitch + p0 + lane;
@@ -501,60 +578,61 @@ __global__ void __launch_bounds__(MAXTHREADS) k_rectwv(const RunParams<T> p) {
                     }
                 }
             }
-        }
-        __syncwarp();
+            __syncwarp();
 
-        // ---- D: cumulative flux at the output borders (32 borders = 31 pixels per
-        //         warp pass), difference, coalesced store, non-zero channel range.
-        //         Lanes past the tile's last border re-read that border: their source
-        //         pixel stays inside this warp's scratch and their result is dropped.
-        {
-            const bool store = y < p.rps;
-            Border<T> next = ldg_struct(border + min(tile.k0 + lane, kend));
-            for (int kb0 = tile.k0; kb0 < kend; kb0 += 31) {
-                const int kb = kb0 + lane;
-                const Border<T> bd = next;
-                next = ldg_struct(border + min(kb + 31, kend));
-                const int ib = bd.idx;
-                const int ibn = __shfl_down_sync(0xffffffffu, ib, 1);
-                const bool col_ok = lane < 31 && kb < kend;
+            // ---- D: cumulative flux at the output borders (32 borders = 31 pixels per
+            //         warp pass), difference, coalesced store, non-zero channel range.
+            //         Lanes past the tile's last border re-read that border: their source
+            //         pixel stays inside this warp's scratch and their result is dropped.
+            {
+                const bool store = y < p.rps;
+                for (int q0 = 0; q0 < tile.nk; q0 += 31) {
+                    const int q = q0 + lane;                   // border, relative to the tile
+                    const Border<T> bd = border[min(q, tile.nk)];
+                    const int ib = bd.idx;
+                    const int ibn = __shfl_down_sync(0xffffffffu, ib, 1);
+                    const bool col_ok = lane < 31 && q < tile.nk;
+                    const int kb = tile.k0 + q;
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const Knot<T> *kr = kread + g * npxp;
-                    const Knot<T> kn = kr[ib];
-                    const T P = steffen_partial_flux(kn.rect, kn.ya, kn.yb, bd.tau);
-                    const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
-                    T whole = (ibn > ib) ? kn.rect : T(0);
-                    if (max_span > 1) {                        // warp-uniform
+                    for (int g = 0; g < G; ++g) {
+                        const Knot<T> *kr = kread + g * npxp;
+                        const Knot<T> kn = kr[ib];
+                        const T P = steffen_partial_flux(kn.rect, kn.ya, kn.yb, bd.tau);
+                        const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
+                        T whole = (ibn > ib) ? kn.rect : T(0);
                         if (ibn > ib + 1) whole += kr[ib + 1].rect;
-                        if (max_span > 2)
+                        if (SPANLOOP)
                             for (int i = ib + 2; i < ibn; ++i) whole += kr[i].rect;
-                    }
-                    const T o = whole + (Pn - P);
-                    const bool okg = col_ok && g < nlive;
-                    if (okg && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o);
-                    if (okg && o != T(0)) {
-                        jmin[g] = min(jmin[g], kb);
-                        jmax[g] = max(jmax[g], kb);
+                        const T o = whole + (Pn - P);
+                        const bool okg = col_ok && g < nlive;
+                        if (okg && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o);
+                        if (okg && o != T(0)) {
+                            jmin[g] = min(jmin[g], kb);
+                            jmax[g] = max(jmax[g], kb);
+                        }
                     }
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
-    }
 
-    // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
-    if (p.jmm != nullptr) {
+        // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
+        if (p.jmm != nullptr) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const int lo = __reduce_min_sync(0xffffffffu, jmin[g]);
-            const int hi = __reduce_max_sync(0xffffffffu, jmax[g]);
-            if (lane == 0 && hi >= 0 && g0 + g < p.nframes) {
-                int32_t *dst = p.jmm + ((size_t)(g0 + g) * p.nsl + s) * 2;
-                atomicMin(dst, lo);
-                atomicMax(dst + 1, hi);
+            for (int g = 0; g < G; ++g) {
+                const int lo = __reduce_min_sync(0xffffffffu, jmin[g]);
+                const int hi = __reduce_max_sync(0xffffffffu, jmax[g]);
+                if (lane == 0 && hi >= 0 && g < nlive) {
+                    int32_t *dst = p.jmm + ((size_t)(g0 + g) * p.nsl + s) * 2;
+                    atomicMin(dst, lo);
+                    atomicMax(dst + 1, hi);
+                }
             }
         }
+
+        if (wnext >= nwork) break;
+        w = wnext;
+        __syncthreads();          // stage (it & 1) is free again for the prefetch of it + 2
     }
 }
 
@@ -585,6 +663,7 @@ struct emirwv_plan {
     int wrows_max = 0, wcols_max = 0, wpitch = 0, npxp = 0, max_span = 0;
     int tune_G = 0, tune_threads = 0;
     bool fast_pitch = false;     // npxp / wpitch equal the compile-time constants
+    int num_sms = 148;
     int64_t table_bytes = 0;
 
     std::mutex mu;
@@ -607,13 +686,24 @@ int env_int(const char *name, int fallback) {
 // launch configuration for a given number of frames per CTA
 struct LaunchCfg {
     int G, threads;
+    int stage_bytes, off_border, off_pix;
     size_t smem;
 };
 
-size_t smem_bytes(const emirwv_plan *pl, int G, int threads) {
-    const size_t win = (size_t)G * pl->wrows_max * pl->wpitch * pl->esize;
-    const size_t scratch = (size_t)(threads / 32) * G * (pl->npxp * 5 + 4) * pl->esize;
-    return win + scratch;
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// shared memory of the persistent kernel:
+//   [3 tile descriptors][2 stages: G windows | border table | pixel table][warp scratch]
+void smem_layout(const emirwv_plan *pl, int G, int threads, LaunchCfg &cfg) {
+    const size_t es = pl->esize;
+    const size_t win = (size_t)G * pl->wrows_max * pl->wpitch * es;
+    const size_t border = align_up((size_t)(pl->tile_k + 1) * 2 * es, 16);
+    const size_t pix = (size_t)pl->npxp * 4 * es;
+    cfg.off_border = (int)align_up(win, 16);
+    cfg.off_pix = (int)(cfg.off_border + border);
+    cfg.stage_bytes = (int)align_up(cfg.off_pix + pix, 128);
+    const size_t scratch = (size_t)(threads / 32) * G * (pl->npxp * 5 + 4) * es;
+    cfg.smem = 3 * sizeof(Tile) + 2 * (size_t)cfg.stage_bytes + scratch;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
@@ -622,34 +712,51 @@ LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
     cfg.threads = std::max(32, std::min(MAXTHREADS, (cfg.threads / 32) * 32));
     int G = pl->tune_G > 0 ? pl->tune_G : env_int("EMIRWV_G", 2);
     G = (G >= 4) ? 4 : (G >= 2 ? 2 : 1);
-    while (G > 1 && (G > nframes || smem_bytes(pl, G, cfg.threads) > (size_t)SMEM_LIMIT)) G >>= 1;
-    while (cfg.threads > 32 && smem_bytes(pl, G, cfg.threads) > (size_t)SMEM_LIMIT)
+    smem_layout(pl, G, cfg.threads, cfg);
+    while (G > 1 && (G > nframes || cfg.smem > (size_t)SMEM_LIMIT)) {
+        G >>= 1;
+        smem_layout(pl, G, cfg.threads, cfg);
+    }
+    while (cfg.threads > 32 && cfg.smem > (size_t)SMEM_LIMIT) {
         cfg.threads -= 32;
+        smem_layout(pl, G, cfg.threads, cfg);
+    }
     cfg.G = G;
-    cfg.smem = smem_bytes(pl, G, cfg.threads);
     return cfg;
 }
 
 constexpr int FAST_NPXP = 144;   // scratch pitch of the specialised kernels
 constexpr int FAST_WP = 160;     // window pitch of the specialised kernels
 
-template <typename T, int K, int G, int NPXP_C, int WP_C>
-int launch_pitch(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
-                 cudaStream_t st) {
-    auto kern = k_rectwv<T, K, G, NPXP_C, WP_C>;
+template <typename T, int K, int G, int NPXP_C, int WP_C, bool SPANLOOP>
+int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, cudaStream_t st) {
+    auto kern = k_rectwv<T, K, G, NPXP_C, WP_C, SPANLOOP>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)cfg.smem));
-    const dim3 grid((rp.nframes + G - 1) / G, pl->ntiles);
-    kern<<<grid, cfg.threads, cfg.smem, st>>>(rp);
-    CUDA_TRY(cudaGetLastError());
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cfg.threads, cfg.smem));
+    if (per_sm < 1) return fail(EMIRWV_E_LIMIT, "kernel does not fit on an SM");
+    rp.ngroups = (rp.nframes + G - 1) / G;
+    const long long nwork = (long long)rp.nlive_tiles * rp.ngroups;
+    if (nwork > 0) {
+        if (nwork > INT_MAX) return fail(EMIRWV_E_LIMIT, "too many frames in one call");
+        const int grid = (int)std::min<long long>(nwork, (long long)pl->num_sms * per_sm);
+        kern<<<grid, cfg.threads, cfg.smem, st>>>(rp);
+        CUDA_TRY(cudaGetLastError());
+    }
     return EMIRWV_OK;
 }
 
 template <typename T, int K, int G>
 int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
                cudaStream_t st) {
-    if (pl->fast_pitch) return launch_pitch<T, K, G, FAST_NPXP, FAST_WP>(pl, rp, cfg, st);
-    return launch_pitch<T, K, G, 0, 0>(pl, rp, cfg, st);
+    const bool span = pl->max_span > 2;
+    if (pl->fast_pitch) {
+        if (span) return launch_final<T, K, G, FAST_NPXP, FAST_WP, true>(pl, rp, cfg, st);
+        return launch_final<T, K, G, FAST_NPXP, FAST_WP, false>(pl, rp, cfg, st);
+    }
+    if (span) return launch_final<T, K, G, 0, 0, true>(pl, rp, cfg, st);
+    return launch_final<T, K, G, 0, 0, false>(pl, rp, cfg, st);
 }
 
 template <typename T, int K>
@@ -691,9 +798,19 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     rp.npxp = pl->npxp;
     rp.max_span = pl->max_span;
     rp.vec_ok = ((size_t)pl->nout * sizeof(T)) % 16 == 0;
+    rp.nlive_tiles = pl->ntiles - pl->ntiles_empty;
+    rp.ngroups = 0;
+    rp.stage_bytes = cfg.stage_bytes;
+    rp.off_border = cfg.off_border;
+    rp.off_pix = cfg.off_pix;
     if (d_jmm != nullptr) {
         const int n = nframes * pl->nsl * 2;
         k_init_jmm<<<(n + 255) / 256, 256, 0, st>>>(d_jmm, n);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (pl->ntiles_empty > 0) {
+        const dim3 grid(pl->ntiles_empty, std::min(nframes, 32));
+        k_zero_fill<T><<<grid, 256, 0, st>>>(rp, rp.nlive_tiles);
         CUDA_TRY(cudaGetLastError());
     }
     switch (pl->K) {
@@ -899,7 +1016,9 @@ int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
         pl->wpitch = FAST_WP;
     }
     if (pl->ntiles > 65535) return fail(EMIRWV_E_LIMIT, "too many tiles (%d)", pl->ntiles);
-    if (smem_bytes(pl, 1, 32) > (size_t)SMEM_LIMIT)
+    LaunchCfg probe;
+    smem_layout(pl, 1, 32, probe);
+    if (probe.smem > (size_t)SMEM_LIMIT)
         return fail(EMIRWV_E_LIMIT,
                     "distortion too strong: a %d x %d source window does not fit in shared memory",
                     pl->wrows_max, pl->wcols_max);
@@ -955,6 +1074,7 @@ int validate(const emirwv_plan_desc *d) {
 int build_plan(emirwv_plan *pl) {
     const emirwv_plan_desc &d = pl->desc;
     CUDA_TRY(cudaGetDevice(&pl->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, pl->device));
     pl->dtype = d.dtype;
     pl->mode = d.resampling;
     pl->esize = d.dtype == EMIRWV_F32 ? 4 : 8;
