@@ -46,7 +46,12 @@ using namespace emirwv;
 constexpr int NROWS = EMIRWV_ROWS_SCANNED;   // 39 rectified rows per slitlet
 constexpr int W = 2048;                      // EMIR_NAXIS1: pitch of per-column tables
 constexpr int MAXK = 4;                      // largest supported footprint
-constexpr int MAXTHREADS = 512;
+constexpr int NTHREADS = 288;                 // 9 warps per CTA of the hot kernel
+constexpr int PX_MAX = 30 * (NTHREADS / 32);  // rectified columns a CTA can hold (270)
+constexpr int TILE_K_MAX = 248;               // output columns per tile (8 x 31)
+constexpr int KNOT_PITCH = 272;               // shared rows of flux / slopes
+constexpr int WIN_ROWS = 16;                  // rolling source window: rows (power of 2)
+constexpr int WIN_PITCH = 288;                // ... and columns, per frame
 constexpr int HOST_SLOTS = 3;                // pipeline depth of emirwv_run_host
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -81,17 +86,19 @@ struct SlitDev {
     double b[EMIRWV_MAX_COEF];
 };
 
+// Work item of the hot kernel: a block of output columns of one slitlet, all rows.
 struct Tile {
     int slit;           // 0-based slitlet
-    int y0, ny;         // rows (of the 39 scanned) handled by this tile
     int k0, nk;         // output columns [k0, k0+nk)
     int jlo, npx;       // rectified columns needed: [jlo, jlo+npx)
-    int r0, c0;         // frame coordinates of the staged source window origin
-    int wrows, wcols;   // c0 and wcols are multiples of 4 (16-byte vector loads)
+    int c0, wcols;      // source window columns (multiples of 4: 16-byte copies)
     int empty;          // no wavelength coverage: the tile is exactly zero
     int nchan;          // bbw of the slitlet
     int pad[3];
+    int32_t span[40];   // per scanned row: source rows needed, lo | hi << 16 (int16 each),
+                        // monotone envelopes (rolling window)
 };
+static_assert(sizeof(Tile) % 16 == 0, "tile descriptors are copied in 16-byte chunks");
 
 struct GeomParams {
     const SlitDev *slit;
@@ -143,14 +150,9 @@ struct RunParams {
     int nout, NB;           // naxis1_out, naxis1_out + 1
     int rps, nrows_out;     // 38, 55*38
     int nsl;
-    int wpitch, wrows;      // shared window: row pitch and rows per frame
-    int npxp;               // scratch pitch (>= max npx)
-    int max_span;           // max whole source pixels inside one output pixel
     int vec_ok;             // rows of the output are 16-byte aligned
     int nlive_tiles;        // tiles [0, nlive_tiles) have wavelength coverage
     int ngroups;            // ceil(nframes / G)
-    int stage_bytes;        // one pipeline stage in shared memory
-    int off_border, off_pix;  // byte offsets of the tables inside a stage
 };
 
 __host__ __device__ inline int32_t pack_base(int r, int c) {
@@ -160,6 +162,9 @@ __host__ __device__ inline int32_t pack_base(int r, int c) {
 }
 __host__ __device__ inline int base_row(int32_t p) { return (int)(int16_t)((uint32_t)p >> 16); }
 __host__ __device__ inline int base_col(int32_t p) { return (int)(int16_t)((uint32_t)p & 0xffffu); }
+
+__host__ __device__ inline int span_lo(int32_t v) { return (int)(int16_t)((uint32_t)v & 0xffffu); }
+__host__ __device__ inline int span_hi(int32_t v) { return (int)(int16_t)((uint32_t)v >> 16); }
 
 __device__ inline double clampd(double v) { return fmin(fmax(v, -1.0e6), 1.0e6); }
 
@@ -366,263 +371,257 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_zero_fill(const RunParams<T> p, int first_tile) {
     using V = typename Vec16<T>::type;
     constexpr int VN = Vec16<T>::N;
-    const Tile tile = p.tiles[first_tile + blockIdx.x];
+    const Tile &tile = p.tiles[first_tile + blockIdx.x];
+    const int slit = tile.slit, k0 = tile.k0, nk = tile.nk;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const size_t frame_out = (size_t)p.nrows_out * p.nout;
-    const int ylast = min(tile.y0 + tile.ny, p.rps);
-    const bool vec = p.vec_ok && ((tile.k0 | tile.nk) % VN) == 0;
+    const bool vec = p.vec_ok && ((k0 | nk) % VN) == 0;
     for (int f = blockIdx.y; f < p.nframes; f += gridDim.y)
-        for (int y = tile.y0 + warp; y < ylast; y += nwarps) {
-            T *orow = p.out + (size_t)f * frame_out + (size_t)(tile.slit * p.rps + y) * p.nout + tile.k0;
+        for (int y = warp; y < p.rps; y += nwarps) {
+            T *orow = p.out + (size_t)f * frame_out + (size_t)(slit * p.rps + y) * p.nout + k0;
             if (vec) {
                 V zero;
                 memset(&zero, 0, sizeof(zero));
-                for (int k = lane; k < tile.nk / VN; k += 32) __stcs(reinterpret_cast<V *>(orow) + k, zero);
+                for (int k = lane; k < nk / VN; k += 32) __stcs(reinterpret_cast<V *>(orow) + k, zero);
             } else {
-                for (int k = lane; k < tile.nk; k += 32) __stcs(orow + k, T(0));
+                for (int k = lane; k < nk; k += 32) __stcs(orow + k, T(0));
             }
         }
 }
 
-// One pipeline stage in shared memory: everything a work item (tile x frame group)
-// needs that does not depend on the rectified row.
-//   [G source windows][Border table of the tile][PixGeom table of the tile]
-// Copied with cp.async while the previous item is being computed.
+// ---------------------------------------------------------------------------------
+// The hot kernel.
+//
+// Persistent: CTA b processes work items b, b + gridDim.x, ...; an item is a live
+// tile (slitlet x block of <= TILE_K output columns) for G consecutive frames, frame
+// group fastest so that CTAs running at the same time share the tile's tables in L2.
+//
+// Inside an item the CTA marches down the 39 scanned rows of the slitlet.  Every
+// thread keeps, for the whole item, ONE rectified pixel column (phases A and C) and
+// ONE border of the output grid (phase D), so the per-column tables (pixel widths,
+// border positions) sit in registers and only the per-row weights are loaded, one
+// row ahead of their use.  Per row:
+//   A  rectified flux of G frames: K*K weighted gather from the rolling window
+//   C  Steffen-limited end slopes from the neighbours' flux (warp shuffles: a warp
+//      covers 32 pixels and produces 30, so no shared-memory round trip)
+//   -- barrier --
+//   D  cumulative-flux difference at the thread's border and the next one (shuffle),
+//      store, non-zero flag
+//   -- barrier (also: next row's source rows have landed) --
+// The source window is a ring of WIN_ROWS rows per frame; the few new source rows
+// of the next rectified row are copied with cp.async while the current one runs.
+//
+// Shared memory: [tile descriptor ring: 3][G windows: WIN_ROWS x WIN_PITCH]
+//                [rect | ya | yb : G x KNOT_PITCH each]
+// ---------------------------------------------------------------------------------
 template <typename T, int G>
-__device__ __forceinline__ void issue_stage(const RunParams<T> &p, const Tile &t, int grp,
-                                            unsigned char *stage, int wp1, int tid, int nthr) {
+__device__ __forceinline__ void load_window_rows(const RunParams<T> &p, const Tile &t, int g0,
+                                                 int nlive, T *win, int r_from, int r_to,
+                                                 int tid, int nthr) {
+    // copy source rows (r_from, r_to] of the live frames into their ring slots
     constexpr int VN = Vec16<T>::N;
-    T *win = reinterpret_cast<T *>(stage);
-    const int wsz = p.wrows * wp1;
     const int vcols = t.wcols / VN;
-    const int nvec = t.wrows * vcols;
-    const float inv = 1.0f / (float)vcols;
     const size_t frame_in = (size_t)W * p.naxis2;
-    const int nlive = min(G, p.nframes - grp * G);
-    for (int g = 0; g < nlive; ++g) {
-        const T *fr = p.in + (size_t)(grp * G + g) * frame_in;
-        T *wg = win + (size_t)g * wsz;
-        for (int e = tid; e < nvec; e += nthr) {
-            const int rr = (int)(((float)e + 0.5f) * inv);     // e / vcols, exact here
-            const int vc = e - rr * vcols;
-            const int r = t.r0 + rr, c = t.c0 + vc * VN;
-            const bool ok = r >= 0 && r < p.naxis2 && c >= 0 && c < W;
-            cp_async_16(wg + rr * wp1 + vc * VN, fr + (ok ? (size_t)r * W + c : 0), ok);
+    for (int r = r_from + 1; r <= r_to; ++r) {
+        const bool rok = r >= 0 && r < p.naxis2;
+        T *dst = win + (r & (WIN_ROWS - 1)) * WIN_PITCH;
+        for (int e = tid; e < nlive * vcols; e += nthr) {
+            int g = 0, vc = e;
+            while (vc >= vcols) {
+                vc -= vcols;
+                ++g;
+            }
+            const int c = t.c0 + vc * VN;
+            const bool ok = rok && c >= 0 && c < W;
+            const T *src = p.in + (size_t)(g0 + g) * frame_in + (ok ? (size_t)r * W + c : 0);
+            cp_async_16(dst + g * (WIN_ROWS * WIN_PITCH) + vc * VN, src, ok);
         }
     }
-    Border<T> *bs = reinterpret_cast<Border<T> *>(stage + p.off_border);
-    const Border<T> *bsrc = p.border + (size_t)t.slit * p.NB + t.k0;
-    for (int e = tid; e <= t.nk; e += nthr) cp_async_small<sizeof(Border<T>)>(bs + e, bsrc + e);
-    PixGeom<T> *ps = reinterpret_cast<PixGeom<T> *>(stage + p.off_pix);
-    const PixGeom<T> *psrc = p.pix + (size_t)t.slit * W + t.jlo;
-    for (int e = tid; e < t.npx * (int)(sizeof(PixGeom<T>) / 16); e += nthr)
-        cp_async_16(reinterpret_cast<char *>(ps) + e * 16,
-                    reinterpret_cast<const char *>(psrc) + e * 16, true);
 }
 
-// NPXP_C / WP_C: compile-time scratch pitch and window pitch (0 = take them from the
-// plan at run time).  SPANLOOP: an output pixel may contain more than one whole
-// source pixel (coarse output grids); the EMIR grids need at most one.
-//
-// Persistent kernel: CTA b processes work items b, b + gridDim.x, ...; item =
-// (live tile, frame group), frame group fastest so that CTAs running at the same
-// time share the tile's tables in L2.  Shared memory:
-//   [tile descriptor ring: 3][stage 0][stage 1][per warp: G x (Knot[npxp], rect[npxp+4])]
-template <typename T, int K, int G, int NPXP_C, int WP_C, bool SPANLOOP>
-__global__ void __launch_bounds__(MAXTHREADS) k_rectwv(const RunParams<T> p) {
+template <typename T, int K, int G, bool SPANLOOP>
+__global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
+    k_rectwv(const RunParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int WSZ = WIN_ROWS * WIN_PITCH;                  // one frame's window
 
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    const int npxp = NPXP_C ? NPXP_C : p.npxp;
-    const int wp1 = WP_C ? WP_C : p.wpitch;
-    const int wsz = p.wrows * wp1;
-    const int rpitch = npxp + 4;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const size_t frame_out = (size_t)p.nrows_out * p.nout;
     const int nwork = p.nlive_tiles * p.ngroups;
 
     Tile *ring = reinterpret_cast<Tile *>(smem_raw);                       // [3]
-    unsigned char *stage0 = smem_raw + 3 * sizeof(Tile);
-    T *scr = reinterpret_cast<T *>(stage0 + 2 * (size_t)p.stage_bytes);
-    int woff = warp * (G * (npxp * 4 + rpitch));                // this warp's scratch
-    pin(woff);
-    Knot<T> *knots = reinterpret_cast<Knot<T> *>(scr + woff);   // [G][npxp]
-    T *rect = scr + woff + G * npxp * 4 + 1;                    // [G][rpitch], halo at -1
+    T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile));           // [G][WSZ]
+    T *rectS = win + G * WSZ;                                              // [G][KNOT_PITCH]
+    T *yaS = rectS + G * KNOT_PITCH;
+    T *ybS = yaS + G * KNOT_PITCH;
 
     int w = blockIdx.x;
     if (w >= nwork) return;
 
-    // prologue: stage of the first item, descriptors of the first two
-    {
-        const Tile t0 = p.tiles[w / p.ngroups];
-        issue_stage<T, G>(p, t0, w % p.ngroups, stage0, wp1, tid, nthr);
-        if (tid < 4) cp_async_16(reinterpret_cast<char *>(&ring[0]) + tid * 16,
-                                 reinterpret_cast<const char *>(p.tiles + w / p.ngroups) + tid * 16, true);
-        const int w1 = w + gridDim.x;
-        if (w1 < nwork && tid >= 4 && tid < 8)
-            cp_async_16(reinterpret_cast<char *>(&ring[1]) + (tid - 4) * 16,
-                        reinterpret_cast<const char *>(p.tiles + w1 / p.ngroups) + (tid - 4) * 16, true);
-    }
+    // descriptors of the first two items
+    constexpr int TCH = sizeof(Tile) / 16;
+    if (tid < TCH)
+        cp_async_16(reinterpret_cast<char *>(&ring[0]) + tid * 16,
+                    reinterpret_cast<const char *>(p.tiles + w / p.ngroups) + tid * 16, true);
+    if (w + (int)gridDim.x < nwork && tid >= 32 && tid < 32 + TCH)
+        cp_async_16(reinterpret_cast<char *>(&ring[1]) + (tid - 32) * 16,
+                    reinterpret_cast<const char *>(p.tiles + (w + gridDim.x) / p.ngroups) +
+                        (tid - 32) * 16, true);
+    cp_async_wait_all();
+    __syncthreads();
 
     unsigned fo = (unsigned)frame_out;                         // < 2^32 elements per frame
     pin(fo);
 
     for (int it = 0;; ++it) {
-        cp_async_wait_all();
-        __syncthreads();                     // stage(it), descriptors it and it+1 have landed
-
-        unsigned char *stage = stage0 + (size_t)(it & 1) * p.stage_bytes;
+        const Tile &tile = ring[it % 3];
         const int wnext = w + gridDim.x;
-        if (wnext < nwork) {
-            // prefetch the next item's stage; its descriptor arrived one iteration ago
-            const Tile tn = ring[(it + 1) % 3];
-            issue_stage<T, G>(p, tn, wnext % p.ngroups,
-                              stage0 + (size_t)((it + 1) & 1) * p.stage_bytes, wp1, tid, nthr);
-            const int w2 = wnext + gridDim.x;
-            if (w2 < nwork && tid < 4)
-                cp_async_16(reinterpret_cast<char *>(&ring[(it + 2) % 3]) + tid * 16,
-                            reinterpret_cast<const char *>(p.tiles + w2 / p.ngroups) + tid * 16, true);
-        }
+        // descriptor of the item after the next one rides along with this item's copies
+        if (wnext + (int)gridDim.x < nwork && tid < TCH)
+            cp_async_16(reinterpret_cast<char *>(&ring[(it + 2) % 3]) + tid * 16,
+                        reinterpret_cast<const char *>(p.tiles + (wnext + gridDim.x) / p.ngroups) +
+                            tid * 16, true);
 
-        // ---------------------------------------------------------------- item `w`
-        const Tile tile = ring[it % 3];
         const int grp = w % p.ngroups;
         const int g0 = grp * G;
+        const int nlive = min(G, p.nframes - g0);
         const int s = tile.slit;
         const int npx = tile.npx;
-        const int nlive = min(G, p.nframes - g0);
-        const T *win = reinterpret_cast<const T *>(stage);
-        const Border<T> *border = reinterpret_cast<const Border<T> *>(stage + p.off_border);
-        const PixGeom<T> *pix = reinterpret_cast<const PixGeom<T> *>(stage + p.off_pix);
-        const Knot<T> *kread = knots - tile.jlo;               // indexed by source pixel
-        T *obase = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
-        int wb = -(tile.r0 * wp1 + tile.c0);                   // window addressed by frame coords
+        const int nk = tile.nk;
+        const int k0 = tile.k0;
+
+        // ---- per-item constants of this thread
+        // pixel column: a warp covers pixels 30*warp-1 .. 30*warp+30 and produces 30
+        const int pp = 30 * warp - 1 + lane;
+        const bool px_ok = pp >= 0 && pp < npx;
+        const bool knot_ok = lane >= 1 && lane <= 30 && pp < npx;
+        PixGeom<T> pg;
+        pg.qm = pg.qp = pg.r0 = pg.r1 = T(0);
+        if (px_ok) pg = ldg_struct(p.pix + (size_t)s * W + tile.jlo + pp);
+        // output border: a warp evaluates 32 borders = 31 pixels
+        const int q = 31 * warp + lane;
+        const Border<T> bd = ldg_struct(p.border + (size_t)s * p.NB + k0 + min(q, nk));
+        const int ibl = bd.idx - tile.jlo;                     // source pixel, tile relative
+        const int ibn = __shfl_down_sync(0xffffffffu, ibl, 1);
+        const bool col_ok = lane < 31 && q < nk;
+        const bool has1 = ibn > ibl, has2 = ibn > ibl + 1;
+        const int kb = k0 + q;
+        unsigned nzmask = 0;                                   // bit g: a non-zero value seen
+
+        // rolling window: rows needed by rectified row 0, and that row's weights
+        int rhi_prev = span_lo(tile.span[0]) - 1;
+        load_window_rows<T, G>(p, tile, g0, nlive, win, rhi_prev, span_hi(tile.span[0]), tid,
+                               NTHREADS);
+        rhi_prev = span_hi(tile.span[0]);
+
+        // tables of row 0 for this pixel column: base[s][y][j], w[s][y][tap][j]
+        const int32_t *bptr = p.base + (size_t)s * NROWS * W + tile.jlo + pp;
+        const T *wptr = p.w + (size_t)s * NROWS * (K * K) * W + tile.jlo + pp;
+        // lanes without a pixel gather from column c0 of ring slot 0 with zero weights
+        int32_t npk = pack_base(0, tile.c0);
+        T nwt[K * K];
+#pragma unroll
+        for (int tap = 0; tap < K * K; ++tap) nwt[tap] = T(0);
+        if (px_ok) {
+            npk = __ldg(bptr);
+#pragma unroll
+            for (int tap = 0; tap < K * K; ++tap) nwt[tap] = __ldg(wptr + tap * W);
+        }
+        T *orow = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
+        int wb = -tile.c0;                                     // window addressed by frame coords
         pin(wb);
 
-        if (lane < G) {
-            rect[lane * rpitch - 1] = T(0);
-            rect[lane * rpitch + npx] = T(0);
-        }
-        int jmin[G], jmax[G];
+        for (int y = 0; y < NROWS; ++y) {
+            cp_async_wait_all();
+            __syncthreads();     // source rows of row y landed; everyone is done with row y-1
+
+            // next row: its new source rows (ring slots of rows no longer needed) ...
+            if (y + 1 < NROWS) {
+                const int rhi = span_hi(tile.span[y + 1]);
+                load_window_rows<T, G>(p, tile, g0, nlive, win, rhi_prev, rhi, tid, NTHREADS);
+                rhi_prev = max(rhi_prev, rhi);
+            }
+            // ... and its weights
+            const int32_t pk = npk;
+            T wt[K * K];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            jmin[g] = INT_MAX;
-            jmax[g] = -1;
-        }
+            for (int tap = 0; tap < K * K; ++tap) wt[tap] = nwt[tap];
+            if (px_ok && y + 1 < NROWS) {
+                bptr += W;
+                wptr += (K * K) * W;
+                npk = __ldg(bptr);
+#pragma unroll
+                for (int tap = 0; tap < K * K; ++tap) nwt[tap] = __ldg(wptr + tap * W);
+            }
 
-        // every warp owns whole rows of the tile: no block-level barrier inside
-        for (int yy = warp; yy < tile.ny; yy += nwarps) {
-            const int y = tile.y0 + yy;
-            const size_t rowtab = (size_t)s * NROWS + y;
-            const int32_t *brow = p.base + rowtab * W + tile.jlo + lane;
-            const T *wrow = p.w + rowtab * (K * K) * W + tile.jlo + lane;
-            T *orow = obase + (size_t)y * p.nout;
-            pin(orow);
-
-            // ---- A: rectified flux, K*K weighted gather from the staged window.
-            //         The table entries of the next 32 pixels are requested before the
-            //         current ones are used (the tables are padded past their end).
+            // ---- A: rectified flux of this pixel column, G frames
+            T rect[G];
             {
-                int32_t npk = __ldg(brow);
-                T nwt[K * K];
+                const int fr = base_row(pk), fc = base_col(pk) + wb;
+                const T *rowp[K];
 #pragma unroll
-                for (int tap = 0; tap < K * K; ++tap) nwt[tap] = __ldg(wrow + tap * W);
-                for (int p0 = 0; p0 < npx; p0 += 32) {
-                    const int32_t pk = npk;
-                    T wt[K * K];
+                for (int a = 0; a < K; ++a)
+                    rowp[a] = win + (((fr + a) & (WIN_ROWS - 1)) * WIN_PITCH + fc);
 #pragma unroll
-                    for (int tap = 0; tap < K * K; ++tap) wt[tap] = nwt[tap];
-                    if (p0 + 32 < npx) {
-                        npk = __ldg(brow + p0 + 32);
+                for (int g = 0; g < G; ++g) {
+                    T acc = T(0);
 #pragma unroll
-                        for (int tap = 0; tap < K * K; ++tap)
-                            nwt[tap] = __ldg(wrow + p0 + 32 + tap * W);
-                    }
-                    if (p0 + lane < npx) {
-                        const T *src = win + (wb + base_row(pk) * wp1 + base_col(pk));
+                    for (int a = 0; a < K; ++a)
 #pragma unroll
-                        for (int g = 0; g < G; ++g) {
-                            const T *sg = src + g * wsz;
-                            T acc = T(0);
-#pragma unroll
-                            for (int a = 0; a < K; ++a)
-#pragma unroll
-                                for (int b = 0; b < K; ++b)
-                                    acc = fma(wt[a * K + b], sg[a * wp1 + b], acc);
-                            rect[g * rpitch + p0 + lane] = acc;
-                        }
-                    }
+                        for (int b = 0; b < K; ++b)
+                            acc = fma(wt[a * K + b], rowp[a][g * WSZ + b], acc);
+                    rect[g] = px_ok ? acc : T(0);
                 }
             }
-            __syncwarp();
 
-            // ---- C: Steffen-limited slopes at both ends of every source pixel, scaled
-            //         by the pixel width (flux units).  Branch-free: the table holds
-            //         qm = 0 for the first pixel of the spectrum and qp = 0 for the last
-            //         one, which gives the zero end slopes; the halo of `rect` is zero.
-            for (int p0 = 0; p0 < npx; p0 += 32) {
-                if (p0 + lane < npx) {
-                    const PixGeom<T> pg = pix[p0 + lane];
+            // ---- C: Steffen-limited slopes at both ends of the pixel, scaled by the
+            //         pixel width (flux units).  qm = 0 / qp = 0 in the table give the
+            //         zero slopes at the two ends of the spectrum.
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const T *rv = rect + g * rpitch + p0 + lane;
-                        const T c = rv[0];
-                        const T cl = rv[-1] * pg.qm;
-                        const T cr = rv[1] * pg.qp;
-                        Knot<T> kn;
-                        kn.rect = c;
-                        kn.ya = steffen_slope(cl, c, pg.r0);
-                        kn.yb = steffen_slope(c, cr, pg.r1);
-                        kn.pad = T(0);
-                        knots[g * npxp + p0 + lane] = kn;
-                    }
+            for (int g = 0; g < G; ++g) {
+                const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
+                const T cr = __shfl_down_sync(0xffffffffu, rect[g], 1) * pg.qp;
+                const T ya = steffen_slope(cl, rect[g], pg.r0);
+                const T yb = steffen_slope(rect[g], cr, pg.r1);
+                if (knot_ok) {
+                    rectS[g * KNOT_PITCH + pp] = rect[g];
+                    yaS[g * KNOT_PITCH + pp] = ya;
+                    ybS[g * KNOT_PITCH + pp] = yb;
                 }
             }
-            __syncwarp();
+            __syncthreads();     // flux and slopes of row y are visible to all warps
 
-            // ---- D: cumulative flux at the output borders (32 borders = 31 pixels per
-            //         warp pass), difference, coalesced store, non-zero channel range.
-            //         Lanes past the tile's last border re-read that border: their source
-            //         pixel stays inside this warp's scratch and their result is dropped.
-            {
-                const bool store = y < p.rps;
-                for (int q0 = 0; q0 < tile.nk; q0 += 31) {
-                    const int q = q0 + lane;                   // border, relative to the tile
-                    const Border<T> bd = border[min(q, tile.nk)];
-                    const int ib = bd.idx;
-                    const int ibn = __shfl_down_sync(0xffffffffu, ib, 1);
-                    const bool col_ok = lane < 31 && q < tile.nk;
-                    const int kb = tile.k0 + q;
+            // ---- D: cumulative flux at this thread's border and at the next one,
+            //         difference = output pixel; store; remember non-zero values
+            const bool store = y < p.rps;
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const Knot<T> *kr = kread + g * npxp;
-                        const Knot<T> kn = kr[ib];
-                        const T P = steffen_partial_flux(kn.rect, kn.ya, kn.yb, bd.tau);
-                        const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
-                        T whole = (ibn > ib) ? kn.rect : T(0);
-                        if (ibn > ib + 1) whole += kr[ib + 1].rect;
-                        if (SPANLOOP)
-                            for (int i = ib + 2; i < ibn; ++i) whole += kr[i].rect;
-                        const T o = whole + (Pn - P);
-                        const bool okg = col_ok && g < nlive;
-                        if (okg && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o);
-                        if (okg && o != T(0)) {
-                            jmin[g] = min(jmin[g], kb);
-                            jmax[g] = max(jmax[g], kb);
-                        }
-                    }
-                }
+            for (int g = 0; g < G; ++g) {
+                const T kr = rectS[g * KNOT_PITCH + ibl];
+                const T ka = yaS[g * KNOT_PITCH + ibl];
+                const T kc = ybS[g * KNOT_PITCH + ibl];
+                const T P = steffen_partial_flux(kr, ka, kc, bd.tau);
+                const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
+                T whole = has1 ? kr : T(0);
+                if (has2) whole += rectS[g * KNOT_PITCH + ibl + 1];
+                if (SPANLOOP)
+                    for (int i = ibl + 2; i < ibn; ++i) whole += rectS[g * KNOT_PITCH + i];
+                const T o = whole + (Pn - P);
+                const bool okg = col_ok && g < nlive;
+                if (okg && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o);
+                if (okg && o != T(0)) nzmask |= 1u << g;
             }
-            __syncwarp();
+            orow += p.nout;
         }
 
         // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
         if (p.jmm != nullptr) {
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const int lo = __reduce_min_sync(0xffffffffu, jmin[g]);
-                const int hi = __reduce_max_sync(0xffffffffu, jmax[g]);
-                if (lane == 0 && hi >= 0 && g < nlive) {
+                const bool nz = (nzmask >> g) & 1u;
+                const int lo = __reduce_min_sync(0xffffffffu, nz ? kb : INT_MAX);
+                const int hi = __reduce_max_sync(0xffffffffu, nz ? kb : -1);
+                if (lane == 0 && hi >= 0) {
                     int32_t *dst = p.jmm + ((size_t)(g0 + g) * p.nsl + s) * 2;
                     atomicMin(dst, lo);
                     atomicMax(dst + 1, hi);
@@ -632,7 +631,8 @@ __global__ void __launch_bounds__(MAXTHREADS) k_rectwv(const RunParams<T> p) {
 
         if (wnext >= nwork) break;
         w = wnext;
-        __syncthreads();          // stage (it & 1) is free again for the prefetch of it + 2
+        cp_async_wait_all();
+        __syncthreads();          // next descriptor landed; window and knots are free again
     }
 }
 
@@ -660,9 +660,8 @@ struct emirwv_plan {
 
     int ntiles = 0, ntiles_empty = 0;
     int tile_k = 0, tile_rows = 0;
-    int wrows_max = 0, wcols_max = 0, wpitch = 0, npxp = 0, max_span = 0;
-    int tune_G = 0, tune_threads = 0;
-    bool fast_pitch = false;     // npxp / wpitch equal the compile-time constants
+    int wrows_max = 0, wcols_max = 0, npx_max = 0, max_span = 0;
+    int tune_G = 0;
     int num_sms = 148;
     int64_t table_bytes = 0;
 
@@ -686,51 +685,30 @@ int env_int(const char *name, int fallback) {
 // launch configuration for a given number of frames per CTA
 struct LaunchCfg {
     int G, threads;
-    int stage_bytes, off_border, off_pix;
     size_t smem;
 };
 
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// shared memory of the persistent kernel:
-//   [3 tile descriptors][2 stages: G windows | border table | pixel table][warp scratch]
-void smem_layout(const emirwv_plan *pl, int G, int threads, LaunchCfg &cfg) {
-    const size_t es = pl->esize;
-    const size_t win = (size_t)G * pl->wrows_max * pl->wpitch * es;
-    const size_t border = align_up((size_t)(pl->tile_k + 1) * 2 * es, 16);
-    const size_t pix = (size_t)pl->npxp * 4 * es;
-    cfg.off_border = (int)align_up(win, 16);
-    cfg.off_pix = (int)(cfg.off_border + border);
-    cfg.stage_bytes = (int)align_up(cfg.off_pix + pix, 128);
-    const size_t scratch = (size_t)(threads / 32) * G * (pl->npxp * 5 + 4) * es;
-    cfg.smem = 3 * sizeof(Tile) + 2 * (size_t)cfg.stage_bytes + scratch;
+// shared memory of the hot kernel:
+//   [3 tile descriptors][G windows: WIN_ROWS x WIN_PITCH][rect | ya | yb: G x KNOT_PITCH]
+size_t smem_bytes(const emirwv_plan *pl, int G) {
+    return 3 * sizeof(Tile) +
+           (size_t)G * (WIN_ROWS * WIN_PITCH + 3 * KNOT_PITCH) * pl->esize;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
     LaunchCfg cfg;
-    cfg.threads = pl->tune_threads > 0 ? pl->tune_threads : env_int("EMIRWV_THREADS", 256);
-    cfg.threads = std::max(32, std::min(MAXTHREADS, (cfg.threads / 32) * 32));
-    int G = pl->tune_G > 0 ? pl->tune_G : env_int("EMIRWV_G", 2);
+    cfg.threads = NTHREADS;
+    int G = pl->tune_G > 0 ? pl->tune_G : env_int("EMIRWV_G", pl->esize == 4 ? 4 : 2);
     G = (G >= 4) ? 4 : (G >= 2 ? 2 : 1);
-    smem_layout(pl, G, cfg.threads, cfg);
-    while (G > 1 && (G > nframes || cfg.smem > (size_t)SMEM_LIMIT)) {
-        G >>= 1;
-        smem_layout(pl, G, cfg.threads, cfg);
-    }
-    while (cfg.threads > 32 && cfg.smem > (size_t)SMEM_LIMIT) {
-        cfg.threads -= 32;
-        smem_layout(pl, G, cfg.threads, cfg);
-    }
+    while (G > 1 && (G > nframes || smem_bytes(pl, G) > (size_t)SMEM_LIMIT)) G >>= 1;
     cfg.G = G;
+    cfg.smem = smem_bytes(pl, G);
     return cfg;
 }
 
-constexpr int FAST_NPXP = 144;   // scratch pitch of the specialised kernels
-constexpr int FAST_WP = 160;     // window pitch of the specialised kernels
-
-template <typename T, int K, int G, int NPXP_C, int WP_C, bool SPANLOOP>
+template <typename T, int K, int G, bool SPANLOOP>
 int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, cudaStream_t st) {
-    auto kern = k_rectwv<T, K, G, NPXP_C, WP_C, SPANLOOP>;
+    auto kern = k_rectwv<T, K, G, SPANLOOP>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)cfg.smem));
     int per_sm = 0;
@@ -750,13 +728,8 @@ int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, c
 template <typename T, int K, int G>
 int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
                cudaStream_t st) {
-    const bool span = pl->max_span > 2;
-    if (pl->fast_pitch) {
-        if (span) return launch_final<T, K, G, FAST_NPXP, FAST_WP, true>(pl, rp, cfg, st);
-        return launch_final<T, K, G, FAST_NPXP, FAST_WP, false>(pl, rp, cfg, st);
-    }
-    if (span) return launch_final<T, K, G, 0, 0, true>(pl, rp, cfg, st);
-    return launch_final<T, K, G, 0, 0, false>(pl, rp, cfg, st);
+    if (pl->max_span > 2) return launch_final<T, K, G, true>(pl, rp, cfg, st);
+    return launch_final<T, K, G, false>(pl, rp, cfg, st);
 }
 
 template <typename T, int K>
@@ -774,7 +747,7 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
              int32_t *d_jmm, cudaStream_t st) {
     const LaunchCfg cfg = choose_cfg(pl, nframes);
     if (cfg.smem > (size_t)SMEM_LIMIT)
-        return fail(EMIRWV_E_LIMIT, "tile needs %zu bytes of shared memory", cfg.smem);
+        return fail(EMIRWV_E_LIMIT, "kernel needs %zu bytes of shared memory", cfg.smem);
     if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
         return fail(EMIRWV_E_VALUE, "device buffers must be 16-byte aligned");
     RunParams<T> rp;
@@ -793,16 +766,9 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     rp.rps = pl->rps;
     rp.nrows_out = pl->nsl * pl->rps;
     rp.nsl = pl->nsl;
-    rp.wpitch = pl->wpitch;
-    rp.wrows = pl->wrows_max;
-    rp.npxp = pl->npxp;
-    rp.max_span = pl->max_span;
     rp.vec_ok = ((size_t)pl->nout * sizeof(T)) % 16 == 0;
     rp.nlive_tiles = pl->ntiles - pl->ntiles_empty;
     rp.ngroups = 0;
-    rp.stage_bytes = cfg.stage_bytes;
-    rp.off_border = cfg.off_border;
-    rp.off_pix = cfg.off_pix;
     if (d_jmm != nullptr) {
         const int n = nframes * pl->nsl * 2;
         k_init_jmm<<<(n + 255) / 256, 256, 0, st>>>(d_jmm, n);
@@ -936,92 +902,98 @@ int build_border_tables(emirwv_plan *pl, std::vector<uint8_t> &covered) {
     return upload_tables<double>(pl, h_tau, h_h);
 }
 
-// Work items: (slitlet, block of rectified rows, block of output columns).
-int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
+// Work items: (slitlet, block of <= tile_k output columns), all 39 scanned rows.
+// Returns 1 when a tile does not fit the kernel's fixed shared-memory geometry with
+// this tile_k (the caller retries with a narrower block), 0 on success.
+int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int TK) {
     const emirwv_plan_desc &d = pl->desc;
     const int nout = pl->nout, NB = pl->NB, K = pl->K;
-    const int TK = pl->tile_k, TR = pl->tile_rows;
     std::vector<Tile> live, dead;
-    pl->wrows_max = pl->wcols_max = 1;
-    int npx_max = 1;
+    int wcols_max = 4, span_max = 1, npx_max = 1;
     for (int s = 0; s < pl->nsl; ++s) {
         const emirwv_slitlet_desc &sl = d.slitlet[s];
         const int nchan = sl.valid ? sl.bb_nc2_orig - sl.bb_nc1_orig + 1 : 0;
-        for (int y0 = 0; y0 < NROWS; y0 += TR) {
-            const int ny = std::min(TR, NROWS - y0);
-            for (int k0 = 0; k0 < nout; k0 += TK) {
-                Tile t;
-                memset(&t, 0, sizeof(t));
-                t.slit = s;
-                t.y0 = y0;
-                t.ny = ny;
-                t.k0 = k0;
-                t.nk = std::min(TK, nout - k0);
-                t.nchan = nchan;
-                bool any = false;
-                if (sl.valid)
-                    for (int k = k0; k <= k0 + t.nk; ++k) any |= covered[(size_t)s * NB + k] != 0;
-                // a pixel whose two borders lie on either side of the spectrum also counts
-                if (sl.valid && !any)
-                    any = pl->h_idx[(size_t)s * NB + k0] != pl->h_idx[(size_t)s * NB + k0 + t.nk];
-                if (!any) {
-                    t.empty = 1;
-                    if (y0 >= pl->rps) continue;           // the ghost row stores nothing
-                    // neighbouring empty tiles become one wide run of zeros
-                    if (!dead.empty() && dead.back().slit == s && dead.back().y0 == y0 &&
-                        dead.back().k0 + dead.back().nk == k0 && dead.back().nk + t.nk <= 1024)
-                        dead.back().nk += t.nk;
-                    else
-                        dead.push_back(t);
-                    continue;
-                }
-                const int ilo = pl->h_idx[(size_t)s * NB + k0];
-                const int ihi = pl->h_idx[(size_t)s * NB + k0 + t.nk];
-                t.jlo = std::max(0, ilo - 1);
-                const int jhi = std::min(nchan - 1, ihi + 1);
-                t.npx = jhi - t.jlo + 1;
-                int r0 = INT_MAX, r1 = INT_MIN, c0 = INT_MAX, c1 = INT_MIN;
-                for (int y = y0; y < y0 + ny; ++y) {
-                    const int32_t *row = pl->h_base.data() + ((size_t)s * NROWS + y) * W;
-                    for (int j = t.jlo; j <= jhi; ++j) {
-                        const int br = base_row(row[j]), bc = base_col(row[j]);
-                        r0 = std::min(r0, br);
-                        r1 = std::max(r1, br + K - 1);
-                        c0 = std::min(c0, bc);
-                        c1 = std::max(c1, bc + K - 1);
-                    }
-                }
-                c0 = (int)(std::floor(c0 / 4.0) * 4.0);    // 16-byte aligned window rows
-                t.r0 = r0;
-                t.c0 = c0;
-                t.wrows = r1 - r0 + 1;
-                t.wcols = ((c1 - c0 + 1) + 3) & ~3;
-                pl->wrows_max = std::max(pl->wrows_max, t.wrows);
-                pl->wcols_max = std::max(pl->wcols_max, t.wcols);
-                npx_max = std::max(npx_max, t.npx);
-                live.push_back(t);
+        for (int k0 = 0; k0 < nout; k0 += TK) {
+            Tile t;
+            memset(&t, 0, sizeof(t));
+            t.slit = s;
+            t.k0 = k0;
+            t.nk = std::min(TK, nout - k0);
+            t.nchan = nchan;
+            bool any = false;
+            if (sl.valid)
+                for (int k = k0; k <= k0 + t.nk; ++k) any |= covered[(size_t)s * NB + k] != 0;
+            // a pixel whose two borders lie on either side of the spectrum also counts
+            if (sl.valid && !any)
+                any = pl->h_idx[(size_t)s * NB + k0] != pl->h_idx[(size_t)s * NB + k0 + t.nk];
+            if (!any) {
+                t.empty = 1;
+                // neighbouring empty tiles become one wide run of zeros
+                if (!dead.empty() && dead.back().slit == s &&
+                    dead.back().k0 + dead.back().nk == k0 && dead.back().nk + t.nk <= 1024)
+                    dead.back().nk += t.nk;
+                else
+                    dead.push_back(t);
+                continue;
             }
+            const int ilo = pl->h_idx[(size_t)s * NB + k0];
+            const int ihi = pl->h_idx[(size_t)s * NB + k0 + t.nk];
+            t.jlo = std::max(0, ilo - 1);
+            const int jhi = std::min(nchan - 1, ihi + 1);
+            t.npx = jhi - t.jlo + 1;
+            if (t.npx > PX_MAX) return 1;
+            int c0 = INT_MAX, c1 = INT_MIN;
+            int rlo[NROWS], rhi[NROWS];
+            for (int y = 0; y < NROWS; ++y) {
+                const int32_t *row = pl->h_base.data() + ((size_t)s * NROWS + y) * W;
+                int r0 = INT_MAX, r1 = INT_MIN;
+                for (int j = t.jlo; j <= jhi; ++j) {
+                    const int br = base_row(row[j]), bc = base_col(row[j]);
+                    r0 = std::min(r0, br);
+                    r1 = std::max(r1, br + K - 1);
+                    c0 = std::min(c0, bc);
+                    c1 = std::max(c1, bc + K - 1);
+                }
+                rlo[y] = r0;
+                rhi[y] = r1;
+            }
+            // rolling window: rows may only be added at the top and dropped at the bottom
+            for (int y = 1; y < NROWS; ++y) rhi[y] = std::max(rhi[y], rhi[y - 1]);
+            for (int y = NROWS - 2; y >= 0; --y) rlo[y] = std::min(rlo[y], rlo[y + 1]);
+            for (int y = 0; y < NROWS; ++y) {
+                const int next_hi = rhi[std::min(y + 1, NROWS - 1)];
+                span_max = std::max(span_max, next_hi - rlo[y] + 1);
+                t.span[y] = (int32_t)(((uint32_t)(rhi[y] & 0xffff) << 16) | (uint32_t)(rlo[y] & 0xffff));
+            }
+            c0 = (int)(std::floor(c0 / 4.0) * 4.0);        // 16-byte aligned window rows
+            t.c0 = c0;
+            t.wcols = ((c1 - c0 + 1) + 3) & ~3;
+            if (t.wcols > WIN_PITCH || span_max > WIN_ROWS) return 1;
+            wcols_max = std::max(wcols_max, t.wcols);
+            npx_max = std::max(npx_max, t.npx);
+            live.push_back(t);
         }
     }
     pl->ntiles_empty = (int)dead.size();
     pl->h_tiles = live;
     pl->h_tiles.insert(pl->h_tiles.end(), dead.begin(), dead.end());
     pl->ntiles = (int)pl->h_tiles.size();
-    pl->wpitch = pl->wcols_max;                       // multiple of 4
-    if ((pl->wpitch & 31) == 0) pl->wpitch += 4;      // rows start in different banks
-    pl->npxp = (npx_max + 3) & ~3;
-    pl->fast_pitch = pl->npxp <= FAST_NPXP && pl->wcols_max <= FAST_WP;
-    if (pl->fast_pitch) {
-        pl->npxp = FAST_NPXP;
-        pl->wpitch = FAST_WP;
-    }
-    if (pl->ntiles > 65535) return fail(EMIRWV_E_LIMIT, "too many tiles (%d)", pl->ntiles);
-    LaunchCfg probe;
-    smem_layout(pl, 1, 32, probe);
-    if (probe.smem > (size_t)SMEM_LIMIT)
+    pl->tile_k = TK;
+    pl->wrows_max = span_max;
+    pl->wcols_max = wcols_max;
+    pl->npx_max = npx_max;
+    return 0;
+}
+
+int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
+    int TK = std::max(31, std::min(pl->tile_k, TILE_K_MAX)) / 31 * 31;
+    for (; TK >= 31; TK -= 31)
+        if (try_build_tiles(pl, covered, TK) == 0) break;
+    if (TK < 31)
         return fail(EMIRWV_E_LIMIT,
-                    "distortion too strong: a %d x %d source window does not fit in shared memory",
-                    pl->wrows_max, pl->wcols_max);
+                    "distortion too strong: the source window of a 31-column block does not fit "
+                    "(%d rows x %d columns available)", WIN_ROWS, WIN_PITCH);
+    if (pl->ntiles_empty > 65535) return fail(EMIRWV_E_LIMIT, "too many tiles");
     CUDA_TRY(cudaMalloc(&pl->d_tiles, pl->h_tiles.size() * sizeof(Tile)));
     CUDA_TRY(cudaMemcpy(pl->d_tiles, pl->h_tiles.data(), pl->h_tiles.size() * sizeof(Tile),
                         cudaMemcpyHostToDevice));
@@ -1082,10 +1054,9 @@ int build_plan(emirwv_plan *pl) {
     pl->rps = d.rows_per_slitlet;
     pl->nout = d.naxis1_out;
     pl->NB = d.naxis1_out + 1;
-    pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", 124);
-    pl->tile_rows = d.tile_rows > 0 ? d.tile_rows : env_int("EMIRWV_TILE_ROWS", NROWS);
-    pl->tile_k = std::max(31, std::min(pl->tile_k, 1024));
-    pl->tile_rows = std::max(1, std::min(pl->tile_rows, NROWS));
+    pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", TILE_K_MAX);
+    pl->tile_rows = NROWS;       // a tile always spans the 39 scanned rows
+    pl->tile_k = std::max(31, std::min(pl->tile_k, TILE_K_MAX));
 
     pl->h_slit.resize(pl->nsl);
     for (int s = 0; s < pl->nsl; ++s) {
@@ -1291,7 +1262,7 @@ int emirwv_plan_get_info(const emirwv_plan *pl, emirwv_plan_info *info) {
 int emirwv_plan_set_tuning(emirwv_plan *pl, int frames_per_cta, int threads) {
     if (pl == nullptr) return fail(EMIRWV_E_VALUE, "null plan");
     pl->tune_G = frames_per_cta;
-    pl->tune_threads = threads;
+    (void)threads;               // the hot kernel has a fixed CTA size
     return EMIRWV_OK;
 }
 
