@@ -52,6 +52,8 @@ constexpr int TILE_K_MAX = 248;               // output columns per tile (8 x 31
 constexpr int KNOT_PITCH = 272;               // shared rows of flux / slopes
 constexpr int WIN_ROWS = 16;                  // rolling source window: rows (power of 2)
 constexpr int WIN_PITCH = 288;                // ... and columns, per frame
+constexpr int PREFETCH = 2;                   // rectified rows between a copy and its use
+constexpr int TAB_PITCH = 276;                // staged table rows (PX_MAX + alignment slack)
 constexpr int HOST_SLOTS = 3;                // pipeline depth of emirwv_run_host
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -329,6 +331,21 @@ __device__ __forceinline__ void cp_async_small(void *smem_dst, const void *gmem_
                  "n"(BYTES)
                  : "memory");
 }
+// same with a precomputed 32-bit shared-memory address
+__device__ __forceinline__ void cp_async_16s(unsigned smem_addr, const void *gmem_src, bool valid) {
+    const int src_bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr),
+                 "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ unsigned smem_addr_of(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
@@ -356,6 +373,25 @@ __device__ __forceinline__ Border<double> ldg_struct(const Border<double> *p) {
     b.tau = __hiloint2double(v.y, v.x);
     b.idx = v.z;
     return b;
+}
+
+// Read-only loads that keep their place in the instruction stream: the compiler would
+// otherwise sink the next row's table loads to just before their first use, which
+// defeats the one-row prefetch distance.
+__device__ __forceinline__ float ldg_here(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldg_here(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int32_t ldg_here(const int32_t *p) {
+    int32_t v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
 // Make a loop-invariant value opaque so that the compiler keeps it in a register
@@ -414,31 +450,6 @@ __global__ void __launch_bounds__(256) k_zero_fill(const RunParams<T> p, int fir
 // Shared memory: [tile descriptor ring: 3][G windows: WIN_ROWS x WIN_PITCH]
 //                [rect | ya | yb : G x KNOT_PITCH each]
 // ---------------------------------------------------------------------------------
-template <typename T, int G>
-__device__ __forceinline__ void load_window_rows(const RunParams<T> &p, const Tile &t, int g0,
-                                                 int nlive, T *win, int r_from, int r_to,
-                                                 int tid, int nthr) {
-    // copy source rows (r_from, r_to] of the live frames into their ring slots
-    constexpr int VN = Vec16<T>::N;
-    const int vcols = t.wcols / VN;
-    const size_t frame_in = (size_t)W * p.naxis2;
-    for (int r = r_from + 1; r <= r_to; ++r) {
-        const bool rok = r >= 0 && r < p.naxis2;
-        T *dst = win + (r & (WIN_ROWS - 1)) * WIN_PITCH;
-        for (int e = tid; e < nlive * vcols; e += nthr) {
-            int g = 0, vc = e;
-            while (vc >= vcols) {
-                vc -= vcols;
-                ++g;
-            }
-            const int c = t.c0 + vc * VN;
-            const bool ok = rok && c >= 0 && c < W;
-            const T *src = p.in + (size_t)(g0 + g) * frame_in + (ok ? (size_t)r * W + c : 0);
-            cp_async_16(dst + g * (WIN_ROWS * WIN_PITCH) + vc * VN, src, ok);
-        }
-    }
-}
-
 template <typename T, int K, int G, bool SPANLOOP>
 __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
     k_rectwv(const RunParams<T> p) {
@@ -455,6 +466,8 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
     T *rectS = win + G * WSZ;                                              // [G][KNOT_PITCH]
     T *yaS = rectS + G * KNOT_PITCH;
     T *ybS = yaS + G * KNOT_PITCH;
+    T *wsm = ybS + G * KNOT_PITCH;                                         // [2][K*K][TAB_PITCH]
+    int32_t *bsm = reinterpret_cast<int32_t *>(wsm + 2 * (K * K) * TAB_PITCH);  // [2][TAB_PITCH]
 
     int w = blockIdx.x;
     if (w >= nwork) return;
@@ -509,51 +522,109 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         const int kb = k0 + q;
         unsigned nzmask = 0;                                   // bit g: a non-zero value seen
 
-        // rolling window: rows needed by rectified row 0, and that row's weights
-        int rhi_prev = span_lo(tile.span[0]) - 1;
-        load_window_rows<T, G>(p, tile, g0, nlive, win, rhi_prev, span_hi(tile.span[0]), tid,
-                               NTHREADS);
-        rhi_prev = span_hi(tile.span[0]);
-
-        // tables of row 0 for this pixel column: base[s][y][j], w[s][y][tap][j]
-        const int32_t *bptr = p.base + (size_t)s * NROWS * W + tile.jlo + pp;
-        const T *wptr = p.w + (size_t)s * NROWS * (K * K) * W + tile.jlo + pp;
-        // lanes without a pixel gather from column c0 of ring slot 0 with zero weights
-        int32_t npk = pack_base(0, tile.c0);
-        T nwt[K * K];
+        // ---- copy plans of this thread for the item: which 16-byte chunks of a table
+        //      row and of a source-window row it moves.  Sources are element offsets,
+        //      destinations 32-bit shared-memory addresses; 0 = no chunk.
+        constexpr int VN = Vec16<T>::N;
+        constexpr int NTA = ((K * K) * (TAB_PITCH / VN) + NTHREADS - 1) / NTHREADS;
+        constexpr int NWA = (G * (WIN_PITCH / VN) + NTHREADS - 1) / NTHREADS;
+        int t_src[NTA], w_src[NWA];
+        unsigned t_dst[NTA], w_dst[NWA];
+        {
+            const int j0 = tile.jlo & ~(VN - 1);
+            const int nch = (tile.jlo - j0 + npx + VN - 1) / VN;
+            const unsigned wsm_a = smem_addr_of(wsm);
 #pragma unroll
-        for (int tap = 0; tap < K * K; ++tap) nwt[tap] = T(0);
-        if (px_ok) {
-            npk = __ldg(bptr);
+            for (int i = 0; i < NTA; ++i) {
+                const int e = tid + i * NTHREADS;
+                const int tap = e / nch, ch = e - tap * nch;
+                t_src[i] = tap * W + ch * VN;
+                t_dst[i] = e < (K * K) * nch
+                               ? wsm_a + (unsigned)((tap * TAB_PITCH + ch * VN) * sizeof(T)) : 0u;
+            }
+            const int vcols = tile.wcols / VN;
+            const unsigned win_a = smem_addr_of(win);
 #pragma unroll
-            for (int tap = 0; tap < K * K; ++tap) nwt[tap] = __ldg(wptr + tap * W);
+            for (int i = 0; i < NWA; ++i) {
+                const int e = tid + i * NTHREADS;
+                const int g = e / vcols, vc = e - g * vcols;
+                const int c = tile.c0 + vc * VN;
+                w_src[i] = (c >= 0 && c < W) ? g * (W * p.naxis2) + c : -1;   // -1: zero fill
+                w_dst[i] = e < nlive * vcols
+                               ? win_a + (unsigned)((g * WSZ + vc * VN) * sizeof(T)) : 0u;
+            }
         }
+        const unsigned b_dst = tid * 4 < (tile.jlo & 3) + npx ? smem_addr_of(bsm) + tid * 16 : 0u;
+        const T *wrow = p.w + (size_t)s * NROWS * (K * K) * W + (tile.jlo & ~(VN - 1));
+        const int32_t *brow = p.base + (size_t)s * NROWS * W + (tile.jlo & ~3) + tid * 4;
+        const T *fin = p.in + (size_t)g0 * W * p.naxis2;
+
+        // table row y -> ring slot y & 1 (base + K*K weights)
+        auto copy_table_row = [&](int y) {
+            const T *src = wrow + (size_t)y * (K * K) * W;
+            const unsigned so = (y & 1) * (unsigned)((K * K) * TAB_PITCH * sizeof(T));
+#pragma unroll
+            for (int i = 0; i < NTA; ++i)
+                if (t_dst[i]) cp_async_16s(t_dst[i] + so, src + t_src[i], true);
+            if (b_dst)
+                cp_async_16s(b_dst + (y & 1) * (unsigned)(TAB_PITCH * 4), brow + (size_t)y * W, true);
+        };
+        // source rows (r_from, r_to] of the live frames -> their ring slots
+        auto copy_window_rows = [&](int r_from, int r_to) {
+            for (int r = r_from + 1; r <= r_to; ++r) {
+                const bool rok = r >= 0 && r < p.naxis2;
+                const unsigned ro = (unsigned)((r & (WIN_ROWS - 1)) * WIN_PITCH * sizeof(T));
+                const T *src = fin + (size_t)(rok ? r : 0) * W;
+#pragma unroll
+                for (int i = 0; i < NWA; ++i)
+                    if (w_dst[i]) {
+                        const bool ok = rok && w_src[i] >= 0;
+                        cp_async_16s(w_dst[i] + ro, src + (ok ? w_src[i] : 0), ok);
+                    }
+            }
+        };
+
+        // Two cp.async pipelines, one commit group each per rectified row:
+        //   R(y): the new source rows that row y needs        (2 rows ahead of its use)
+        //   W(y): the table row (base + K*K weights) of row y  (1 row ahead)
+        // committed in the order R(0) W(0) R(1) | W(1) R(2) | W(2) R(3) ... so that
+        // "all but the newest group" is exactly what row y needs at its start.
+        int rhi_prev = span_hi(tile.span[0]);
+        copy_window_rows(span_lo(tile.span[0]) - 1, rhi_prev);
+        cp_async_commit();
+        copy_table_row(0);
+        cp_async_commit();
+        copy_window_rows(rhi_prev, span_hi(tile.span[1]));
+        cp_async_commit();
+        rhi_prev = max(rhi_prev, span_hi(tile.span[1]));
+        // this thread's slot in the staged table rows (lanes without a pixel read a
+        // neighbour's entry; their result is discarded)
+        const int ppc = min(max(pp, 0), npx - 1);
+        const int boff = ppc + (tile.jlo & 3);
+        const int woff = ppc + (tile.jlo & (Vec16<T>::N - 1));
         T *orow = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
         int wb = -tile.c0;                                     // window addressed by frame coords
         pin(wb);
 
         for (int y = 0; y < NROWS; ++y) {
-            cp_async_wait_all();
-            __syncthreads();     // source rows of row y landed; everyone is done with row y-1
+            cp_async_wait_group<1>();
+            __syncthreads();     // R(y), W(y) landed; everyone is done with row y-1
 
-            // next row: its new source rows (ring slots of rows no longer needed) ...
-            if (y + 1 < NROWS) {
-                const int rhi = span_hi(tile.span[y + 1]);
-                load_window_rows<T, G>(p, tile, g0, nlive, win, rhi_prev, rhi, tid, NTHREADS);
+            if (y + 1 < NROWS) copy_table_row(y + 1);
+            cp_async_commit();                                 // W(y+1)
+            if (y + 2 < NROWS) {
+                const int rhi = span_hi(tile.span[y + 2]);
+                copy_window_rows(rhi_prev, rhi);
                 rhi_prev = max(rhi_prev, rhi);
             }
-            // ... and its weights
-            const int32_t pk = npk;
+            cp_async_commit();                                 // R(y+2)
+
+            const int slot = y & 1;
+            const int32_t pk = bsm[slot * TAB_PITCH + boff];
             T wt[K * K];
 #pragma unroll
-            for (int tap = 0; tap < K * K; ++tap) wt[tap] = nwt[tap];
-            if (px_ok && y + 1 < NROWS) {
-                bptr += W;
-                wptr += (K * K) * W;
-                npk = __ldg(bptr);
-#pragma unroll
-                for (int tap = 0; tap < K * K; ++tap) nwt[tap] = __ldg(wptr + tap * W);
-            }
+            for (int tap = 0; tap < K * K; ++tap)
+                wt[tap] = wsm[(slot * (K * K) + tap) * TAB_PITCH + woff];
 
             // ---- A: rectified flux of this pixel column, G frames
             T rect[G];
@@ -580,10 +651,12 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
             //         zero slopes at the two ends of the spectrum.
 #pragma unroll
             for (int g = 0; g < G; ++g) {
+                // slope at the left knot from this pixel and its left neighbour; the slope
+                // at the right knot is the right neighbour's left-knot slope rescaled by
+                // the ratio of the pixel widths (one limiter evaluation per pixel)
                 const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
-                const T cr = __shfl_down_sync(0xffffffffu, rect[g], 1) * pg.qp;
                 const T ya = steffen_slope(cl, rect[g], pg.r0);
-                const T yb = steffen_slope(rect[g], cr, pg.r1);
+                const T yb = __shfl_down_sync(0xffffffffu, ya, 1) * pg.qp;
                 if (knot_ok) {
                     rectS[g * KNOT_PITCH + pp] = rect[g];
                     yaS[g * KNOT_PITCH + pp] = ya;
@@ -692,7 +765,8 @@ struct LaunchCfg {
 //   [3 tile descriptors][G windows: WIN_ROWS x WIN_PITCH][rect | ya | yb: G x KNOT_PITCH]
 size_t smem_bytes(const emirwv_plan *pl, int G) {
     return 3 * sizeof(Tile) +
-           (size_t)G * (WIN_ROWS * WIN_PITCH + 3 * KNOT_PITCH) * pl->esize;
+           (size_t)G * (WIN_ROWS * WIN_PITCH + 3 * KNOT_PITCH) * pl->esize +
+           (size_t)2 * pl->K * pl->K * TAB_PITCH * pl->esize + (size_t)2 * TAB_PITCH * 4;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
@@ -961,7 +1035,7 @@ int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int TK
             for (int y = 1; y < NROWS; ++y) rhi[y] = std::max(rhi[y], rhi[y - 1]);
             for (int y = NROWS - 2; y >= 0; --y) rlo[y] = std::min(rlo[y], rlo[y + 1]);
             for (int y = 0; y < NROWS; ++y) {
-                const int next_hi = rhi[std::min(y + 1, NROWS - 1)];
+                const int next_hi = rhi[std::min(y + PREFETCH, NROWS - 1)];
                 span_max = std::max(span_max, next_hi - rlo[y] + 1);
                 t.span[y] = (int32_t)(((uint32_t)(rhi[y] & 0xffff) << 16) | (uint32_t)(rlo[y] & 0xffff));
             }
@@ -1115,8 +1189,9 @@ int build_plan(emirwv_plan *pl) {
     }
 
     const size_t nrowtab = (size_t)pl->nsl * NROWS;
-    CUDA_TRY(cudaMalloc(&pl->d_base, nrowtab * W * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&pl->d_w, nrowtab * pl->K * pl->K * W * pl->esize));
+    // (+64 bytes: the kernel copies table rows in 16-byte chunks)
+    CUDA_TRY(cudaMalloc(&pl->d_base, nrowtab * W * sizeof(int32_t) + 64));
+    CUDA_TRY(cudaMalloc(&pl->d_w, nrowtab * pl->K * pl->K * W * pl->esize + 64));
     pl->table_bytes += (int64_t)(nrowtab * W * sizeof(int32_t));
     pl->table_bytes += (int64_t)(nrowtab * pl->K * pl->K * W * pl->esize);
     gp.K = pl->K;
