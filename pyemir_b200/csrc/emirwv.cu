@@ -331,6 +331,37 @@ __device__ __forceinline__ void cp_async_small(void *smem_dst, const void *gmem_
                  "n"(BYTES)
                  : "memory");
 }
+// ---- TMA bulk copies (cp.async.bulk) completed through an mbarrier transaction count
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared, 16-byte aligned addresses and size; completes `bytes` on the barrier
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
 // same with a precomputed 32-bit shared-memory address
 __device__ __forceinline__ void cp_async_16s(unsigned smem_addr, const void *gmem_src, bool valid) {
     const int src_bytes = valid ? 16 : 0;
@@ -462,7 +493,9 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
     const int nwork = p.nlive_tiles * p.ngroups;
 
     Tile *ring = reinterpret_cast<Tile *>(smem_raw);                       // [3]
-    T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile));           // [G][WSZ]
+    // mbarriers: [0..2] source-row groups R, [3..4] table-row groups W
+    const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
+    T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + 64);      // [G][WSZ]
     T *rectS = win + G * WSZ;                                              // [G][KNOT_PITCH]
     T *yaS = rectS + G * KNOT_PITCH;
     T *ybS = yaS + G * KNOT_PITCH;
@@ -481,11 +514,17 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         cp_async_16(reinterpret_cast<char *>(&ring[1]) + (tid - 32) * 16,
                     reinterpret_cast<const char *>(p.tiles + (w + gridDim.x) / p.ngroups) +
                         (tid - 32) * 16, true);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) mbar_init(bars + 8 * i, 1);
+        mbar_fence_init();
+    }
     cp_async_wait_all();
     __syncthreads();
 
     unsigned fo = (unsigned)frame_out;                         // < 2^32 elements per frame
     pin(fo);
+    unsigned rseq = 0, wseq = 0;    // R / W groups consumed so far (same in every thread)
 
     for (int it = 0;; ++it) {
         const Tile &tile = ring[it % 3];
@@ -522,80 +561,73 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         const int kb = k0 + q;
         unsigned nzmask = 0;                                   // bit g: a non-zero value seen
 
-        // ---- copy plans of this thread for the item: which 16-byte chunks of a table
-        //      row and of a source-window row it moves.  Sources are element offsets,
-        //      destinations 32-bit shared-memory addresses; 0 = no chunk.
+        // ---- the two copy pipelines of the item, fed by thread 0 with TMA bulk copies:
+        //   R(y): the new source rows that rectified row y needs (2 rows ahead of use),
+        //         one copy per row and frame into the ring slot (row & 15)
+        //   W(y): the table row of row y, base + K*K weight arrays (1 row ahead),
+        //         one copy per array into slot y & 1
+        // Each group completes on its own mbarrier (3 for R, 2 for W, used round-robin).
         constexpr int VN = Vec16<T>::N;
-        constexpr int NTA = ((K * K) * (TAB_PITCH / VN) + NTHREADS - 1) / NTHREADS;
-        constexpr int NWA = (G * (WIN_PITCH / VN) + NTHREADS - 1) / NTHREADS;
-        int t_src[NTA], w_src[NWA];
-        unsigned t_dst[NTA], w_dst[NWA];
-        {
-            const int j0 = tile.jlo & ~(VN - 1);
-            const int nch = (tile.jlo - j0 + npx + VN - 1) / VN;
-            const unsigned wsm_a = smem_addr_of(wsm);
-#pragma unroll
-            for (int i = 0; i < NTA; ++i) {
-                const int e = tid + i * NTHREADS;
-                const int tap = e / nch, ch = e - tap * nch;
-                t_src[i] = tap * W + ch * VN;
-                t_dst[i] = e < (K * K) * nch
-                               ? wsm_a + (unsigned)((tap * TAB_PITCH + ch * VN) * sizeof(T)) : 0u;
-            }
-            const int vcols = tile.wcols / VN;
-            const unsigned win_a = smem_addr_of(win);
-#pragma unroll
-            for (int i = 0; i < NWA; ++i) {
-                const int e = tid + i * NTHREADS;
-                const int g = e / vcols, vc = e - g * vcols;
-                const int c = tile.c0 + vc * VN;
-                w_src[i] = (c >= 0 && c < W) ? g * (W * p.naxis2) + c : -1;   // -1: zero fill
-                w_dst[i] = e < nlive * vcols
-                               ? win_a + (unsigned)((g * WSZ + vc * VN) * sizeof(T)) : 0u;
-            }
-        }
-        const unsigned b_dst = tid * 4 < (tile.jlo & 3) + npx ? smem_addr_of(bsm) + tid * 16 : 0u;
-        const T *wrow = p.w + (size_t)s * NROWS * (K * K) * W + (tile.jlo & ~(VN - 1));
-        const int32_t *brow = p.base + (size_t)s * NROWS * W + (tile.jlo & ~3) + tid * 4;
-        const T *fin = p.in + (size_t)g0 * W * p.naxis2;
+        const int cv0 = max(tile.c0, 0), cv1 = min(tile.c0 + tile.wcols, W);   // valid columns
+        const unsigned row_bytes = (unsigned)((cv1 - cv0) * sizeof(T));
+        const unsigned win_a = smem_addr_of(win) + (unsigned)((cv0 - tile.c0) * sizeof(T));
+        const T *fin = p.in + (size_t)g0 * W * p.naxis2 + cv0;
+        const int jw0 = tile.jlo & ~(VN - 1), jb0 = tile.jlo & ~3;
+        const unsigned wrow_bytes = (unsigned)(((tile.jlo - jw0 + npx + VN - 1) / VN) * 16);
+        const unsigned brow_bytes = (unsigned)(((tile.jlo - jb0 + npx + 3) / 4) * 16);
+        const T *wrow = p.w + (size_t)s * NROWS * (K * K) * W + jw0;
+        const int32_t *brow = p.base + (size_t)s * NROWS * W + jb0;
+        const unsigned wsm_a = smem_addr_of(wsm), bsm_a = smem_addr_of(bsm);
 
-        // table row y -> ring slot y & 1 (base + K*K weights)
-        auto copy_table_row = [&](int y) {
-            const T *src = wrow + (size_t)y * (K * K) * W;
-            const unsigned so = (y & 1) * (unsigned)((K * K) * TAB_PITCH * sizeof(T));
-#pragma unroll
-            for (int i = 0; i < NTA; ++i)
-                if (t_dst[i]) cp_async_16s(t_dst[i] + so, src + t_src[i], true);
-            if (b_dst)
-                cp_async_16s(b_dst + (y & 1) * (unsigned)(TAB_PITCH * 4), brow + (size_t)y * W, true);
-        };
-        // source rows (r_from, r_to] of the live frames -> their ring slots
-        auto copy_window_rows = [&](int r_from, int r_to) {
+        // columns of the window that fall outside the detector stay zero for the item
+        if (cv0 > tile.c0 || cv1 < tile.c0 + tile.wcols)
+            for (int e = tid; e < G * WIN_ROWS * tile.wcols; e += NTHREADS) {
+                const int c = e % tile.wcols, rg = e / tile.wcols;
+                if (tile.c0 + c < cv0 || tile.c0 + c >= cv1)
+                    win[(rg / WIN_ROWS) * WSZ + (rg % WIN_ROWS) * WIN_PITCH + c] = T(0);
+            }
+
+        // R group `seq`: source rows (r_from, r_to]; rows outside the detector are zeroed.
+        // Thread 0 posts the byte count, lane 0 of warp g issues the copies of frame g.
+        auto copy_window_rows = [&](unsigned seq, int r_from, int r_to) {
+            const unsigned bar = bars + 8 * (seq % 3);
+            if (tid == 0) {
+                const int nin = max(0, min(r_to, p.naxis2 - 1) - max(r_from + 1, 0) + 1);
+                mbar_expect_tx(bar, (unsigned)(nin * nlive) * row_bytes);
+            }
             for (int r = r_from + 1; r <= r_to; ++r) {
-                const bool rok = r >= 0 && r < p.naxis2;
                 const unsigned ro = (unsigned)((r & (WIN_ROWS - 1)) * WIN_PITCH * sizeof(T));
-                const T *src = fin + (size_t)(rok ? r : 0) * W;
-#pragma unroll
-                for (int i = 0; i < NWA; ++i)
-                    if (w_dst[i]) {
-                        const bool ok = rok && w_src[i] >= 0;
-                        cp_async_16s(w_dst[i] + ro, src + (ok ? w_src[i] : 0), ok);
-                    }
+                if (r >= 0 && r < p.naxis2) {
+                    if (lane == 0 && warp < nlive)
+                        bulk_g2s(win_a + ro + (unsigned)(warp * WSZ * sizeof(T)),
+                                 fin + (size_t)warp * W * p.naxis2 + (size_t)r * W, row_bytes, bar);
+                } else {
+                    for (int e = tid; e < nlive * tile.wcols; e += NTHREADS)
+                        win[(e / tile.wcols) * WSZ + (r & (WIN_ROWS - 1)) * WIN_PITCH +
+                            e % tile.wcols] = T(0);
+                }
+            }
+        };
+        // W group `seq`: table row y.  Thread 0 posts the byte count; lane 0 of warp w
+        // issues the copies of weight arrays w, w + 9, ...; warp 8 also the coordinates.
+        auto copy_table_row = [&](unsigned seq, int y) {
+            const unsigned bar = bars + 8 * (3 + (seq & 1));
+            if (tid == 0) mbar_expect_tx(bar, (K * K) * wrow_bytes + brow_bytes);
+            if (lane == 0) {
+                const unsigned so = (y & 1) * (unsigned)((K * K) * TAB_PITCH * sizeof(T));
+                for (int tap = warp; tap < K * K; tap += NTHREADS / 32)
+                    bulk_g2s(wsm_a + so + (unsigned)(tap * TAB_PITCH * sizeof(T)),
+                             wrow + (size_t)y * (K * K) * W + (size_t)tap * W, wrow_bytes, bar);
+                if (warp == NTHREADS / 32 - 1)
+                    bulk_g2s(bsm_a + (y & 1) * (unsigned)(TAB_PITCH * 4), brow + (size_t)y * W,
+                             brow_bytes, bar);
             }
         };
 
-        // Two cp.async pipelines, one commit group each per rectified row:
-        //   R(y): the new source rows that row y needs        (2 rows ahead of its use)
-        //   W(y): the table row (base + K*K weights) of row y  (1 row ahead)
-        // committed in the order R(0) W(0) R(1) | W(1) R(2) | W(2) R(3) ... so that
-        // "all but the newest group" is exactly what row y needs at its start.
         int rhi_prev = span_hi(tile.span[0]);
-        copy_window_rows(span_lo(tile.span[0]) - 1, rhi_prev);
-        cp_async_commit();
-        copy_table_row(0);
-        cp_async_commit();
-        copy_window_rows(rhi_prev, span_hi(tile.span[1]));
-        cp_async_commit();
+        copy_window_rows(rseq, span_lo(tile.span[0]) - 1, rhi_prev);            // R(0)
+        copy_table_row(wseq, 0);                                                // W(0)
+        copy_window_rows(rseq + 1, rhi_prev, span_hi(tile.span[1]));            // R(1)
         rhi_prev = max(rhi_prev, span_hi(tile.span[1]));
         // this thread's slot in the staged table rows (lanes without a pixel read a
         // neighbour's entry; their result is discarded)
@@ -607,17 +639,18 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         pin(wb);
 
         for (int y = 0; y < NROWS; ++y) {
-            cp_async_wait_group<1>();
-            __syncthreads();     // R(y), W(y) landed; everyone is done with row y-1
+            mbar_wait(bars + 8 * (rseq % 3), (rseq / 3) & 1);          // R(y) landed
+            mbar_wait(bars + 8 * (3 + (wseq & 1)), (wseq >> 1) & 1);   // W(y) landed
+            ++rseq;
+            ++wseq;
+            __syncthreads();     // everyone is done with row y-1 (knots, ring slots, W slot)
 
-            if (y + 1 < NROWS) copy_table_row(y + 1);
-            cp_async_commit();                                 // W(y+1)
-            if (y + 2 < NROWS) {
+            if (y + 1 < NROWS) copy_table_row(wseq, y + 1);            // W(y+1)
+            if (y + 2 < NROWS) {                                       // R(y+2)
                 const int rhi = span_hi(tile.span[y + 2]);
-                copy_window_rows(rhi_prev, rhi);
+                copy_window_rows(rseq + 1, rhi_prev, rhi);
                 rhi_prev = max(rhi_prev, rhi);
             }
-            cp_async_commit();                                 // R(y+2)
 
             const int slot = y & 1;
             const int32_t pk = bsm[slot * TAB_PITCH + boff];
@@ -764,7 +797,7 @@ struct LaunchCfg {
 // shared memory of the hot kernel:
 //   [3 tile descriptors][G windows: WIN_ROWS x WIN_PITCH][rect | ya | yb: G x KNOT_PITCH]
 size_t smem_bytes(const emirwv_plan *pl, int G) {
-    return 3 * sizeof(Tile) +
+    return 3 * sizeof(Tile) + 64 +
            (size_t)G * (WIN_ROWS * WIN_PITCH + 3 * KNOT_PITCH) * pl->esize +
            (size_t)2 * pl->K * pl->K * TAB_PITCH * pl->esize + (size_t)2 * TAB_PITCH * 4;
 }
