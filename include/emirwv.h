@@ -86,8 +86,10 @@ typedef struct emirwv_plan_desc {
     double crpix1;                  /* crpix1_enlarged (1.0)                       */
     double crval1;                  /* crval1_enlarged                             */
     double cdelt1;                  /* cdelt1_enlarged                             */
-    int32_t tile_k;                 /* tuning, 0 = default: output columns per tile */
-    int32_t tile_rows;              /* tuning, 0 = default: rectified rows per tile */
+    int32_t tile_k;                 /* tuning, 0 = default (248): output columns per tile,
+                                       a multiple of 31; narrowed automatically when the
+                                       distortion needs a larger source window           */
+    int32_t tile_rows;              /* reserved (a tile always spans the 39 scanned rows) */
     emirwv_slitlet_desc slitlet[EMIRWV_MAX_SLITLETS];
 } emirwv_plan_desc;
 
@@ -136,7 +138,8 @@ void emirwv_plan_destroy(emirwv_plan *plan);
 int emirwv_plan_get_info(const emirwv_plan *plan, emirwv_plan_info *info);
 
 /* Launch tuning for subsequent runs (0 keeps the default): frames per CTA
- * (1, 2 or 4) and threads per CTA (multiple of 32, at most 512). */
+ * (1, 2 or 4).  `threads` is accepted for compatibility: the hot kernel has a fixed
+ * CTA size (288 threads). */
 int emirwv_plan_set_tuning(emirwv_plan *plan, int frames_per_cta, int threads);
 
 /*
@@ -170,6 +173,16 @@ void emirwv_host_free(void *ptr);
  */
 int emirwv_rectify_slitlet(const emirwv_plan *plan, const void *d_frame, int islitlet,
                            void *d_rect, void *cuda_stream);
+
+/*
+ * rectify2d on an arbitrary float64 image with an explicit polynomial map (rectified ->
+ * original, term order 1, x, y, x^2, xy, y^2, ...): output has the shape of the input.
+ * Replaces numina.array.distortion.rectify2d as called by Slitlet2D.rectify
+ * (slitlet2d.py:413-423) with ttd_* (direct) or tti_* (inverse=True) coefficients.
+ */
+int emirwv_rectify2d_host(const double *h_image, int naxis2, int naxis1, const double *aij,
+                          const double *bij, int ncoef, int resampling, int max_order,
+                          double *h_out);
 
 /*
  * Parity hooks (tests): the plan's geometry for one slitlet, copied to the host.

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "emirwv_plan_create", "emirwv_plan_destroy", "emirwv_plan_get_info",
     "emirwv_plan_set_tuning", "emirwv_run", "emirwv_run_host",
     "emirwv_host_alloc", "emirwv_host_free", "emirwv_rectify_slitlet",
-    "emirwv_debug_geometry", "emirwv_debug_borders",
+    "emirwv_rectify2d_host", "emirwv_debug_geometry", "emirwv_debug_borders",
 )
 
 
@@ -145,6 +145,8 @@ def load():
     lib.emirwv_host_free.argtypes = [vp]
     lib.emirwv_rectify_slitlet.restype = i32
     lib.emirwv_rectify_slitlet.argtypes = [vp, vp, i32, vp, vp]
+    lib.emirwv_rectify2d_host.restype = i32
+    lib.emirwv_rectify2d_host.argtypes = [vp, i32, i32, vp, vp, i32, i32, i32, vp]
     lib.emirwv_debug_geometry.restype = i32
     lib.emirwv_debug_geometry.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.emirwv_debug_borders.restype = i32

@@ -273,6 +273,52 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
     p.base[rowtab * W + j] = pack_base(fr0, fc0);
 }
 
+// General rectify2d on an arbitrary image (numina.array.distortion.rectify2d as called
+// by Slitlet2D.rectify, slitlet2d.py:421-423, direct or inverse map): one thread per
+// output pixel, geometry evaluated on the fly, float64, accumulation in the reference's
+// order.  Not the streaming path: it serves the per-slitlet API of the reference.
+__global__ void k_rectify2d(const double *img, int naxis2, int naxis1, SlitDev sd, int mode,
+                            double *out, int naxis2out, int naxis1out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= naxis1out || i >= naxis2out) return;
+    double acc = 0.0;
+    if (mode == EMIRWV_AREA) {
+        double qu[4], qv[4];
+        map_corners(sd, j, i, qu, qv);
+        int c0, c1, r0, r1;
+        quad_extent(qu, c0, c1);
+        quad_extent(qv, r0, r1);
+        for (int ii = max(r0, 0); ii <= min(r1, naxis2 - 1); ++ii)
+            for (int jj = max(c0, 0); jj <= min(c1, naxis1 - 1); ++jj) {
+                const double area = quad_box_area(qu, qv, (double)jj - 0.5, (double)jj + 0.5,
+                                                  (double)ii - 0.5, (double)ii + 0.5);
+                if (area != 0.0) acc = add_rn(acc, mul_rn(area, img[(size_t)ii * naxis1 + jj]));
+            }
+    } else {
+        double u, v;
+        fmap(sd.order, sd.a, sd.b, (double)j, (double)i, u, v);
+        u = clampd(u);
+        v = clampd(v);
+        if (mode == EMIRWV_NEAREST) {
+            const int ju = (int)rint(u), iv = (int)rint(v);
+            if (ju >= 0 && ju < naxis1 && iv >= 0 && iv < naxis2) acc = img[(size_t)iv * naxis1 + ju];
+        } else {
+            const double u0 = floor(u), v0 = floor(v);
+            const double fu = u - u0, fv = v - v0;
+            const double wv[2] = {1.0 - fv, fv}, wu[2] = {1.0 - fu, fu};
+            for (int dv = 0; dv < 2; ++dv)
+                for (int du = 0; du < 2; ++du) {
+                    const int cu = (int)u0 + du, cv = (int)v0 + dv;
+                    const double val = (cu >= 0 && cu < naxis1 && cv >= 0 && cv < naxis2)
+                                           ? img[(size_t)cv * naxis1 + cu] : 0.0;
+                    acc = add_rn(acc, mul_rn(mul_rn(wv[dv], wu[du]), val));
+                }
+        }
+    }
+    out[(size_t)i * naxis1out + j] = acc;
+}
+
 __global__ void k_init_jmm(int32_t *jmm, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) jmm[i] = (i & 1) ? -1 : INT_MAX;
@@ -1462,6 +1508,40 @@ int emirwv_rectify_slitlet(const emirwv_plan *pl, const void *d_frame, int islit
             static_cast<const double *>(pl->d_w), s, pl->K, bbw, pl->desc.naxis1,
             pl->desc.naxis2);
     CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+int emirwv_rectify2d_host(const double *h_image, int naxis2, int naxis1, const double *aij,
+                          const double *bij, int ncoef, int resampling, int max_order,
+                          double *h_out) {
+    if (h_image == nullptr || aij == nullptr || bij == nullptr || h_out == nullptr)
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (naxis1 < 1 || naxis2 < 1) return fail(EMIRWV_E_VALUE, "empty image");
+    if (resampling < 1 || resampling > 3)
+        return fail(EMIRWV_E_VALUE, "Sorry, resampling method must be 1 or 2");
+    const int cap = max_order > 0 ? max_order : 4;
+    SlitDev sd;
+    memset(&sd, 0, sizeof(sd));
+    sd.order = order_from_ncoef(ncoef);
+    if (sd.order < 0 || sd.order > cap) return fail(EMIRWV_E_VALUE, "order > %d not implemented", cap);
+    sd.valid = 1;
+    memcpy(sd.a, aij, sizeof(double) * ncoef);
+    memcpy(sd.b, bij, sizeof(double) * ncoef);
+    const size_t nbytes = (size_t)naxis1 * naxis2 * sizeof(double);
+    double *d_in = nullptr, *d_out = nullptr;
+    cudaError_t err = cudaMalloc(&d_in, nbytes);
+    if (err == cudaSuccess) err = cudaMalloc(&d_out, nbytes);
+    if (err == cudaSuccess) err = cudaMemcpy(d_in, h_image, nbytes, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) {
+        const dim3 grid((naxis1 + 127) / 128, naxis2);
+        k_rectify2d<<<grid, 128>>>(d_in, naxis2, naxis1, sd, resampling, d_out, naxis2, naxis1);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpy(h_out, d_out, nbytes, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (err != cudaSuccess)
+        return fail(EMIRWV_E_CUDA, "rectify2d failed: %s", cudaGetErrorString(err));
     return EMIRWV_OK;
 }
 

@@ -357,3 +357,83 @@ def test_plan_cache_reuse(coeff_j):
     c = copy.deepcopy(coeff_j)
     c.global_integer_offset_x_pix += 1
     assert get_plan(c, 2, "float32") is not a
+
+
+# ------------------------------------------------------------------ per-slitlet API
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_rectify2d_matches_oracle_all_rows(coeff_j, frame_j, mode):
+    from pyemir_b200.slitlet2d import rectify2d
+    entry = coeff_j.contents[19]
+    crop = frame_j[entry["bb_ns1_orig"] - 1:entry["bb_ns2_orig"]].astype(float)
+    want = nr.rectify2d(crop, entry["ttd_aij"], entry["ttd_bij"], mode)
+    got = rectify2d(crop, entry["ttd_aij"], entry["ttd_bij"], mode)
+    assert got.shape == want.shape and got.dtype == np.float64
+    assert np.array_equal(got, want)          # same operation order: bit-identical float64
+
+
+def test_slitlet2d_mirror_direct_and_inverse(coeff_j, frame_j):
+    from oracle.pipeline import OracleSlitlet2D
+    from pyemir_b200.slitlet2d import Slitlet2D
+    for islitlet in (3, 54):
+        slt = Slitlet2D(islitlet, coeff_j, debugplot=0)
+        ref = OracleSlitlet2D(islitlet, coeff_j)
+        assert (slt.iminslt, slt.imaxslt, slt.ttd_order) == (ref.iminslt, ref.imaxslt, 2)
+        crop = slt.extract_slitlet2d(frame_j)
+        assert np.array_equal(crop, ref.extract_slitlet2d(frame_j))
+        for resampling in (1, 2):
+            rect = slt.rectify(crop, resampling)
+            assert np.array_equal(rect, ref.rectify(crop, resampling))
+            back = slt.rectify(rect, resampling, inverse=True)
+            assert np.array_equal(back, ref.rectify(rect, resampling, inverse=True))
+        with pytest.raises(ValueError, match="Unexpected resampling value=3"):
+            slt.rectify(crop, 3)
+        with pytest.raises(ValueError, match="Unexpected slitlet2d_rect naxis2"):
+            slt.rectify(crop[:-1], 2)
+    with pytest.raises(ValueError, match="Unexpected naxis1"):
+        Slitlet2D(3, coeff_j).extract_slitlet2d(frame_j[:, :100])
+    broken = copy.deepcopy(coeff_j)
+    del broken.contents[2]["corr_yrect_a"]
+    with pytest.raises(KeyError):
+        Slitlet2D(3, broken)
+
+
+# ------------------------------------------------------------------ remaining BASELINE configs
+def test_config2_hh_float32_full_frame():
+    """BASELINE config 2 geometry (grism H + filter H), one full frame, float32."""
+    coeff = synthetic.make_config(2)
+    frame = synthetic.make_frames(coeff, 1, seed=1002)[0]
+    hdul = synthetic.make_hdulist(frame, coeff)
+    ref, ref64 = oracle_apply(hdul, coeff, only_needed_rows=True, return_float64=True)
+    got = apply_rectwv_coeff(hdul, coeff)
+    assert header_cards(got) == header_cards(ref)
+    assert_flux_close(got[0].data, ref64, 1e-5, 2e-7)
+    assert np.array_equal(got[0].data == 0, ref64 == 0)
+
+
+def test_config3_order5_batch_tail_and_nearest():
+    """Order-5 map (K + Ksp), modes 1 and 2, a 7-frame batch (odd tail of a G=4 group)."""
+    coeff = only_slitlets(synthetic.make_config(3), [2, 27, 28, 55])
+    frames = synthetic.make_frames(coeff, 7, seed=1003)
+    for mode in (1, 2):
+        out, kw = rectify_frames(frames, coeff, mode, dtype="float32", max_order=5)
+        for i in (0, 6):
+            hdul = synthetic.make_hdulist(frames[i], coeff)
+            ref, ref64 = oracle_apply(hdul, coeff, args_resampling=mode, only_needed_rows=True,
+                                      return_float64=True, nmax_order=5)
+            assert_flux_close(out[i], ref64, 1e-5, 2e-7, f"mode {mode} frame {i}")
+            assert np.array_equal(out[i] == 0, ref64 == 0)
+            for islitlet, (_, _, jmn, jmx) in enumerate(kw[i], start=1):
+                assert (jmn, jmx) == (ref[0].header[f"JMNSLT{islitlet:02d}"],
+                                      ref[0].header[f"JMXSLT{islitlet:02d}"])
+
+
+def test_lr_float32_unaligned_rows():
+    """LR + HK: naxis1 = 1435 (rows not 16-byte aligned: scalar zero-fill path)."""
+    coeff = only_slitlets(synthetic.make_config("4b"), [10, 40])
+    frame = synthetic.make_frames(coeff, 1, seed=1004)[0]
+    hdul = synthetic.make_hdulist(frame, coeff)
+    _, ref64 = oracle_apply(hdul, coeff, only_needed_rows=True, return_float64=True)
+    out, _ = rectify_frames(frame, coeff, 2, dtype="float32")
+    assert out.shape == (1, 2090, 1435)
+    assert_flux_close(out[0], ref64, 1e-5, 2e-7)
+    assert np.array_equal(out[0] == 0, ref64 == 0)
