@@ -51,9 +51,11 @@ constexpr int PX_MAX = 30 * (NTHREADS / 32);  // rectified columns a CTA can hol
 constexpr int TILE_K_MAX = 248;               // output columns per tile (8 x 31)
 constexpr int KNOT_PITCH = 272;               // shared rows of flux / slopes
 constexpr int WIN_ROWS = 16;                  // rolling source window: rows (power of 2)
-constexpr int WIN_PITCH = 288;                // ... and columns, per frame
+constexpr int WIN_PITCH = 272;                // ... and columns, per frame
 constexpr int PREFETCH = 2;                   // rectified rows between a copy and its use
-constexpr int TAB_PITCH = 276;                // staged table rows (PX_MAX + alignment slack)
+// Per output pixel table record: K*K weights followed by the packed source coordinates
+// (int32 bits), padded to a multiple of 4 elements so that records are 16-byte aligned.
+__host__ __device__ constexpr int rec_size(int K) { return (K * K + 1 + 3) & ~3; }
 constexpr int HOST_SLOTS = 3;                // pipeline depth of emirwv_run_host
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -214,10 +216,12 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
     if (j >= W) return;
     const int K = p.K, KK = K * K;
     const size_t rowtab = (size_t)s * NROWS + y;
-    T *wp = w + rowtab * KK * W + j;
+    const int RS = rec_size(K);
+    T *wp = w + (rowtab * W + j) * RS;
     if (!sd.valid || j >= sd.bbw) {
         p.base[rowtab * W + j] = pack_base(0, 0);
-        for (int tap = 0; tap < KK; ++tap) wp[(size_t)tap * W] = T(0);
+        for (int tap = 0; tap < RS; ++tap) wp[tap] = T(0);
+        *reinterpret_cast<int32_t *>(wp + KK) = pack_base(0, 0);
         return;
     }
     const int row = sd.min_row + y;
@@ -268,8 +272,10 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
             const int fr = fr0 + a, fc = fc0 + b;
             const bool inside = r >= 0 && r < sd.bbh && c >= 0 && c < sd.bbw && fr >= 0 &&
                                 fr < p.naxis2 && fc >= 0 && fc < p.naxis1;
-            wp[(size_t)(a * K + b) * W] = inside ? (T)wt[a * K + b] : T(0);
+            wp[a * K + b] = inside ? (T)wt[a * K + b] : T(0);
         }
+    for (int tap = KK; tap < RS; ++tap) wp[tap] = T(0);
+    *reinterpret_cast<int32_t *>(wp + KK) = pack_base(fr0, fc0);
     p.base[rowtab * W + j] = pack_base(fr0, fc0);
 }
 
@@ -334,11 +340,11 @@ __global__ void k_rectify_only(const T *frame, T *rect, const int32_t *base, con
     const size_t rowtab = (size_t)s * NROWS + y;
     const int32_t pk = base[rowtab * W + j];
     const int r0 = base_row(pk), c0 = base_col(pk);
-    const T *wp = w + rowtab * (K * K) * W + j;
+    const T *wp = w + (rowtab * W + j) * rec_size(K);
     T acc = T(0);
     for (int a = 0; a < K; ++a)
         for (int b = 0; b < K; ++b) {
-            const T wt = wp[(size_t)(a * K + b) * W];
+            const T wt = wp[a * K + b];
             const int r = min(max(r0 + a, 0), naxis2 - 1);
             const int c = min(max(c0 + b, 0), naxis1 - 1);
             acc = fma(wt, frame[(size_t)r * naxis1 + c], acc);
@@ -545,8 +551,8 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
     T *rectS = win + G * WSZ;                                              // [G][KNOT_PITCH]
     T *yaS = rectS + G * KNOT_PITCH;
     T *ybS = yaS + G * KNOT_PITCH;
-    T *wsm = ybS + G * KNOT_PITCH;                                         // [2][K*K][TAB_PITCH]
-    int32_t *bsm = reinterpret_cast<int32_t *>(wsm + 2 * (K * K) * TAB_PITCH);  // [2][TAB_PITCH]
+    constexpr int RS = rec_size(K);
+    T *tsm = ybS + G * KNOT_PITCH;                                         // [2][PX_MAX][RS]
 
     int w = blockIdx.x;
     if (w >= nwork) return;
@@ -618,12 +624,9 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         const unsigned row_bytes = (unsigned)((cv1 - cv0) * sizeof(T));
         const unsigned win_a = smem_addr_of(win) + (unsigned)((cv0 - tile.c0) * sizeof(T));
         const T *fin = p.in + (size_t)g0 * W * p.naxis2 + cv0;
-        const int jw0 = tile.jlo & ~(VN - 1), jb0 = tile.jlo & ~3;
-        const unsigned wrow_bytes = (unsigned)(((tile.jlo - jw0 + npx + VN - 1) / VN) * 16);
-        const unsigned brow_bytes = (unsigned)(((tile.jlo - jb0 + npx + 3) / 4) * 16);
-        const T *wrow = p.w + (size_t)s * NROWS * (K * K) * W + jw0;
-        const int32_t *brow = p.base + (size_t)s * NROWS * W + jb0;
-        const unsigned wsm_a = smem_addr_of(wsm), bsm_a = smem_addr_of(bsm);
+        const unsigned trow_bytes = (unsigned)(npx * RS * sizeof(T));
+        const T *trow = p.w + ((size_t)s * NROWS * W + tile.jlo) * RS;
+        const unsigned tsm_a = smem_addr_of(tsm);
 
         // columns of the window that fall outside the detector stay zero for the item
         if (cv0 > tile.c0 || cv1 < tile.c0 + tile.wcols)
@@ -654,19 +657,13 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                 }
             }
         };
-        // W group `seq`: table row y.  Thread 0 posts the byte count; lane 0 of warp w
-        // issues the copies of weight arrays w, w + 9, ...; warp 8 also the coordinates.
+        // W group `seq`: table row y = npx contiguous records, one bulk copy
         auto copy_table_row = [&](unsigned seq, int y) {
-            const unsigned bar = bars + 8 * (3 + (seq & 1));
-            if (tid == 0) mbar_expect_tx(bar, (K * K) * wrow_bytes + brow_bytes);
-            if (lane == 0) {
-                const unsigned so = (y & 1) * (unsigned)((K * K) * TAB_PITCH * sizeof(T));
-                for (int tap = warp; tap < K * K; tap += NTHREADS / 32)
-                    bulk_g2s(wsm_a + so + (unsigned)(tap * TAB_PITCH * sizeof(T)),
-                             wrow + (size_t)y * (K * K) * W + (size_t)tap * W, wrow_bytes, bar);
-                if (warp == NTHREADS / 32 - 1)
-                    bulk_g2s(bsm_a + (y & 1) * (unsigned)(TAB_PITCH * 4), brow + (size_t)y * W,
-                             brow_bytes, bar);
+            if (tid == 0) {
+                const unsigned bar = bars + 8 * (3 + (seq & 1));
+                mbar_expect_tx(bar, trow_bytes);
+                bulk_g2s(tsm_a + (y & 1) * (unsigned)(PX_MAX * RS * sizeof(T)),
+                         trow + (size_t)y * W * RS, trow_bytes, bar);
             }
         };
 
@@ -678,8 +675,6 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         // this thread's slot in the staged table rows (lanes without a pixel read a
         // neighbour's entry; their result is discarded)
         const int ppc = min(max(pp, 0), npx - 1);
-        const int boff = ppc + (tile.jlo & 3);
-        const int woff = ppc + (tile.jlo & (Vec16<T>::N - 1));
         T *orow = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
         int wb = -tile.c0;                                     // window addressed by frame coords
         pin(wb);
@@ -698,12 +693,16 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                 rhi_prev = max(rhi_prev, rhi);
             }
 
-            const int slot = y & 1;
-            const int32_t pk = bsm[slot * TAB_PITCH + boff];
-            T wt[K * K];
+            // this pixel's record: K*K weights + packed source coordinates (16-byte loads)
+            T wt[RS];
+            {
+                using V = typename Vec16<T>::type;
+                const V *rec = reinterpret_cast<const V *>(tsm + ((y & 1) * PX_MAX + ppc) * RS);
 #pragma unroll
-            for (int tap = 0; tap < K * K; ++tap)
-                wt[tap] = wsm[(slot * (K * K) + tap) * TAB_PITCH + woff];
+                for (int i = 0; i < RS / VN; ++i)
+                    *reinterpret_cast<V *>(wt + i * VN) = rec[i];
+            }
+            const int32_t pk = *reinterpret_cast<const int32_t *>(wt + K * K);
 
             // ---- A: rectified flux of this pixel column, G frames
             T rect[G];
@@ -845,7 +844,7 @@ struct LaunchCfg {
 size_t smem_bytes(const emirwv_plan *pl, int G) {
     return 3 * sizeof(Tile) + 64 +
            (size_t)G * (WIN_ROWS * WIN_PITCH + 3 * KNOT_PITCH) * pl->esize +
-           (size_t)2 * pl->K * pl->K * TAB_PITCH * pl->esize + (size_t)2 * TAB_PITCH * 4;
+           (size_t)2 * PX_MAX * rec_size(pl->K) * pl->esize;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
@@ -1270,9 +1269,9 @@ int build_plan(emirwv_plan *pl) {
     const size_t nrowtab = (size_t)pl->nsl * NROWS;
     // (+64 bytes: the kernel copies table rows in 16-byte chunks)
     CUDA_TRY(cudaMalloc(&pl->d_base, nrowtab * W * sizeof(int32_t) + 64));
-    CUDA_TRY(cudaMalloc(&pl->d_w, nrowtab * pl->K * pl->K * W * pl->esize + 64));
+    CUDA_TRY(cudaMalloc(&pl->d_w, nrowtab * W * rec_size(pl->K) * pl->esize + 64));
     pl->table_bytes += (int64_t)(nrowtab * W * sizeof(int32_t));
-    pl->table_bytes += (int64_t)(nrowtab * pl->K * pl->K * W * pl->esize);
+    pl->table_bytes += (int64_t)(nrowtab * W * rec_size(pl->K) * pl->esize);
     gp.K = pl->K;
     gp.base = pl->d_base;
     gp.kmax = nullptr;
@@ -1564,7 +1563,8 @@ int emirwv_debug_geometry(const emirwv_plan *pl, int islitlet, int32_t *h_row, i
             if (h_ok) h_ok[(size_t)y * sd.bbw + j] = (r >= 0 && r < sd.bbh && c >= 0 && c < sd.bbw);
         }
     if (h_weights) {
-        const size_t n = (size_t)NROWS * KK * W;
+        const int RS = rec_size(pl->K);
+        const size_t n = (size_t)NROWS * W * RS;
         std::vector<unsigned char> raw(n * pl->esize);
         CUDA_TRY(cudaMemcpy(raw.data(),
                             static_cast<const char *>(pl->d_w) + (size_t)s * n * pl->esize,
@@ -1572,7 +1572,7 @@ int emirwv_debug_geometry(const emirwv_plan *pl, int islitlet, int32_t *h_row, i
         for (int y = 0; y < NROWS; ++y)
             for (int tap = 0; tap < KK; ++tap)
                 for (int j = 0; j < sd.bbw; ++j) {
-                    const size_t src = ((size_t)y * KK + tap) * W + j;
+                    const size_t src = ((size_t)y * W + j) * RS + tap;
                     const double v = pl->dtype == EMIRWV_F32
                                          ? (double)reinterpret_cast<const float *>(raw.data())[src]
                                          : reinterpret_cast<const double *>(raw.data())[src];
