@@ -816,6 +816,12 @@ struct emirwv_plan {
     int num_sms = 148;
     int64_t table_bytes = 0;
 
+    // side stream for the zero-fill kernel (memory bound) so that it overlaps with the
+    // hot kernel (issue bound); fork/join with events around every run
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    mutable std::mutex aux_mu;
+
     std::mutex mu;
     struct Slot {
         void *d_in = nullptr;
@@ -926,18 +932,37 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
         k_init_jmm<<<(n + 255) / 256, 256, 0, st>>>(d_jmm, n);
         CUDA_TRY(cudaGetLastError());
     }
-    if (pl->ntiles_empty > 0) {
-        const dim3 grid(pl->ntiles_empty, std::min(nframes, 32));
-        k_zero_fill<T><<<grid, 256, 0, st>>>(rp, rp.nlive_tiles);
+    // The zero-fill kernel is memory bound and the hot kernel issue bound: when a side
+    // stream is available the hot kernel is enqueued first (it takes its shared memory
+    // and registers on every SM) and the fill blocks run next to it in what is left.
+    const bool forked = pl->ntiles_empty > 0 && pl->aux != nullptr;
+    const dim3 zgrid(std::max(pl->ntiles_empty, 1), std::min(nframes, 32));
+    if (pl->ntiles_empty > 0 && !forked) {
+        k_zero_fill<T><<<zgrid, 256, 0, st>>>(rp, rp.nlive_tiles);
         CUDA_TRY(cudaGetLastError());
     }
-    switch (pl->K) {
-        case 1: return launch_k<T, 1>(pl, rp, cfg, st);
-        case 2: return launch_k<T, 2>(pl, rp, cfg, st);
-        case 3: return launch_k<T, 3>(pl, rp, cfg, st);
-        case 4: return launch_k<T, 4>(pl, rp, cfg, st);
+    std::unique_lock<std::mutex> lock(pl->aux_mu, std::defer_lock);
+    if (forked) {
+        lock.lock();
+        CUDA_TRY(cudaEventRecord(pl->ev_fork, st));
     }
-    return fail(EMIRWV_E_LIMIT, "unsupported footprint %d", pl->K);
+    int rc;
+    switch (pl->K) {
+        case 1: rc = launch_k<T, 1>(pl, rp, cfg, st); break;
+        case 2: rc = launch_k<T, 2>(pl, rp, cfg, st); break;
+        case 3: rc = launch_k<T, 3>(pl, rp, cfg, st); break;
+        case 4: rc = launch_k<T, 4>(pl, rp, cfg, st); break;
+        default: rc = fail(EMIRWV_E_LIMIT, "unsupported footprint %d", pl->K);
+    }
+    if (forked) {
+        // the two kernels write disjoint parts of the output
+        CUDA_TRY(cudaStreamWaitEvent(pl->aux, pl->ev_fork, 0));
+        k_zero_fill<T><<<zgrid, 256, 0, pl->aux>>>(rp, rp.nlive_tiles);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(pl->ev_join, pl->aux));
+        CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
+    }
+    return rc;
 }
 
 // numpy.polynomial.polynomial.polyval: Horner, one rounding per operation
@@ -1287,7 +1312,14 @@ int build_plan(emirwv_plan *pl) {
     std::vector<uint8_t> covered;
     int rc = build_border_tables(pl, covered);
     if (rc) return rc;
-    return build_tiles(pl, covered);
+    rc = build_tiles(pl, covered);
+    if (rc) return rc;
+    if (env_int("EMIRWV_NO_AUX", 0) == 0) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&pl->aux, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+    }
+    return EMIRWV_OK;
 }
 
 void release_workspace(emirwv_plan *pl) {
@@ -1378,6 +1410,9 @@ void emirwv_plan_destroy(emirwv_plan *pl) {
     if (pl == nullptr) return;
     DeviceGuard guard(pl->device);
     release_workspace(pl);
+    if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+    if (pl->ev_join) cudaEventDestroy(pl->ev_join);
+    if (pl->aux) cudaStreamDestroy(pl->aux);
     cudaFree(pl->d_slit);
     cudaFree(pl->d_base);
     cudaFree(pl->d_w);
