@@ -50,7 +50,8 @@ constexpr int NTHREADS = 288;                 // 9 warps per CTA of the hot kern
 constexpr int PX_MAX = 30 * (NTHREADS / 32);  // rectified columns a CTA can hold (270)
 constexpr int TILE_K_MAX = 248;               // output columns per tile (8 x 31)
 constexpr int KNOT_PITCH = 272;               // shared rows of flux / slopes
-constexpr int WIN_ROWS = 16;                  // rolling source window: rows (power of 2)
+constexpr int WIN_ROWS = 12;                  // rolling source window: rows per frame
+constexpr int RING_BIAS = 12 * 1024;          // makes (row + bias) % WIN_ROWS non-negative
 constexpr int WIN_PITCH = 272;                // ... and columns, per frame
 constexpr int PREFETCH = 2;                   // rectified rows between a copy and its use
 // Per output pixel table record: K*K weights followed by the packed source coordinates
@@ -548,11 +549,11 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
     // mbarriers: [0..2] source-row groups R, [3..4] table-row groups W
     const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
     T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + 64);      // [G][WSZ]
-    T *rectS = win + G * WSZ;                                              // [G][KNOT_PITCH]
-    T *yaS = rectS + G * KNOT_PITCH;
-    T *ybS = yaS + G * KNOT_PITCH;
+    T *rectS = win + G * WSZ;                                              // [2][G][KNOT_PITCH]
+    T *yaS = rectS + 2 * G * KNOT_PITCH;
+    T *ybS = yaS + 2 * G * KNOT_PITCH;
     constexpr int RS = rec_size(K);
-    T *tsm = ybS + G * KNOT_PITCH;                                         // [2][PX_MAX][RS]
+    T *tsm = ybS + 2 * G * KNOT_PITCH;                                     // [2][PX_MAX][RS]
 
     int w = blockIdx.x;
     if (w >= nwork) return;
@@ -630,7 +631,7 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
 
         // columns of the window that fall outside the detector stay zero for the item
         if (cv0 > tile.c0 || cv1 < tile.c0 + tile.wcols)
-            for (int e = tid; e < G * WIN_ROWS * tile.wcols; e += NTHREADS) {
+            for (int e = tid; e < G * WIN_ROWS * tile.wcols; e += NTHREADS) {   // (rare)
                 const int c = e % tile.wcols, rg = e / tile.wcols;
                 if (tile.c0 + c < cv0 || tile.c0 + c >= cv1)
                     win[(rg / WIN_ROWS) * WSZ + (rg % WIN_ROWS) * WIN_PITCH + c] = T(0);
@@ -645,14 +646,15 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                 mbar_expect_tx(bar, (unsigned)(nin * nlive) * row_bytes);
             }
             for (int r = r_from + 1; r <= r_to; ++r) {
-                const unsigned ro = (unsigned)((r & (WIN_ROWS - 1)) * WIN_PITCH * sizeof(T));
+                const unsigned slot = (unsigned)(r + RING_BIAS) % WIN_ROWS;
+                const unsigned ro = (unsigned)(slot * WIN_PITCH * sizeof(T));
                 if (r >= 0 && r < p.naxis2) {
                     if (lane == 0 && warp < nlive)
                         bulk_g2s(win_a + ro + (unsigned)(warp * WSZ * sizeof(T)),
                                  fin + (size_t)warp * W * p.naxis2 + (size_t)r * W, row_bytes, bar);
                 } else {
                     for (int e = tid; e < nlive * tile.wcols; e += NTHREADS)
-                        win[(e / tile.wcols) * WSZ + (r & (WIN_ROWS - 1)) * WIN_PITCH +
+                        win[(e / tile.wcols) * WSZ + slot * WIN_PITCH +
                             e % tile.wcols] = T(0);
                 }
             }
@@ -679,12 +681,18 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         int wb = -tile.c0;                                     // window addressed by frame coords
         pin(wb);
 
-        for (int y = 0; y < NROWS; ++y) {
-            mbar_wait(bars + 8 * (rseq % 3), (rseq / 3) & 1);          // R(y) landed
-            mbar_wait(bars + 8 * (3 + (wseq & 1)), (wseq >> 1) & 1);   // W(y) landed
-            ++rseq;
-            ++wseq;
-            __syncthreads();     // everyone is done with row y-1 (knots, ring slots, W slot)
+        // Software-pipelined row loop, ONE block barrier per rectified row: iteration y
+        // evaluates the borders of row y-1 (phase D, reading knot buffer (y-1)&1) and the
+        // flux and slopes of row y (phases A and C, writing knot buffer y&1).
+        for (int y = 0; y <= NROWS; ++y) {
+            if (y < NROWS) {
+                mbar_wait(bars + 8 * (rseq % 3), (rseq / 3) & 1);          // R(y) landed
+                mbar_wait(bars + 8 * (3 + (wseq & 1)), (wseq >> 1) & 1);   // W(y) landed
+                ++rseq;
+                ++wseq;
+            }
+            __syncthreads();     // knots of row y-1 are visible; everyone is done with the
+                                 // knot buffer, ring slots and table slot of iteration y-1
 
             if (y + 1 < NROWS) copy_table_row(wseq, y + 1);            // W(y+1)
             if (y + 2 < NROWS) {                                       // R(y+2)
@@ -693,76 +701,85 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                 rhi_prev = max(rhi_prev, rhi);
             }
 
-            // this pixel's record: K*K weights + packed source coordinates (16-byte loads)
-            T wt[RS];
-            {
-                using V = typename Vec16<T>::type;
-                const V *rec = reinterpret_cast<const V *>(tsm + ((y & 1) * PX_MAX + ppc) * RS);
-#pragma unroll
-                for (int i = 0; i < RS / VN; ++i)
-                    *reinterpret_cast<V *>(wt + i * VN) = rec[i];
-            }
-            const int32_t pk = *reinterpret_cast<const int32_t *>(wt + K * K);
-
-            // ---- A: rectified flux of this pixel column, G frames
-            T rect[G];
-            {
-                const int fr = base_row(pk), fc = base_col(pk) + wb;
-                const T *rowp[K];
-#pragma unroll
-                for (int a = 0; a < K; ++a)
-                    rowp[a] = win + (((fr + a) & (WIN_ROWS - 1)) * WIN_PITCH + fc);
+            // ---- D (row y-1): cumulative flux at this thread's border and at the next
+            //      one, difference = output pixel; store; remember non-zero values
+            if (y >= 1) {
+                const T *kb_rect = rectS + ((y - 1) & 1) * (G * KNOT_PITCH) + ibl;
+                const T *kb_ya = yaS + ((y - 1) & 1) * (G * KNOT_PITCH) + ibl;
+                const T *kb_yb = ybS + ((y - 1) & 1) * (G * KNOT_PITCH) + ibl;
+                const bool store = y - 1 < p.rps;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    T acc = T(0);
+                    const T kr = kb_rect[g * KNOT_PITCH];
+                    const T ka = kb_ya[g * KNOT_PITCH];
+                    const T kc = kb_yb[g * KNOT_PITCH];
+                    const T P = steffen_partial_flux(kr, ka, kc, bd.tau);
+                    const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
+                    T whole = has1 ? kr : T(0);
+                    if (has2) whole += kb_rect[g * KNOT_PITCH + 1];
+                    if (SPANLOOP)
+                        for (int i = 2; i < ibn - ibl; ++i) whole += kb_rect[g * KNOT_PITCH + i];
+                    const T o = whole + (Pn - P);
+                    const bool okg = col_ok && g < nlive;
+                    if (okg && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o);
+                    if (okg && o != T(0)) nzmask |= 1u << g;
+                }
+                orow += p.nout;
+            }
+
+            if (y < NROWS) {
+                // this pixel's record: K*K weights + packed source coordinates
+                T wt[RS];
+                {
+                    using V = typename Vec16<T>::type;
+                    const V *rec = reinterpret_cast<const V *>(tsm + ((y & 1) * PX_MAX + ppc) * RS);
+#pragma unroll
+                    for (int i = 0; i < RS / VN; ++i)
+                        *reinterpret_cast<V *>(wt + i * VN) = rec[i];
+                }
+                const int32_t pk = *reinterpret_cast<const int32_t *>(wt + K * K);
+
+                // ---- A (row y): rectified flux of this pixel column, G frames
+                T rect[G];
+                {
+                    const int fr = base_row(pk) + RING_BIAS, fc = base_col(pk) + wb;
+                    const T *rowp[K];
 #pragma unroll
                     for (int a = 0; a < K; ++a)
+                        rowp[a] = win + ((unsigned)(fr + a) % WIN_ROWS) * WIN_PITCH + fc;
 #pragma unroll
-                        for (int b = 0; b < K; ++b)
-                            acc = fma(wt[a * K + b], rowp[a][g * WSZ + b], acc);
-                    rect[g] = px_ok ? acc : T(0);
+                    for (int g = 0; g < G; ++g) {
+                        T acc = T(0);
+#pragma unroll
+                        for (int a = 0; a < K; ++a)
+#pragma unroll
+                            for (int b = 0; b < K; ++b)
+                                acc = fma(wt[a * K + b], rowp[a][g * WSZ + b], acc);
+                        rect[g] = px_ok ? acc : T(0);
+                    }
+                }
+
+                // ---- C (row y): Steffen-limited slopes at both ends of the pixel, scaled
+                //      by the pixel width (flux units).  qm = 0 / qp = 0 in the table give
+                //      the zero slopes at the two ends of the spectrum.
+                T *kw_rect = rectS + (y & 1) * (G * KNOT_PITCH) + pp;
+                T *kw_ya = yaS + (y & 1) * (G * KNOT_PITCH) + pp;
+                T *kw_yb = ybS + (y & 1) * (G * KNOT_PITCH) + pp;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    // slope at the left knot from this pixel and its left neighbour; the
+                    // slope at the right knot is the right neighbour's left-knot slope
+                    // rescaled by the ratio of the pixel widths (one limiter per pixel)
+                    const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
+                    const T ya = steffen_slope(cl, rect[g], pg.r0);
+                    const T yb = __shfl_down_sync(0xffffffffu, ya, 1) * pg.qp;
+                    if (knot_ok) {
+                        kw_rect[g * KNOT_PITCH] = rect[g];
+                        kw_ya[g * KNOT_PITCH] = ya;
+                        kw_yb[g * KNOT_PITCH] = yb;
+                    }
                 }
             }
-
-            // ---- C: Steffen-limited slopes at both ends of the pixel, scaled by the
-            //         pixel width (flux units).  qm = 0 / qp = 0 in the table give the
-            //         zero slopes at the two ends of the spectrum.
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                // slope at the left knot from this pixel and its left neighbour; the slope
-                // at the right knot is the right neighbour's left-knot slope rescaled by
-                // the ratio of the pixel widths (one limiter evaluation per pixel)
-                const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
-                const T ya = steffen_slope(cl, rect[g], pg.r0);
-                const T yb = __shfl_down_sync(0xffffffffu, ya, 1) * pg.qp;
-                if (knot_ok) {
-                    rectS[g * KNOT_PITCH + pp] = rect[g];
-                    yaS[g * KNOT_PITCH + pp] = ya;
-                    ybS[g * KNOT_PITCH + pp] = yb;
-                }
-            }
-            __syncthreads();     // flux and slopes of row y are visible to all warps
-
-            // ---- D: cumulative flux at this thread's border and at the next one,
-            //         difference = output pixel; store; remember non-zero values
-            const bool store = y < p.rps;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const T kr = rectS[g * KNOT_PITCH + ibl];
-                const T ka = yaS[g * KNOT_PITCH + ibl];
-                const T kc = ybS[g * KNOT_PITCH + ibl];
-                const T P = steffen_partial_flux(kr, ka, kc, bd.tau);
-                const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
-                T whole = has1 ? kr : T(0);
-                if (has2) whole += rectS[g * KNOT_PITCH + ibl + 1];
-                if (SPANLOOP)
-                    for (int i = ibl + 2; i < ibn; ++i) whole += rectS[g * KNOT_PITCH + i];
-                const T o = whole + (Pn - P);
-                const bool okg = col_ok && g < nlive;
-                if (okg && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o);
-                if (okg && o != T(0)) nzmask |= 1u << g;
-            }
-            orow += p.nout;
         }
 
         // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
@@ -849,7 +866,7 @@ struct LaunchCfg {
 //   [3 tile descriptors][G windows: WIN_ROWS x WIN_PITCH][rect | ya | yb: G x KNOT_PITCH]
 size_t smem_bytes(const emirwv_plan *pl, int G) {
     return 3 * sizeof(Tile) + 64 +
-           (size_t)G * (WIN_ROWS * WIN_PITCH + 3 * KNOT_PITCH) * pl->esize +
+           (size_t)G * (WIN_ROWS * WIN_PITCH + 6 * KNOT_PITCH) * pl->esize +
            (size_t)2 * PX_MAX * rec_size(pl->K) * pl->esize;
 }
 
