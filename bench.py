@@ -32,8 +32,8 @@ FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="2", help="BASELINE config number (1,2,3,4,4b,5)")
     ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step")
@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--tile-k", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--combine", default="none", choices=["none", "mean", "gather"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=3,
                     help="frames of the CPU-baseline sample (0 disables it)")
     ap.add_argument("--ref-budget-s", type=float, default=200.0)
