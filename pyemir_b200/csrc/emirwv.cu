@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                         (tid - 32) * 16, true);
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) mbar_init(bars + 8 * i, 1);
+        for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 2);   // R part + W part of a row
         mbar_fence_init();
     }
     cp_async_wait_all();
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
 
     unsigned fo = (unsigned)frame_out;                         // < 2^32 elements per frame
     pin(fo);
-    unsigned rseq = 0, wseq = 0;    // R / W groups consumed so far (same in every thread)
+    unsigned rowseq = 0;            // rectified rows started so far (same in every thread)
 
     for (int it = 0;; ++it) {
         const Tile &tile = ring[it % 3];
@@ -637,32 +637,35 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                     win[(rg / WIN_ROWS) * WSZ + (rg % WIN_ROWS) * WIN_PITCH + c] = T(0);
             }
 
-        // R group `seq`: source rows (r_from, r_to]; rows outside the detector are zeroed.
-        // Thread 0 posts the byte count, lane 0 of warp g issues the copies of frame g.
+        // Row number n (counted across items) completes on mbarrier n % 3 with two
+        // arrivals: the source rows it adds (posted two rows earlier) and its table row
+        // (posted one row earlier).  Warp 0 is the producer: lane 0 posts the byte counts
+        // and issues the bulk copies; rows outside the detector (rare) are zero-filled by
+        // all threads.
+        const bool oob_rows = span_lo(tile.span[0]) < 0 || span_hi(tile.span[NROWS - 1]) >= p.naxis2;
         auto copy_window_rows = [&](unsigned seq, int r_from, int r_to) {
-            const unsigned bar = bars + 8 * (seq % 3);
-            if (tid == 0) {
-                const int nin = max(0, min(r_to, p.naxis2 - 1) - max(r_from + 1, 0) + 1);
-                mbar_expect_tx(bar, (unsigned)(nin * nlive) * row_bytes);
+            if (warp == 0) {
+                const unsigned bar = bars + 8 * (seq % 3);
+                const int lo = max(r_from + 1, 0), hi = min(r_to, p.naxis2 - 1);
+                if (lane == 0) mbar_expect_tx(bar, (unsigned)(max(hi - lo + 1, 0) * nlive) * row_bytes);
+                if (lane < nlive)
+                    for (int r = lo; r <= hi; ++r)
+                        bulk_g2s(win_a + (unsigned)(((unsigned)(r + RING_BIAS) % WIN_ROWS) * WIN_PITCH * sizeof(T)) +
+                                     (unsigned)(lane * WSZ * sizeof(T)),
+                                 fin + (size_t)lane * W * p.naxis2 + (size_t)r * W, row_bytes, bar);
             }
-            for (int r = r_from + 1; r <= r_to; ++r) {
-                const unsigned slot = (unsigned)(r + RING_BIAS) % WIN_ROWS;
-                const unsigned ro = (unsigned)(slot * WIN_PITCH * sizeof(T));
-                if (r >= 0 && r < p.naxis2) {
-                    if (lane == 0 && warp < nlive)
-                        bulk_g2s(win_a + ro + (unsigned)(warp * WSZ * sizeof(T)),
-                                 fin + (size_t)warp * W * p.naxis2 + (size_t)r * W, row_bytes, bar);
-                } else {
-                    for (int e = tid; e < nlive * tile.wcols; e += NTHREADS)
-                        win[(e / tile.wcols) * WSZ + slot * WIN_PITCH +
-                            e % tile.wcols] = T(0);
-                }
-            }
+            if (oob_rows)
+                for (int r = r_from + 1; r <= r_to; ++r)
+                    if (r < 0 || r >= p.naxis2) {
+                        const unsigned slot = (unsigned)(r + RING_BIAS) % WIN_ROWS;
+                        for (int e = tid; e < nlive * tile.wcols; e += NTHREADS)
+                            win[(e / tile.wcols) * WSZ + slot * WIN_PITCH + e % tile.wcols] = T(0);
+                    }
         };
-        // W group `seq`: table row y = npx contiguous records, one bulk copy
+        // table row y = npx contiguous records, one bulk copy
         auto copy_table_row = [&](unsigned seq, int y) {
             if (tid == 0) {
-                const unsigned bar = bars + 8 * (3 + (seq & 1));
+                const unsigned bar = bars + 8 * (seq % 3);
                 mbar_expect_tx(bar, trow_bytes);
                 bulk_g2s(tsm_a + (y & 1) * (unsigned)(PX_MAX * RS * sizeof(T)),
                          trow + (size_t)y * W * RS, trow_bytes, bar);
@@ -670,9 +673,9 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         };
 
         int rhi_prev = span_hi(tile.span[0]);
-        copy_window_rows(rseq, span_lo(tile.span[0]) - 1, rhi_prev);            // R(0)
-        copy_table_row(wseq, 0);                                                // W(0)
-        copy_window_rows(rseq + 1, rhi_prev, span_hi(tile.span[1]));            // R(1)
+        copy_window_rows(rowseq, span_lo(tile.span[0]) - 1, rhi_prev);          // rows of row 0
+        copy_table_row(rowseq, 0);                                              // table of row 0
+        copy_window_rows(rowseq + 1, rhi_prev, span_hi(tile.span[1]));          // rows of row 1
         rhi_prev = max(rhi_prev, span_hi(tile.span[1]));
         // this thread's slot in the staged table rows (lanes without a pixel read a
         // neighbour's entry; their result is discarded)
@@ -686,18 +689,17 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         // flux and slopes of row y (phases A and C, writing knot buffer y&1).
         for (int y = 0; y <= NROWS; ++y) {
             if (y < NROWS) {
-                mbar_wait(bars + 8 * (rseq % 3), (rseq / 3) & 1);          // R(y) landed
-                mbar_wait(bars + 8 * (3 + (wseq & 1)), (wseq >> 1) & 1);   // W(y) landed
-                ++rseq;
-                ++wseq;
+                mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);      // rows + table landed
+                ++rowseq;
             }
             __syncthreads();     // knots of row y-1 are visible; everyone is done with the
                                  // knot buffer, ring slots and table slot of iteration y-1
 
-            if (y + 1 < NROWS) copy_table_row(wseq, y + 1);            // W(y+1)
-            if (y + 2 < NROWS) {                                       // R(y+2)
+            // (rowseq now counts row y as started: row y+1 is number rowseq, y+2 rowseq+1)
+            if (y + 1 < NROWS) copy_table_row(rowseq, y + 1);
+            if (y + 2 < NROWS) {
                 const int rhi = span_hi(tile.span[y + 2]);
-                copy_window_rows(rseq + 1, rhi_prev, rhi);
+                copy_window_rows(rowseq + 1, rhi_prev, rhi);
                 rhi_prev = max(rhi_prev, rhi);
             }
 
