@@ -485,6 +485,49 @@ __device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
 template <typename P>
 __device__ __forceinline__ void pin(P *&x) { asm volatile("" : "+l"(x)); }
 
+// ---- packed float32 pairs (SASS FFMA2 / FADD2 / FMUL2): one issue slot does the same
+// IEEE operation for two frames.  Every packed expression below keeps the operation
+// order and the roundings of its scalar counterpart, so both paths give the same bits.
+__device__ __forceinline__ unsigned long long f2_bits(float2 a) {
+    return *reinterpret_cast<unsigned long long *>(&a);
+}
+__device__ __forceinline__ float2 f2_from(unsigned long long a) {
+    return *reinterpret_cast<float2 *>(&a);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return f2_from(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+
+// The G values of one knot (one per frame of the item), moved as one vector.
+template <typename T, int G>
+struct alignas((sizeof(T) * G >= 16) ? 16 : sizeof(T) * G) KnotVec {
+    T v[G];
+};
+
+// non-zero test that accumulates with one logic instruction: bits other than the sign
+__device__ __forceinline__ unsigned nz_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+__device__ __forceinline__ unsigned nz_bits(double v) {
+    return ((unsigned)__double2hiint(v) & 0x7fffffffu) | (unsigned)__double2loint(v);
+}
+
 // Zero-coverage tiles (outside the wavelength range of a slitlet, or a missing
 // slitlet): exact zeros, written with 16-byte stores where the row alignment allows.
 template <typename T>
@@ -549,11 +592,14 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
     // mbarriers: [0..2] source-row groups R, [3..4] table-row groups W
     const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
     T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + 64);      // [G][WSZ]
-    T *rectS = win + G * WSZ;                                              // [2][G][KNOT_PITCH]
+    T *rectS = win + G * WSZ;                                              // [2][KNOT_PITCH][G]
     T *yaS = rectS + 2 * G * KNOT_PITCH;
     T *ybS = yaS + 2 * G * KNOT_PITCH;
     constexpr int RS = rec_size(K);
     T *tsm = ybS + 2 * G * KNOT_PITCH;                                     // [2][PX_MAX][RS]
+    // float32 with an even number of frames: two frames per arithmetic instruction
+    constexpr bool PACKED = sizeof(T) == 4 && (G % 2) == 0;
+    using KV = KnotVec<T, G>;
 
     int w = blockIdx.x;
     if (w >= nwork) return;
@@ -604,6 +650,7 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         PixGeom<T> pg;
         pg.qm = pg.qp = pg.r0 = pg.r1 = T(0);
         if (px_ok) pg = ldg_struct(p.pix + (size_t)s * W + tile.jlo + pp);
+        const float qm2 = (float)(pg.qm + pg.qm), hr0 = (float)(T(0.5) * pg.r0);   // packed path
         // output border: a warp evaluates 32 borders = 31 pixels
         const int q = 31 * warp + lane;
         const Border<T> bd = ldg_struct(p.border + (size_t)s * p.NB + k0 + min(q, nk));
@@ -612,7 +659,9 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         const bool col_ok = lane < 31 && q < nk;
         const bool has1 = ibn > ibl, has2 = ibn > ibl + 1;
         const int kb = k0 + q;
-        unsigned nzmask = 0;                                   // bit g: a non-zero value seen
+        unsigned nzb[G];                                       // OR of the value bits seen
+#pragma unroll
+        for (int g = 0; g < G; ++g) nzb[g] = 0;
 
         // ---- the two copy pipelines of the item, fed by thread 0 with TMA bulk copies:
         //   R(y): the new source rows that rectified row y needs (2 rows ahead of use),
@@ -706,26 +755,57 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
             // ---- D (row y-1): cumulative flux at this thread's border and at the next
             //      one, difference = output pixel; store; remember non-zero values
             if (y >= 1) {
-                const T *kb_rect = rectS + ((y - 1) & 1) * (G * KNOT_PITCH) + ibl;
-                const T *kb_ya = yaS + ((y - 1) & 1) * (G * KNOT_PITCH) + ibl;
-                const T *kb_yb = ybS + ((y - 1) & 1) * (G * KNOT_PITCH) + ibl;
+                const KV *kb_rect = reinterpret_cast<const KV *>(rectS) + ((y - 1) & 1) * KNOT_PITCH + ibl;
+                const KV *kb_ya = reinterpret_cast<const KV *>(yaS) + ((y - 1) & 1) * KNOT_PITCH + ibl;
+                const KV *kb_yb = reinterpret_cast<const KV *>(ybS) + ((y - 1) & 1) * KNOT_PITCH + ibl;
                 const bool store = y - 1 < p.rps;
+                const KV kr = kb_rect[0], ka = kb_ya[0], kc = kb_yb[0];
+                KV k1;
+#pragma unroll
+                for (int g = 0; g < G; ++g) k1.v[g] = T(0);
+                if (has2) k1 = kb_rect[1];
+                T o[G];
+                if constexpr (PACKED) {
+                    const float2 tau2 = dup2(bd.tau);
+#pragma unroll
+                    for (int h = 0; h < G / 2; ++h) {
+                        const float2 r = make_float2(kr.v[2 * h], kr.v[2 * h + 1]);
+                        const float2 a = make_float2(ka.v[2 * h], ka.v[2 * h + 1]);
+                        const float2 c = make_float2(kc.v[2 * h], kc.v[2 * h + 1]);
+                        // steffen_partial_flux, two frames at a time
+                        const float2 A = fma2(r, dup2(-2.0f), add2(a, c));
+                        const float2 B = sub2(sub2(r, a), A);
+                        const float2 P = mul2(tau2, fma2(tau2, fma2(tau2, A, B), a));
+                        const float2 Pn = make_float2(__shfl_down_sync(0xffffffffu, P.x, 1),
+                                                      __shfl_down_sync(0xffffffffu, P.y, 1));
+                        float2 whole = make_float2(has1 ? r.x : 0.0f, has1 ? r.y : 0.0f);
+                        if (has2) whole = add2(whole, make_float2(k1.v[2 * h], k1.v[2 * h + 1]));
+                        if (SPANLOOP)
+                            for (int i = 2; i < ibn - ibl; ++i) {
+                                const KV ki = kb_rect[i];
+                                whole = add2(whole, make_float2(ki.v[2 * h], ki.v[2 * h + 1]));
+                            }
+                        const float2 o2 = add2(whole, sub2(Pn, P));
+                        o[2 * h] = o2.x;
+                        o[2 * h + 1] = o2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const T P = steffen_partial_flux(kr.v[g], ka.v[g], kc.v[g], bd.tau);
+                        const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
+                        T whole = has1 ? kr.v[g] : T(0);
+                        if (has2) whole += k1.v[g];
+                        if (SPANLOOP)
+                            for (int i = 2; i < ibn - ibl; ++i) whole += kb_rect[i].v[g];
+                        o[g] = whole + (Pn - P);
+                    }
+                }
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const T kr = kb_rect[g * KNOT_PITCH];
-                    const T ka = kb_ya[g * KNOT_PITCH];
-                    const T kc = kb_yb[g * KNOT_PITCH];
-                    const T P = steffen_partial_flux(kr, ka, kc, bd.tau);
-                    const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
-                    T whole = has1 ? kr : T(0);
-                    if (has2) whole += kb_rect[g * KNOT_PITCH + 1];
-                    if (SPANLOOP)
-                        for (int i = 2; i < ibn - ibl; ++i) whole += kb_rect[g * KNOT_PITCH + i];
-                    const T o = whole + (Pn - P);
-                    const bool okg = col_ok && g < nlive;
-                    if (okg && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o);
-                    if (okg && o != T(0)) nzmask |= 1u << g;
-                }
+                    if (col_ok && g < nlive && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o[g]);
+                    nzb[g] |= nz_bits(o[g]);       // lanes / frames that do not count are masked
+                }                                  // once, after the last row
                 orow += p.nout;
             }
 
@@ -749,37 +829,91 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
 #pragma unroll
                     for (int a = 0; a < K; ++a)
                         rowp[a] = win + ((unsigned)(fr + a) % WIN_ROWS) * WIN_PITCH + fc;
+                    if constexpr (PACKED) {
+                        float2 acc[G / 2];
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        T acc = T(0);
+                        for (int h = 0; h < G / 2; ++h) acc[h] = make_float2(0.0f, 0.0f);
 #pragma unroll
                         for (int a = 0; a < K; ++a)
 #pragma unroll
-                            for (int b = 0; b < K; ++b)
-                                acc = fma(wt[a * K + b], rowp[a][g * WSZ + b], acc);
-                        rect[g] = px_ok ? acc : T(0);
+                            for (int b = 0; b < K; ++b) {
+                                const float2 wgt = dup2(wt[a * K + b]);
+#pragma unroll
+                                for (int h = 0; h < G / 2; ++h)
+                                    acc[h] = fma2(wgt,
+                                                  make_float2(rowp[a][(2 * h) * WSZ + b],
+                                                              rowp[a][(2 * h + 1) * WSZ + b]),
+                                                  acc[h]);
+                            }
+#pragma unroll
+                        for (int h = 0; h < G / 2; ++h) {
+                            rect[2 * h] = px_ok ? acc[h].x : 0.0f;
+                            rect[2 * h + 1] = px_ok ? acc[h].y : 0.0f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            T acc = T(0);
+#pragma unroll
+                            for (int a = 0; a < K; ++a)
+#pragma unroll
+                                for (int b = 0; b < K; ++b)
+                                    acc = fma(wt[a * K + b], rowp[a][g * WSZ + b], acc);
+                            rect[g] = px_ok ? acc : T(0);
+                        }
                     }
                 }
 
                 // ---- C (row y): Steffen-limited slopes at both ends of the pixel, scaled
                 //      by the pixel width (flux units).  qm = 0 / qp = 0 in the table give
                 //      the zero slopes at the two ends of the spectrum.
-                T *kw_rect = rectS + (y & 1) * (G * KNOT_PITCH) + pp;
-                T *kw_ya = yaS + (y & 1) * (G * KNOT_PITCH) + pp;
-                T *kw_yb = ybS + (y & 1) * (G * KNOT_PITCH) + pp;
+                KV vr, va, vb;
+                if constexpr (PACKED) {
+                    // steffen_slope with everything doubled (exact): 2*min(|sl|,|sr|,|p|/2) =
+                    // min(|2 sl|, |2 sr|, |p|); the sign test folds into the minimum by
+                    // giving 2 sl the sign it has relative to sr.
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    // slope at the left knot from this pixel and its left neighbour; the
-                    // slope at the right knot is the right neighbour's left-knot slope
-                    // rescaled by the ratio of the pixel widths (one limiter per pixel)
-                    const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
-                    const T ya = steffen_slope(cl, rect[g], pg.r0);
-                    const T yb = __shfl_down_sync(0xffffffffu, ya, 1) * pg.qp;
-                    if (knot_ok) {
-                        kw_rect[g * KNOT_PITCH] = rect[g];
-                        kw_ya[g * KNOT_PITCH] = ya;
-                        kw_yb[g * KNOT_PITCH] = yb;
+                    for (int h = 0; h < G / 2; ++h) {
+                        const float2 r = make_float2(rect[2 * h], rect[2 * h + 1]);
+                        const float2 l = make_float2(__shfl_up_sync(0xffffffffu, r.x, 1),
+                                                     __shfl_up_sync(0xffffffffu, r.y, 1));
+                        const float2 cl2 = mul2(l, dup2(qm2));
+                        const float2 rr = add2(r, r);
+                        const float2 pq = fma2(dup2(hr0), sub2(cl2, rr), r);
+                        float ya[2];
+                        const float clv[2] = {cl2.x, cl2.y}, rv[2] = {r.x, r.y}, rrv[2] = {rr.x, rr.y},
+                                    pv[2] = {pq.x, pq.y};
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const unsigned sgn = __float_as_uint(rv[e]) & 0x80000000u;
+                            const float x = __uint_as_float(__float_as_uint(clv[e]) ^ sgn);
+                            const float m = fmaxf(fminf(fminf(x, fabsf(rrv[e])), fabsf(pv[e])), 0.0f);
+                            ya[e] = __uint_as_float(__float_as_uint(m) | sgn);
+                        }
+                        const float2 yb = mul2(make_float2(__shfl_down_sync(0xffffffffu, ya[0], 1),
+                                                           __shfl_down_sync(0xffffffffu, ya[1], 1)),
+                                               dup2(pg.qp));
+                        vr.v[2 * h] = r.x, vr.v[2 * h + 1] = r.y;
+                        va.v[2 * h] = ya[0], va.v[2 * h + 1] = ya[1];
+                        vb.v[2 * h] = yb.x, vb.v[2 * h + 1] = yb.y;
                     }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        // slope at the left knot from this pixel and its left neighbour; the
+                        // slope at the right knot is the right neighbour's left-knot slope
+                        // rescaled by the ratio of the pixel widths (one limiter per pixel)
+                        const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
+                        const T ya = steffen_slope(cl, rect[g], pg.r0);
+                        vr.v[g] = rect[g];
+                        va.v[g] = ya;
+                        vb.v[g] = __shfl_down_sync(0xffffffffu, ya, 1) * pg.qp;
+                    }
+                }
+                if (knot_ok) {
+                    reinterpret_cast<KV *>(rectS)[(y & 1) * KNOT_PITCH + pp] = vr;
+                    reinterpret_cast<KV *>(yaS)[(y & 1) * KNOT_PITCH + pp] = va;
+                    reinterpret_cast<KV *>(ybS)[(y & 1) * KNOT_PITCH + pp] = vb;
                 }
             }
         }
@@ -788,7 +922,7 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         if (p.jmm != nullptr) {
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const bool nz = (nzmask >> g) & 1u;
+                const bool nz = col_ok && g < nlive && nzb[g] != 0;
                 const int lo = __reduce_min_sync(0xffffffffu, nz ? kb : INT_MAX);
                 const int hi = __reduce_max_sync(0xffffffffu, nz ? kb : -1);
                 if (lane == 0 && hi >= 0) {
