@@ -87,7 +87,7 @@ typedef struct emirwv_plan_desc {
     double crval1;                  /* crval1_enlarged                             */
     double cdelt1;                  /* cdelt1_enlarged                             */
     int32_t tile_k;                 /* tuning, 0 = default (248): output columns per tile,
-                                       a multiple of 31; narrowed automatically when the
+                                       a multiple of 4; narrowed automatically when the
                                        distortion needs a larger source window           */
     int32_t tile_rows;              /* reserved (a tile always spans the 39 scanned rows) */
     emirwv_slitlet_desc slitlet[EMIRWV_MAX_SLITLETS];
@@ -111,7 +111,7 @@ typedef struct emirwv_plan_info {
     int32_t frames_per_cta;         /* G chosen for the next launch                */
     int32_t threads;                /* threads per CTA of that launch              */
     int32_t smem_bytes;             /* dynamic shared memory of that launch        */
-    int32_t reserved;
+    int32_t reserved;               /* frame subgroups of the pixel phases (1 or 2) */
     int64_t table_bytes;            /* device memory held by the plan              */
     int64_t in_frame_bytes;
     int64_t out_frame_bytes;
@@ -139,7 +139,7 @@ int emirwv_plan_get_info(const emirwv_plan *plan, emirwv_plan_info *info);
 
 /* Launch tuning for subsequent runs (0 keeps the default): frames per CTA
  * (1, 2 or 4).  `threads` is accepted for compatibility: the hot kernel has a fixed
- * CTA size (288 threads). */
+ * CTA size (256 threads). */
 int emirwv_plan_set_tuning(emirwv_plan *plan, int frames_per_cta, int threads);
 
 /*

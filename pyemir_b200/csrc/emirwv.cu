@@ -46,13 +46,17 @@ using namespace emirwv;
 constexpr int NROWS = EMIRWV_ROWS_SCANNED;   // 39 rectified rows per slitlet
 constexpr int W = 2048;                      // EMIR_NAXIS1: pitch of per-column tables
 constexpr int MAXK = 4;                      // largest supported footprint
-constexpr int NTHREADS = 288;                 // 9 warps per CTA of the hot kernel
-constexpr int PX_MAX = 30 * (NTHREADS / 32);  // rectified columns a CTA can hold (270)
-constexpr int TILE_K_MAX = 248;               // output columns per tile (8 x 31)
-constexpr int KNOT_PITCH = 272;               // shared rows of flux / slopes
+constexpr int NWARPS = 8;                     // two warps per SM sub-partition and CTA
+constexpr int NTHREADS = 32 * NWARPS;         // threads per CTA of the hot kernel
+constexpr int TILE_K_MAX = 31 * NWARPS;       // output columns per tile (a warp does 31)
 constexpr int WIN_ROWS = 12;                  // rolling source window: rows per frame
 constexpr int RING_BIAS = 12 * 1024;          // makes (row + bias) % WIN_ROWS non-negative
-constexpr int WIN_PITCH = 272;                // ... and columns, per frame
+// Phases A and C of the hot kernel split the G frames of an item over PS groups of
+// NWARPS / PS warps (PS = 2 when there are more output columns than source pixels):
+// the CTA then holds PXCAP rectified columns.
+__host__ __device__ constexpr int px_cap(int PS) { return 30 * (NWARPS / PS); }
+__host__ __device__ constexpr int knot_pitch(int PS) { return px_cap(PS) + 8; }
+__host__ __device__ constexpr int win_pitch(int PS) { return px_cap(PS) + 24; }
 constexpr int PREFETCH = 2;                   // rectified rows between a copy and its use
 // Per output pixel table record: K*K weights followed by the packed source coordinates
 // (int32 bits), padded to a multiple of 4 elements so that records are 16-byte aligned.
@@ -277,6 +281,11 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
         }
     for (int tap = KK; tap < RS; ++tap) wp[tap] = T(0);
     *reinterpret_cast<int32_t *>(wp + KK) = pack_base(fr0, fc0);
+    // ring slot of each of the K source rows in the hot kernel's rolling window
+    uint32_t slots = 0;
+    for (int a = 0; a < K; ++a)
+        slots |= (uint32_t)((fr0 + a + RING_BIAS) % WIN_ROWS) << (8 * a);
+    *reinterpret_cast<uint32_t *>(wp + KK + 1) = slots;
     p.base[rowtab * W + j] = pack_base(fr0, fc0);
 }
 
@@ -577,29 +586,36 @@ __global__ void __launch_bounds__(256) k_zero_fill(const RunParams<T> p, int fir
 // Shared memory: [tile descriptor ring: 3][G windows: WIN_ROWS x WIN_PITCH]
 //                [rect | ya | yb : G x KNOT_PITCH each]
 // ---------------------------------------------------------------------------------
-template <typename T, int K, int G, bool SPANLOOP>
-__global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
+template <typename T, int K, int G, int PS, bool SPANLOOP>
+__global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
     k_rectwv(const RunParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int GA = G / PS;                                 // frames per thread, phases A, C
+    constexpr int NWP = NWARPS / PS;                           // warps per frame subgroup
+    constexpr int PXCAP = px_cap(PS), KNOT_PITCH = knot_pitch(PS), WIN_PITCH = win_pitch(PS);
     constexpr int WSZ = WIN_ROWS * WIN_PITCH;                  // one frame's window
+    static_assert(G % PS == 0, "frames must split evenly");
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp == NWARPS - 1;   // this warp also issues the bulk copies
     const size_t frame_out = (size_t)p.nrows_out * p.nout;
     const int nwork = p.nlive_tiles * p.ngroups;
 
     Tile *ring = reinterpret_cast<Tile *>(smem_raw);                       // [3]
-    // mbarriers: [0..2] source-row groups R, [3..4] table-row groups W
+    // mbarriers [0..2]: one per rectified row in flight
     const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
     T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + 64);      // [G][WSZ]
     T *rectS = win + G * WSZ;                                              // [2][KNOT_PITCH][G]
     T *yaS = rectS + 2 * G * KNOT_PITCH;
     T *ybS = yaS + 2 * G * KNOT_PITCH;
     constexpr int RS = rec_size(K);
-    T *tsm = ybS + 2 * G * KNOT_PITCH;                                     // [2][PX_MAX][RS]
-    // float32 with an even number of frames: two frames per arithmetic instruction
-    constexpr bool PACKED = sizeof(T) == 4 && (G % 2) == 0;
+    T *tsm = ybS + 2 * G * KNOT_PITCH;                                     // [2][PXCAP][RS]
+    // float32: two frames per arithmetic instruction wherever a thread holds a pair
+    constexpr bool PACKED_D = sizeof(T) == 4 && (G % 2) == 0;
+    constexpr bool PACKED_A = sizeof(T) == 4 && (GA % 2) == 0;
     using KV = KnotVec<T, G>;
+    using KA = KnotVec<T, GA>;
 
     int w = blockIdx.x;
     if (w >= nwork) return;
@@ -615,7 +631,7 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                         (tid - 32) * 16, true);
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 2);   // R part + W part of a row
+        for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 2);   // rows part + table part
         mbar_fence_init();
     }
     cp_async_wait_all();
@@ -624,6 +640,12 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
     unsigned fo = (unsigned)frame_out;                         // < 2^32 elements per frame
     pin(fo);
     unsigned rowseq = 0;            // rectified rows started so far (same in every thread)
+
+    // phases A, C: frame subgroup and pixel block of this warp
+    const int sub = warp / NWP, wl = warp - sub * NWP;
+    // producer lanes: one (source row, frame) pair each
+    const int cg = lane % G, cr = lane / G;
+    constexpr int ROWS_PER_ISSUE = 32 / G;
 
     for (int it = 0;; ++it) {
         const Tile &tile = ring[it % 3];
@@ -643,16 +665,19 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         const int k0 = tile.k0;
 
         // ---- per-item constants of this thread
-        // pixel column: a warp covers pixels 30*warp-1 .. 30*warp+30 and produces 30
-        const int pp = 30 * warp - 1 + lane;
+        // pixel column: a warp covers pixels 30*wl-1 .. 30*wl+30 and produces 30 of them,
+        // for the GA frames of its subgroup
+        const int pp = 30 * wl - 1 + lane;
         const bool px_ok = pp >= 0 && pp < npx;
         const bool knot_ok = lane >= 1 && lane <= 30 && pp < npx;
+        const bool awarp = 30 * wl - 1 < npx;                  // the warp has pixels at all
         PixGeom<T> pg;
         pg.qm = pg.qp = pg.r0 = pg.r1 = T(0);
         if (px_ok) pg = ldg_struct(p.pix + (size_t)s * W + tile.jlo + pp);
         const float qm2 = (float)(pg.qm + pg.qm), hr0 = (float)(T(0.5) * pg.r0);   // packed path
-        // output border: a warp evaluates 32 borders = 31 pixels
+        // output border: a warp evaluates 32 borders = 31 pixels, all G frames
         const int q = 31 * warp + lane;
+        const bool dwarp = 31 * warp < nk;                     // the warp has borders at all
         const Border<T> bd = ldg_struct(p.border + (size_t)s * p.NB + k0 + min(q, nk));
         const int ibl = bd.idx - tile.jlo;                     // source pixel, tile relative
         const int ibn = __shfl_down_sync(0xffffffffu, ibl, 1);
@@ -663,17 +688,16 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
 #pragma unroll
         for (int g = 0; g < G; ++g) nzb[g] = 0;
 
-        // ---- the two copy pipelines of the item, fed by thread 0 with TMA bulk copies:
-        //   R(y): the new source rows that rectified row y needs (2 rows ahead of use),
-        //         one copy per row and frame into the ring slot (row & 15)
-        //   W(y): the table row of row y, base + K*K weight arrays (1 row ahead),
-        //         one copy per array into slot y & 1
-        // Each group completes on its own mbarrier (3 for R, 2 for W, used round-robin).
+        // ---- the copy pipeline of the item, fed by the producer warp with TMA bulk copies:
+        //   the new source rows that rectified row y needs (two rows ahead of their use),
+        //   one copy per row and frame into ring slot (row + bias) % WIN_ROWS, and
+        //   the table row of row y, npx records in one copy (one row ahead), slot y & 1.
         constexpr int VN = Vec16<T>::N;
         const int cv0 = max(tile.c0, 0), cv1 = min(tile.c0 + tile.wcols, W);   // valid columns
         const unsigned row_bytes = (unsigned)((cv1 - cv0) * sizeof(T));
-        const unsigned win_a = smem_addr_of(win) + (unsigned)((cv0 - tile.c0) * sizeof(T));
-        const T *fin = p.in + (size_t)g0 * W * p.naxis2 + cv0;
+        const unsigned win_a = smem_addr_of(win) + (unsigned)((cv0 - tile.c0) * sizeof(T)) +
+                               (unsigned)(cg * WSZ * sizeof(T));
+        const T *fin = p.in + ((size_t)g0 + cg) * W * p.naxis2 + cv0;
         const unsigned trow_bytes = (unsigned)(npx * RS * sizeof(T));
         const T *trow = p.w + ((size_t)s * NROWS * W + tile.jlo) * RS;
         const unsigned tsm_a = smem_addr_of(tsm);
@@ -688,20 +712,21 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
 
         // Row number n (counted across items) completes on mbarrier n % 3 with two
         // arrivals: the source rows it adds (posted two rows earlier) and its table row
-        // (posted one row earlier).  Warp 0 is the producer: lane 0 posts the byte counts
-        // and issues the bulk copies; rows outside the detector (rare) are zero-filled by
-        // all threads.
+        // (posted one row earlier).  Lane 0 of the producer warp posts the byte counts, every
+        // lane issues the copy of one (row, frame); rows outside the detector (rare) are
+        // zero-filled by all threads.
         const bool oob_rows = span_lo(tile.span[0]) < 0 || span_hi(tile.span[NROWS - 1]) >= p.naxis2;
         auto copy_window_rows = [&](unsigned seq, int r_from, int r_to) {
-            if (warp == 0) {
+            if (producer) {
                 const unsigned bar = bars + 8 * (seq % 3);
                 const int lo = max(r_from + 1, 0), hi = min(r_to, p.naxis2 - 1);
                 if (lane == 0) mbar_expect_tx(bar, (unsigned)(max(hi - lo + 1, 0) * nlive) * row_bytes);
-                if (lane < nlive)
-                    for (int r = lo; r <= hi; ++r)
-                        bulk_g2s(win_a + (unsigned)(((unsigned)(r + RING_BIAS) % WIN_ROWS) * WIN_PITCH * sizeof(T)) +
-                                     (unsigned)(lane * WSZ * sizeof(T)),
-                                 fin + (size_t)lane * W * p.naxis2 + (size_t)r * W, row_bytes, bar);
+                __syncwarp();
+                if (cg < nlive)
+                    for (int r = lo + cr; r <= hi; r += ROWS_PER_ISSUE)
+                        bulk_g2s(win_a + (unsigned)(((unsigned)(r + RING_BIAS) % WIN_ROWS) *
+                                                    (WIN_PITCH * sizeof(T))),
+                                 fin + (size_t)r * W, row_bytes, bar);
             }
             if (oob_rows)
                 for (int r = r_from + 1; r <= r_to; ++r)
@@ -713,10 +738,10 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         };
         // table row y = npx contiguous records, one bulk copy
         auto copy_table_row = [&](unsigned seq, int y) {
-            if (tid == 0) {
+            if (producer && lane == 0) {
                 const unsigned bar = bars + 8 * (seq % 3);
                 mbar_expect_tx(bar, trow_bytes);
-                bulk_g2s(tsm_a + (y & 1) * (unsigned)(PX_MAX * RS * sizeof(T)),
+                bulk_g2s(tsm_a + (y & 1) * (unsigned)(PXCAP * RS * sizeof(T)),
                          trow + (size_t)y * W * RS, trow_bytes, bar);
             }
         };
@@ -730,6 +755,7 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
         // neighbour's entry; their result is discarded)
         const int ppc = min(max(pp, 0), npx - 1);
         T *orow = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
+        const T *winsub = win + sub * (GA * WSZ);              // windows of this subgroup
         int wb = -tile.c0;                                     // window addressed by frame coords
         pin(wb);
 
@@ -754,7 +780,7 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
 
             // ---- D (row y-1): cumulative flux at this thread's border and at the next
             //      one, difference = output pixel; store; remember non-zero values
-            if (y >= 1) {
+            if (y >= 1 && dwarp) {
                 const KV *kb_rect = reinterpret_cast<const KV *>(rectS) + ((y - 1) & 1) * KNOT_PITCH + ibl;
                 const KV *kb_ya = reinterpret_cast<const KV *>(yaS) + ((y - 1) & 1) * KNOT_PITCH + ibl;
                 const KV *kb_yb = reinterpret_cast<const KV *>(ybS) + ((y - 1) & 1) * KNOT_PITCH + ibl;
@@ -765,7 +791,7 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                 for (int g = 0; g < G; ++g) k1.v[g] = T(0);
                 if (has2) k1 = kb_rect[1];
                 T o[G];
-                if constexpr (PACKED) {
+                if constexpr (PACKED_D) {
                     const float2 tau2 = dup2(bd.tau);
 #pragma unroll
                     for (int h = 0; h < G / 2; ++h) {
@@ -806,53 +832,55 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                     if (col_ok && g < nlive && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o[g]);
                     nzb[g] |= nz_bits(o[g]);       // lanes / frames that do not count are masked
                 }                                  // once, after the last row
-                orow += p.nout;
             }
+            if (y >= 1) orow += p.nout;
 
-            if (y < NROWS) {
-                // this pixel's record: K*K weights + packed source coordinates
+            if (y < NROWS && awarp) {
+                // this pixel's record: K*K weights, packed source column, ring slots of the
+                // K source rows
                 T wt[RS];
                 {
                     using V = typename Vec16<T>::type;
-                    const V *rec = reinterpret_cast<const V *>(tsm + ((y & 1) * PX_MAX + ppc) * RS);
+                    const V *rec = reinterpret_cast<const V *>(tsm + ((y & 1) * PXCAP + ppc) * RS);
 #pragma unroll
                     for (int i = 0; i < RS / VN; ++i)
                         *reinterpret_cast<V *>(wt + i * VN) = rec[i];
                 }
                 const int32_t pk = *reinterpret_cast<const int32_t *>(wt + K * K);
+                const uint32_t slots = *reinterpret_cast<const uint32_t *>(wt + K * K + 1);
 
-                // ---- A (row y): rectified flux of this pixel column, G frames
-                T rect[G];
+                // ---- A (row y): rectified flux of this pixel column, GA frames
+                T rect[GA];
                 {
-                    const int fr = base_row(pk) + RING_BIAS, fc = base_col(pk) + wb;
+                    const int fc = base_col(pk) + wb;
                     const T *rowp[K];
 #pragma unroll
                     for (int a = 0; a < K; ++a)
-                        rowp[a] = win + ((unsigned)(fr + a) % WIN_ROWS) * WIN_PITCH + fc;
-                    if constexpr (PACKED) {
-                        float2 acc[G / 2];
+                        rowp[a] = winsub + ((slots >> (8 * a)) & 0xffu) * WIN_PITCH + fc;
+                    if constexpr (PACKED_A) {
+                        float2 acc[GA / 2];
 #pragma unroll
-                        for (int h = 0; h < G / 2; ++h) acc[h] = make_float2(0.0f, 0.0f);
+                        for (int h = 0; h < GA / 2; ++h) acc[h] = make_float2(0.0f, 0.0f);
 #pragma unroll
                         for (int a = 0; a < K; ++a)
 #pragma unroll
                             for (int b = 0; b < K; ++b) {
                                 const float2 wgt = dup2(wt[a * K + b]);
 #pragma unroll
-                                for (int h = 0; h < G / 2; ++h)
+                                for (int h = 0; h < GA / 2; ++h)
                                     acc[h] = fma2(wgt,
                                                   make_float2(rowp[a][(2 * h) * WSZ + b],
                                                               rowp[a][(2 * h + 1) * WSZ + b]),
                                                   acc[h]);
                             }
 #pragma unroll
-                        for (int h = 0; h < G / 2; ++h) {
+                        for (int h = 0; h < GA / 2; ++h) {
                             rect[2 * h] = px_ok ? acc[h].x : 0.0f;
                             rect[2 * h + 1] = px_ok ? acc[h].y : 0.0f;
                         }
                     } else {
 #pragma unroll
-                        for (int g = 0; g < G; ++g) {
+                        for (int g = 0; g < GA; ++g) {
                             T acc = T(0);
 #pragma unroll
                             for (int a = 0; a < K; ++a)
@@ -867,13 +895,13 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                 // ---- C (row y): Steffen-limited slopes at both ends of the pixel, scaled
                 //      by the pixel width (flux units).  qm = 0 / qp = 0 in the table give
                 //      the zero slopes at the two ends of the spectrum.
-                KV vr, va, vb;
-                if constexpr (PACKED) {
+                KA vr, va, vb;
+                if constexpr (PACKED_A) {
                     // steffen_slope with everything doubled (exact): 2*min(|sl|,|sr|,|p|/2) =
                     // min(|2 sl|, |2 sr|, |p|); the sign test folds into the minimum by
                     // giving 2 sl the sign it has relative to sr.
 #pragma unroll
-                    for (int h = 0; h < G / 2; ++h) {
+                    for (int h = 0; h < GA / 2; ++h) {
                         const float2 r = make_float2(rect[2 * h], rect[2 * h + 1]);
                         const float2 l = make_float2(__shfl_up_sync(0xffffffffu, r.x, 1),
                                                      __shfl_up_sync(0xffffffffu, r.y, 1));
@@ -899,7 +927,7 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                     }
                 } else {
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
+                    for (int g = 0; g < GA; ++g) {
                         // slope at the left knot from this pixel and its left neighbour; the
                         // slope at the right knot is the right neighbour's left-knot slope
                         // rescaled by the ratio of the pixel widths (one limiter per pixel)
@@ -911,15 +939,17 @@ __global__ void __launch_bounds__(NTHREADS, (G == 4 || sizeof(T) == 8) ? 2 : 3)
                     }
                 }
                 if (knot_ok) {
-                    reinterpret_cast<KV *>(rectS)[(y & 1) * KNOT_PITCH + pp] = vr;
-                    reinterpret_cast<KV *>(yaS)[(y & 1) * KNOT_PITCH + pp] = va;
-                    reinterpret_cast<KV *>(ybS)[(y & 1) * KNOT_PITCH + pp] = vb;
+                    // knot (y & 1, pp), components sub*GA .. sub*GA+GA-1 of its frame vector
+                    const int e = ((y & 1) * KNOT_PITCH + pp) * PS + sub;
+                    reinterpret_cast<KA *>(rectS)[e] = vr;
+                    reinterpret_cast<KA *>(yaS)[e] = va;
+                    reinterpret_cast<KA *>(ybS)[e] = vb;
                 }
             }
         }
 
         // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
-        if (p.jmm != nullptr) {
+        if (p.jmm != nullptr && dwarp) {
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 const bool nz = col_ok && g < nlive && nzb[g] != 0;
@@ -966,6 +996,7 @@ struct emirwv_plan {
     int tile_k = 0, tile_rows = 0;
     int wrows_max = 0, wcols_max = 0, npx_max = 0, max_span = 0;
     int tune_G = 0;
+    int ps = 1;                  // frame subgroups of phases A, C the tiles are sized for
     int num_sms = 148;
     int64_t table_bytes = 0;
 
@@ -994,16 +1025,17 @@ int env_int(const char *name, int fallback) {
 
 // launch configuration for a given number of frames per CTA
 struct LaunchCfg {
-    int G, threads;
+    int G, PS, threads;
     size_t smem;
 };
 
 // shared memory of the hot kernel:
-//   [3 tile descriptors][G windows: WIN_ROWS x WIN_PITCH][rect | ya | yb: G x KNOT_PITCH]
-size_t smem_bytes(const emirwv_plan *pl, int G) {
+//   [3 tile descriptors][mbarriers][G windows: WIN_ROWS x win_pitch]
+//   [rect | ya | yb: 2 x knot_pitch x G each][2 table rows: px_cap records]
+size_t smem_bytes(const emirwv_plan *pl, int G, int PS) {
     return 3 * sizeof(Tile) + 64 +
-           (size_t)G * (WIN_ROWS * WIN_PITCH + 6 * KNOT_PITCH) * pl->esize +
-           (size_t)2 * PX_MAX * rec_size(pl->K) * pl->esize;
+           (size_t)G * (WIN_ROWS * win_pitch(PS) + 6 * knot_pitch(PS)) * pl->esize +
+           (size_t)2 * px_cap(PS) * rec_size(pl->K) * pl->esize;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
@@ -1011,15 +1043,18 @@ LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
     cfg.threads = NTHREADS;
     int G = pl->tune_G > 0 ? pl->tune_G : env_int("EMIRWV_G", pl->esize == 4 ? 4 : 2);
     G = (G >= 4) ? 4 : (G >= 2 ? 2 : 1);
-    while (G > 1 && (G > nframes || smem_bytes(pl, G) > (size_t)SMEM_LIMIT)) G >>= 1;
+    while (G > 1 && (G > nframes || smem_bytes(pl, G, 1) > (size_t)SMEM_LIMIT)) G >>= 1;
     cfg.G = G;
-    cfg.smem = smem_bytes(pl, G);
+    // the tiles were sized for pl->ps frame subgroups; a single frame cannot be split
+    // (tiles sized for two subgroups always fit the unsplit kernel as well)
+    cfg.PS = (pl->ps == 2 && G >= 2) ? 2 : 1;
+    cfg.smem = smem_bytes(pl, G, cfg.PS);
     return cfg;
 }
 
-template <typename T, int K, int G, bool SPANLOOP>
+template <typename T, int K, int G, int PS, bool SPANLOOP>
 int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, cudaStream_t st) {
-    auto kern = k_rectwv<T, K, G, SPANLOOP>;
+    auto kern = k_rectwv<T, K, G, PS, SPANLOOP>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)cfg.smem));
     int per_sm = 0;
@@ -1039,8 +1074,14 @@ int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, c
 template <typename T, int K, int G>
 int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
                cudaStream_t st) {
-    if (pl->max_span > 2) return launch_final<T, K, G, true>(pl, rp, cfg, st);
-    return launch_final<T, K, G, false>(pl, rp, cfg, st);
+    if constexpr (G >= 2) {
+        if (cfg.PS == 2) {
+            if (pl->max_span > 2) return launch_final<T, K, G, 2, true>(pl, rp, cfg, st);
+            return launch_final<T, K, G, 2, false>(pl, rp, cfg, st);
+        }
+    }
+    if (pl->max_span > 2) return launch_final<T, K, G, 1, true>(pl, rp, cfg, st);
+    return launch_final<T, K, G, 1, false>(pl, rp, cfg, st);
 }
 
 template <typename T, int K>
@@ -1271,7 +1312,7 @@ int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int TK
             t.jlo = std::max(0, ilo - 1);
             const int jhi = std::min(nchan - 1, ihi + 1);
             t.npx = jhi - t.jlo + 1;
-            if (t.npx > PX_MAX) return 1;
+            if (t.npx > px_cap(pl->ps)) return 1;
             int c0 = INT_MAX, c1 = INT_MIN;
             int rlo[NROWS], rhi[NROWS];
             for (int y = 0; y < NROWS; ++y) {
@@ -1298,7 +1339,7 @@ int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int TK
             c0 = (int)(std::floor(c0 / 4.0) * 4.0);        // 16-byte aligned window rows
             t.c0 = c0;
             t.wcols = ((c1 - c0 + 1) + 3) & ~3;
-            if (t.wcols > WIN_PITCH || span_max > WIN_ROWS) return 1;
+            if (t.wcols > win_pitch(pl->ps) || span_max > WIN_ROWS) return 1;
             wcols_max = std::max(wcols_max, t.wcols);
             npx_max = std::max(npx_max, t.npx);
             live.push_back(t);
@@ -1316,13 +1357,15 @@ int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int TK
 }
 
 int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
-    int TK = std::max(31, std::min(pl->tile_k, TILE_K_MAX)) / 31 * 31;
-    for (; TK >= 31; TK -= 31)
+    // widest block (a multiple of 4 columns keeps the zero-fill stores vectorised) whose
+    // source pixels fit the CTA
+    int TK = std::max(32, std::min(pl->tile_k, TILE_K_MAX)) / 4 * 4;
+    for (; TK >= 32; TK -= 4)
         if (try_build_tiles(pl, covered, TK) == 0) break;
-    if (TK < 31)
+    if (TK < 32)
         return fail(EMIRWV_E_LIMIT,
-                    "distortion too strong: the source window of a 31-column block does not fit "
-                    "(%d rows x %d columns available)", WIN_ROWS, WIN_PITCH);
+                    "distortion too strong: the source window of a 32-column block does not fit "
+                    "(%d rows x %d columns available)", WIN_ROWS, win_pitch(pl->ps));
     if (pl->ntiles_empty > 65535) return fail(EMIRWV_E_LIMIT, "too many tiles");
     CUDA_TRY(cudaMalloc(&pl->d_tiles, pl->h_tiles.size() * sizeof(Tile)));
     CUDA_TRY(cudaMemcpy(pl->d_tiles, pl->h_tiles.data(), pl->h_tiles.size() * sizeof(Tile),
@@ -1386,7 +1429,7 @@ int build_plan(emirwv_plan *pl) {
     pl->NB = d.naxis1_out + 1;
     pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", TILE_K_MAX);
     pl->tile_rows = NROWS;       // a tile always spans the 39 scanned rows
-    pl->tile_k = std::max(31, std::min(pl->tile_k, TILE_K_MAX));
+    pl->tile_k = std::max(32, std::min(pl->tile_k, TILE_K_MAX));
 
     pl->h_slit.resize(pl->nsl);
     for (int s = 0; s < pl->nsl; ++s) {
@@ -1465,6 +1508,18 @@ int build_plan(emirwv_plan *pl) {
     std::vector<uint8_t> covered;
     int rc = build_border_tables(pl, covered);
     if (rc) return rc;
+    {
+        // Output columns inside the wavelength coverage per source pixel.  Well above 1 the
+        // border phase needs more threads than the pixel phases, and the pixel phases split
+        // the frames of an item over two groups of warps instead.
+        double ncov = 0, npix = 0;
+        for (int s = 0; s < pl->nsl; ++s) {
+            if (!d.slitlet[s].valid) continue;
+            for (int k = 0; k < pl->nout; ++k) ncov += covered[(size_t)s * pl->NB + k] != 0;
+            npix += d.slitlet[s].bb_nc2_orig - d.slitlet[s].bb_nc1_orig + 1;
+        }
+        pl->ps = env_int("EMIRWV_PS", (npix > 0 && ncov > 1.5 * npix) ? 2 : 1) == 2 ? 2 : 1;
+    }
     rc = build_tiles(pl, covered);
     if (rc) return rc;
     if (env_int("EMIRWV_NO_AUX", 0) == 0) {
@@ -1594,6 +1649,7 @@ int emirwv_plan_get_info(const emirwv_plan *pl, emirwv_plan_info *info) {
     info->frames_per_cta = cfg.G;
     info->threads = cfg.threads;
     info->smem_bytes = (int32_t)cfg.smem;
+    info->reserved = cfg.PS;     // frame subgroups of the pixel phases
     info->table_bytes = pl->table_bytes;
     info->in_frame_bytes = (int64_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
     info->out_frame_bytes = (int64_t)pl->nsl * pl->rps * pl->nout * pl->esize;
