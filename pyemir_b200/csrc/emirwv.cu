@@ -759,10 +759,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
         int wb = -tile.c0;                                     // window addressed by frame coords
         pin(wb);
 
-        // Software-pipelined row loop, ONE block barrier per rectified row: iteration y
-        // evaluates the borders of row y-1 (phase D, reading knot buffer (y-1)&1) and the
-        // flux and slopes of row y (phases A and C, writing knot buffer y&1).
-        for (int y = 0; y <= NROWS; ++y) {
+        auto row_top = [&](int y) {
             if (y < NROWS) {
                 mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);      // rows + table landed
                 ++rowseq;
@@ -777,14 +774,15 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
                 copy_window_rows(rowseq + 1, rhi_prev, rhi);
                 rhi_prev = max(rhi_prev, rhi);
             }
-
-            // ---- D (row y-1): cumulative flux at this thread's border and at the next
-            //      one, difference = output pixel; store; remember non-zero values
-            if (y >= 1 && dwarp) {
-                const KV *kb_rect = reinterpret_cast<const KV *>(rectS) + ((y - 1) & 1) * KNOT_PITCH + ibl;
-                const KV *kb_ya = reinterpret_cast<const KV *>(yaS) + ((y - 1) & 1) * KNOT_PITCH + ibl;
-                const KV *kb_yb = reinterpret_cast<const KV *>(ybS) + ((y - 1) & 1) * KNOT_PITCH + ibl;
-                const bool store = y - 1 < p.rps;
+        };
+        // ---- D (row yr): cumulative flux at this thread's border and at the next one,
+        //      difference = output pixel; store; remember non-zero values
+        auto phase_d = [&](int yr) {
+            if (PS == 1 || dwarp) {
+                const KV *kb_rect = reinterpret_cast<const KV *>(rectS) + (yr & 1) * KNOT_PITCH + ibl;
+                const KV *kb_ya = reinterpret_cast<const KV *>(yaS) + (yr & 1) * KNOT_PITCH + ibl;
+                const KV *kb_yb = reinterpret_cast<const KV *>(ybS) + (yr & 1) * KNOT_PITCH + ibl;
+                const bool store = yr < p.rps;
                 const KV kr = kb_rect[0], ka = kb_ya[0], kc = kb_yb[0];
                 KV k1;
 #pragma unroll
@@ -833,9 +831,12 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
                     nzb[g] |= nz_bits(o[g]);       // lanes / frames that do not count are masked
                 }                                  // once, after the last row
             }
-            if (y >= 1) orow += p.nout;
+            orow += p.nout;
+        };
 
-            if (y < NROWS && awarp) {
+        // ---- A, C (row y)
+        auto phase_ac = [&](int y) {
+            if (PS == 1 || awarp) {
                 // this pixel's record: K*K weights, packed source column, ring slots of the
                 // K source rows
                 T wt[RS];
@@ -946,7 +947,22 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
                     reinterpret_cast<KA *>(ybS)[e] = vb;
                 }
             }
+        };
+
+        // Software-pipelined row loop, ONE block barrier per rectified row: iteration y
+        // evaluates the borders of row y-1 (phase D, reading knot buffer (y-1)&1) and the
+        // flux and slopes of row y (phases A and C, writing knot buffer y&1).  The two are
+        // independent instruction streams in one basic block, which the scheduler interleaves.
+        row_top(0);
+        phase_ac(0);
+#pragma unroll 1
+        for (int y = 1; y < NROWS; ++y) {
+            row_top(y);
+            phase_d(y - 1);
+            phase_ac(y);
         }
+        row_top(NROWS);
+        phase_d(NROWS - 1);
 
         // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
         if (p.jmm != nullptr && dwarp) {
