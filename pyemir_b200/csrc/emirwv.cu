@@ -51,12 +51,10 @@ constexpr int NTHREADS = 32 * NWARPS;         // threads per CTA of the hot kern
 constexpr int TILE_K_MAX = 31 * NWARPS;       // output columns per tile (a warp does 31)
 constexpr int WIN_ROWS = 12;                  // rolling source window: rows per frame
 constexpr int RING_BIAS = 12 * 1024;          // makes (row + bias) % WIN_ROWS non-negative
-// Phases A and C of the hot kernel split the G frames of an item over PS groups of
-// NWARPS / PS warps (PS = 2 when there are more output columns than source pixels):
-// the CTA then holds PXCAP rectified columns.
-__host__ __device__ constexpr int px_cap(int PS) { return 30 * (NWARPS / PS); }
-__host__ __device__ constexpr int knot_pitch(int PS) { return px_cap(PS) + 8; }
-__host__ __device__ constexpr int win_pitch(int PS) { return px_cap(PS) + 24; }
+constexpr int PXCAP = 30 * NWARPS;            // rectified columns a CTA can stage (240)
+constexpr int WIN_PITCH = PXCAP + 24;         // source window columns, per frame
+constexpr int WARP_PX = 30;                   // rectified columns a warp owns
+constexpr int WARP_BORDERS = 31;              // output columns a warp evaluates
 constexpr int PREFETCH = 2;                   // rectified rows between a copy and its use
 // Per output pixel table record: K*K weights followed by the packed source coordinates
 // (int32 bits), padded to a multiple of 4 elements so that records are 16-byte aligned.
@@ -103,7 +101,7 @@ struct Tile {
     int c0, wcols;      // source window columns (multiples of 4: 16-byte copies)
     int empty;          // no wavelength coverage: the tile is exactly zero
     int nchan;          // bbw of the slitlet
-    int pad[3];
+    uint8_t kw[12];     // kw[w] .. kw[w+1]-1: output columns (relative to k0) of warp w
     int32_t span[40];   // per scanned row: source rows needed, lo | hi << 16 (int16 each),
                         // monotone envelopes (rolling window)
 };
@@ -586,36 +584,29 @@ __global__ void __launch_bounds__(256) k_zero_fill(const RunParams<T> p, int fir
 // Shared memory: [tile descriptor ring: 3][G windows: WIN_ROWS x WIN_PITCH]
 //                [rect | ya | yb : G x KNOT_PITCH each]
 // ---------------------------------------------------------------------------------
-template <typename T, int K, int G, int PS, bool SPANLOOP>
-__global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
+template <typename T, int K, int G, bool SPANLOOP>
+__global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && G <= 2) ? 3 : 2)
     k_rectwv(const RunParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int GA = G / PS;                                 // frames per thread, phases A, C
-    constexpr int NWP = NWARPS / PS;                           // warps per frame subgroup
-    constexpr int PXCAP = px_cap(PS), KNOT_PITCH = knot_pitch(PS), WIN_PITCH = win_pitch(PS);
     constexpr int WSZ = WIN_ROWS * WIN_PITCH;                  // one frame's window
-    static_assert(G % PS == 0, "frames must split evenly");
+    constexpr int KNOT_WARP = 2 * 3 * 32 * G;                  // knot elements of one warp
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const bool producer = warp == NWARPS - 1;   // this warp also issues the bulk copies
     const size_t frame_out = (size_t)p.nrows_out * p.nout;
     const int nwork = p.nlive_tiles * p.ngroups;
 
     Tile *ring = reinterpret_cast<Tile *>(smem_raw);                       // [3]
-    // mbarriers [0..2]: one per rectified row in flight
+    // mbarriers [0..2]: one per rectified row in flight; then 3 arrival counters
     const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
+    int *done_cnt = reinterpret_cast<int *>(smem_raw + 3 * sizeof(Tile) + 32);   // [3]
     T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + 64);      // [G][WSZ]
-    T *rectS = win + G * WSZ;                                              // [2][KNOT_PITCH][G]
-    T *yaS = rectS + 2 * G * KNOT_PITCH;
-    T *ybS = yaS + 2 * G * KNOT_PITCH;
+    T *knots = win + G * WSZ + warp * KNOT_WARP;           // this warp: [2][rect|ya|yb][32][G]
     constexpr int RS = rec_size(K);
-    T *tsm = ybS + 2 * G * KNOT_PITCH;                                     // [2][PXCAP][RS]
-    // float32: two frames per arithmetic instruction wherever a thread holds a pair
-    constexpr bool PACKED_D = sizeof(T) == 4 && (G % 2) == 0;
-    constexpr bool PACKED_A = sizeof(T) == 4 && (GA % 2) == 0;
+    T *tsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [3][PXCAP][RS]
+    // float32 with an even number of frames: two frames per arithmetic instruction
+    constexpr bool PACKED = sizeof(T) == 4 && (G % 2) == 0;
     using KV = KnotVec<T, G>;
-    using KA = KnotVec<T, GA>;
 
     int w = blockIdx.x;
     if (w >= nwork) return;
@@ -631,7 +622,10 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
                         (tid - 32) * 16, true);
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 2);   // rows part + table part
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(bars + 8 * i, 2);                 // rows part + table part of a row
+            done_cnt[i] = 0;
+        }
         mbar_fence_init();
     }
     cp_async_wait_all();
@@ -641,9 +635,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
     pin(fo);
     unsigned rowseq = 0;            // rectified rows started so far (same in every thread)
 
-    // phases A, C: frame subgroup and pixel block of this warp
-    const int sub = warp / NWP, wl = warp - sub * NWP;
-    // producer lanes: one (source row, frame) pair each
+    // copy lanes: one (source row, frame) pair each
     const int cg = lane % G, cr = lane / G;
     constexpr int ROWS_PER_ISSUE = 32 / G;
 
@@ -661,37 +653,37 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
         const int nlive = min(G, p.nframes - g0);
         const int s = tile.slit;
         const int npx = tile.npx;
-        const int nk = tile.nk;
         const int k0 = tile.k0;
 
         // ---- per-item constants of this thread
-        // pixel column: a warp covers pixels 30*wl-1 .. 30*wl+30 and produces 30 of them,
-        // for the GA frames of its subgroup
-        const int pp = 30 * wl - 1 + lane;
+        // The warp owns the borders kw[warp] .. kw[warp+1]-1 of the tile (at most 31) and
+        // every rectified pixel they touch (at most 30, lanes 1..30; lanes 0 and 31 hold the
+        // neighbours the slope limiter needs), so a row needs no exchange between warps.
+        const int kw0 = tile.kw[warp], nb = tile.kw[warp + 1] - kw0;
+        const bool wwarp = nb > 0;                             // the warp has work at all
+        const int q = kw0 + min(lane, nb);                     // border, tile relative
+        const Border<T> bd = ldg_struct(p.border + (size_t)s * p.NB + k0 + q);
+        const int ibl = bd.idx - tile.jlo;                     // source pixel, tile relative
+        const int ibn = __shfl_down_sync(0xffffffffu, ibl, 1);
+        const int plo = __shfl_sync(0xffffffffu, ibl, 0);      // first pixel the warp owns
+        const int kl = ibl - plo + 1;                          // lane that holds pixel ibl
+        const bool col_ok = lane < nb;
+        const bool has1 = ibn > ibl, has2 = ibn > ibl + 1;
+        const int kb = k0 + q;
+        const int pp = plo - 1 + lane;                         // pixel column, tile relative
         const bool px_ok = pp >= 0 && pp < npx;
-        const bool knot_ok = lane >= 1 && lane <= 30 && pp < npx;
-        const bool awarp = 30 * wl - 1 < npx;                  // the warp has pixels at all
         PixGeom<T> pg;
         pg.qm = pg.qp = pg.r0 = pg.r1 = T(0);
         if (px_ok) pg = ldg_struct(p.pix + (size_t)s * W + tile.jlo + pp);
         const float qm2 = (float)(pg.qm + pg.qm), hr0 = (float)(T(0.5) * pg.r0);   // packed path
-        // output border: a warp evaluates 32 borders = 31 pixels, all G frames
-        const int q = 31 * warp + lane;
-        const bool dwarp = 31 * warp < nk;                     // the warp has borders at all
-        const Border<T> bd = ldg_struct(p.border + (size_t)s * p.NB + k0 + min(q, nk));
-        const int ibl = bd.idx - tile.jlo;                     // source pixel, tile relative
-        const int ibn = __shfl_down_sync(0xffffffffu, ibl, 1);
-        const bool col_ok = lane < 31 && q < nk;
-        const bool has1 = ibn > ibl, has2 = ibn > ibl + 1;
-        const int kb = k0 + q;
         unsigned nzb[G];                                       // OR of the value bits seen
 #pragma unroll
         for (int g = 0; g < G; ++g) nzb[g] = 0;
 
-        // ---- the copy pipeline of the item, fed by the producer warp with TMA bulk copies:
-        //   the new source rows that rectified row y needs (two rows ahead of their use),
-        //   one copy per row and frame into ring slot (row + bias) % WIN_ROWS, and
-        //   the table row of row y, npx records in one copy (one row ahead), slot y & 1.
+        // ---- the copy pipeline of the item (TMA bulk copies completing on mbarriers):
+        //   the new source rows that rectified row y needs, one copy per row and frame into
+        //   ring slot (row + bias) % WIN_ROWS, and the table row of row y, npx records in one
+        //   copy, slot y % 3.
         constexpr int VN = Vec16<T>::N;
         const int cv0 = max(tile.c0, 0), cv1 = min(tile.c0 + tile.wcols, W);   // valid columns
         const unsigned row_bytes = (unsigned)((cv1 - cv0) * sizeof(T));
@@ -703,269 +695,270 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
         const unsigned tsm_a = smem_addr_of(tsm);
 
         // columns of the window that fall outside the detector stay zero for the item
-        if (cv0 > tile.c0 || cv1 < tile.c0 + tile.wcols)
-            for (int e = tid; e < G * WIN_ROWS * tile.wcols; e += NTHREADS) {   // (rare)
+        if (cv0 > tile.c0 || cv1 < tile.c0 + tile.wcols) {                      // (rare)
+            for (int e = tid; e < G * WIN_ROWS * tile.wcols; e += NTHREADS) {
                 const int c = e % tile.wcols, rg = e / tile.wcols;
                 if (tile.c0 + c < cv0 || tile.c0 + c >= cv1)
                     win[(rg / WIN_ROWS) * WSZ + (rg % WIN_ROWS) * WIN_PITCH + c] = T(0);
             }
+            __syncthreads();
+        }
 
         // Row number n (counted across items) completes on mbarrier n % 3 with two
-        // arrivals: the source rows it adds (posted two rows earlier) and its table row
-        // (posted one row earlier).  Lane 0 of the producer warp posts the byte counts, every
-        // lane issues the copy of one (row, frame); rows outside the detector (rare) are
-        // zero-filled by all threads.
+        // arrivals: the source rows it adds and its table row.  Whichever warp issues them
+        // does so with all its lanes: lane 0 posts the byte counts, every lane copies one
+        // (row, frame); rows outside the detector (rare) are zero-filled instead.
         const bool oob_rows = span_lo(tile.span[0]) < 0 || span_hi(tile.span[NROWS - 1]) >= p.naxis2;
         auto copy_window_rows = [&](unsigned seq, int r_from, int r_to) {
-            if (producer) {
-                const unsigned bar = bars + 8 * (seq % 3);
-                const int lo = max(r_from + 1, 0), hi = min(r_to, p.naxis2 - 1);
-                if (lane == 0) mbar_expect_tx(bar, (unsigned)(max(hi - lo + 1, 0) * nlive) * row_bytes);
-                __syncwarp();
-                if (cg < nlive)
-                    for (int r = lo + cr; r <= hi; r += ROWS_PER_ISSUE)
-                        bulk_g2s(win_a + (unsigned)(((unsigned)(r + RING_BIAS) % WIN_ROWS) *
-                                                    (WIN_PITCH * sizeof(T))),
-                                 fin + (size_t)r * W, row_bytes, bar);
-            }
-            if (oob_rows)
+            const unsigned bar = bars + 8 * (seq % 3);
+            const int lo = max(r_from + 1, 0), hi = min(r_to, p.naxis2 - 1);
+            if (oob_rows) {
                 for (int r = r_from + 1; r <= r_to; ++r)
                     if (r < 0 || r >= p.naxis2) {
                         const unsigned slot = (unsigned)(r + RING_BIAS) % WIN_ROWS;
-                        for (int e = tid; e < nlive * tile.wcols; e += NTHREADS)
+                        for (int e = lane; e < nlive * tile.wcols; e += 32)
                             win[(e / tile.wcols) * WSZ + slot * WIN_PITCH + e % tile.wcols] = T(0);
                     }
+                __syncwarp();
+            }
+            if (lane == 0) mbar_expect_tx(bar, (unsigned)(max(hi - lo + 1, 0) * nlive) * row_bytes);
+            __syncwarp();
+            if (cg < nlive)
+                for (int r = lo + cr; r <= hi; r += ROWS_PER_ISSUE)
+                    bulk_g2s(win_a + (unsigned)(((unsigned)(r + RING_BIAS) % WIN_ROWS) *
+                                                (WIN_PITCH * sizeof(T))),
+                             fin + (size_t)r * W, row_bytes, bar);
         };
         // table row y = npx contiguous records, one bulk copy
         auto copy_table_row = [&](unsigned seq, int y) {
-            if (producer && lane == 0) {
+            if (lane == 0) {
                 const unsigned bar = bars + 8 * (seq % 3);
                 mbar_expect_tx(bar, trow_bytes);
-                bulk_g2s(tsm_a + (y & 1) * (unsigned)(PXCAP * RS * sizeof(T)),
+                bulk_g2s(tsm_a + (y % 3) * (unsigned)(PXCAP * RS * sizeof(T)),
                          trow + (size_t)y * W * RS, trow_bytes, bar);
             }
         };
 
-        int rhi_prev = span_hi(tile.span[0]);
-        copy_window_rows(rowseq, span_lo(tile.span[0]) - 1, rhi_prev);          // rows of row 0
-        copy_table_row(rowseq, 0);                                              // table of row 0
-        copy_window_rows(rowseq + 1, rhi_prev, span_hi(tile.span[1]));          // rows of row 1
-        rhi_prev = max(rhi_prev, span_hi(tile.span[1]));
+        // rows 0..2 and their table rows are requested up front by warp 0; afterwards the
+        // last warp to finish row y requests the table row and the source rows of row y+3
+        // (nobody reads the slots they overwrite any more)
+        if (warp == 0) {
+            copy_window_rows(rowseq, span_lo(tile.span[0]) - 1, span_hi(tile.span[0]));
+            copy_table_row(rowseq, 0);
+            copy_window_rows(rowseq + 1, span_hi(tile.span[0]), span_hi(tile.span[1]));
+            copy_table_row(rowseq + 1, 1);
+            copy_window_rows(rowseq + 2, span_hi(tile.span[1]), span_hi(tile.span[2]));
+            copy_table_row(rowseq + 2, 2);
+        }
         // this thread's slot in the staged table rows (lanes without a pixel read a
         // neighbour's entry; their result is discarded)
         const int ppc = min(max(pp, 0), npx - 1);
         T *orow = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
-        const T *winsub = win + sub * (GA * WSZ);              // windows of this subgroup
         int wb = -tile.c0;                                     // window addressed by frame coords
         pin(wb);
 
-        auto row_top = [&](int y) {
-            if (y < NROWS) {
-                mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);      // rows + table landed
-                ++rowseq;
-            }
-            __syncthreads();     // knots of row y-1 are visible; everyone is done with the
-                                 // knot buffer, ring slots and table slot of iteration y-1
-
-            // (rowseq now counts row y as started: row y+1 is number rowseq, y+2 rowseq+1)
-            if (y + 1 < NROWS) copy_table_row(rowseq, y + 1);
-            if (y + 2 < NROWS) {
-                const int rhi = span_hi(tile.span[y + 2]);
-                copy_window_rows(rowseq + 1, rhi_prev, rhi);
-                rhi_prev = max(rhi_prev, rhi);
-            }
-        };
         // ---- D (row yr): cumulative flux at this thread's border and at the next one,
         //      difference = output pixel; store; remember non-zero values
         auto phase_d = [&](int yr) {
-            if (PS == 1 || dwarp) {
-                const KV *kb_rect = reinterpret_cast<const KV *>(rectS) + (yr & 1) * KNOT_PITCH + ibl;
-                const KV *kb_ya = reinterpret_cast<const KV *>(yaS) + (yr & 1) * KNOT_PITCH + ibl;
-                const KV *kb_yb = reinterpret_cast<const KV *>(ybS) + (yr & 1) * KNOT_PITCH + ibl;
-                const bool store = yr < p.rps;
-                const KV kr = kb_rect[0], ka = kb_ya[0], kc = kb_yb[0];
-                KV k1;
+            const KV *kbase = reinterpret_cast<const KV *>(knots) + (yr & 1) * (3 * 32) + kl;
+            const KV *kb_rect = kbase, *kb_ya = kbase + 32, *kb_yb = kbase + 64;
+            const bool store = yr < p.rps;
+            const KV kr = kb_rect[0], ka = kb_ya[0], kc = kb_yb[0];
+            KV k1;
 #pragma unroll
-                for (int g = 0; g < G; ++g) k1.v[g] = T(0);
-                if (has2) k1 = kb_rect[1];
-                T o[G];
-                if constexpr (PACKED_D) {
-                    const float2 tau2 = dup2(bd.tau);
+            for (int g = 0; g < G; ++g) k1.v[g] = T(0);
+            if (has2) k1 = kb_rect[1];
+            T o[G];
+            if constexpr (PACKED) {
+                const float2 tau2 = dup2(bd.tau);
 #pragma unroll
-                    for (int h = 0; h < G / 2; ++h) {
-                        const float2 r = make_float2(kr.v[2 * h], kr.v[2 * h + 1]);
-                        const float2 a = make_float2(ka.v[2 * h], ka.v[2 * h + 1]);
-                        const float2 c = make_float2(kc.v[2 * h], kc.v[2 * h + 1]);
-                        // steffen_partial_flux, two frames at a time
-                        const float2 A = fma2(r, dup2(-2.0f), add2(a, c));
-                        const float2 B = sub2(sub2(r, a), A);
-                        const float2 P = mul2(tau2, fma2(tau2, fma2(tau2, A, B), a));
-                        const float2 Pn = make_float2(__shfl_down_sync(0xffffffffu, P.x, 1),
-                                                      __shfl_down_sync(0xffffffffu, P.y, 1));
-                        float2 whole = make_float2(has1 ? r.x : 0.0f, has1 ? r.y : 0.0f);
-                        if (has2) whole = add2(whole, make_float2(k1.v[2 * h], k1.v[2 * h + 1]));
-                        if (SPANLOOP)
-                            for (int i = 2; i < ibn - ibl; ++i) {
-                                const KV ki = kb_rect[i];
-                                whole = add2(whole, make_float2(ki.v[2 * h], ki.v[2 * h + 1]));
-                            }
-                        const float2 o2 = add2(whole, sub2(Pn, P));
-                        o[2 * h] = o2.x;
-                        o[2 * h + 1] = o2.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const T P = steffen_partial_flux(kr.v[g], ka.v[g], kc.v[g], bd.tau);
-                        const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
-                        T whole = has1 ? kr.v[g] : T(0);
-                        if (has2) whole += k1.v[g];
-                        if (SPANLOOP)
-                            for (int i = 2; i < ibn - ibl; ++i) whole += kb_rect[i].v[g];
-                        o[g] = whole + (Pn - P);
-                    }
+                for (int h = 0; h < G / 2; ++h) {
+                    const float2 r = make_float2(kr.v[2 * h], kr.v[2 * h + 1]);
+                    const float2 a = make_float2(ka.v[2 * h], ka.v[2 * h + 1]);
+                    const float2 c = make_float2(kc.v[2 * h], kc.v[2 * h + 1]);
+                    // steffen_partial_flux, two frames at a time
+                    const float2 A = fma2(r, dup2(-2.0f), add2(a, c));
+                    const float2 B = sub2(sub2(r, a), A);
+                    const float2 P = mul2(tau2, fma2(tau2, fma2(tau2, A, B), a));
+                    const float2 Pn = make_float2(__shfl_down_sync(0xffffffffu, P.x, 1),
+                                                  __shfl_down_sync(0xffffffffu, P.y, 1));
+                    float2 whole = make_float2(has1 ? r.x : 0.0f, has1 ? r.y : 0.0f);
+                    if (has2) whole = add2(whole, make_float2(k1.v[2 * h], k1.v[2 * h + 1]));
+                    if (SPANLOOP)
+                        for (int i = 2; i < ibn - ibl; ++i) {
+                            const KV ki = kb_rect[i];
+                            whole = add2(whole, make_float2(ki.v[2 * h], ki.v[2 * h + 1]));
+                        }
+                    const float2 o2 = add2(whole, sub2(Pn, P));
+                    o[2 * h] = o2.x;
+                    o[2 * h + 1] = o2.y;
                 }
+            } else {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    if (col_ok && g < nlive && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o[g]);
-                    nzb[g] |= nz_bits(o[g]);       // lanes / frames that do not count are masked
-                }                                  // once, after the last row
+                    const T P = steffen_partial_flux(kr.v[g], ka.v[g], kc.v[g], bd.tau);
+                    const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
+                    T whole = has1 ? kr.v[g] : T(0);
+                    if (has2) whole += k1.v[g];
+                    if (SPANLOOP)
+                        for (int i = 2; i < ibn - ibl; ++i) whole += kb_rect[i].v[g];
+                    o[g] = whole + (Pn - P);
+                }
             }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (col_ok && g < nlive && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o[g]);
+                nzb[g] |= nz_bits(o[g]);       // lanes / frames that do not count are masked
+            }                                  // once, after the last row
             orow += p.nout;
         };
 
         // ---- A, C (row y)
         auto phase_ac = [&](int y) {
-            if (PS == 1 || awarp) {
-                // this pixel's record: K*K weights, packed source column, ring slots of the
-                // K source rows
-                T wt[RS];
-                {
-                    using V = typename Vec16<T>::type;
-                    const V *rec = reinterpret_cast<const V *>(tsm + ((y & 1) * PXCAP + ppc) * RS);
+            // this pixel's record: K*K weights, packed source column, ring slots of the
+            // K source rows
+            T wt[RS];
+            {
+                using V = typename Vec16<T>::type;
+                const V *rec = reinterpret_cast<const V *>(tsm + ((y % 3) * PXCAP + ppc) * RS);
 #pragma unroll
-                    for (int i = 0; i < RS / VN; ++i)
-                        *reinterpret_cast<V *>(wt + i * VN) = rec[i];
-                }
-                const int32_t pk = *reinterpret_cast<const int32_t *>(wt + K * K);
-                const uint32_t slots = *reinterpret_cast<const uint32_t *>(wt + K * K + 1);
+                for (int i = 0; i < RS / VN; ++i)
+                    *reinterpret_cast<V *>(wt + i * VN) = rec[i];
+            }
+            const int32_t pk = *reinterpret_cast<const int32_t *>(wt + K * K);
+            const uint32_t slots = *reinterpret_cast<const uint32_t *>(wt + K * K + 1);
 
-                // ---- A (row y): rectified flux of this pixel column, GA frames
-                T rect[GA];
-                {
-                    const int fc = base_col(pk) + wb;
-                    const T *rowp[K];
+            // ---- A (row y): rectified flux of this pixel column, G frames
+            T rect[G];
+            {
+                const int fc = base_col(pk) + wb;
+                const T *rowp[K];
+#pragma unroll
+                for (int a = 0; a < K; ++a)
+                    rowp[a] = win + ((slots >> (8 * a)) & 0xffu) * WIN_PITCH + fc;
+                if constexpr (PACKED) {
+                    float2 acc[G / 2];
+#pragma unroll
+                    for (int h = 0; h < G / 2; ++h) acc[h] = make_float2(0.0f, 0.0f);
 #pragma unroll
                     for (int a = 0; a < K; ++a)
-                        rowp[a] = winsub + ((slots >> (8 * a)) & 0xffu) * WIN_PITCH + fc;
-                    if constexpr (PACKED_A) {
-                        float2 acc[GA / 2];
 #pragma unroll
-                        for (int h = 0; h < GA / 2; ++h) acc[h] = make_float2(0.0f, 0.0f);
+                        for (int b = 0; b < K; ++b) {
+                            const float2 wgt = dup2(wt[a * K + b]);
 #pragma unroll
-                        for (int a = 0; a < K; ++a)
-#pragma unroll
-                            for (int b = 0; b < K; ++b) {
-                                const float2 wgt = dup2(wt[a * K + b]);
-#pragma unroll
-                                for (int h = 0; h < GA / 2; ++h)
-                                    acc[h] = fma2(wgt,
-                                                  make_float2(rowp[a][(2 * h) * WSZ + b],
-                                                              rowp[a][(2 * h + 1) * WSZ + b]),
-                                                  acc[h]);
-                            }
-#pragma unroll
-                        for (int h = 0; h < GA / 2; ++h) {
-                            rect[2 * h] = px_ok ? acc[h].x : 0.0f;
-                            rect[2 * h + 1] = px_ok ? acc[h].y : 0.0f;
+                            for (int h = 0; h < G / 2; ++h)
+                                acc[h] = fma2(wgt,
+                                              make_float2(rowp[a][(2 * h) * WSZ + b],
+                                                          rowp[a][(2 * h + 1) * WSZ + b]),
+                                              acc[h]);
                         }
-                    } else {
 #pragma unroll
-                        for (int g = 0; g < GA; ++g) {
-                            T acc = T(0);
-#pragma unroll
-                            for (int a = 0; a < K; ++a)
-#pragma unroll
-                                for (int b = 0; b < K; ++b)
-                                    acc = fma(wt[a * K + b], rowp[a][g * WSZ + b], acc);
-                            rect[g] = px_ok ? acc : T(0);
-                        }
-                    }
-                }
-
-                // ---- C (row y): Steffen-limited slopes at both ends of the pixel, scaled
-                //      by the pixel width (flux units).  qm = 0 / qp = 0 in the table give
-                //      the zero slopes at the two ends of the spectrum.
-                KA vr, va, vb;
-                if constexpr (PACKED_A) {
-                    // steffen_slope with everything doubled (exact): 2*min(|sl|,|sr|,|p|/2) =
-                    // min(|2 sl|, |2 sr|, |p|); the sign test folds into the minimum by
-                    // giving 2 sl the sign it has relative to sr.
-#pragma unroll
-                    for (int h = 0; h < GA / 2; ++h) {
-                        const float2 r = make_float2(rect[2 * h], rect[2 * h + 1]);
-                        const float2 l = make_float2(__shfl_up_sync(0xffffffffu, r.x, 1),
-                                                     __shfl_up_sync(0xffffffffu, r.y, 1));
-                        const float2 cl2 = mul2(l, dup2(qm2));
-                        const float2 rr = add2(r, r);
-                        const float2 pq = fma2(dup2(hr0), sub2(cl2, rr), r);
-                        float ya[2];
-                        const float clv[2] = {cl2.x, cl2.y}, rv[2] = {r.x, r.y}, rrv[2] = {rr.x, rr.y},
-                                    pv[2] = {pq.x, pq.y};
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const unsigned sgn = __float_as_uint(rv[e]) & 0x80000000u;
-                            const float x = __uint_as_float(__float_as_uint(clv[e]) ^ sgn);
-                            const float m = fmaxf(fminf(fminf(x, fabsf(rrv[e])), fabsf(pv[e])), 0.0f);
-                            ya[e] = __uint_as_float(__float_as_uint(m) | sgn);
-                        }
-                        const float2 yb = mul2(make_float2(__shfl_down_sync(0xffffffffu, ya[0], 1),
-                                                           __shfl_down_sync(0xffffffffu, ya[1], 1)),
-                                               dup2(pg.qp));
-                        vr.v[2 * h] = r.x, vr.v[2 * h + 1] = r.y;
-                        va.v[2 * h] = ya[0], va.v[2 * h + 1] = ya[1];
-                        vb.v[2 * h] = yb.x, vb.v[2 * h + 1] = yb.y;
+                    for (int h = 0; h < G / 2; ++h) {
+                        rect[2 * h] = px_ok ? acc[h].x : 0.0f;
+                        rect[2 * h + 1] = px_ok ? acc[h].y : 0.0f;
                     }
                 } else {
 #pragma unroll
-                    for (int g = 0; g < GA; ++g) {
-                        // slope at the left knot from this pixel and its left neighbour; the
-                        // slope at the right knot is the right neighbour's left-knot slope
-                        // rescaled by the ratio of the pixel widths (one limiter per pixel)
-                        const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
-                        const T ya = steffen_slope(cl, rect[g], pg.r0);
-                        vr.v[g] = rect[g];
-                        va.v[g] = ya;
-                        vb.v[g] = __shfl_down_sync(0xffffffffu, ya, 1) * pg.qp;
+                    for (int g = 0; g < G; ++g) {
+                        T acc = T(0);
+#pragma unroll
+                        for (int a = 0; a < K; ++a)
+#pragma unroll
+                            for (int b = 0; b < K; ++b)
+                                acc = fma(wt[a * K + b], rowp[a][g * WSZ + b], acc);
+                        rect[g] = px_ok ? acc : T(0);
                     }
                 }
-                if (knot_ok) {
-                    // knot (y & 1, pp), components sub*GA .. sub*GA+GA-1 of its frame vector
-                    const int e = ((y & 1) * KNOT_PITCH + pp) * PS + sub;
-                    reinterpret_cast<KA *>(rectS)[e] = vr;
-                    reinterpret_cast<KA *>(yaS)[e] = va;
-                    reinterpret_cast<KA *>(ybS)[e] = vb;
+            }
+
+            // ---- C (row y): Steffen-limited slopes at both ends of the pixel, scaled
+            //      by the pixel width (flux units).  qm = 0 / qp = 0 in the table give
+            //      the zero slopes at the two ends of the spectrum.
+            KV vr, va, vb;
+            if constexpr (PACKED) {
+                // steffen_slope with everything doubled (exact): 2*min(|sl|,|sr|,|p|/2) =
+                // min(|2 sl|, |2 sr|, |p|); the sign test folds into the minimum by
+                // giving 2 sl the sign it has relative to sr.
+#pragma unroll
+                for (int h = 0; h < G / 2; ++h) {
+                    const float2 r = make_float2(rect[2 * h], rect[2 * h + 1]);
+                    const float2 l = make_float2(__shfl_up_sync(0xffffffffu, r.x, 1),
+                                                 __shfl_up_sync(0xffffffffu, r.y, 1));
+                    const float2 cl2 = mul2(l, dup2(qm2));
+                    const float2 rr = add2(r, r);
+                    const float2 pq = fma2(dup2(hr0), sub2(cl2, rr), r);
+                    float ya[2];
+                    const float clv[2] = {cl2.x, cl2.y}, rv[2] = {r.x, r.y}, rrv[2] = {rr.x, rr.y},
+                                pv[2] = {pq.x, pq.y};
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const unsigned sgn = __float_as_uint(rv[e]) & 0x80000000u;
+                        const float x = __uint_as_float(__float_as_uint(clv[e]) ^ sgn);
+                        const float m = fmaxf(fminf(fminf(x, fabsf(rrv[e])), fabsf(pv[e])), 0.0f);
+                        ya[e] = __uint_as_float(__float_as_uint(m) | sgn);
+                    }
+                    const float2 yb = mul2(make_float2(__shfl_down_sync(0xffffffffu, ya[0], 1),
+                                                       __shfl_down_sync(0xffffffffu, ya[1], 1)),
+                                           dup2(pg.qp));
+                    vr.v[2 * h] = r.x, vr.v[2 * h + 1] = r.y;
+                    va.v[2 * h] = ya[0], va.v[2 * h + 1] = ya[1];
+                    vb.v[2 * h] = yb.x, vb.v[2 * h + 1] = yb.y;
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    // slope at the left knot from this pixel and its left neighbour; the
+                    // slope at the right knot is the right neighbour's left-knot slope
+                    // rescaled by the ratio of the pixel widths (one limiter per pixel)
+                    const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
+                    const T ya = steffen_slope(cl, rect[g], pg.r0);
+                    vr.v[g] = rect[g];
+                    va.v[g] = ya;
+                    vb.v[g] = __shfl_down_sync(0xffffffffu, ya, 1) * pg.qp;
                 }
             }
+            // the warp's own knot rows (lanes 0 and 31 hold incomplete slopes, never read)
+            KV *kdst = reinterpret_cast<KV *>(knots) + (y & 1) * (3 * 32) + lane;
+            kdst[0] = vr;
+            kdst[32] = va;
+            kdst[64] = vb;
         };
 
-        // Software-pipelined row loop, ONE block barrier per rectified row: iteration y
-        // evaluates the borders of row y-1 (phase D, reading knot buffer (y-1)&1) and the
-        // flux and slopes of row y (phases A and C, writing knot buffer y&1).  The two are
-        // independent instruction streams in one basic block, which the scheduler interleaves.
-        row_top(0);
-        phase_ac(0);
+        // Row loop without block barriers.  A warp waits for the data of row y, evaluates
+        // the borders of row y-1 from its own knots (phase D) and the flux and slopes of
+        // row y (phases A, C: independent instruction streams in one basic block), then
+        // reports row y done; warps may drift apart by up to two rows.
+        auto row_done = [&](int y) {
+            __syncwarp();
+            int last = 0;
+            if (lane == 0) {
+                last = atomicAdd(&done_cnt[rowseq % 3], 1) == NWARPS - 1;
+                if (last) done_cnt[rowseq % 3] = 0;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                if (y + 3 < NROWS) copy_table_row(rowseq + 3, y + 3);
+                if (y + 3 < NROWS)
+                    copy_window_rows(rowseq + 3, span_hi(tile.span[y + 2]), span_hi(tile.span[y + 3]));
+            }
+            ++rowseq;
+        };
+        mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);              // rows + table landed
+        if (wwarp) phase_ac(0);
+        row_done(0);
 #pragma unroll 1
         for (int y = 1; y < NROWS; ++y) {
-            row_top(y);
-            phase_d(y - 1);
-            phase_ac(y);
+            mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);
+            if (wwarp) {
+                phase_d(y - 1);
+                phase_ac(y);
+            }
+            row_done(y);
         }
-        row_top(NROWS);
-        phase_d(NROWS - 1);
+        if (wwarp) phase_d(NROWS - 1);
 
         // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
-        if (p.jmm != nullptr && dwarp) {
+        if (p.jmm != nullptr && wwarp) {
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 const bool nz = col_ok && g < nlive && nzb[g] != 0;
@@ -982,7 +975,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && PS == 2) ? 3 : 2)
         if (wnext >= nwork) break;
         w = wnext;
         cp_async_wait_all();
-        __syncthreads();          // next descriptor landed; window and knots are free again
+        __syncthreads();          // next descriptor landed; window and table slots are free
     }
 }
 
@@ -1012,7 +1005,6 @@ struct emirwv_plan {
     int tile_k = 0, tile_rows = 0;
     int wrows_max = 0, wcols_max = 0, npx_max = 0, max_span = 0;
     int tune_G = 0;
-    int ps = 1;                  // frame subgroups of phases A, C the tiles are sized for
     int num_sms = 148;
     int64_t table_bytes = 0;
 
@@ -1041,17 +1033,17 @@ int env_int(const char *name, int fallback) {
 
 // launch configuration for a given number of frames per CTA
 struct LaunchCfg {
-    int G, PS, threads;
+    int G, threads;
     size_t smem;
 };
 
 // shared memory of the hot kernel:
-//   [3 tile descriptors][mbarriers][G windows: WIN_ROWS x win_pitch]
-//   [rect | ya | yb: 2 x knot_pitch x G each][2 table rows: px_cap records]
-size_t smem_bytes(const emirwv_plan *pl, int G, int PS) {
+//   [3 tile descriptors][mbarriers, counters][G windows: WIN_ROWS x WIN_PITCH]
+//   [per warp: 2 x (rect | ya | yb) x 32 x G knots][2 table rows: PXCAP records]
+size_t smem_bytes(const emirwv_plan *pl, int G) {
     return 3 * sizeof(Tile) + 64 +
-           (size_t)G * (WIN_ROWS * win_pitch(PS) + 6 * knot_pitch(PS)) * pl->esize +
-           (size_t)2 * px_cap(PS) * rec_size(pl->K) * pl->esize;
+           (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 6 * 32) * pl->esize +
+           (size_t)3 * PXCAP * rec_size(pl->K) * pl->esize;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
@@ -1059,18 +1051,15 @@ LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
     cfg.threads = NTHREADS;
     int G = pl->tune_G > 0 ? pl->tune_G : env_int("EMIRWV_G", pl->esize == 4 ? 4 : 2);
     G = (G >= 4) ? 4 : (G >= 2 ? 2 : 1);
-    while (G > 1 && (G > nframes || smem_bytes(pl, G, 1) > (size_t)SMEM_LIMIT)) G >>= 1;
+    while (G > 1 && (G > nframes || smem_bytes(pl, G) > (size_t)SMEM_LIMIT)) G >>= 1;
     cfg.G = G;
-    // the tiles were sized for pl->ps frame subgroups; a single frame cannot be split
-    // (tiles sized for two subgroups always fit the unsplit kernel as well)
-    cfg.PS = (pl->ps == 2 && G >= 2) ? 2 : 1;
-    cfg.smem = smem_bytes(pl, G, cfg.PS);
+    cfg.smem = smem_bytes(pl, G);
     return cfg;
 }
 
-template <typename T, int K, int G, int PS, bool SPANLOOP>
+template <typename T, int K, int G, bool SPANLOOP>
 int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, cudaStream_t st) {
-    auto kern = k_rectwv<T, K, G, PS, SPANLOOP>;
+    auto kern = k_rectwv<T, K, G, SPANLOOP>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)cfg.smem));
     int per_sm = 0;
@@ -1090,14 +1079,8 @@ int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, c
 template <typename T, int K, int G>
 int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
                cudaStream_t st) {
-    if constexpr (G >= 2) {
-        if (cfg.PS == 2) {
-            if (pl->max_span > 2) return launch_final<T, K, G, 2, true>(pl, rp, cfg, st);
-            return launch_final<T, K, G, 2, false>(pl, rp, cfg, st);
-        }
-    }
-    if (pl->max_span > 2) return launch_final<T, K, G, 1, true>(pl, rp, cfg, st);
-    return launch_final<T, K, G, 1, false>(pl, rp, cfg, st);
+    if (pl->max_span > 2) return launch_final<T, K, G, true>(pl, rp, cfg, st);
+    return launch_final<T, K, G, false>(pl, rp, cfg, st);
 }
 
 template <typename T, int K>
@@ -1289,46 +1272,78 @@ int build_border_tables(emirwv_plan *pl, std::vector<uint8_t> &covered) {
     return upload_tables<double>(pl, h_tau, h_h);
 }
 
-// Work items: (slitlet, block of <= tile_k output columns), all 39 scanned rows.
-// Returns 1 when a tile does not fit the kernel's fixed shared-memory geometry with
-// this tile_k (the caller retries with a narrower block), 0 on success.
-int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int TK) {
+// Work items: (slitlet, run of output columns), all 39 scanned rows.  A live tile is cut
+// into at most NWARPS consecutive pieces, one per warp: at most BW output columns whose
+// borders touch at most WARP_PX rectified pixels.  Columns without wavelength coverage
+// (and missing slitlets) become wide runs of zeros for the fill kernel.
+// Returns 1 when a tile does not fit the kernel's fixed shared-memory geometry with this
+// BW (the caller retries with narrower pieces), 0 on success.
+int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int BW) {
     const emirwv_plan_desc &d = pl->desc;
     const int nout = pl->nout, NB = pl->NB, K = pl->K;
     std::vector<Tile> live, dead;
-    int wcols_max = 4, span_max = 1, npx_max = 1;
+    int wcols_max = 4, span_max = 1, npx_max = 1, nk_max = 0;
     for (int s = 0; s < pl->nsl; ++s) {
         const emirwv_slitlet_desc &sl = d.slitlet[s];
         const int nchan = sl.valid ? sl.bb_nc2_orig - sl.bb_nc1_orig + 1 : 0;
-        for (int k0 = 0; k0 < nout; k0 += TK) {
+        const uint8_t *cov = covered.data() + (size_t)s * NB;
+        const int32_t *idx = pl->h_idx.data() + (size_t)s * NB;
+        // output column k carries flux when one of its borders lies inside the spectrum or
+        // the spectrum lies between them
+        auto is_live = [&](int k) {
+            return sl.valid && (cov[k] != 0 || cov[k + 1] != 0 || idx[k] != idx[k + 1]);
+        };
+        // length of the run of dead columns starting at k
+        auto dead_run = [&](int k) {
+            int n = 0;
+            while (k + n < nout && !is_live(k + n)) ++n;
+            return n;
+        };
+        int k0 = 0;
+        while (k0 < nout) {
             Tile t;
             memset(&t, 0, sizeof(t));
             t.slit = s;
             t.k0 = k0;
-            t.nk = std::min(TK, nout - k0);
             t.nchan = nchan;
-            bool any = false;
-            if (sl.valid)
-                for (int k = k0; k <= k0 + t.nk; ++k) any |= covered[(size_t)s * NB + k] != 0;
-            // a pixel whose two borders lie on either side of the spectrum also counts
-            if (sl.valid && !any)
-                any = pl->h_idx[(size_t)s * NB + k0] != pl->h_idx[(size_t)s * NB + k0 + t.nk];
-            if (!any) {
+            int run = dead_run(k0);
+            if (k0 + run < nout) run &= ~3;        // keep the next tile 16-byte aligned
+            if (run >= 32 || k0 + run == nout) {
                 t.empty = 1;
-                // neighbouring empty tiles become one wide run of zeros
-                if (!dead.empty() && dead.back().slit == s &&
-                    dead.back().k0 + dead.back().nk == k0 && dead.back().nk + t.nk <= 1024)
-                    dead.back().nk += t.nk;
-                else
-                    dead.push_back(t);
+                t.nk = std::min(run, 1024);
+                dead.push_back(t);
+                k0 += t.nk;
                 continue;
             }
-            const int ilo = pl->h_idx[(size_t)s * NB + k0];
-            const int ihi = pl->h_idx[(size_t)s * NB + k0 + t.nk];
+            // live tile: one piece per warp
+            int k = k0, nw = 0;
+            t.kw[0] = 0;
+            while (nw < NWARPS && k < nout) {
+                if (nw > 0 && dead_run(k) >= 32) break;        // a fill run starts here
+                int kend = std::min(k + BW, nout);
+                while (kend > k + 1 && idx[kend] - idx[k] + 1 > WARP_PX) --kend;
+                if (idx[kend] - idx[k] + 1 > WARP_PX) return 1;   // one column spans too much
+                k = kend;
+                t.kw[++nw] = (uint8_t)(k - k0);
+            }
+            if (k < nout && (k & 3)) {
+                // end on a multiple of 4 so that a following fill run stays vectorised:
+                // lengthen the last piece if it stays within its limits, else shorten it
+                const int kprev = k0 + t.kw[nw - 1];
+                const int up = std::min((k + 3) & ~3, nout), down = k & ~3;
+                if (up - kprev <= WARP_BORDERS && idx[up] - idx[kprev] + 1 <= WARP_PX)
+                    k = up;
+                else if (down > kprev)
+                    k = down;
+                t.kw[nw] = (uint8_t)(k - k0);
+            }
+            for (int wq = nw + 1; wq <= NWARPS; ++wq) t.kw[wq] = t.kw[nw];
+            t.nk = k - k0;
+            const int ilo = idx[k0], ihi = idx[k0 + t.nk];
             t.jlo = std::max(0, ilo - 1);
             const int jhi = std::min(nchan - 1, ihi + 1);
             t.npx = jhi - t.jlo + 1;
-            if (t.npx > px_cap(pl->ps)) return 1;
+            if (t.npx > PXCAP) return 1;
             int c0 = INT_MAX, c1 = INT_MIN;
             int rlo[NROWS], rhi[NROWS];
             for (int y = 0; y < NROWS; ++y) {
@@ -1355,17 +1370,19 @@ int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int TK
             c0 = (int)(std::floor(c0 / 4.0) * 4.0);        // 16-byte aligned window rows
             t.c0 = c0;
             t.wcols = ((c1 - c0 + 1) + 3) & ~3;
-            if (t.wcols > win_pitch(pl->ps) || span_max > WIN_ROWS) return 1;
+            if (t.wcols > WIN_PITCH || span_max > WIN_ROWS) return 1;
             wcols_max = std::max(wcols_max, t.wcols);
             npx_max = std::max(npx_max, t.npx);
+            nk_max = std::max(nk_max, t.nk);
             live.push_back(t);
+            k0 += t.nk;
         }
     }
     pl->ntiles_empty = (int)dead.size();
     pl->h_tiles = live;
     pl->h_tiles.insert(pl->h_tiles.end(), dead.begin(), dead.end());
     pl->ntiles = (int)pl->h_tiles.size();
-    pl->tile_k = TK;
+    pl->tile_k = nk_max;
     pl->wrows_max = span_max;
     pl->wcols_max = wcols_max;
     pl->npx_max = npx_max;
@@ -1373,15 +1390,14 @@ int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int TK
 }
 
 int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
-    // widest block (a multiple of 4 columns keeps the zero-fill stores vectorised) whose
-    // source pixels fit the CTA
-    int TK = std::max(32, std::min(pl->tile_k, TILE_K_MAX)) / 4 * 4;
-    for (; TK >= 32; TK -= 4)
-        if (try_build_tiles(pl, covered, TK) == 0) break;
-    if (TK < 32)
+    // widest pieces whose source window fits the CTA
+    int BW = std::max(4, std::min(pl->tile_k / NWARPS, WARP_BORDERS));
+    for (; BW >= 4; BW -= (BW > 8 ? 4 : 1))
+        if (try_build_tiles(pl, covered, BW) == 0) break;
+    if (BW < 4)
         return fail(EMIRWV_E_LIMIT,
                     "distortion too strong: the source window of a 32-column block does not fit "
-                    "(%d rows x %d columns available)", WIN_ROWS, win_pitch(pl->ps));
+                    "(%d rows x %d columns available)", WIN_ROWS, WIN_PITCH);
     if (pl->ntiles_empty > 65535) return fail(EMIRWV_E_LIMIT, "too many tiles");
     CUDA_TRY(cudaMalloc(&pl->d_tiles, pl->h_tiles.size() * sizeof(Tile)));
     CUDA_TRY(cudaMemcpy(pl->d_tiles, pl->h_tiles.data(), pl->h_tiles.size() * sizeof(Tile),
@@ -1524,18 +1540,6 @@ int build_plan(emirwv_plan *pl) {
     std::vector<uint8_t> covered;
     int rc = build_border_tables(pl, covered);
     if (rc) return rc;
-    {
-        // Output columns inside the wavelength coverage per source pixel.  Well above 1 the
-        // border phase needs more threads than the pixel phases, and the pixel phases split
-        // the frames of an item over two groups of warps instead.
-        double ncov = 0, npix = 0;
-        for (int s = 0; s < pl->nsl; ++s) {
-            if (!d.slitlet[s].valid) continue;
-            for (int k = 0; k < pl->nout; ++k) ncov += covered[(size_t)s * pl->NB + k] != 0;
-            npix += d.slitlet[s].bb_nc2_orig - d.slitlet[s].bb_nc1_orig + 1;
-        }
-        pl->ps = env_int("EMIRWV_PS", (npix > 0 && ncov > 1.5 * npix) ? 2 : 1) == 2 ? 2 : 1;
-    }
     rc = build_tiles(pl, covered);
     if (rc) return rc;
     if (env_int("EMIRWV_NO_AUX", 0) == 0) {
@@ -1665,7 +1669,6 @@ int emirwv_plan_get_info(const emirwv_plan *pl, emirwv_plan_info *info) {
     info->frames_per_cta = cfg.G;
     info->threads = cfg.threads;
     info->smem_bytes = (int32_t)cfg.smem;
-    info->reserved = cfg.PS;     // frame subgroups of the pixel phases
     info->table_bytes = pl->table_bytes;
     info->in_frame_bytes = (int64_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
     info->out_frame_bytes = (int64_t)pl->nsl * pl->rps * pl->nout * pl->esize;
