@@ -139,7 +139,7 @@ int emirwv_plan_get_info(const emirwv_plan *plan, emirwv_plan_info *info);
 
 /* Launch tuning for subsequent runs (0 keeps the default): frames per CTA
  * (1, 2 or 4).  `threads` is accepted for compatibility: the hot kernel has a fixed
- * CTA size (256 threads). */
+ * CTA size (288 threads: 8 compute warps + 1 copy warp). */
 int emirwv_plan_set_tuning(emirwv_plan *plan, int frames_per_cta, int threads);
 
 /*

@@ -46,8 +46,8 @@ using namespace emirwv;
 constexpr int NROWS = EMIRWV_ROWS_SCANNED;   // 39 rectified rows per slitlet
 constexpr int W = 2048;                      // EMIR_NAXIS1: pitch of per-column tables
 constexpr int MAXK = 4;                      // largest supported footprint
-constexpr int NWARPS = 8;                     // two warps per SM sub-partition and CTA
-constexpr int NTHREADS = 32 * NWARPS;         // threads per CTA of the hot kernel
+constexpr int NWARPS = 8;                     // compute warps: two per SM sub-partition and CTA
+constexpr int NTHREADS = 32 * (NWARPS + 1);   // threads per CTA: compute warps + one copy warp
 constexpr int TILE_K_MAX = 31 * NWARPS;       // output columns per tile (a warp does 31)
 constexpr int WIN_ROWS = 12;                  // rolling source window: rows per frame
 constexpr int RING_BIAS = 12 * 1024;          // makes (row + bias) % WIN_ROWS non-negative
@@ -402,6 +402,9 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned done;
     do {
@@ -585,7 +588,7 @@ __global__ void __launch_bounds__(256) k_zero_fill(const RunParams<T> p, int fir
 //                [rect | ya | yb : G x KNOT_PITCH each]
 // ---------------------------------------------------------------------------------
 template <typename T, int K, int G, bool SPANLOOP>
-__global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && G <= 2) ? 3 : 2)
+__global__ void __launch_bounds__(NTHREADS, 2)
     k_rectwv(const RunParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int WSZ = WIN_ROWS * WIN_PITCH;                  // one frame's window
@@ -593,15 +596,15 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && G <= 2) ? 3 : 2)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp == NWARPS;          // the copy warp computes nothing
     const size_t frame_out = (size_t)p.nrows_out * p.nout;
     const int nwork = p.nlive_tiles * p.ngroups;
 
     Tile *ring = reinterpret_cast<Tile *>(smem_raw);                       // [3]
-    // mbarriers [0..2]: one per rectified row in flight; then 3 arrival counters
+    // mbarriers: "full" [0..2] and "done" [3..5], one pair per rectified row in flight
     const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
-    int *done_cnt = reinterpret_cast<int *>(smem_raw + 3 * sizeof(Tile) + 32);   // [3]
     T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + 64);      // [G][WSZ]
-    T *knots = win + G * WSZ + warp * KNOT_WARP;           // this warp: [2][rect|ya|yb][32][G]
+    T *knots = win + G * WSZ + min(warp, NWARPS - 1) * KNOT_WARP;   // this warp: [2][rect|ya|yb][32][G]
     constexpr int RS = rec_size(K);
     T *tsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [3][PXCAP][RS]
     // float32 with an even number of frames: two frames per arithmetic instruction
@@ -623,8 +626,8 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && G <= 2) ? 3 : 2)
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            mbar_init(bars + 8 * i, 2);                 // rows part + table part of a row
-            done_cnt[i] = 0;
+            mbar_init(bars + 8 * i, 2);                 // "full": rows part + table part of a row
+            mbar_init(bars + 24 + 8 * i, NWARPS);       // "done": every compute warp is through
         }
         mbar_fence_init();
     }
@@ -659,8 +662,9 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && G <= 2) ? 3 : 2)
         // The warp owns the borders kw[warp] .. kw[warp+1]-1 of the tile (at most 31) and
         // every rectified pixel they touch (at most 30, lanes 1..30; lanes 0 and 31 hold the
         // neighbours the slope limiter needs), so a row needs no exchange between warps.
-        const int kw0 = tile.kw[warp], nb = tile.kw[warp + 1] - kw0;
-        const bool wwarp = nb > 0;                             // the warp has work at all
+        const int wc = min(warp, NWARPS - 1);
+        const int kw0 = tile.kw[wc], nb = tile.kw[wc + 1] - kw0;
+        const bool wwarp = nb > 0 && !producer;                // the warp has work at all
         const int q = kw0 + min(lane, nb);                     // border, tile relative
         const Border<T> bd = ldg_struct(p.border + (size_t)s * p.NB + k0 + q);
         const int ibl = bd.idx - tile.jlo;                     // source pixel, tile relative
@@ -739,10 +743,10 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && G <= 2) ? 3 : 2)
             }
         };
 
-        // rows 0..2 and their table rows are requested up front by warp 0; afterwards the
-        // last warp to finish row y requests the table row and the source rows of row y+3
-        // (nobody reads the slots they overwrite any more)
-        if (warp == 0) {
+        // rows 0..2 and their table rows are requested up front; once every compute warp
+        // is through row y the copy warp requests the table row and the source rows of row
+        // y+3 (nobody reads the slots they overwrite any more)
+        if (producer) {
             copy_window_rows(rowseq, span_lo(tile.span[0]) - 1, span_hi(tile.span[0]));
             copy_table_row(rowseq, 0);
             copy_window_rows(rowseq + 1, span_hi(tile.span[0]), span_hi(tile.span[1]));
@@ -928,32 +932,34 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 4 && G <= 2) ? 3 : 2)
         // the borders of row y-1 from its own knots (phase D) and the flux and slopes of
         // row y (phases A, C: independent instruction streams in one basic block), then
         // reports row y done; warps may drift apart by up to two rows.
-        auto row_done = [&](int y) {
-            __syncwarp();
-            int last = 0;
-            if (lane == 0) {
-                last = atomicAdd(&done_cnt[rowseq % 3], 1) == NWARPS - 1;
-                if (last) done_cnt[rowseq % 3] = 0;
-            }
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-                if (y + 3 < NROWS) copy_table_row(rowseq + 3, y + 3);
-                if (y + 3 < NROWS)
-                    copy_window_rows(rowseq + 3, span_hi(tile.span[y + 2]), span_hi(tile.span[y + 3]));
-            }
-            ++rowseq;
-        };
-        mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);              // rows + table landed
-        if (wwarp) phase_ac(0);
-        row_done(0);
+        if (producer) {
 #pragma unroll 1
-        for (int y = 1; y < NROWS; ++y) {
-            mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);
-            if (wwarp) {
-                phase_d(y - 1);
-                phase_ac(y);
+            for (int y = 0; y < NROWS; ++y) {
+                mbar_wait(bars + 24 + 8 * (rowseq % 3), (rowseq / 3) & 1);  // row y is done
+                if (y + 3 < NROWS) {
+                    copy_table_row(rowseq + 3, y + 3);
+                    copy_window_rows(rowseq + 3, span_hi(tile.span[y + 2]), span_hi(tile.span[y + 3]));
+                }
+                ++rowseq;
             }
-            row_done(y);
+        } else {
+            auto row_done = [&]() {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + 24 + 8 * (rowseq % 3));
+                ++rowseq;
+            };
+            mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);          // rows + table landed
+            if (wwarp) phase_ac(0);
+            row_done();
+#pragma unroll 1
+            for (int y = 1; y < NROWS; ++y) {
+                mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);
+                if (wwarp) {
+                    phase_d(y - 1);
+                    phase_ac(y);
+                }
+                row_done();
+            }
         }
         if (wwarp) phase_d(NROWS - 1);
 
