@@ -6,15 +6,16 @@
 //   plan  (once per RectWaveCoeff, float64, on the GPU + a little host code)
 //     k_extent / k_build_geometry : 2-D polynomial map of every output pixel
 //         (its centre, or its four corners) and the exact overlap areas with the
-//         source pixels  ->  frame-independent tables  base[s][y][j], w[s][y][tap][j]
+//         source pixels  ->  frame-independent records  tab[s][y][j] = {w[K*K], col, slots}
 //     build_border_tables (host)  : for every border of the linear wavelength grid
 //         the source interval it falls in and the fractional position inside it
-//     build_tiles (host)          : work items (slitlet, row block, column block)
-//         with the source window each one needs
+//     build_tiles (host)          : work items (slitlet, run of output columns cut into one
+//         piece per warp) with the source window each one needs
 //
 //   run   (per batch of frames; one fused kernel, nothing intermediate touches HBM)
-//     k_rectwv<T,K,G>: stage the source window of G frames in shared memory, then
-//       every warp owns whole rectified rows of the tile:
+//     k_rectwv<T,K,G>: a copy warp streams the source window of G frames and the table
+//       records into shared memory (TMA bulk copies, mbarriers); every compute warp owns a
+//       piece of the tile and marches down its 39 rows:
 //         A: rectified flux = K*K weighted gather            (kernel 1 of the spec)
 //         C: Steffen-limited end slopes of every source pixel (kernel 2)
 //         D: cumulative-flux difference at the output borders (kernel 2), coalesced
@@ -570,22 +571,24 @@ __global__ void __launch_bounds__(256) k_zero_fill(const RunParams<T> p, int fir
 // group fastest so that CTAs running at the same time share the tile's tables in L2.
 //
 // Inside an item the CTA marches down the 39 scanned rows of the slitlet.  Every
-// thread keeps, for the whole item, ONE rectified pixel column (phases A and C) and
-// ONE border of the output grid (phase D), so the per-column tables (pixel widths,
-// border positions) sit in registers and only the per-row weights are loaded, one
-// row ahead of their use.  Per row:
-//   A  rectified flux of G frames: K*K weighted gather from the rolling window
-//   C  Steffen-limited end slopes from the neighbours' flux (warp shuffles: a warp
-//      covers 32 pixels and produces 30, so no shared-memory round trip)
-//   -- barrier --
-//   D  cumulative-flux difference at the thread's border and the next one (shuffle),
-//      store, non-zero flag
-//   -- barrier (also: next row's source rows have landed) --
-// The source window is a ring of WIN_ROWS rows per frame; the few new source rows
-// of the next rectified row are copied with cp.async while the current one runs.
+// compute thread keeps, for the whole item, ONE rectified pixel column (phases A and C)
+// and ONE border of the output grid (phase D), so the per-column tables (pixel widths,
+// border positions) sit in registers and only the per-row table records are loaded.
+// A warp owns the borders of its piece of the tile and every pixel they touch, so the
+// rows need no exchange between warps and no block barrier.  Per row and warp:
+//   wait   full[y]: the source rows and the table row of row y have landed (TMA)
+//   D      (row y-1) cumulative-flux difference at the thread's border and the next one
+//          (shuffle), store, non-zero flag -- from the warp's own knot rows
+//   A      rectified flux of G frames: K*K weighted gather from the rolling window
+//   C      Steffen-limited end slopes from the neighbours' flux (warp shuffles: a warp
+//          covers 32 pixels and produces 30), written to the warp's knot rows
+//   arrive done[y]
+// The copy warp waits for done[y] (all compute warps) and requests the table row and
+// the new source rows of row y+3 into the slots row y has just released.
+// The source window is a ring of WIN_ROWS rows per frame.
 //
-// Shared memory: [tile descriptor ring: 3][G windows: WIN_ROWS x WIN_PITCH]
-//                [rect | ya | yb : G x KNOT_PITCH each]
+// Shared memory: [tile descriptor ring: 3][mbarriers][G windows: WIN_ROWS x WIN_PITCH]
+//                [per warp: 2 x (rect | ya | yb) x 32 pixels x G][3 table rows]
 // ---------------------------------------------------------------------------------
 template <typename T, int K, int G, bool SPANLOOP>
 __global__ void __launch_bounds__(NTHREADS, 2)
