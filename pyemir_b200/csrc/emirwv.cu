@@ -53,7 +53,8 @@ constexpr int TILE_K_MAX = 31 * NWARPS;       // output columns per tile (a warp
 constexpr int WIN_ROWS = 12;                  // rolling source window: rows per frame
 constexpr int RING_BIAS = 12 * 1024;          // makes (row + bias) % WIN_ROWS non-negative
 constexpr int PXCAP = 30 * NWARPS;            // rectified columns a CTA can stage (240)
-constexpr int WIN_PITCH = PXCAP + 24;         // source window columns, per frame
+constexpr int WIN_PITCH = 288;                // source window columns, per frame: a multiple of
+                                              // 32 banks, so lanes on two ring rows never collide
 constexpr int WARP_PX = 30;                   // rectified columns a warp owns
 constexpr int WARP_BORDERS = 31;              // output columns a warp evaluates
 constexpr int PREFETCH = 2;                   // rectified rows between a copy and its use
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     k_rectwv(const RunParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int WSZ = WIN_ROWS * WIN_PITCH;                  // one frame's window
-    constexpr int KNOT_WARP = 2 * 3 * 32 * G;                  // knot elements of one warp
+    constexpr int KNOT_WARP = 2 * 2 * 32 * G;                  // knot elements of one warp
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     // mbarriers: "full" [0..2] and "done" [3..5], one pair per rectified row in flight
     const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
     T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + 64);      // [G][WSZ]
-    T *knots = win + G * WSZ + min(warp, NWARPS - 1) * KNOT_WARP;   // this warp: [2][rect|ya|yb][32][G]
+    T *knots = win + G * WSZ + min(warp, NWARPS - 1) * KNOT_WARP;   // this warp: [2][rect|ya][32][G]
     constexpr int RS = rec_size(K);
     T *tsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [3][PXCAP][RS]
     // float32 with an even number of frames: two frames per arithmetic instruction
@@ -683,6 +684,9 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         pg.qm = pg.qp = pg.r0 = pg.r1 = T(0);
         if (px_ok) pg = ldg_struct(p.pix + (size_t)s * W + tile.jlo + pp);
         const float qm2 = (float)(pg.qm + pg.qm), hr0 = (float)(T(0.5) * pg.r0);   // packed path
+        // width ratio that turns the next pixel's left-knot slope into this border's pixel's
+        // right-knot slope (the table holds 0 at the red end of the spectrum)
+        const T qpb = __ldg(&p.pix[(size_t)s * W + bd.idx].qp);
         unsigned nzb[G];                                       // OR of the value bits seen
 #pragma unroll
         for (int g = 0; g < G; ++g) nzb[g] = 0;
@@ -767,10 +771,12 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // ---- D (row yr): cumulative flux at this thread's border and at the next one,
         //      difference = output pixel; store; remember non-zero values
         auto phase_d = [&](int yr) {
-            const KV *kbase = reinterpret_cast<const KV *>(knots) + (yr & 1) * (3 * 32) + kl;
-            const KV *kb_rect = kbase, *kb_ya = kbase + 32, *kb_yb = kbase + 64;
+            const KV *kbase = reinterpret_cast<const KV *>(knots) + (yr & 1) * (2 * 32) + kl;
+            const KV *kb_rect = kbase, *kb_ya = kbase + 32;
             const bool store = yr < p.rps;
-            const KV kr = kb_rect[0], ka = kb_ya[0], kc = kb_yb[0];
+            // flux and left-knot slope of the border's pixel; its right-knot slope is the
+            // next pixel's left-knot slope rescaled by the ratio of the pixel widths
+            const KV kr = kb_rect[0], ka = kb_ya[0], kn = kb_ya[1];
             KV k1;
 #pragma unroll
             for (int g = 0; g < G; ++g) k1.v[g] = T(0);
@@ -782,7 +788,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                 for (int h = 0; h < G / 2; ++h) {
                     const float2 r = make_float2(kr.v[2 * h], kr.v[2 * h + 1]);
                     const float2 a = make_float2(ka.v[2 * h], ka.v[2 * h + 1]);
-                    const float2 c = make_float2(kc.v[2 * h], kc.v[2 * h + 1]);
+                    const float2 c = mul2(make_float2(kn.v[2 * h], kn.v[2 * h + 1]), dup2(qpb));
                     // steffen_partial_flux, two frames at a time
                     const float2 A = fma2(r, dup2(-2.0f), add2(a, c));
                     const float2 B = sub2(sub2(r, a), A);
@@ -803,7 +809,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             } else {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const T P = steffen_partial_flux(kr.v[g], ka.v[g], kc.v[g], bd.tau);
+                    const T P = steffen_partial_flux(kr.v[g], ka.v[g], kn.v[g] * qpb, bd.tau);
                     const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
                     T whole = has1 ? kr.v[g] : T(0);
                     if (has2) whole += k1.v[g];
@@ -881,7 +887,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             // ---- C (row y): Steffen-limited slopes at both ends of the pixel, scaled
             //      by the pixel width (flux units).  qm = 0 / qp = 0 in the table give
             //      the zero slopes at the two ends of the spectrum.
-            KV vr, va, vb;
+            KV vr, va;
             if constexpr (PACKED) {
                 // steffen_slope with everything doubled (exact): 2*min(|sl|,|sr|,|p|/2) =
                 // min(|2 sl|, |2 sr|, |p|); the sign test folds into the minimum by
@@ -904,31 +910,23 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                         const float m = fmaxf(fminf(fminf(x, fabsf(rrv[e])), fabsf(pv[e])), 0.0f);
                         ya[e] = __uint_as_float(__float_as_uint(m) | sgn);
                     }
-                    const float2 yb = mul2(make_float2(__shfl_down_sync(0xffffffffu, ya[0], 1),
-                                                       __shfl_down_sync(0xffffffffu, ya[1], 1)),
-                                           dup2(pg.qp));
                     vr.v[2 * h] = r.x, vr.v[2 * h + 1] = r.y;
                     va.v[2 * h] = ya[0], va.v[2 * h + 1] = ya[1];
-                    vb.v[2 * h] = yb.x, vb.v[2 * h + 1] = yb.y;
                 }
             } else {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    // slope at the left knot from this pixel and its left neighbour; the
-                    // slope at the right knot is the right neighbour's left-knot slope
-                    // rescaled by the ratio of the pixel widths (one limiter per pixel)
+                    // slope at the left knot from this pixel and its left neighbour (one
+                    // limiter per pixel)
                     const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
-                    const T ya = steffen_slope(cl, rect[g], pg.r0);
                     vr.v[g] = rect[g];
-                    va.v[g] = ya;
-                    vb.v[g] = __shfl_down_sync(0xffffffffu, ya, 1) * pg.qp;
+                    va.v[g] = steffen_slope(cl, rect[g], pg.r0);
                 }
             }
-            // the warp's own knot rows (lanes 0 and 31 hold incomplete slopes, never read)
-            KV *kdst = reinterpret_cast<KV *>(knots) + (y & 1) * (3 * 32) + lane;
+            // the warp's own knot rows (lane 0 holds an incomplete slope, never read)
+            KV *kdst = reinterpret_cast<KV *>(knots) + (y & 1) * (2 * 32) + lane;
             kdst[0] = vr;
             kdst[32] = va;
-            kdst[64] = vb;
         };
 
         // Row loop without block barriers.  A warp waits for the data of row y, evaluates
@@ -1048,10 +1046,10 @@ struct LaunchCfg {
 
 // shared memory of the hot kernel:
 //   [3 tile descriptors][mbarriers, counters][G windows: WIN_ROWS x WIN_PITCH]
-//   [per warp: 2 x (rect | ya | yb) x 32 x G knots][2 table rows: PXCAP records]
+//   [per warp: 2 x (rect | ya) x 32 x G knots][3 table rows: PXCAP records]
 size_t smem_bytes(const emirwv_plan *pl, int G) {
     return 3 * sizeof(Tile) + 64 +
-           (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 6 * 32) * pl->esize +
+           (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 4 * 32) * pl->esize +
            (size_t)3 * PXCAP * rec_size(pl->K) * pl->esize;
 }
 
