@@ -185,6 +185,25 @@ int emirwv_rectify2d_host(const double *h_image, int naxis2, int naxis1, const d
                           double *h_out);
 
 /*
+ * median_slitlets_rectified, modes 0 and 1 (median_slitlets_rectified.py:31-164, the consumer
+ * right behind the path: stare.py:144-153, refine_rectwv_coeff.py:109-112): for every
+ * slitlet and column the median over its rows_per_slitlet (38) rows of the rectified
+ * product, with numpy.median's semantics (mean of the two middle values, NaN if any NaN).
+ *   d_in  [nframes][nslitlets * rows_per_slitlet][naxis1]
+ *   mode 0: d_out has the shape of d_in, the median spectrum repeated over the slitlet rows
+ *   mode 1: d_out [nframes][nslitlets][naxis1]
+ * Asynchronous on the given stream.  (Mode 2 of the reference is mode 1 followed by a masked
+ * median of at most 55 values per column, done by the Python shim.)
+ */
+int emirwv_median_slitlets(const void *d_in, void *d_out, int nframes, int nslitlets,
+                           int rows_per_slitlet, int naxis1, int mode, int dtype,
+                           void *cuda_stream);
+
+/* Same from host buffers (copies in, runs, copies out, returns when h_out is complete). */
+int emirwv_median_slitlets_host(const void *h_in, void *h_out, int nframes, int nslitlets,
+                                int rows_per_slitlet, int naxis1, int mode, int dtype);
+
+/*
  * Parity hooks (tests): the plan's geometry for one slitlet, copied to the host.
  *   h_row, h_col [39][bbw]       source pixel of tap (0,0) in bounding-box array
  *                                coordinates (for EMIRWV_NEAREST: the index maps

@@ -318,3 +318,27 @@ def find_pix_borders(sp, sought_value):
             if sp[jborder_max] != sought_value:
                 break
     return jborder_min, jborder_max
+
+
+# ---------------------------------------------------------------------------
+# numina.array.wavecalib.fix_pix_borders.define_mask_borders
+# (median_slitlets_rectified.py:19,118)  [numina, recalled]
+# ---------------------------------------------------------------------------
+def define_mask_borders(image2d, sought_value, nadditional=0):
+    """Mask the borders of every row up to and including its first / last value that
+    differs from ``sought_value`` (plus ``nadditional`` pixels); rows made only of
+    ``sought_value`` stay unmasked.  Returns ``(mask2d, borders)``.
+    """
+    image2d = np.asarray(image2d)
+    naxis2, naxis1 = image2d.shape
+    mask2d = np.zeros((naxis2, naxis1), dtype=bool)
+    borders = []
+    for i in range(naxis2):
+        jborder_min, jborder_max = find_pix_borders(image2d[i, :], sought_value=sought_value)
+        borders.append((jborder_min, jborder_max))
+        if (jborder_min, jborder_max) != (-1, naxis1):
+            if jborder_min != -1:
+                mask2d[i, 0:(jborder_min + nadditional + 1)] = True
+            if jborder_max != naxis1:
+                mask2d[i, (jborder_max - nadditional):naxis1] = True
+    return mask2d, borders

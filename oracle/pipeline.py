@@ -241,3 +241,45 @@ def apply_rectwv_coeff(reduced_image, rectwv_coeff, args_resampling=2,
     if return_float64:
         return rectwv_image, image2d_f64
     return rectwv_image
+
+
+def median_slitlets_rectified(input_image, mode=0, list_useful_slitlets=None, debugplot=0):
+    """Oracle for the consumer right behind the path: median spectrum of every slitlet.
+
+    Follows ``emirdrp/processing/wavecal/median_slitlets_rectified.py:31-164``: modes 0 and
+    1 are plain numpy (pinned by ``tests/golden``: the reference's own function was
+    executed); mode 2 adds numina's ``define_mask_borders`` (restated, unpinned) and a
+    masked median over the useful slitlets.
+    """
+    result = copy_img(input_image)
+    image_header = input_image[0].header
+    image2d = input_image[0].data
+    naxis2_expected = EMIR_NBARS * EMIR_NPIXPERSLIT_RECTIFIED
+    naxis2, naxis1 = image2d.shape
+    if naxis2 != naxis2_expected:
+        raise ValueError("NAXIS2={0} should be {1}".format(naxis2, naxis2_expected))
+    if image_header["instrume"] != "EMIR":
+        raise ValueError("INSTRUME keyword is not 'EMIR'!")
+    nrows = naxis2 if mode == 0 else EMIR_NBARS
+    image2d_median = np.zeros((nrows, naxis1), dtype="float32")
+    for i in range(EMIR_NBARS):
+        ns1 = i * EMIR_NPIXPERSLIT_RECTIFIED
+        sp_median = np.median(image2d[ns1:ns1 + EMIR_NPIXPERSLIT_RECTIFIED, :], axis=0)
+        if mode == 0:
+            image2d_median[ns1:ns1 + EMIR_NPIXPERSLIT_RECTIFIED, :] = sp_median
+        else:
+            image2d_median[i] = sp_median
+    if mode == 2:
+        if list_useful_slitlets is None:
+            list_not_useful = []
+        else:
+            list_not_useful = [i for i in range(1, EMIR_NBARS + 1)
+                               if i not in list_useful_slitlets]
+        mask2d, _ = nr.define_mask_borders(image2d_median, sought_value=0)
+        for islitlet in list_not_useful:
+            mask2d[islitlet - 1, :] = True
+        masked = np.ma.masked_array(image2d_median, mask=mask2d)
+        result[0].data = np.ma.median(masked, axis=0).data.astype("float32")
+    else:
+        result[0].data = image2d_median.astype("float32")
+    return result

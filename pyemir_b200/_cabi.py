@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "emirwv_plan_set_tuning", "emirwv_run", "emirwv_run_host",
     "emirwv_host_alloc", "emirwv_host_free", "emirwv_rectify_slitlet",
     "emirwv_rectify2d_host", "emirwv_debug_geometry", "emirwv_debug_borders",
+    "emirwv_median_slitlets", "emirwv_median_slitlets_host",
 )
 
 
@@ -147,6 +148,10 @@ def load():
     lib.emirwv_rectify_slitlet.argtypes = [vp, vp, i32, vp, vp]
     lib.emirwv_rectify2d_host.restype = i32
     lib.emirwv_rectify2d_host.argtypes = [vp, i32, i32, vp, vp, i32, i32, i32, vp]
+    lib.emirwv_median_slitlets.restype = i32
+    lib.emirwv_median_slitlets.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.emirwv_median_slitlets_host.restype = i32
+    lib.emirwv_median_slitlets_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32]
     lib.emirwv_debug_geometry.restype = i32
     lib.emirwv_debug_geometry.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.emirwv_debug_borders.restype = i32

@@ -565,6 +565,71 @@ __global__ void __launch_bounds__(256) k_zero_fill(const RunParams<T> p, int fir
 }
 
 // ---------------------------------------------------------------------------------
+// median_slitlets_rectified, modes 0 and 1 (median_slitlets_rectified.py:85-97): the
+// consumer right behind the path.  For every slitlet and column the median over the R = 38
+// rows of the rectified product, i.e. numpy.median(axis=0) of an even number of values:
+// the mean of the two middle ones, NaN when any value is NaN.
+//
+// One thread per column keeps a working set of R/2 + 2 values in registers: its smallest
+// and largest element cannot be one of the two middle values of the whole column, so both
+// are dropped and the next value of the column takes a free place; when the column is
+// exhausted the working set shrinks to the two middle values.  Loads and stores are
+// coalesced along the columns; the kernel reads the product once (HBM bound).
+template <typename T>
+__device__ __forceinline__ void order2(T &a, T &b) {
+    const T lo = fmin(a, b), hi = fmax(a, b);
+    a = lo;
+    b = hi;
+}
+
+template <typename T, int R>
+__global__ void __launch_bounds__(128) k_median_slitlets(const T *__restrict__ in,
+                                                        T *__restrict__ out, int naxis1,
+                                                        int nsl, int mode) {
+    static_assert(R % 2 == 0 && R >= 4, "even number of rows per slitlet");
+    constexpr int M = R / 2 + 2;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slit = blockIdx.y, f = blockIdx.z;
+    if (j >= naxis1) return;
+    const T *src = in + ((size_t)f * nsl + slit) * R * naxis1 + j;
+    T w[M];
+    bool anynan = false;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        w[i] = __ldcs(src + (size_t)i * naxis1);
+        anynan |= w[i] != w[i];
+    }
+#pragma unroll
+    for (int step = 0; step <= R - M; ++step) {
+        const int m = M - step;                                // current working-set size
+#pragma unroll
+        for (int i = 0; i + 1 < m; ++i) order2(w[i], w[i + 1]);          // maximum -> w[m-1]
+#pragma unroll
+        for (int i = m - 2; i >= 1; --i) order2(w[i - 1], w[i]);         // minimum -> w[0]
+        if (step < R - M) {                                    // drop both, take the next value
+            w[0] = __ldcs(src + (size_t)(M + step) * naxis1);
+            anynan |= w[0] != w[0];
+        }
+    }
+    // m = 4 after the last step: w[1] <= w[2] are the two middle values of the column
+    constexpr int LAST = M - (R - M);
+    static_assert(LAST == 4, "working set ends with min, the two middle values, max");
+    T med;
+    if (sizeof(T) == 4)
+        med = (T)__fmul_rn(__fadd_rn((float)w[1], (float)w[2]), 0.5f);
+    else
+        med = (T)__dmul_rn(__dadd_rn((double)w[1], (double)w[2]), 0.5);
+    if (anynan) med = (T)NAN;
+    if (mode == 1) {
+        out[((size_t)f * nsl + slit) * naxis1 + j] = med;
+    } else {
+        T *dst = out + ((size_t)f * nsl + slit) * R * naxis1 + j;
+#pragma unroll 2
+        for (int i = 0; i < R; ++i) __stcs(dst + (size_t)i * naxis1, med);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // The hot kernel.
 //
 // Persistent: CTA b processes work items b, b + gridDim.x, ...; an item is a live
@@ -1811,6 +1876,58 @@ int emirwv_rectify2d_host(const double *h_image, int naxis2, int naxis1, const d
     cudaFree(d_out);
     if (err != cudaSuccess)
         return fail(EMIRWV_E_CUDA, "rectify2d failed: %s", cudaGetErrorString(err));
+    return EMIRWV_OK;
+}
+
+int emirwv_median_slitlets(const void *d_in, void *d_out, int nframes, int nslitlets,
+                           int rows_per_slitlet, int naxis1, int mode, int dtype,
+                           void *cuda_stream) {
+    if (d_in == nullptr || d_out == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (mode != 0 && mode != 1) return fail(EMIRWV_E_VALUE, "mode must be 0 or 1");
+    if (dtype != EMIRWV_F32 && dtype != EMIRWV_F64) return fail(EMIRWV_E_VALUE, "unknown dtype");
+    if (rows_per_slitlet != NROWS - 1)
+        return fail(EMIRWV_E_VALUE, "rows_per_slitlet must be %d", NROWS - 1);
+    if (nframes < 0 || nslitlets < 1 || nslitlets > 65535 || naxis1 < 1 || nframes > 65535)
+        return fail(EMIRWV_E_VALUE, "size out of range");
+    if (nframes == 0) return EMIRWV_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const dim3 grid((naxis1 + 127) / 128, nslitlets, nframes);
+    if (dtype == EMIRWV_F32)
+        k_median_slitlets<float, NROWS - 1><<<grid, 128, 0, st>>>(
+            static_cast<const float *>(d_in), static_cast<float *>(d_out), naxis1, nslitlets, mode);
+    else
+        k_median_slitlets<double, NROWS - 1><<<grid, 128, 0, st>>>(
+            static_cast<const double *>(d_in), static_cast<double *>(d_out), naxis1, nslitlets, mode);
+    CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+int emirwv_median_slitlets_host(const void *h_in, void *h_out, int nframes, int nslitlets,
+                                int rows_per_slitlet, int naxis1, int mode, int dtype) {
+    if (h_in == nullptr || h_out == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (mode != 0 && mode != 1) return fail(EMIRWV_E_VALUE, "mode must be 0 or 1");
+    if (dtype != EMIRWV_F32 && dtype != EMIRWV_F64) return fail(EMIRWV_E_VALUE, "unknown dtype");
+    if (nframes < 0 || nslitlets < 1 || naxis1 < 1 || rows_per_slitlet < 1)
+        return fail(EMIRWV_E_VALUE, "size out of range");
+    const size_t esize = dtype == EMIRWV_F32 ? 4 : 8;
+    const size_t nin = (size_t)nframes * nslitlets * rows_per_slitlet * naxis1 * esize;
+    const size_t nout = mode == 0 ? nin : (size_t)nframes * nslitlets * naxis1 * esize;
+    if (nframes == 0) return EMIRWV_OK;
+    void *d_in = nullptr, *d_out = nullptr;
+    cudaError_t err = cudaMalloc(&d_in, nin);
+    if (err == cudaSuccess) err = cudaMalloc(&d_out, nout);
+    if (err == cudaSuccess) err = cudaMemcpy(d_in, h_in, nin, cudaMemcpyHostToDevice);
+    int rc = EMIRWV_OK;
+    if (err == cudaSuccess)
+        rc = emirwv_median_slitlets(d_in, d_out, nframes, nslitlets, rows_per_slitlet, naxis1,
+                                    mode, dtype, nullptr);
+    if (err == cudaSuccess && rc == EMIRWV_OK)
+        err = cudaMemcpy(h_out, d_out, nout, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (rc != EMIRWV_OK) return rc;
+    if (err != cudaSuccess)
+        return fail(EMIRWV_E_CUDA, "median_slitlets failed: %s", cudaGetErrorString(err));
     return EMIRWV_OK;
 }
 

@@ -8,6 +8,8 @@ What runs unmodified from /root/reference/src/emirdrp:
     processing/wavecal/apply_rectwv_coeff.py   (orchestration, paste, JMN/JMX scan, header)
     processing/wavecal/slitlet2d.py            (Slitlet2D: unpacking, crop, rectify call)
     processing/wavecal/set_wv_parameters.py    (grism/filter table)
+    processing/wavecal/median_slitlets_rectified.py  (modes 0, 1: numpy only; mode 2 uses
+                                                numina's define_mask_borders -> restated)
     core/__init__.py                           (EMIR constants)
 
 What cannot run here and is replaced by shims (numina and astropy are not installed and
@@ -74,7 +76,8 @@ def install_shims():
     _module("numina.array.display.ximshow", ximshow=lambda *a, **k: None)
     _module("numina.array.wavecalib.apply_integer_offsets",
             apply_integer_offsets=nr.apply_integer_offsets)
-    _module("numina.array.wavecalib.fix_pix_borders", find_pix_borders=nr.find_pix_borders)
+    _module("numina.array.wavecalib.fix_pix_borders", find_pix_borders=nr.find_pix_borders,
+            define_mask_borders=nr.define_mask_borders)
     _module("numina.array.wavecalib.resample", resample_image2d_flux=nr.resample_image2d_flux)
     _module("numina.array.distortion", order_fmap=nr.order_fmap, rectify2d=nr.rectify2d,
             fmap=nr.fmap)
@@ -89,6 +92,8 @@ def install_shims():
     _package("emirdrp.instrument.components")
     _module("emirdrp.instrument.components.dtu", DtuConf=dtu.DtuConf)
     _module("emirdrp.products", RectWaveCoeff=products.RectWaveCoeff)
+    _module("emirdrp.datamodel")                      # only used by the CLI entry points
+    _module("emirdrp.instrument.csu_configuration", CsuConfiguration=object)
     # emirdrp.core is a plain constants module: load the real one
     spec = importlib.util.spec_from_file_location("emirdrp.core",
                                                   os.path.join(REF, "core", "__init__.py"))
@@ -135,6 +140,19 @@ def cards_of(header):
         elif isinstance(value, (np.floating,)):
             value = float(value)
         out.append([keyword, value, comment])
+    return out
+
+
+def median_input(ref):
+    """Input of the median_slitlets_rectified vectors: the reference's rectified image of
+    case j_area with a NaN, exact ties and an all-zero slitlet planted in it."""
+    hdul, coeff = build_case(*CASES[0])
+    out = ref.apply_rectwv_coeff(hdul, coeff, args_resampling=2)
+    data = out[0].data
+    data[38 * 4 + 7, 1500] = np.nan                       # slitlet 5: one NaN column
+    data[38 * 9:38 * 9 + 38, 1200:1300] = np.float32(3.25)   # slitlet 10: ties
+    data[38 * 19:38 * 20, :] = 0.0                        # slitlet 20: empty
+    data[38 * 29:38 * 29 + 19, 1000] = -0.0               # signed zeros
     return out
 
 
@@ -225,6 +243,31 @@ def main():
         errors["bad_resampling"] = str(exc)
     meta["errors"] = errors
     print(errors)
+
+    # ---- median_slitlets_rectified: the reference function on the rectified j_area image,
+    #      with a NaN, ties and an all-zero slitlet planted in it
+    med = importlib.import_module("emirdrp.processing.wavecal.median_slitlets_rectified")
+    med_in = median_input(ref)
+    meta["median"] = {}
+    for mode, useful in ((0, None), (1, None), (2, None), (2, list(range(3, 50)))):
+        out = med.median_slitlets_rectified(med_in, mode=mode, list_useful_slitlets=useful)
+        data = out[0].data
+        assert data.dtype == np.float32
+        key = f"mode{mode}" + ("" if useful is None else "_useful3to49")
+        meta["median"][key] = {
+            "mode": mode, "useful": useful, "shape": list(data.shape),
+            "sha256": hashlib.sha256(np.ascontiguousarray(data).tobytes()).hexdigest()}
+        arrays["median_" + key] = (np.ascontiguousarray(data[::ROW_STEP, ::COL_STEP])
+                                   if data.ndim == 2 and data.shape[0] > 55 else data[..., ::7])
+        print("median", key, data.shape, meta["median"][key]["sha256"][:16])
+    for what, bad in (("naxis2", lambda h: setattr(h[0], "data", h[0].data[:100])),
+                      ("instrume", lambda h: h[0].header.__setitem__("instrume", "OSIRIS"))):
+        hdul = hdu.copy_img(med_in)
+        bad(hdul)
+        try:
+            med.median_slitlets_rectified(hdul)
+        except ValueError as exc:
+            meta["median"]["error_" + what] = str(exc)
 
     with open(os.path.join(HERE, "apply_rectwv_coeff.json"), "w") as fh:
         json.dump(meta, fh, indent=1, sort_keys=True)

@@ -154,3 +154,71 @@ def test_cuda_dropin_errors_match_reference():
     with pytest.raises(ValueError) as exc:
         apply_rectwv_coeff(hdul, coeff, args_ignore_dtu_configuration=False)
     assert str(exc.value) == errors["dtu_mismatch"]
+
+
+# ---------------------------------------------------------------- median_slitlets_rectified
+MEDIAN_KEYS = sorted(k for k in META["median"] if k.startswith("mode"))
+
+
+@pytest.fixture(scope="module")
+def median_input():
+    # the oracle's image is bit-identical to the reference's (sha256 test above), so the
+    # generator's input can be rebuilt without the reference
+    return GEN.median_input(pipeline)
+
+
+def _check_median(out, key):
+    want = META["median"][key]
+    data = out[0].data
+    assert list(data.shape) == want["shape"] and data.dtype == np.float32
+    assert hashlib.sha256(np.ascontiguousarray(data).tobytes()).hexdigest() == want["sha256"]
+
+
+@pytest.mark.parametrize("key", MEDIAN_KEYS)
+def test_oracle_median_slitlets_reproduces_reference(median_input, key):
+    want = META["median"][key]
+    out = pipeline.median_slitlets_rectified(median_input, mode=want["mode"],
+                                             list_useful_slitlets=want["useful"])
+    _check_median(out, key)
+
+
+def test_oracle_median_slitlets_errors(median_input):
+    from pyemir_b200.hdu import copy_img
+    bad = copy_img(median_input)
+    bad[0].data = bad[0].data[:100]
+    with pytest.raises(ValueError) as exc:
+        pipeline.median_slitlets_rectified(bad)
+    assert str(exc.value) == META["median"]["error_naxis2"]
+    bad = copy_img(median_input)
+    bad[0].header["instrume"] = "OSIRIS"
+    with pytest.raises(ValueError) as exc:
+        pipeline.median_slitlets_rectified(bad)
+    assert str(exc.value) == META["median"]["error_instrume"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", MEDIAN_KEYS)
+def test_cuda_median_slitlets_reproduces_reference(median_input, key):
+    from pyemir_b200.median_slitlets_rectified import median_slitlets_rectified
+    want = META["median"][key]
+    before = median_input[0].data.copy()
+    out = median_slitlets_rectified(median_input, mode=want["mode"],
+                                    list_useful_slitlets=want["useful"])
+    assert np.array_equal(median_input[0].data, before, equal_nan=True)    # input untouched
+    _check_median(out, key)                                                # bit exact
+
+
+@pytest.mark.gpu
+def test_cuda_median_slitlets_errors(median_input):
+    from pyemir_b200.hdu import copy_img
+    from pyemir_b200.median_slitlets_rectified import median_slitlets_rectified
+    bad = copy_img(median_input)
+    bad[0].data = bad[0].data[:100]
+    with pytest.raises(ValueError) as exc:
+        median_slitlets_rectified(bad)
+    assert str(exc.value) == META["median"]["error_naxis2"]
+    bad = copy_img(median_input)
+    bad[0].header["instrume"] = "OSIRIS"
+    with pytest.raises(ValueError) as exc:
+        median_slitlets_rectified(bad)
+    assert str(exc.value) == META["median"]["error_instrume"]

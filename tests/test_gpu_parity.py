@@ -437,3 +437,45 @@ def test_lr_float32_unaligned_rows():
     assert out.shape == (1, 2090, 1435)
     assert_flux_close(out[0], ref64, 1e-5, 2e-7)
     assert np.array_equal(out[0] == 0, ref64 == 0)
+
+
+# ---------------------------------------------------------------- median_slitlets_rectified
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_median_slitlets_matches_numpy(dtype, mode):
+    """k_median_slitlets against numpy.median (what the reference calls,
+    median_slitlets_rectified.py:89): random stacks with ties, signed zeros, infinities and
+    NaNs; ragged width (not a multiple of the block)."""
+    from pyemir_b200.median_slitlets_rectified import median_frames
+    rng = np.random.default_rng(7)
+    n, naxis1 = 3, 1271
+    stack = rng.normal(100.0, 30.0, size=(n, 2090, naxis1)).astype(dtype)
+    stack[0, :, 10:60] = np.round(stack[0, :, 10:60] / 25.0) * 25.0      # many ties
+    stack[1, 38 * 3:38 * 4, :] = 0.0
+    stack[1, 38 * 3 + 5, 100:200] = -0.0
+    stack[2, 38 * 7 + 11, 300] = np.nan
+    stack[2, 38 * 8 + 1, 301] = np.inf
+    stack[2, 38 * 8 + 2, 301] = -np.inf
+    got = median_frames(stack, mode=mode)
+    want = np.median(stack.reshape(n, 55, 38, naxis1), axis=2)
+    if mode == 0:
+        want = np.repeat(want, 38, axis=1)
+    assert got.dtype == dtype and got.shape == want.shape
+    assert np.array_equal(got, want, equal_nan=True)                      # bit exact
+
+
+@pytest.mark.gpu
+def test_median_slitlets_torch_device_resident(coeff_j, frame_j):
+    """Product of the hot kernel -> median kernel, both device resident."""
+    import torch
+    from pyemir_b200.median_slitlets_rectified import median_frames_torch
+    plan = get_plan(coeff_j, 2, "float32")
+    frames = torch.from_numpy(np.stack([frame_j, frame_j[::-1].copy()])).cuda()
+    out, _ = plan.run_torch(frames)
+    med = median_frames_torch(out, mode=1)
+    torch.cuda.synchronize()
+    want = np.median(out.cpu().numpy().reshape(2, 55, 38, -1), axis=2)
+    assert np.array_equal(med.cpu().numpy(), want, equal_nan=True)
+    with pytest.raises(ValueError):
+        median_frames_torch(out[:, :100].contiguous(), mode=1)
