@@ -164,6 +164,19 @@ struct RunParams {
     int ngroups;            // ceil(nframes / G)
 };
 
+// flags in the top byte of a table record's slot word
+constexpr uint32_t REC_COMPACT = 1u;          // bits 1-2: a0, bits 3-4: b0 of the 2 x 2 block
+
+// weight of tap (a, b) of a table record (host and plan kernels; the hot kernel has its own
+// unpacking)
+template <typename T>
+__host__ __device__ inline T record_weight(const T *rec, int K, int a, int b) {
+    const uint32_t flags = *reinterpret_cast<const uint32_t *>(rec + K * K + 1) >> 24;
+    if (!(flags & REC_COMPACT)) return rec[a * K + b];
+    const int da = a - (int)((flags >> 1) & 3u), db = b - (int)((flags >> 3) & 3u);
+    return (da >= 0 && da < 2 && db >= 0 && db < 2) ? rec[da * 2 + db] : T(0);
+}
+
 __host__ __device__ inline int32_t pack_base(int r, int c) {
     r = max(-30000, min(30000, r));
     c = max(-30000, min(30000, c));
@@ -280,12 +293,39 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
             wp[a * K + b] = inside ? (T)wt[a * K + b] : T(0);
         }
     for (int tap = KK; tap < RS; ++tap) wp[tap] = T(0);
-    *reinterpret_cast<int32_t *>(wp + KK) = pack_base(fr0, fc0);
+    // Compact form (K >= 3): almost every footprint fits a 2 x 2 block of source pixels.
+    // Such a record holds the block's four weights in words 0..3 (zeros elsewhere) and the
+    // coordinates of the block; the hot kernel then gathers 4 taps instead of K*K, with the
+    // same result (the skipped taps have weight zero).
+    int a0 = 0, b0 = 0;
+    uint32_t flags = 0;
+    if (K >= 3) {
+        int alo = K, ahi = -1, blo = K, bhi = -1;
+        for (int a = 0; a < K; ++a)
+            for (int b = 0; b < K; ++b)
+                if (wp[a * K + b] != T(0)) {
+                    alo = min(alo, a), ahi = max(ahi, a);
+                    blo = min(blo, b), bhi = max(bhi, b);
+                }
+        if (ahi < 0) alo = ahi = blo = bhi = 0;                // no contribution at all
+        if (ahi - alo <= 1 && bhi - blo <= 1) {
+            a0 = min(alo, K - 2);
+            b0 = min(blo, K - 2);
+            const T c00 = wp[a0 * K + b0], c01 = wp[a0 * K + b0 + 1];
+            const T c10 = wp[(a0 + 1) * K + b0], c11 = wp[(a0 + 1) * K + b0 + 1];
+            for (int tap = 0; tap < KK; ++tap) wp[tap] = T(0);
+            wp[0] = c00, wp[1] = c01, wp[2] = c10, wp[3] = c11;
+            flags = REC_COMPACT | ((uint32_t)a0 << 1) | ((uint32_t)b0 << 3);
+        }
+    }
+    *reinterpret_cast<int32_t *>(wp + KK) = pack_base(fr0 + a0, fc0 + b0);
     // ring slot of each of the K source rows in the hot kernel's rolling window
-    uint32_t slots = 0;
-    for (int a = 0; a < K; ++a)
-        slots |= (uint32_t)((fr0 + a + RING_BIAS) % WIN_ROWS) << (8 * a);
+    uint32_t slots = flags << 24;
+    for (int a = 0; a < K && a < 3; ++a)
+        slots |= (uint32_t)((fr0 + a0 + a + RING_BIAS) % WIN_ROWS) << (8 * a);
     *reinterpret_cast<uint32_t *>(wp + KK + 1) = slots;
+    if (K == 4)          // the fourth row of a 4 x 4 footprint has its own word
+        *reinterpret_cast<uint32_t *>(wp + KK + 2) = (uint32_t)((fr0 + a0 + 3 + RING_BIAS) % WIN_ROWS);
     p.base[rowtab * W + j] = pack_base(fr0, fc0);
 }
 
@@ -354,7 +394,7 @@ __global__ void k_rectify_only(const T *frame, T *rect, const int32_t *base, con
     T acc = T(0);
     for (int a = 0; a < K; ++a)
         for (int b = 0; b < K; ++b) {
-            const T wt = wp[a * K + b];
+            const T wt = record_weight(wp, K, a, b);
             const int r = min(max(r0 + a, 0), naxis2 - 1);
             const int c = min(max(c0 + b, 0), naxis1 - 1);
             acc = fma(wt, frame[(size_t)r * naxis1 + c], acc);
@@ -629,6 +669,47 @@ __global__ void __launch_bounds__(128) k_median_slitlets(const T *__restrict__ i
     }
 }
 
+// Weighted gather of KT x KT taps for the G frames of an item: rowp[a] points at tap (a, 0)
+// of frame 0 in the rolling window, frame g lies g * FRAME elements further.  float32 with
+// an even G runs two frames per instruction.  Taps are accumulated row by row, left to right.
+template <typename T, int KT, int G, int FRAME>
+__device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T *wv, int wstride,
+                                            bool px_ok, T (&rect)[G]) {
+    if constexpr (sizeof(T) == 4 && (G % 2) == 0) {
+        float2 acc[G / 2];
+#pragma unroll
+        for (int h = 0; h < G / 2; ++h) acc[h] = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int a = 0; a < KT; ++a)
+#pragma unroll
+            for (int b = 0; b < KT; ++b) {
+                const float2 wgt = dup2(wv[a * wstride + b]);
+#pragma unroll
+                for (int h = 0; h < G / 2; ++h)
+                    acc[h] = fma2(wgt,
+                                  make_float2(rowp[a][(2 * h) * FRAME + b],
+                                              rowp[a][(2 * h + 1) * FRAME + b]),
+                                  acc[h]);
+            }
+#pragma unroll
+        for (int h = 0; h < G / 2; ++h) {
+            rect[2 * h] = px_ok ? acc[h].x : 0.0f;
+            rect[2 * h + 1] = px_ok ? acc[h].y : 0.0f;
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            T acc = T(0);
+#pragma unroll
+            for (int a = 0; a < KT; ++a)
+#pragma unroll
+                for (int b = 0; b < KT; ++b)
+                    acc = fma(wv[a * wstride + b], rowp[a][g * FRAME + b], acc);
+            rect[g] = px_ok ? acc : T(0);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // The hot kernel.
 //
@@ -700,6 +781,8 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         }
         mbar_fence_init();
     }
+    // the window starts out finite: taps with weight zero may read slots no copy has filled
+    for (int e = tid; e < G * WSZ; e += NTHREADS) win[e] = T(0);
     cp_async_wait_all();
     __syncthreads();
 
@@ -895,58 +978,52 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         auto phase_ac = [&](int y) {
             // this pixel's record: K*K weights, packed source column, ring slots of the
             // K source rows
+            using V = typename Vec16<T>::type;
+            const V *rec = reinterpret_cast<const V *>(tsm + ((y % 3) * PXCAP + ppc) * RS);
             T wt[RS];
-            {
-                using V = typename Vec16<T>::type;
-                const V *rec = reinterpret_cast<const V *>(tsm + ((y % 3) * PXCAP + ppc) * RS);
+            // the vector(s) with the source column, the ring slots and the flags come first
+            constexpr int KK = K * K;
+            constexpr int VM0 = KK / VN;
+            constexpr int VM1 = (KK + 2) / VN < RS / VN - 1 ? (KK + 2) / VN : RS / VN - 1;
 #pragma unroll
-                for (int i = 0; i < RS / VN; ++i)
-                    *reinterpret_cast<V *>(wt + i * VN) = rec[i];
-            }
-            const int32_t pk = *reinterpret_cast<const int32_t *>(wt + K * K);
-            const uint32_t slots = *reinterpret_cast<const uint32_t *>(wt + K * K + 1);
+            for (int i = VM0; i <= VM1; ++i) *reinterpret_cast<V *>(wt + i * VN) = rec[i];
+            const int32_t pk = *reinterpret_cast<const int32_t *>(wt + KK);
+            const uint32_t slots = *reinterpret_cast<const uint32_t *>(wt + KK + 1);
+            const int fc = base_col(pk) + wb;
 
             // ---- A (row y): rectified flux of this pixel column, G frames
             T rect[G];
-            {
-                const int fc = base_col(pk) + wb;
-                const T *rowp[K];
+            bool all_compact = false;
+            if constexpr (K >= 3)
+                all_compact = __all_sync(0xffffffffu, (slots >> 24) & REC_COMPACT);
+            if (K >= 3 && all_compact) {
+                // every footprint of the warp fits 2 x 2 source pixels: four taps
 #pragma unroll
-                for (int a = 0; a < K; ++a)
+                for (int i = 0; i <= 3 / VN; ++i) *reinterpret_cast<V *>(wt + i * VN) = rec[i];
+                const T *rowp[2];
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
                     rowp[a] = win + ((slots >> (8 * a)) & 0xffu) * WIN_PITCH + fc;
-                if constexpr (PACKED) {
-                    float2 acc[G / 2];
+                gather_taps<T, 2, G, WSZ>(rowp, wt, 2, px_ok, rect);
+            } else {
 #pragma unroll
-                    for (int h = 0; h < G / 2; ++h) acc[h] = make_float2(0.0f, 0.0f);
+                for (int i = 0; i < VM0; ++i) *reinterpret_cast<V *>(wt + i * VN) = rec[i];
+                if constexpr (K >= 3) {
+                    if ((slots >> 24) & REC_COMPACT) {         // spread the block over K x K
+                        const T c00 = wt[0], c01 = wt[1], c10 = wt[2], c11 = wt[3];
 #pragma unroll
-                    for (int a = 0; a < K; ++a)
-#pragma unroll
-                        for (int b = 0; b < K; ++b) {
-                            const float2 wgt = dup2(wt[a * K + b]);
-#pragma unroll
-                            for (int h = 0; h < G / 2; ++h)
-                                acc[h] = fma2(wgt,
-                                              make_float2(rowp[a][(2 * h) * WSZ + b],
-                                                          rowp[a][(2 * h + 1) * WSZ + b]),
-                                              acc[h]);
-                        }
-#pragma unroll
-                    for (int h = 0; h < G / 2; ++h) {
-                        rect[2 * h] = px_ok ? acc[h].x : 0.0f;
-                        rect[2 * h + 1] = px_ok ? acc[h].y : 0.0f;
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        T acc = T(0);
-#pragma unroll
-                        for (int a = 0; a < K; ++a)
-#pragma unroll
-                            for (int b = 0; b < K; ++b)
-                                acc = fma(wt[a * K + b], rowp[a][g * WSZ + b], acc);
-                        rect[g] = px_ok ? acc : T(0);
+                        for (int i = 0; i < KK; ++i) wt[i] = T(0);
+                        wt[0] = c00, wt[1] = c01, wt[K] = c10, wt[K + 1] = c11;
                     }
                 }
+                const T *rowp[K];
+#pragma unroll
+                for (int a = 0; a < K; ++a) {
+                    const uint32_t slot = a < 3 ? (slots >> (8 * a)) & 0xffu
+                                                : *reinterpret_cast<const uint32_t *>(wt + KK + 2);
+                    rowp[a] = win + slot * WIN_PITCH + fc;
+                }
+                gather_taps<T, K, G, WSZ>(rowp, wt, K, px_ok, rect);
             }
 
             // ---- C (row y): Steffen-limited slopes at both ends of the pixel, scaled
@@ -1959,10 +2036,14 @@ int emirwv_debug_geometry(const emirwv_plan *pl, int islitlet, int32_t *h_row, i
         for (int y = 0; y < NROWS; ++y)
             for (int tap = 0; tap < KK; ++tap)
                 for (int j = 0; j < sd.bbw; ++j) {
-                    const size_t src = ((size_t)y * W + j) * RS + tap;
-                    const double v = pl->dtype == EMIRWV_F32
-                                         ? (double)reinterpret_cast<const float *>(raw.data())[src]
-                                         : reinterpret_cast<const double *>(raw.data())[src];
+                    const size_t rec = ((size_t)y * W + j) * RS;
+                    const int K = pl->K;
+                    const double v =
+                        pl->dtype == EMIRWV_F32
+                            ? (double)record_weight(reinterpret_cast<const float *>(raw.data()) + rec,
+                                                    K, tap / K, tap % K)
+                            : record_weight(reinterpret_cast<const double *>(raw.data()) + rec, K,
+                                            tap / K, tap % K);
                     h_weights[((size_t)y * sd.bbw + j) * KK + tap] = v;
                 }
     }
