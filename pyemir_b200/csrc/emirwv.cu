@@ -974,6 +974,14 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             orow += p.nout;
         };
 
+        // the warp has read everything row y needs from the window and the table slot: the
+        // copy warp may overwrite them
+        auto row_done = [&]() {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 24 + 8 * (rowseq % 3));
+            ++rowseq;
+        };
+
         // ---- A, C (row y)
         auto phase_ac = [&](int y) {
             // this pixel's record: K*K weights, packed source column, ring slots of the
@@ -1025,6 +1033,8 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                 }
                 gather_taps<T, K, G, WSZ>(rowp, wt, K, px_ok, rect);
             }
+
+            row_done();       // (phase C works on registers and the warp's own knot rows)
 
             // ---- C (row y): Steffen-limited slopes at both ends of the pixel, scaled
             //      by the pixel width (flux units).  qm = 0 / qp = 0 in the table give
@@ -1086,22 +1096,20 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                 ++rowseq;
             }
         } else {
-            auto row_done = [&]() {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + 24 + 8 * (rowseq % 3));
-                ++rowseq;
-            };
             mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);          // rows + table landed
-            if (wwarp) phase_ac(0);
-            row_done();
+            if (wwarp)
+                phase_ac(0);
+            else
+                row_done();
 #pragma unroll 1
             for (int y = 1; y < NROWS; ++y) {
                 mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);
                 if (wwarp) {
                     phase_d(y - 1);
-                    phase_ac(y);
+                    phase_ac(y);                               // reports the row done itself
+                } else {
+                    row_done();
                 }
-                row_done();
             }
         }
         if (wwarp) phase_d(NROWS - 1);
