@@ -57,7 +57,9 @@ constexpr int WIN_PITCH = 288;                // source window columns, per fram
                                               // 32 banks, so lanes on two ring rows never collide
 constexpr int WARP_PX = 30;                   // rectified columns a warp owns
 constexpr int WARP_BORDERS = 31;              // output columns a warp evaluates
-constexpr int PREFETCH = 2;                   // rectified rows between a copy and its use
+constexpr int NSTAGE = 4;                     // rectified rows in flight: a row's copies are
+                                              // requested NSTAGE rows ahead of its use
+constexpr int PREFETCH = NSTAGE - 1;          // rows that share the ring with the current one
 // Per output pixel table record: K*K weights followed by the packed source coordinates
 // (int32 bits), padded to a multiple of 4 elements so that records are 16-byte aligned.
 __host__ __device__ constexpr int rec_size(int K) { return (K * K + 1 + 3) & ~3; }
@@ -731,7 +733,7 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 //          covers 32 pixels and produces 30), written to the warp's knot rows
 //   arrive done[y]
 // The copy warp waits for done[y] (all compute warps) and requests the table row and
-// the new source rows of row y+3 into the slots row y has just released.
+// the new source rows of row y+NSTAGE into the slots row y has just released.
 // The source window is a ring of WIN_ROWS rows per frame.
 //
 // Shared memory: [tile descriptor ring: 3][mbarriers][G windows: WIN_ROWS x WIN_PITCH]
@@ -742,7 +744,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     k_rectwv(const RunParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int WSZ = WIN_ROWS * WIN_PITCH;                  // one frame's window
-    constexpr int KNOT_WARP = 2 * 2 * 32 * G;                  // knot elements of one warp
+    constexpr int KNOT_WARP = 2 * 32 * G;                      // knot elements of one warp
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -754,9 +756,9 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     // mbarriers: "full" [0..2] and "done" [3..5], one pair per rectified row in flight
     const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
     T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + 64);      // [G][WSZ]
-    T *knots = win + G * WSZ + min(warp, NWARPS - 1) * KNOT_WARP;   // this warp: [2][rect|ya][32][G]
+    T *knots = win + G * WSZ + min(warp, NWARPS - 1) * KNOT_WARP;   // this warp: [rect|ya][32][G]
     constexpr int RS = rec_size(K);
-    T *tsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [3][PXCAP][RS]
+    T *tsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [NSTAGE][PXCAP][RS]
     // float32 with an even number of frames: two frames per arithmetic instruction
     constexpr bool PACKED = sizeof(T) == 4 && (G % 2) == 0;
     using KV = KnotVec<T, G>;
@@ -775,9 +777,9 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                         (tid - 32) * 16, true);
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(bars + 8 * i, 2);                 // "full": rows part + table part of a row
-            mbar_init(bars + 24 + 8 * i, NWARPS);       // "done": every compute warp is through
+            mbar_init(bars + 8 * NSTAGE + 8 * i, NWARPS);       // "done": every compute warp is through
         }
         mbar_fence_init();
     }
@@ -842,7 +844,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // ---- the copy pipeline of the item (TMA bulk copies completing on mbarriers):
         //   the new source rows that rectified row y needs, one copy per row and frame into
         //   ring slot (row + bias) % WIN_ROWS, and the table row of row y, npx records in one
-        //   copy, slot y % 3.
+        //   copy, slot y % NSTAGE.
         constexpr int VN = Vec16<T>::N;
         const int cv0 = max(tile.c0, 0), cv1 = min(tile.c0 + tile.wcols, W);   // valid columns
         const unsigned row_bytes = (unsigned)((cv1 - cv0) * sizeof(T));
@@ -863,13 +865,13 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             __syncthreads();
         }
 
-        // Row number n (counted across items) completes on mbarrier n % 3 with two
+        // Row number n (counted across items) completes on mbarrier n % NSTAGE with two
         // arrivals: the source rows it adds and its table row.  Whichever warp issues them
         // does so with all its lanes: lane 0 posts the byte counts, every lane copies one
         // (row, frame); rows outside the detector (rare) are zero-filled instead.
         const bool oob_rows = span_lo(tile.span[0]) < 0 || span_hi(tile.span[NROWS - 1]) >= p.naxis2;
         auto copy_window_rows = [&](unsigned seq, int r_from, int r_to) {
-            const unsigned bar = bars + 8 * (seq % 3);
+            const unsigned bar = bars + 8 * (seq % NSTAGE);
             const int lo = max(r_from + 1, 0), hi = min(r_to, p.naxis2 - 1);
             if (oob_rows) {
                 for (int r = r_from + 1; r <= r_to; ++r)
@@ -891,16 +893,16 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // table row y = npx contiguous records, one bulk copy
         auto copy_table_row = [&](unsigned seq, int y) {
             if (lane == 0) {
-                const unsigned bar = bars + 8 * (seq % 3);
+                const unsigned bar = bars + 8 * (seq % NSTAGE);
                 mbar_expect_tx(bar, trow_bytes);
-                bulk_g2s(tsm_a + (y % 3) * (unsigned)(PXCAP * RS * sizeof(T)),
+                bulk_g2s(tsm_a + (y % NSTAGE) * (unsigned)(PXCAP * RS * sizeof(T)),
                          trow + (size_t)y * W * RS, trow_bytes, bar);
             }
         };
 
-        // rows 0..2 and their table rows are requested up front; once every compute warp
+        // the first NSTAGE rows and their table rows are requested up front; once every compute warp
         // is through row y the copy warp requests the table row and the source rows of row
-        // y+3 (nobody reads the slots they overwrite any more)
+        // y+NSTAGE (nobody reads the slots they overwrite any more)
         if (producer) {
             copy_window_rows(rowseq, span_lo(tile.span[0]) - 1, span_hi(tile.span[0]));
             copy_table_row(rowseq, 0);
@@ -908,6 +910,8 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             copy_table_row(rowseq + 1, 1);
             copy_window_rows(rowseq + 2, span_hi(tile.span[1]), span_hi(tile.span[2]));
             copy_table_row(rowseq + 2, 2);
+            copy_window_rows(rowseq + 3, span_hi(tile.span[2]), span_hi(tile.span[3]));
+            copy_table_row(rowseq + 3, 3);
         }
         // this thread's slot in the staged table rows (lanes without a pixel read a
         // neighbour's entry; their result is discarded)
@@ -919,7 +923,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // ---- D (row yr): cumulative flux at this thread's border and at the next one,
         //      difference = output pixel; store; remember non-zero values
         auto phase_d = [&](int yr) {
-            const KV *kbase = reinterpret_cast<const KV *>(knots) + (yr & 1) * (2 * 32) + kl;
+            const KV *kbase = reinterpret_cast<const KV *>(knots) + kl;
             const KV *kb_rect = kbase, *kb_ya = kbase + 32;
             const bool store = yr < p.rps;
             // flux and left-knot slope of the border's pixel; its right-knot slope is the
@@ -978,7 +982,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // copy warp may overwrite them
         auto row_done = [&]() {
             __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 24 + 8 * (rowseq % 3));
+            if (lane == 0) mbar_arrive(bars + 8 * NSTAGE + 8 * (rowseq % NSTAGE));
             ++rowseq;
         };
 
@@ -987,7 +991,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             // this pixel's record: K*K weights, packed source column, ring slots of the
             // K source rows
             using V = typename Vec16<T>::type;
-            const V *rec = reinterpret_cast<const V *>(tsm + ((y % 3) * PXCAP + ppc) * RS);
+            const V *rec = reinterpret_cast<const V *>(tsm + ((y % NSTAGE) * PXCAP + ppc) * RS);
             T wt[RS];
             // the vector(s) with the source column, the ring slots and the flags come first
             constexpr int KK = K * K;
@@ -1076,7 +1080,9 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                 }
             }
             // the warp's own knot rows (lane 0 holds an incomplete slope, never read)
-            KV *kdst = reinterpret_cast<KV *>(knots) + (y & 1) * (2 * 32) + lane;
+            // (one buffer is enough: the warp's border phase of the previous row comes first
+            // in program order)
+            KV *kdst = reinterpret_cast<KV *>(knots) + lane;
             kdst[0] = vr;
             kdst[32] = va;
         };
@@ -1084,26 +1090,27 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // Row loop without block barriers.  A warp waits for the data of row y, evaluates
         // the borders of row y-1 from its own knots (phase D) and the flux and slopes of
         // row y (phases A, C: independent instruction streams in one basic block), then
-        // reports row y done; warps may drift apart by up to two rows.
+        // reports row y done; warps may drift apart by up to NSTAGE-1 rows.
         if (producer) {
 #pragma unroll 1
             for (int y = 0; y < NROWS; ++y) {
-                mbar_wait(bars + 24 + 8 * (rowseq % 3), (rowseq / 3) & 1);  // row y is done
-                if (y + 3 < NROWS) {
-                    copy_table_row(rowseq + 3, y + 3);
-                    copy_window_rows(rowseq + 3, span_hi(tile.span[y + 2]), span_hi(tile.span[y + 3]));
+                mbar_wait(bars + 8 * NSTAGE + 8 * (rowseq % NSTAGE), (rowseq / NSTAGE) & 1);  // row y is done
+                if (y + NSTAGE < NROWS) {
+                    copy_table_row(rowseq + NSTAGE, y + NSTAGE);
+                    copy_window_rows(rowseq + NSTAGE, span_hi(tile.span[y + NSTAGE - 1]),
+                                     span_hi(tile.span[y + NSTAGE]));
                 }
                 ++rowseq;
             }
         } else {
-            mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);          // rows + table landed
+            mbar_wait(bars + 8 * (rowseq % NSTAGE), (rowseq / NSTAGE) & 1);   // rows + table landed
             if (wwarp)
                 phase_ac(0);
             else
                 row_done();
 #pragma unroll 1
             for (int y = 1; y < NROWS; ++y) {
-                mbar_wait(bars + 8 * (rowseq % 3), (rowseq / 3) & 1);
+                mbar_wait(bars + 8 * (rowseq % NSTAGE), (rowseq / NSTAGE) & 1);
                 if (wwarp) {
                     phase_d(y - 1);
                     phase_ac(y);                               // reports the row done itself
@@ -1199,8 +1206,8 @@ struct LaunchCfg {
 //   [per warp: 2 x (rect | ya) x 32 x G knots][3 table rows: PXCAP records]
 size_t smem_bytes(const emirwv_plan *pl, int G) {
     return 3 * sizeof(Tile) + 64 +
-           (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 4 * 32) * pl->esize +
-           (size_t)3 * PXCAP * rec_size(pl->K) * pl->esize;
+           (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 2 * 32) * pl->esize +
+           (size_t)NSTAGE * PXCAP * rec_size(pl->K) * pl->esize;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
