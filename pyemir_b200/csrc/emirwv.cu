@@ -856,11 +856,13 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         const unsigned tsm_a = smem_addr_of(tsm);
 
         // columns of the window that fall outside the detector stay zero for the item
-        if (cv0 > tile.c0 || cv1 < tile.c0 + tile.wcols) {                      // (rare)
-            for (int e = tid; e < G * WIN_ROWS * tile.wcols; e += NTHREADS) {
-                const int c = e % tile.wcols, rg = e / tile.wcols;
-                if (tile.c0 + c < cv0 || tile.c0 + c >= cv1)
-                    win[(rg / WIN_ROWS) * WSZ + (rg % WIN_ROWS) * WIN_PITCH + c] = T(0);
+        // (first and last tile of a slitlet: a handful of columns)
+        if (cv0 > tile.c0 || cv1 < tile.c0 + tile.wcols) {
+            const int nl = cv0 - tile.c0, nr = tile.c0 + tile.wcols - cv1, nbad = nl + nr;
+            for (int e = tid; e < G * WIN_ROWS * nbad; e += NTHREADS) {
+                const int cb = e % nbad, rg = e / nbad;
+                const int c = cb < nl ? cb : cv1 - tile.c0 + (cb - nl);
+                win[rg * WIN_PITCH + c] = T(0);               // rg = frame * WIN_ROWS + ring row
             }
             __syncthreads();
         }
