@@ -163,6 +163,7 @@ struct RunParams {
     int nsl;
     int vec_ok;             // rows of the output are 16-byte aligned
     int nlive_tiles;        // tiles [0, nlive_tiles) have wavelength coverage
+    int ndead_tiles;        // the tiles after them are exactly zero
     int ngroups;            // ceil(nframes / G)
 };
 
@@ -582,28 +583,41 @@ __device__ __forceinline__ unsigned nz_bits(double v) {
     return ((unsigned)__double2hiint(v) & 0x7fffffffu) | (unsigned)__double2loint(v);
 }
 
-// Zero-coverage tiles (outside the wavelength range of a slitlet, or a missing
-// slitlet): exact zeros, written with 16-byte stores where the row alignment allows.
+// Zero-coverage runs (outside the wavelength range of a slitlet, or a missing slitlet):
+// exact zeros.  A small persistent grid: every warp takes rows (dead tile, frame, row) in a
+// grid-stride loop and writes them with 16-byte stores (scalar head and tail where the run
+// is not aligned), so the fill trickles along next to the hot kernel instead of bursting.
 template <typename T>
-__global__ void __launch_bounds__(256) k_zero_fill(const RunParams<T> p, int first_tile) {
+__global__ void __launch_bounds__(128) k_zero_fill(const RunParams<T> p, int first_tile) {
     using V = typename Vec16<T>::type;
     constexpr int VN = Vec16<T>::N;
-    const Tile &tile = p.tiles[first_tile + blockIdx.x];
-    const int slit = tile.slit, k0 = tile.k0, nk = tile.nk;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const size_t frame_out = (size_t)p.nrows_out * p.nout;
-    const bool vec = p.vec_ok && ((k0 | nk) % VN) == 0;
-    for (int f = blockIdx.y; f < p.nframes; f += gridDim.y)
-        for (int y = warp; y < p.rps; y += nwarps) {
-            T *orow = p.out + (size_t)f * frame_out + (size_t)(slit * p.rps + y) * p.nout + k0;
-            if (vec) {
-                V zero;
-                memset(&zero, 0, sizeof(zero));
-                for (int k = lane; k < nk / VN; k += 32) __stcs(reinterpret_cast<V *>(orow) + k, zero);
-            } else {
-                for (int k = lane; k < nk; k += 32) __stcs(orow + k, T(0));
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long units = (long long)p.ndead_tiles * p.nframes * p.rps;
+    V zero;
+    memset(&zero, 0, sizeof(zero));
+    for (long long u = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units;
+         u += nwarps) {
+        const int y = (int)(u % p.rps);
+        const long long tf = u / p.rps;
+        const int f = (int)(tf % p.nframes);
+        const Tile &tile = p.tiles[first_tile + (int)(tf / p.nframes)];
+        const int k0 = tile.k0, k1 = k0 + tile.nk;
+        T *orow = p.out + ((size_t)f * p.nrows_out + (size_t)tile.slit * p.rps + y) * p.nout;
+        if (p.vec_ok) {
+            for (int c = (k0 / VN + lane) * VN; c < k1; c += 32 * VN) {
+                if (c >= k0 && c + VN <= k1) {
+                    __stcs(reinterpret_cast<V *>(orow + c), zero);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j)
+                        if (c + j >= k0 && c + j < k1) __stcs(orow + c + j, T(0));
+                }
             }
+        } else {
+            for (int c = k0 + lane; c < k1; c += 32) __stcs(orow + c, T(0));
         }
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -1295,9 +1309,10 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     // stream is available the hot kernel is enqueued first (it takes its shared memory
     // and registers on every SM) and the fill blocks run next to it in what is left.
     const bool forked = pl->ntiles_empty > 0 && pl->aux != nullptr;
-    const dim3 zgrid(std::max(pl->ntiles_empty, 1), std::min(nframes, 32));
+    rp.ndead_tiles = pl->ntiles_empty;
+    const int zgrid = std::max(1, env_int("EMIRWV_FILL_BLOCKS", 4 * pl->num_sms));
     if (pl->ntiles_empty > 0 && !forked) {
-        k_zero_fill<T><<<zgrid, 256, 0, st>>>(rp, rp.nlive_tiles);
+        k_zero_fill<T><<<zgrid, 128, 0, st>>>(rp, rp.nlive_tiles);
         CUDA_TRY(cudaGetLastError());
     }
     std::unique_lock<std::mutex> lock(pl->aux_mu, std::defer_lock);
@@ -1316,7 +1331,7 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     if (forked) {
         // the two kernels write disjoint parts of the output
         CUDA_TRY(cudaStreamWaitEvent(pl->aux, pl->ev_fork, 0));
-        k_zero_fill<T><<<zgrid, 256, 0, pl->aux>>>(rp, rp.nlive_tiles);
+        k_zero_fill<T><<<zgrid, 128, 0, pl->aux>>>(rp, rp.nlive_tiles);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(pl->ev_join, pl->aux));
         CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
