@@ -38,6 +38,16 @@
 #include <vector>
 
 #include "emirwv.h"
+
+#ifndef EMIRWV_NSTAGE
+#define EMIRWV_NSTAGE 4
+#endif
+#ifndef EMIRWV_WIN_PITCH
+#define EMIRWV_WIN_PITCH 288
+#endif
+#ifndef EMIRWV_PXCAP
+#define EMIRWV_PXCAP 240
+#endif
 #include "geom.cuh"
 
 namespace {
@@ -52,14 +62,15 @@ constexpr int NTHREADS = 32 * (NWARPS + 1);   // threads per CTA: compute warps 
 constexpr int TILE_K_MAX = 31 * NWARPS;       // output columns per tile (a warp does 31)
 constexpr int WIN_ROWS = 12;                  // rolling source window: rows per frame
 constexpr int RING_BIAS = 12 * 1024;          // makes (row + bias) % WIN_ROWS non-negative
-constexpr int PXCAP = 30 * NWARPS;            // rectified columns a CTA can stage (240)
-constexpr int WIN_PITCH = 288;                // source window columns, per frame: a multiple of
+constexpr int PXCAP = EMIRWV_PXCAP;            // rectified columns a CTA can stage (8 x 29 + 3 at most)
+constexpr int WIN_PITCH = EMIRWV_WIN_PITCH;                // source window columns, per frame: a multiple of
                                               // 32 banks, so lanes on two ring rows never collide
 constexpr int WARP_PX = 30;                   // rectified columns a warp owns
 constexpr int WARP_BORDERS = 31;              // output columns a warp evaluates
-constexpr int NSTAGE = 4;                     // rectified rows in flight: a row's copies are
+constexpr int NSTAGE = EMIRWV_NSTAGE;                     // rectified rows in flight: a row's copies are
                                               // requested NSTAGE rows ahead of its use
 constexpr int PREFETCH = NSTAGE - 1;          // rows that share the ring with the current one
+constexpr int BAR_BYTES = ((2 * NSTAGE * 8) + 63) / 64 * 64;   // "full" and "done" mbarriers
 // Per output pixel table record: K*K weights followed by the packed source coordinates
 // (int32 bits), padded to a multiple of 4 elements so that records are 16-byte aligned.
 __host__ __device__ constexpr int rec_size(int K) { return (K * K + 1 + 3) & ~3; }
@@ -769,7 +780,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     Tile *ring = reinterpret_cast<Tile *>(smem_raw);                       // [3]
     // mbarriers: "full" [0..2] and "done" [3..5], one pair per rectified row in flight
     const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
-    T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + 64);      // [G][WSZ]
+    T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + BAR_BYTES);   // [G][WSZ]
     T *knots = win + G * WSZ + min(warp, NWARPS - 1) * KNOT_WARP;   // this warp: [rect|ya][32][G]
     constexpr int RS = rec_size(K);
     T *tsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [NSTAGE][PXCAP][RS]
@@ -920,14 +931,11 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // is through row y the copy warp requests the table row and the source rows of row
         // y+NSTAGE (nobody reads the slots they overwrite any more)
         if (producer) {
-            copy_window_rows(rowseq, span_lo(tile.span[0]) - 1, span_hi(tile.span[0]));
-            copy_table_row(rowseq, 0);
-            copy_window_rows(rowseq + 1, span_hi(tile.span[0]), span_hi(tile.span[1]));
-            copy_table_row(rowseq + 1, 1);
-            copy_window_rows(rowseq + 2, span_hi(tile.span[1]), span_hi(tile.span[2]));
-            copy_table_row(rowseq + 2, 2);
-            copy_window_rows(rowseq + 3, span_hi(tile.span[2]), span_hi(tile.span[3]));
-            copy_table_row(rowseq + 3, 3);
+            for (int y = 0; y < NSTAGE; ++y) {
+                copy_window_rows(rowseq + y, y == 0 ? span_lo(tile.span[0]) - 1 : span_hi(tile.span[y - 1]),
+                                 span_hi(tile.span[y]));
+                copy_table_row(rowseq + y, y);
+            }
         }
         // this thread's slot in the staged table rows (lanes without a pixel read a
         // neighbour's entry; their result is discarded)
@@ -1221,7 +1229,7 @@ struct LaunchCfg {
 //   [3 tile descriptors][mbarriers, counters][G windows: WIN_ROWS x WIN_PITCH]
 //   [per warp: 2 x (rect | ya) x 32 x G knots][3 table rows: PXCAP records]
 size_t smem_bytes(const emirwv_plan *pl, int G) {
-    return 3 * sizeof(Tile) + 64 +
+    return 3 * sizeof(Tile) + BAR_BYTES +
            (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 2 * 32) * pl->esize +
            (size_t)NSTAGE * PXCAP * rec_size(pl->K) * pl->esize;
 }
