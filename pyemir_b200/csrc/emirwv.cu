@@ -438,15 +438,6 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src
                  "r"(src_bytes)
                  : "memory");
 }
-// 8- or 16-byte asynchronous copy of one table record
-template <int BYTES>
-__device__ __forceinline__ void cp_async_small(void *smem_dst, const void *gmem_src) {
-    static_assert(BYTES == 8 || BYTES == 16, "record size");
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(dst), "l"(gmem_src),
-                 "n"(BYTES)
-                 : "memory");
-}
 // ---- TMA bulk copies (cp.async.bulk) completed through an mbarrier transaction count
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -481,20 +472,8 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
         : "memory");
 }
 
-// same with a precomputed 32-bit shared-memory address
-__device__ __forceinline__ void cp_async_16s(unsigned smem_addr, const void *gmem_src, bool valid) {
-    const int src_bytes = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr),
-                 "l"(gmem_src), "r"(src_bytes)
-                 : "memory");
-}
 __device__ __forceinline__ unsigned smem_addr_of(const void *p) {
     return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -523,25 +502,6 @@ __device__ __forceinline__ Border<double> ldg_struct(const Border<double> *p) {
     b.tau = __hiloint2double(v.y, v.x);
     b.idx = v.z;
     return b;
-}
-
-// Read-only loads that keep their place in the instruction stream: the compiler would
-// otherwise sink the next row's table loads to just before their first use, which
-// defeats the one-row prefetch distance.
-__device__ __forceinline__ float ldg_here(const float *p) {
-    float v;
-    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double ldg_here(const double *p) {
-    double v;
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int32_t ldg_here(const int32_t *p) {
-    int32_t v;
-    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
 }
 
 // Make a loop-invariant value opaque so that the compiler keeps it in a register
