@@ -1851,7 +1851,7 @@ int emirwv_run_host(emirwv_plan *pl, const void *h_in, void *h_out, int nframes,
     if (nframes == 0) return EMIRWV_OK;
     DeviceGuard guard(pl->device);
     std::lock_guard<std::mutex> lock(pl->mu);
-    const int chunk = std::max(1, std::min(nframes, env_int("EMIRWV_HOST_CHUNK", 8)));
+    const int chunk = std::max(1, std::min(nframes, env_int("EMIRWV_HOST_CHUNK", 4)));
     int rc = ensure_workspace(pl, chunk);
     if (rc) return rc;
     const size_t in_b = (size_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
