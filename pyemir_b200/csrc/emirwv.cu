@@ -597,11 +597,10 @@ __global__ void __launch_bounds__(128) k_zero_fill(const RunParams<T> p, int fir
 // rows of the rectified product, i.e. numpy.median(axis=0) of an even number of values:
 // the mean of the two middle ones, NaN when any value is NaN.
 //
-// One thread per column keeps a working set of R/2 + 2 values in registers: its smallest
-// and largest element cannot be one of the two middle values of the whole column, so both
-// are dropped and the next value of the column takes a free place; when the column is
-// exhausted the working set shrinks to the two middle values.  Loads and stores are
-// coalesced along the columns; the kernel reads the product once (HBM bound).
+// One thread per column holds its 38 values in registers and runs a pruned selection network
+// (compare-exchanges only, no data-dependent branches) that leaves the two middle values on
+// two known wires.  Loads and stores are coalesced along the columns; the kernel reads the
+// product once.
 template <typename T>
 __device__ __forceinline__ void order2(T &a, T &b) {
     const T lo = fmin(a, b), hi = fmax(a, b);
@@ -614,38 +613,57 @@ __global__ void __launch_bounds__(128) k_median_slitlets(const T *__restrict__ i
                                                         T *__restrict__ out, int naxis1,
                                                         int nsl, int mode) {
     static_assert(R % 2 == 0 && R >= 4, "even number of rows per slitlet");
-    constexpr int M = R / 2 + 2;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int slit = blockIdx.y, f = blockIdx.z;
     if (j >= naxis1) return;
     const T *src = in + ((size_t)f * nsl + slit) * R * naxis1 + j;
-    T w[M];
     bool anynan = false;
+    T lo_mid, hi_mid;                                          // the two middle values
+    if constexpr (R == 38) {
+        // selection network: 223 compare-exchanges bring the two middle values of the 38
+        // inputs to wires 18 and 19 (scripts/gen_median_net.py)
+        T w[R];
 #pragma unroll
-    for (int i = 0; i < M; ++i) {
-        w[i] = __ldcs(src + (size_t)i * naxis1);
-        anynan |= w[i] != w[i];
-    }
-#pragma unroll
-    for (int step = 0; step <= R - M; ++step) {
-        const int m = M - step;                                // current working-set size
-#pragma unroll
-        for (int i = 0; i + 1 < m; ++i) order2(w[i], w[i + 1]);          // maximum -> w[m-1]
-#pragma unroll
-        for (int i = m - 2; i >= 1; --i) order2(w[i - 1], w[i]);         // minimum -> w[0]
-        if (step < R - M) {                                    // drop both, take the next value
-            w[0] = __ldcs(src + (size_t)(M + step) * naxis1);
-            anynan |= w[0] != w[0];
+        for (int i = 0; i < R; ++i) {
+            w[i] = __ldcs(src + (size_t)i * naxis1);
+            anynan |= w[i] != w[i];
         }
+#define CE(a, b) order2(w[a], w[b]);
+#include "median_net38.inc"
+#undef CE
+        lo_mid = w[R / 2 - 1];
+        hi_mid = w[R / 2];
+    } else {
+        // any even R: a working set of R/2 + 2 values; its smallest and largest element
+        // cannot be one of the two middle values of the whole column, so both are dropped
+        // and the next value of the column takes a free place
+        constexpr int M = R / 2 + 2;
+        T w[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            w[i] = __ldcs(src + (size_t)i * naxis1);
+            anynan |= w[i] != w[i];
+        }
+#pragma unroll
+        for (int step = 0; step <= R - M; ++step) {
+            const int m = M - step;                            // current working-set size
+#pragma unroll
+            for (int i = 0; i + 1 < m; ++i) order2(w[i], w[i + 1]);      // maximum -> w[m-1]
+#pragma unroll
+            for (int i = m - 2; i >= 1; --i) order2(w[i - 1], w[i]);     // minimum -> w[0]
+            if (step < R - M) {                                // drop both, take the next value
+                w[0] = __ldcs(src + (size_t)(M + step) * naxis1);
+                anynan |= w[0] != w[0];
+            }
+        }
+        lo_mid = w[1];            // 4 values are left: minimum, the two middle ones, maximum
+        hi_mid = w[2];
     }
-    // m = 4 after the last step: w[1] <= w[2] are the two middle values of the column
-    constexpr int LAST = M - (R - M);
-    static_assert(LAST == 4, "working set ends with min, the two middle values, max");
     T med;
     if (sizeof(T) == 4)
-        med = (T)__fmul_rn(__fadd_rn((float)w[1], (float)w[2]), 0.5f);
+        med = (T)__fmul_rn(__fadd_rn((float)lo_mid, (float)hi_mid), 0.5f);
     else
-        med = (T)__dmul_rn(__dadd_rn((double)w[1], (double)w[2]), 0.5);
+        med = (T)__dmul_rn(__dadd_rn((double)lo_mid, (double)hi_mid), 0.5);
     if (anynan) med = (T)NAN;
     if (mode == 1) {
         out[((size_t)f * nsl + slit) * naxis1 + j] = med;
