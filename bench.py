@@ -43,7 +43,9 @@ def parse_args():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--tile-k", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=0)
-    ap.add_argument("--combine", default="none", choices=["none", "mean", "gather"])
+    ap.add_argument("--combine", default="none", choices=["none", "mean", "gather", "abba"],
+                    help="combined product per step: mean image (torch sum + reduce), gather, or\n"
+                         "the ABBA A-B mean combination (own kernels + reduce)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=3,
                     help="frames of the CPU-baseline sample (0 disables it)")
@@ -241,7 +243,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from pyemir_b200 import synthetic
+    from pyemir_b200 import abba, synthetic
     from pyemir_b200.distributed import gather_frames, init_from_env, reduce_mean
     from pyemir_b200.plan import RectWavePlan
 
@@ -271,10 +273,15 @@ def run_ours(args):
     d_jmm = torch.empty((F, 55, 2), dtype=torch.int32, device=dev)
     counts = [F] * world
 
+    abba_labels = abba.labels_of(abba.build_full_set("ABBA", 1, (F + 3) // 4)[:F])
+
     def step():
         plan.run_torch(d_in, d_out, d_jmm)
         if args.combine == "mean":
             reduce_mean(d_out, F * world, 0)
+        elif args.combine == "abba":
+            abba.combine_abba_mean(d_out, abba_labels, world * abba_labels.count(1),
+                                   world * abba_labels.count(-1), 0)
         elif args.combine == "gather":
             gather_frames(d_out, counts, 0)
 

@@ -204,6 +204,20 @@ int emirwv_median_slitlets_host(const void *h_in, void *h_out, int nframes, int 
                                 int rows_per_slitlet, int naxis1, int mode, int dtype);
 
 /*
+ * ABBA combination with method "mean" (recipes/spec/abba.py:579-606): per-rank partial sums
+ * of the rectified frames per nodding position, float64, in frame order.
+ *   d_frames [nframes][npix] plan dtype; d_labels [nframes] int8: +1 = A, -1 = B, 0 = unused
+ *   d_sum_a, d_sum_b [npix] float64; accumulate != 0 adds to their current contents
+ * The sums of all ranks are added by a collective (NCCL reduce, pyemir_b200/abba.py), then
+ * emirwv_abba_finish forms float32(mean A) - float32(mean B) like abba.py:604-610.
+ */
+int emirwv_abba_partial(const void *d_frames, const int8_t *d_labels, int nframes, int64_t npix,
+                        int dtype, double *d_sum_a, double *d_sum_b, int accumulate,
+                        void *cuda_stream);
+int emirwv_abba_finish(const double *d_sum_a, const double *d_sum_b, int count_a, int count_b,
+                       int64_t npix, float *d_out, void *cuda_stream);
+
+/*
  * Parity hooks (tests): the plan's geometry for one slitlet, copied to the host.
  *   h_row, h_col [39][bbw]       source pixel of tap (0,0) in bounding-box array
  *                                coordinates (for EMIRWV_NEAREST: the index maps

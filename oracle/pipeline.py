@@ -283,3 +283,20 @@ def median_slitlets_rectified(input_image, mode=0, list_useful_slitlets=None, de
     else:
         result[0].data = image2d_median.astype("float32")
     return result
+
+
+def combine_abba_mean(frames, full_set):
+    """Oracle of the ABBA "mean" combination (``recipes/spec/abba.py:579-606``).
+
+    ``combine_imgs(list, method=mean)`` is numina code [recalled]: the mean of the stack in
+    float64; the recipe then casts each mean to float32 and subtracts (``abba.py:604-606``).
+    Sums run in frame order, like numpy's reduction over the first axis.
+    """
+    frames = np.asarray(frames)
+    is_a = np.array([c == "A" for c in full_set])
+    is_b = np.array([c == "B" for c in full_set])
+    if not (is_a | is_b).all():
+        raise ValueError("Unexpected char value")
+    data_a = frames[is_a].astype(np.float64).sum(axis=0) / float(is_a.sum())
+    data_b = frames[is_b].astype(np.float64).sum(axis=0) / float(is_b.sum())
+    return data_a.astype("float32") - data_b.astype("float32")

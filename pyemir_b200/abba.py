@@ -1,0 +1,139 @@
+"""ABBA bookkeeping and the "mean" combination of rectified frames on the GPU.
+
+Host-side mirror of the pieces of ``emirdrp/recipes/spec/abba.py`` that sit right behind the
+hot path in the ABBA recipe:
+
+* ``build_full_set`` (``abba.py:151-160,236``) and ``get_isky`` (``abba.py:46-75``): which
+  frame is an A, which a B, and which frame serves as sky for which (pure bookkeeping,
+  pinned by golden vectors produced with the reference's own ``get_isky``);
+* ``combine_abba_mean``: ``combine_imgs(list_a, mean)`` and ``combine_imgs(list_b, mean)``
+  followed by ``data_a.astype("float32") - data_b.astype("float32")`` (``abba.py:579-606``)
+  for frames that live sharded on the GPUs: each rank adds its A and its B frames in
+  float64 (``emirwv_abba_partial``), one reduce brings the two sums to the destination rank
+  (NCCL; gloo in the CPU tests), ``emirwv_abba_finish`` forms the difference of the means.
+
+The per-frame vertical offsets (``shift_image2d``, ``abba.py:556``) and the median /
+sigma-clip methods are not covered here (the latter need ``gather_frames``).  The mean of
+numina's ``combine`` is restated (float64 accumulation, parity unpinned).
+"""
+
+import ctypes
+
+from . import _cabi
+
+
+def build_full_set(basic_pattern, repeat, nsequences):
+    """``"ABBA", 2, 3 -> "AABBBBAA" * 3`` (``abba.py:151-160,236``)."""
+    if basic_pattern not in ("AB", "ABBA"):
+        raise ValueError(f"Unexpected pattern: {basic_pattern}")
+    pattern = ""
+    for char in basic_pattern:
+        pattern += char * repeat
+    return pattern * nsequences
+
+
+def get_isky(i, basic_pattern, repeat):
+    """Index of the image to be employed as sky for image ``i`` (``abba.py:46-75``)."""
+    len_pattern = len(basic_pattern * repeat)
+    n_previous_sequences = (i + 1) // len_pattern
+    if (i + 1) % len_pattern == 0:
+        n_previous_sequences -= 1
+    ieff = i - n_previous_sequences * len_pattern
+    if basic_pattern == "AB":
+        first_half = ieff < repeat
+    elif basic_pattern == "ABBA":
+        first_half = ieff < repeat or 2 * repeat <= ieff < 3 * repeat
+    else:
+        raise ValueError(f"Unexpected pattern: {basic_pattern}")
+    return i + repeat if first_half else i - repeat
+
+
+def labels_of(full_set):
+    """int8 labels of ``emirwv_abba_partial``: +1 for A, -1 for B."""
+    out = []
+    for char in full_set:
+        if char == "A":
+            out.append(1)
+        elif char == "B":
+            out.append(-1)
+        else:
+            raise ValueError("Unexpected char value: {}".format(char))
+    return out
+
+
+_LABEL_CACHE = {}
+
+
+def _labels_on(device, labels):
+    """int8 label vector on the device (cached: the upload would synchronise every call)."""
+    import torch
+    key = (str(device), labels)
+    if key not in _LABEL_CACHE:
+        if len(_LABEL_CACHE) > 64:
+            _LABEL_CACHE.clear()
+        _LABEL_CACHE[key] = torch.tensor(labels, dtype=torch.int8, device=device)
+    return _LABEL_CACHE[key]
+
+
+def partial_sums(frames, labels, sums=None):
+    """float64 sums of this rank's A frames and B frames: a (2, H, W) CUDA tensor.
+
+    frames: (n, H, W) contiguous float32/float64 CUDA tensor; labels: n ints (+1 A, -1 B,
+    0 unused).  ``sums`` accumulates over several calls (chunked stacks).
+    """
+    import torch
+    if frames.dim() != 3 or not frames.is_cuda or not frames.is_contiguous() or \
+            frames.dtype not in (torch.float32, torch.float64):
+        raise ValueError("frames must be a contiguous (n, H, W) float32/float64 CUDA tensor")
+    n, height, width = frames.shape
+    if len(labels) != n:
+        raise ValueError("one label per frame is needed")
+    accumulate = sums is not None
+    if sums is None:
+        sums = torch.empty((2, height, width), dtype=torch.float64, device=frames.device)
+    lab = _labels_on(frames.device, tuple(int(v) for v in labels))
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    vp = ctypes.c_void_p
+    _cabi.check(_cabi.load().emirwv_abba_partial(
+        vp(frames.data_ptr()), vp(lab.data_ptr()), n, height * width,
+        _cabi.F32 if frames.dtype == torch.float32 else _cabi.F64,
+        vp(sums[0].data_ptr()), vp(sums[1].data_ptr()), int(accumulate),
+        vp(stream) if stream else None))
+    return sums
+
+
+def reduce_sums(sums, dst=0):
+    """Add the (2, H, W) partial sums of every rank on ``dst`` (None elsewhere)."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(sums, dst=dst, op=dist.ReduceOp.SUM)
+        if dist.get_rank() != dst:
+            return None
+    return sums
+
+
+def finish(sums, count_a, count_b):
+    """float32(mean A) - float32(mean B) from the reduced sums (``abba.py:604-606``)."""
+    import torch
+    if count_a < 1 or count_b < 1:
+        raise ValueError("both A and B images are needed")
+    out = torch.empty(sums.shape[1:], dtype=torch.float32, device=sums.device)
+    stream = torch.cuda.current_stream(sums.device).cuda_stream
+    vp = ctypes.c_void_p
+    _cabi.check(_cabi.load().emirwv_abba_finish(
+        vp(sums[0].data_ptr()), vp(sums[1].data_ptr()), int(count_a), int(count_b),
+        sums.shape[1] * sums.shape[2], vp(out.data_ptr()), vp(stream) if stream else None))
+    return out
+
+
+def combine_abba_mean(frames_local, labels_local, count_a, count_b, dst=0):
+    """A - B image of an ABBA sequence whose rectified frames are sharded over the ranks.
+
+    frames_local / labels_local: this rank's frames and their labels; count_a / count_b:
+    number of A and B frames of the whole sequence.  Returns the (H, W) float32 image on
+    ``dst`` and None on the other ranks.
+    """
+    sums = reduce_sums(partial_sums(frames_local, labels_local), dst)
+    if sums is None:
+        return None
+    return finish(sums, count_a, count_b)

@@ -674,6 +674,57 @@ __global__ void __launch_bounds__(128) k_median_slitlets(const T *__restrict__ i
     }
 }
 
+// ---------------------------------------------------------------------------------
+// ABBA combination, method "mean" (recipes/spec/abba.py:579-606): the rectified frames of a
+// rank are summed per nodding position in float64, in frame order, one pass over the stack
+// (labels: +1 = A, -1 = B, 0 = not used).  The sums of all ranks are added by a collective;
+// k_abba_finish forms mean(A) and mean(B), casts both to float32 as the reference does, and
+// subtracts.
+template <typename T>
+__global__ void __launch_bounds__(256) k_abba_partial(const T *__restrict__ frames,
+                                                      const int8_t *__restrict__ labels, int nframes,
+                                                      size_t npix, double *__restrict__ sum_a,
+                                                      double *__restrict__ sum_b, int accumulate) {
+    constexpr int U = 8;                                       // frames in flight per thread
+    extern __shared__ int8_t lab_s[];
+    for (int f = threadIdx.x; f < nframes; f += blockDim.x) lab_s[f] = labels[f];
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        double a = accumulate ? sum_a[i] : 0.0, b = accumulate ? sum_b[i] : 0.0;
+        int f0 = 0;
+        for (; f0 + U <= nframes; f0 += U) {                   // branch-free: U loads in flight
+            T v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = __ldcs(frames + (size_t)(f0 + u) * npix + i);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                      // frame order, one rounding each
+                const int lab = lab_s[f0 + u];                 // (adding +0.0 changes nothing)
+                a = __dadd_rn(a, lab > 0 ? (double)v[u] : 0.0);
+                b = __dadd_rn(b, lab < 0 ? (double)v[u] : 0.0);
+            }
+        }
+        for (; f0 < nframes; ++f0) {
+            const int lab = lab_s[f0];
+            const double v = (double)__ldcs(frames + (size_t)f0 * npix + i);
+            a = __dadd_rn(a, lab > 0 ? v : 0.0);
+            b = __dadd_rn(b, lab < 0 ? v : 0.0);
+        }
+        sum_a[i] = a;
+        sum_b[i] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_abba_finish(const double *__restrict__ sum_a,
+                                                     const double *__restrict__ sum_b, double na,
+                                                     double nb, size_t npix, float *__restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        const float ma = (float)__ddiv_rn(sum_a[i], na), mb = (float)__ddiv_rn(sum_b[i], nb);
+        out[i] = __fsub_rn(ma, mb);
+    }
+}
+
 // Weighted gather of KT x KT taps for the G frames of an item: rowp[a] points at tap (a, 0)
 // of frame 0 in the rolling window, frame g lies g * FRAME elements further.  float32 with
 // an even G runs two frames per instruction.  Taps are accumulated row by row, left to right.
@@ -2023,6 +2074,48 @@ int emirwv_median_slitlets_host(const void *h_in, void *h_out, int nframes, int 
     if (rc != EMIRWV_OK) return rc;
     if (err != cudaSuccess)
         return fail(EMIRWV_E_CUDA, "median_slitlets failed: %s", cudaGetErrorString(err));
+    return EMIRWV_OK;
+}
+
+int emirwv_abba_partial(const void *d_frames, const int8_t *d_labels, int nframes, int64_t npix,
+                        int dtype, double *d_sum_a, double *d_sum_b, int accumulate,
+                        void *cuda_stream) {
+    if (d_sum_a == nullptr || d_sum_b == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (nframes < 0 || nframes > 32768 || npix < 1) return fail(EMIRWV_E_VALUE, "size out of range");
+    if (nframes > 0 && (d_frames == nullptr || d_labels == nullptr))
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (dtype != EMIRWV_F32 && dtype != EMIRWV_F64) return fail(EMIRWV_E_VALUE, "unknown dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)sms * 32);
+    if (dtype == EMIRWV_F32)
+        k_abba_partial<float><<<grid, 256, (size_t)nframes, st>>>(static_cast<const float *>(d_frames), d_labels,
+                                                    nframes, (size_t)npix, d_sum_a, d_sum_b,
+                                                    accumulate);
+    else
+        k_abba_partial<double><<<grid, 256, (size_t)nframes, st>>>(static_cast<const double *>(d_frames), d_labels,
+                                                     nframes, (size_t)npix, d_sum_a, d_sum_b,
+                                                     accumulate);
+    CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+int emirwv_abba_finish(const double *d_sum_a, const double *d_sum_b, int count_a, int count_b,
+                       int64_t npix, float *d_out, void *cuda_stream) {
+    if (d_sum_a == nullptr || d_sum_b == nullptr || d_out == nullptr)
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (count_a < 1 || count_b < 1) return fail(EMIRWV_E_VALUE, "both A and B images are needed");
+    if (npix < 1) return fail(EMIRWV_E_VALUE, "size out of range");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)sms * 16);
+    k_abba_finish<<<grid, 256, 0, st>>>(d_sum_a, d_sum_b, (double)count_a, (double)count_b,
+                                        (size_t)npix, d_out);
+    CUDA_TRY(cudaGetLastError());
     return EMIRWV_OK;
 }
 

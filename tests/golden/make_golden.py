@@ -156,6 +156,27 @@ def median_input(ref):
     return out
 
 
+def abba_vectors():
+    import ast
+    path = os.path.join(REF, "recipes", "spec", "abba.py")
+    tree = ast.parse(open(path).read())
+    func = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_isky")
+    namespace = {}
+    exec(compile(ast.Module(body=[func], type_ignores=[]), path, "exec"), namespace)
+    get_isky = namespace["get_isky"]
+    out = {}
+    for basic_pattern in ("AB", "ABBA"):
+        for repeat in (1, 2, 3):
+            nimages = len(basic_pattern) * repeat * 3
+            out[f"{basic_pattern}_{repeat}"] = [get_isky(i, basic_pattern, repeat)
+                                                for i in range(nimages)]
+    try:
+        get_isky(0, "ABAB", 1)
+    except ValueError as exc:
+        out["error"] = str(exc)
+    return out
+
+
 def plain(v):
     """JSON-friendly copy of one set_wv_parameters value."""
     if hasattr(v, "coef"):                                   # numpy Polynomial
@@ -268,6 +289,10 @@ def main():
             med.median_slitlets_rectified(hdul)
         except ValueError as exc:
             meta["median"]["error_" + what] = str(exc)
+
+    # ---- ABBA bookkeeping: the reference's own get_isky (recipes/spec/abba.py:46-75), taken
+    #      out of the module source because the module itself needs numina / astropy / scipy
+    meta["abba"] = abba_vectors()
 
     with open(os.path.join(HERE, "apply_rectwv_coeff.json"), "w") as fh:
         json.dump(meta, fh, indent=1, sort_keys=True)

@@ -64,3 +64,38 @@ def test_gather_and_mean_world2(tmp_path, nframes):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, nframes, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok.npy")
+
+
+def _abba_worker(rank, world, port, result_dir):
+    """ABBA "mean" combination over two ranks: the partial sums are formed here with torch
+    (on a GPU box emirwv_abba_partial does it), the reduction is the code under test."""
+    from pyemir_b200 import abba
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full_set = abba.build_full_set("ABBA", 1, 3)                 # 12 frames
+        labels = abba.labels_of(full_set)
+        start, stop = shard_range(len(full_set), rank, world)
+        rng = np.random.default_rng(5)
+        stack = torch.from_numpy(rng.normal(size=(len(full_set), 4, 7)))
+        sums = torch.zeros((2, 4, 7), dtype=torch.float64)
+        for f in range(start, stop):
+            sums[0 if labels[f] > 0 else 1] += stack[f]
+        reduced = abba.reduce_sums(sums, dst=0)
+        if rank == 0:
+            want_a = stack[[i for i, c in enumerate(full_set) if c == "A"]].sum(dim=0)
+            want_b = stack[[i for i, c in enumerate(full_set) if c == "B"]].sum(dim=0)
+            assert torch.allclose(reduced[0], want_a, rtol=0, atol=1e-12)
+            assert torch.allclose(reduced[1], want_b, rtol=0, atol=1e-12)
+            np.save(os.path.join(result_dir, "abba_ok.npy"), np.array([1]))
+        else:
+            assert reduced is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_abba_reduce_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_abba_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "abba_ok.npy")

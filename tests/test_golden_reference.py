@@ -222,3 +222,26 @@ def test_cuda_median_slitlets_errors(median_input):
     with pytest.raises(ValueError) as exc:
         median_slitlets_rectified(bad)
     assert str(exc.value) == META["median"]["error_instrume"]
+
+
+# ---------------------------------------------------------------- ABBA bookkeeping
+@pytest.mark.parametrize("key", sorted(k for k in META["abba"] if k != "error"))
+def test_get_isky_matches_reference(key):
+    from pyemir_b200.abba import build_full_set, get_isky
+    basic_pattern, repeat = key.split("_")
+    want = META["abba"][key]
+    assert [get_isky(i, basic_pattern, int(repeat)) for i in range(len(want))] == want
+    # the sky image of an A is a B and vice versa
+    full_set = build_full_set(basic_pattern, int(repeat), 3)
+    assert len(full_set) == len(want)
+    assert all(full_set[i] != full_set[j] for i, j in enumerate(want))
+
+
+def test_get_isky_error_matches_reference():
+    from pyemir_b200.abba import build_full_set, get_isky
+    with pytest.raises(ValueError) as exc:
+        get_isky(0, "ABAB", 1)
+    assert str(exc.value) == META["abba"]["error"]
+    with pytest.raises(ValueError):
+        build_full_set("ABAB", 1, 1)
+    assert build_full_set("ABBA", 2, 2) == "AABBBBAA" * 2

@@ -479,3 +479,48 @@ def test_median_slitlets_torch_device_resident(coeff_j, frame_j):
     assert np.array_equal(med.cpu().numpy(), want, equal_nan=True)
     with pytest.raises(ValueError):
         median_frames_torch(out[:, :100].contiguous(), mode=1)
+
+
+# ---------------------------------------------------------------- ABBA mean combination
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_abba_mean_matches_oracle(dtype):
+    """emirwv_abba_partial / _finish against the restated combination (abba.py:579-606):
+    float64 sums in frame order, float32 means, float32 difference: bit exact."""
+    import torch
+    from oracle.pipeline import combine_abba_mean as oracle_abba
+    from pyemir_b200 import abba
+    rng = np.random.default_rng(11)
+    full_set = abba.build_full_set("ABBA", 2, 2)                     # 16 frames
+    stack = (rng.normal(500.0, 200.0, size=(len(full_set), 77, 1031))).astype(dtype)
+    labels = abba.labels_of(full_set)
+    frames = torch.from_numpy(stack).cuda()
+    got = abba.combine_abba_mean(frames, labels, full_set.count("A"), full_set.count("B"))
+    torch.cuda.synchronize()
+    want = oracle_abba(stack, full_set)
+    assert got.dtype == torch.float32 and tuple(got.shape) == want.shape
+    assert np.array_equal(got.cpu().numpy(), want)
+    # the same in two chunks (accumulating partial sums), with an unused frame in between
+    sums = abba.partial_sums(frames[:5].contiguous(), labels[:5])
+    sums = abba.partial_sums(frames[4:].contiguous(), [0] + labels[5:], sums=sums)
+    got2 = abba.finish(sums, full_set.count("A"), full_set.count("B"))
+    assert np.array_equal(got2.cpu().numpy(), want)
+    with pytest.raises(ValueError):
+        abba.finish(sums, 0, 8)
+    with pytest.raises(ValueError):
+        abba.partial_sums(frames, labels[:3])
+
+
+@pytest.mark.gpu
+def test_abba_mean_of_rectified_frames(coeff_j, frame_j):
+    """Hot kernel -> ABBA combination, device resident: A - B of identical exposures is zero
+    where both contribute, and the combination of (A, B) = (2x, x) returns x."""
+    import torch
+    from pyemir_b200 import abba
+    plan = get_plan(coeff_j, 2, "float32")
+    base = torch.from_numpy(frame_j).cuda()
+    frames = torch.stack([base * 2.0, base, base, base * 2.0])
+    out, _ = plan.run_torch(frames)
+    diff = abba.combine_abba_mean(out, abba.labels_of("ABBA"), 2, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(diff, out[1])          # mean(2x, 2x) - mean(x, x) = x exactly
