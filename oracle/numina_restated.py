@@ -342,3 +342,13 @@ def define_mask_borders(image2d, sought_value, nadditional=0):
             if jborder_max != naxis1:
                 mask2d[i, (jborder_max - nadditional):naxis1] = True
     return mask2d, borders
+
+
+# ---------------------------------------------------------------------------
+# numina.array.distortion.shift_image2d (recipes/spec/abba.py:27,556)  [numina, recalled]
+# ---------------------------------------------------------------------------
+def shift_image2d(image2d, xoffset=0.0, yoffset=0.0, resampling=2):
+    """Shift by (xoffset, yoffset) pixels with ``rectify2d`` and a pure translation map."""
+    aij = np.array([-xoffset, 1.0, 0.0])
+    bij = np.array([-yoffset, 0.0, 1.0])
+    return rectify2d(image2d, aij, bij, resampling)

@@ -12,9 +12,12 @@ hot path in the ABBA recipe:
   float64 (``emirwv_abba_partial``), one reduce brings the two sums to the destination rank
   (NCCL; gloo in the CPU tests), ``emirwv_abba_finish`` forms the difference of the means.
 
-The per-frame vertical offsets (``shift_image2d``, ``abba.py:556``) and the median /
-sigma-clip methods are not covered here (the latter need ``gather_frames``).  The mean of
-numina's ``combine`` is restated (float64 accumulation, parity unpinned).
+* ``shift_image2d`` (``abba.py:556``, numina [recalled]): the per-frame vertical offset is a
+  flux-preserving resampling with a pure translation map, i.e. ``rectify2d`` with
+  ``aij = [-xoffset, 1, 0]``, ``bij = [-yoffset, 0, 1]`` (GPU, float64).
+
+The median / sigma-clip methods are not covered here (they need ``gather_frames``).  The
+mean of numina's ``combine`` and ``shift_image2d`` are restated (parity unpinned).
 """
 
 import ctypes
@@ -46,6 +49,18 @@ def get_isky(i, basic_pattern, repeat):
     else:
         raise ValueError(f"Unexpected pattern: {basic_pattern}")
     return i + repeat if first_half else i - repeat
+
+
+def shift_image2d(image2d, xoffset=0.0, yoffset=0.0, resampling=2):
+    """Shift an image by fractional (or integer) offsets, flux preserving by default.
+
+    ``reduced_mos_image[0].data = shift_image2d(data, yoffset=-offset)`` in the recipe
+    (``abba.py:556``); the pixel at (x, y) of the result comes from (x - xoffset,
+    y - yoffset) of the input.
+    """
+    from .slitlet2d import rectify2d
+    return rectify2d(image2d, [-float(xoffset), 1.0, 0.0], [-float(yoffset), 0.0, 1.0],
+                     resampling)
 
 
 def labels_of(full_set):

@@ -524,3 +524,20 @@ def test_abba_mean_of_rectified_frames(coeff_j, frame_j):
     diff = abba.combine_abba_mean(out, abba.labels_of("ABBA"), 2, 2)
     torch.cuda.synchronize()
     assert torch.equal(diff, out[1])          # mean(2x, 2x) - mean(x, x) = x exactly
+
+
+@pytest.mark.gpu
+def test_shift_image2d_matches_oracle_and_integer_shift():
+    from pyemir_b200.abba import shift_image2d
+    rng = np.random.default_rng(3)
+    img = rng.normal(100.0, 10.0, size=(40, 300))
+    got = shift_image2d(img, yoffset=-1.3)                            # abba.py:556 usage
+    want = nr.shift_image2d(img, yoffset=-1.3)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12 * np.abs(want).max())
+    # an integer offset moves the pixels exactly; what enters from outside is zero
+    got = shift_image2d(img, xoffset=3, yoffset=2)
+    assert np.array_equal(got[2:, 3:], img[:-2, :-3])
+    assert not got[:2].any() and not got[:, :3].any()
+    # flux is conserved away from the borders
+    got = shift_image2d(img, xoffset=0.25, yoffset=-0.5)
+    assert abs(got[2:-2, 2:-2].sum() - img[2:-2, 2:-2].sum()) < 0.02 * img[2:-2, 2:-2].sum()
