@@ -728,9 +728,11 @@ __global__ void __launch_bounds__(256) k_abba_finish(const double *__restrict__ 
 // Weighted gather of KT x KT taps for the G frames of an item: rowp[a] points at tap (a, 0)
 // of frame 0 in the rolling window, frame g lies g * FRAME elements further.  float32 with
 // an even G runs two frames per instruction.  Taps are accumulated row by row, left to right.
+// (Lanes without a pixel of their own gather through a neighbour's record: a finite value
+// that only ever reaches knots nobody reads.)
 template <typename T, int KT, int G, int FRAME>
 __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T *wv, int wstride,
-                                            bool px_ok, T (&rect)[G]) {
+                                            T (&rect)[G]) {
     if constexpr (sizeof(T) == 4 && (G % 2) == 0) {
         float2 acc[G / 2];
 #pragma unroll
@@ -749,8 +751,8 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
             }
 #pragma unroll
         for (int h = 0; h < G / 2; ++h) {
-            rect[2 * h] = px_ok ? acc[h].x : 0.0f;
-            rect[2 * h + 1] = px_ok ? acc[h].y : 0.0f;
+            rect[2 * h] = acc[h].x;
+            rect[2 * h + 1] = acc[h].y;
         }
     } else {
 #pragma unroll
@@ -761,7 +763,7 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 #pragma unroll
                 for (int b = 0; b < KT; ++b)
                     acc = fma(wv[a * wstride + b], rowp[a][g * FRAME + b], acc);
-            rect[g] = px_ok ? acc : T(0);
+            rect[g] = acc;
         }
     }
 }
@@ -1069,7 +1071,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
                     rowp[a] = win + ((slots >> (8 * a)) & 0xffu) * WIN_PITCH + fc;
-                gather_taps<T, 2, G, WSZ>(rowp, wt, 2, px_ok, rect);
+                gather_taps<T, 2, G, WSZ>(rowp, wt, 2, rect);
             } else {
 #pragma unroll
                 for (int i = 0; i < VM0; ++i) *reinterpret_cast<V *>(wt + i * VN) = rec[i];
@@ -1088,7 +1090,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                                                 : *reinterpret_cast<const uint32_t *>(wt + KK + 2);
                     rowp[a] = win + slot * WIN_PITCH + fc;
                 }
-                gather_taps<T, K, G, WSZ>(rowp, wt, K, px_ok, rect);
+                gather_taps<T, K, G, WSZ>(rowp, wt, K, rect);
             }
 
             row_done();       // (phase C works on registers and the warp's own knot rows)
