@@ -35,6 +35,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "emirwv.h"
@@ -893,6 +894,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // width ratio that turns the next pixel's left-knot slope into this border's pixel's
         // right-knot slope (the table holds 0 at the red end of the spectrum)
         const T qpb = __ldg(&p.pix[(size_t)s * W + bd.idx].qp);
+        const unsigned stmask = col_ok ? (1u << nlive) - 1u : 0u;   // frames this lane stores
         unsigned nzb[G];                                       // OR of the value bits seen
 #pragma unroll
         for (int g = 0; g < G; ++g) nzb[g] = 0;
@@ -977,10 +979,10 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 
         // ---- D (row yr): cumulative flux at this thread's border and at the next one,
         //      difference = output pixel; store; remember non-zero values
-        auto phase_d = [&](int yr) {
+        auto phase_d = [&](auto store_row) {                   // the 39th row is only scanned
+            constexpr bool store = decltype(store_row)::value;
             const KV *kbase = reinterpret_cast<const KV *>(knots) + kl;
             const KV *kb_rect = kbase, *kb_ya = kbase + 32;
-            const bool store = yr < p.rps;
             // flux and left-knot slope of the border's pixel; its right-knot slope is the
             // next pixel's left-knot slope rescaled by the ratio of the pixel widths
             const KV kr = kb_rect[0], ka = kb_ya[0], kn = kb_ya[1];
@@ -1027,7 +1029,8 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             }
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                if (col_ok && g < nlive && store) __stcs(orow + ((unsigned)kb + (unsigned)g * fo), o[g]);
+                T *dst = orow + ((unsigned)kb + (unsigned)g * fo);
+                if (store && ((stmask >> g) & 1u)) __stcs(dst, o[g]);
                 nzb[g] |= nz_bits(o[g]);       // lanes / frames that do not count are masked
             }                                  // once, after the last row
             orow += p.nout;
@@ -1167,14 +1170,14 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             for (int y = 1; y < NROWS; ++y) {
                 mbar_wait(bars + 8 * (rowseq % NSTAGE), (rowseq / NSTAGE) & 1);
                 if (wwarp) {
-                    phase_d(y - 1);
+                    phase_d(std::true_type{});
                     phase_ac(y);                               // reports the row done itself
                 } else {
                     row_done();
                 }
             }
         }
-        if (wwarp) phase_d(NROWS - 1);
+        if (wwarp) phase_d(std::false_type{});
 
         // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
         if (p.jmm != nullptr && wwarp) {
