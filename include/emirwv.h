@@ -163,6 +163,22 @@ int emirwv_run(const emirwv_plan *plan, const void *d_in, void *d_out, int nfram
 int emirwv_run_host(emirwv_plan *plan, const void *h_in, void *h_out, int nframes,
                     int32_t *h_jminmax);
 
+/*
+ * emirwv_run_host with options.
+ *   EMIRWV_HOST_OUT_ZEROED: the caller guarantees that h_out already holds zeros wherever the
+ *   plan has no wavelength coverage (a zero-initialised buffer, or one filled by an earlier
+ *   call with the same plan -- the usual loop over exposures).  Only the covered columns of
+ *   every slitlet (emirwv_plan_get_coverage) are copied back: about 62 % of the product for
+ *   the J/H/K grisms.  The result in h_out is the same as without the flag.
+ */
+#define EMIRWV_HOST_OUT_ZEROED 1u
+int emirwv_run_host_ex(emirwv_plan *plan, const void *h_in, void *h_out, int nframes,
+                       int32_t *h_jminmax, uint32_t flags);
+
+/* h_cover [nslitlets][2] int32: output columns [lo, hi) of each slitlet that can hold flux
+ * (0, 0 for a missing slitlet); everything outside is exactly zero in every product. */
+int emirwv_plan_get_coverage(const emirwv_plan *plan, int32_t *h_cover);
+
 void *emirwv_host_alloc(int64_t nbytes);   /* pinned host memory, NULL on failure */
 void emirwv_host_free(void *ptr);
 

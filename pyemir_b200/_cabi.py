@@ -16,6 +16,7 @@ MAX_WPOLY = 16
 ROWS_SCANNED = 39
 
 F32, F64 = 0, 1
+HOST_OUT_ZEROED = 1
 NEAREST, AREA, BILINEAR = 1, 2, 3
 
 E_VALUE, E_INDEX, E_CUDA, E_NOMEM, E_LIMIT = -1, -2, -3, -4, -5
@@ -25,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "emirwv_version", "emirwv_last_error", "emirwv_device_count", "emirwv_set_device",
     "emirwv_plan_create", "emirwv_plan_destroy", "emirwv_plan_get_info",
     "emirwv_plan_set_tuning", "emirwv_run", "emirwv_run_host",
+    "emirwv_run_host_ex", "emirwv_plan_get_coverage",
     "emirwv_host_alloc", "emirwv_host_free", "emirwv_rectify_slitlet",
     "emirwv_rectify2d_host", "emirwv_debug_geometry", "emirwv_debug_borders",
     "emirwv_median_slitlets", "emirwv_median_slitlets_host",
@@ -141,6 +143,10 @@ def load():
     lib.emirwv_run.argtypes = [vp, vp, vp, i32, vp, vp]
     lib.emirwv_run_host.restype = i32
     lib.emirwv_run_host.argtypes = [vp, vp, vp, i32, vp]
+    lib.emirwv_run_host_ex.restype = i32
+    lib.emirwv_run_host_ex.argtypes = [vp, vp, vp, i32, vp, ctypes.c_uint32]
+    lib.emirwv_plan_get_coverage.restype = i32
+    lib.emirwv_plan_get_coverage.argtypes = [vp, vp]
     lib.emirwv_host_alloc.restype = vp
     lib.emirwv_host_alloc.argtypes = [ctypes.c_int64]
     lib.emirwv_host_free.restype = None

@@ -796,7 +796,7 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 // Shared memory: [tile descriptor ring: 3][mbarriers][G windows: WIN_ROWS x WIN_PITCH]
 //                [per warp: 2 x (rect | ya | yb) x 32 pixels x G][3 table rows]
 // ---------------------------------------------------------------------------------
-template <typename T, int K, int G, bool SPANLOOP>
+template <typename T, int K, int G, bool SPANLOOP, bool KREG>
 __global__ void __launch_bounds__(NTHREADS, 2)
     k_rectwv(const RunParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -898,6 +898,14 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         unsigned nzb[G];                                       // OR of the value bits seen
 #pragma unroll
         for (int g = 0; g < G; ++g) nzb[g] = 0;
+        // KREG: the knots of the row in flight stay in the registers of the lane that owns
+        // the pixel (flux, left-knot slope); the border phase fetches them with indexed warp
+        // shuffles instead of a round trip through shared memory.
+        KV kvr, kva;
+#pragma unroll
+        for (int g = 0; g < G; ++g) kvr.v[g] = kva.v[g] = T(0);
+        const bool any2 = KREG && __any_sync(0xffffffffu, has2);
+        const int wspan = (KREG && SPANLOOP) ? __reduce_max_sync(0xffffffffu, ibn - ibl) : 0;
 
         // ---- the copy pipeline of the item (TMA bulk copies completing on mbarriers):
         //   the new source rows that rectified row y needs, one copy per row and frame into
@@ -981,15 +989,31 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         //      difference = output pixel; store; remember non-zero values
         auto phase_d = [&](auto store_row) {                   // the 39th row is only scanned
             constexpr bool store = decltype(store_row)::value;
-            const KV *kbase = reinterpret_cast<const KV *>(knots) + kl;
-            const KV *kb_rect = kbase, *kb_ya = kbase + 32;
+            [[maybe_unused]] const KV *kb_rect = reinterpret_cast<const KV *>(knots) + kl;
+            [[maybe_unused]] const KV *kb_ya = kb_rect + 32;
             // flux and left-knot slope of the border's pixel; its right-knot slope is the
             // next pixel's left-knot slope rescaled by the ratio of the pixel widths
-            const KV kr = kb_rect[0], ka = kb_ya[0], kn = kb_ya[1];
-            KV k1;
+            KV kr, ka, kn, k1;
 #pragma unroll
             for (int g = 0; g < G; ++g) k1.v[g] = T(0);
-            if (has2) k1 = kb_rect[1];
+            if constexpr (KREG) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    kr.v[g] = __shfl_sync(0xffffffffu, kvr.v[g], kl);
+                    ka.v[g] = __shfl_sync(0xffffffffu, kva.v[g], kl);
+                    kn.v[g] = __shfl_sync(0xffffffffu, kva.v[g], kl + 1);
+                }
+                if (any2) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const T t = __shfl_sync(0xffffffffu, kvr.v[g], kl + 1);
+                        k1.v[g] = has2 ? t : T(0);
+                    }
+                }
+            } else {
+                kr = kb_rect[0], ka = kb_ya[0], kn = kb_ya[1];
+                if (has2) k1 = kb_rect[1];
+            }
             T o[G];
             if constexpr (PACKED) {
                 const float2 tau2 = dup2(bd.tau);
@@ -1006,11 +1030,19 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                                                   __shfl_down_sync(0xffffffffu, P.y, 1));
                     float2 whole = make_float2(has1 ? r.x : 0.0f, has1 ? r.y : 0.0f);
                     if (has2) whole = add2(whole, make_float2(k1.v[2 * h], k1.v[2 * h + 1]));
-                    if (SPANLOOP)
+                    if constexpr (SPANLOOP && KREG) {
+                        for (int i = 2; i < wspan; ++i) {       // warp-uniform trip count
+                            const float2 ki =
+                                make_float2(__shfl_sync(0xffffffffu, kvr.v[2 * h], kl + i),
+                                            __shfl_sync(0xffffffffu, kvr.v[2 * h + 1], kl + i));
+                            if (i < ibn - ibl) whole = add2(whole, ki);
+                        }
+                    } else if constexpr (SPANLOOP) {
                         for (int i = 2; i < ibn - ibl; ++i) {
                             const KV ki = kb_rect[i];
                             whole = add2(whole, make_float2(ki.v[2 * h], ki.v[2 * h + 1]));
                         }
+                    }
                     const float2 o2 = add2(whole, sub2(Pn, P));
                     o[2 * h] = o2.x;
                     o[2 * h + 1] = o2.y;
@@ -1022,8 +1054,14 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                     const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
                     T whole = has1 ? kr.v[g] : T(0);
                     if (has2) whole += k1.v[g];
-                    if (SPANLOOP)
+                    if constexpr (SPANLOOP && KREG) {
+                        for (int i = 2; i < wspan; ++i) {       // warp-uniform trip count
+                            const T ki = __shfl_sync(0xffffffffu, kvr.v[g], kl + i);
+                            if (i < ibn - ibl) whole += ki;
+                        }
+                    } else if constexpr (SPANLOOP) {
                         for (int i = 2; i < ibn - ibl; ++i) whole += kb_rect[i].v[g];
+                    }
                     o[g] = whole + (Pn - P);
                 }
             }
@@ -1140,9 +1178,14 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             // the warp's own knot rows (lane 0 holds an incomplete slope, never read)
             // (one buffer is enough: the warp's border phase of the previous row comes first
             // in program order)
-            KV *kdst = reinterpret_cast<KV *>(knots) + lane;
-            kdst[0] = vr;
-            kdst[32] = va;
+            if constexpr (KREG) {
+                kvr = vr;
+                kva = va;
+            } else {
+                KV *kdst = reinterpret_cast<KV *>(knots) + lane;
+                kdst[0] = vr;
+                kdst[32] = va;
+            }
         };
 
         // Row loop without block barriers.  A warp waits for the data of row y, evaluates
@@ -1226,6 +1269,8 @@ struct emirwv_plan {
     int ntiles = 0, ntiles_empty = 0;
     int tile_k = 0, tile_rows = 0;
     int wrows_max = 0, wcols_max = 0, npx_max = 0, max_span = 0;
+    int knots_reg = 1;
+    std::vector<int32_t> h_cover;      // [nsl][2]: live output columns [lo, hi) of a slitlet
     int tune_G = 0;
     int num_sms = 148;
     int64_t table_bytes = 0;
@@ -1279,9 +1324,9 @@ LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
     return cfg;
 }
 
-template <typename T, int K, int G, bool SPANLOOP>
+template <typename T, int K, int G, bool SPANLOOP, bool KREG>
 int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, cudaStream_t st) {
-    auto kern = k_rectwv<T, K, G, SPANLOOP>;
+    auto kern = k_rectwv<T, K, G, SPANLOOP, KREG>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)cfg.smem));
     int per_sm = 0;
@@ -1301,8 +1346,14 @@ int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, c
 template <typename T, int K, int G>
 int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
                cudaStream_t st) {
-    if (pl->max_span > 2) return launch_final<T, K, G, true>(pl, rp, cfg, st);
-    return launch_final<T, K, G, false>(pl, rp, cfg, st);
+    // knots of the row in flight: registers + indexed shuffles (default) or the warp's
+    // shared-memory knot rows (EMIRWV_KNOTS=smem)
+    if (pl->knots_reg) {
+        if (pl->max_span > 2) return launch_final<T, K, G, true, true>(pl, rp, cfg, st);
+        return launch_final<T, K, G, false, true>(pl, rp, cfg, st);
+    }
+    if (pl->max_span > 2) return launch_final<T, K, G, true, false>(pl, rp, cfg, st);
+    return launch_final<T, K, G, false, false>(pl, rp, cfg, st);
 }
 
 template <typename T, int K>
@@ -1601,6 +1652,13 @@ int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int BW
             k0 += t.nk;
         }
     }
+    pl->h_cover.assign((size_t)pl->nsl * 2, 0);
+    for (const Tile &t : live) {
+        int32_t *c = pl->h_cover.data() + 2 * t.slit;
+        if (c[1] == 0) c[0] = t.k0;
+        c[0] = std::min(c[0], t.k0);
+        c[1] = std::max(c[1], t.k0 + t.nk);
+    }
     pl->ntiles_empty = (int)dead.size();
     pl->h_tiles = live;
     pl->h_tiles.insert(pl->h_tiles.end(), dead.begin(), dead.end());
@@ -1684,6 +1742,10 @@ int build_plan(emirwv_plan *pl) {
     pl->NB = d.naxis1_out + 1;
     pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", TILE_K_MAX);
     pl->tile_rows = NROWS;       // a tile always spans the 39 scanned rows
+    {
+        const char *kn = getenv("EMIRWV_KNOTS");       // "smem": knots through shared memory
+        pl->knots_reg = !(kn != nullptr && strcmp(kn, "smem") == 0);
+    }
     pl->tile_k = std::max(32, std::min(pl->tile_k, TILE_K_MAX));
 
     pl->h_slit.resize(pl->nsl);
@@ -1917,12 +1979,25 @@ int emirwv_run(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes
     return launch_t<double>(pl, d_in, d_out, nframes, d_jminmax, st);
 }
 
+int emirwv_plan_get_coverage(const emirwv_plan *pl, int32_t *h_cover) {
+    if (pl == nullptr || h_cover == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    memcpy(h_cover, pl->h_cover.data(), pl->h_cover.size() * sizeof(int32_t));
+    return EMIRWV_OK;
+}
+
 int emirwv_run_host(emirwv_plan *pl, const void *h_in, void *h_out, int nframes,
                     int32_t *h_jminmax) {
+    return emirwv_run_host_ex(pl, h_in, h_out, nframes, h_jminmax, 0u);
+}
+
+int emirwv_run_host_ex(emirwv_plan *pl, const void *h_in, void *h_out, int nframes,
+                       int32_t *h_jminmax, uint32_t flags) {
     if (pl == nullptr || h_in == nullptr || h_out == nullptr)
         return fail(EMIRWV_E_VALUE, "null argument");
     if (nframes < 0) return fail(EMIRWV_E_VALUE, "negative frame count");
+    if (flags & ~(uint32_t)EMIRWV_HOST_OUT_ZEROED) return fail(EMIRWV_E_VALUE, "unknown flag");
     if (nframes == 0) return EMIRWV_OK;
+    const bool sparse = (flags & EMIRWV_HOST_OUT_ZEROED) != 0;
     DeviceGuard guard(pl->device);
     std::lock_guard<std::mutex> lock(pl->mu);
     const int chunk = std::max(1, std::min(nframes, env_int("EMIRWV_HOST_CHUNK", 4)));
@@ -1942,8 +2017,31 @@ int emirwv_run_host(emirwv_plan *pl, const void *h_in, void *h_out, int nframes,
         else
             rc = launch_t<double>(pl, sl.d_in, sl.d_out, n, sl.d_jmm, sl.stream);
         if (rc) break;
-        CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(h_out) + (size_t)f0 * out_b, sl.d_out,
-                                 out_b * n, cudaMemcpyDeviceToHost, sl.stream));
+        if (!sparse) {
+            CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(h_out) + (size_t)f0 * out_b, sl.d_out,
+                                     out_b * n, cudaMemcpyDeviceToHost, sl.stream));
+        } else {
+            // only the columns with wavelength coverage travel: one strided copy per
+            // slitlet (its live columns x 38 rows x n frames); the rest of h_out already
+            // holds the zeros the reference writes there
+            const size_t pitch = (size_t)pl->nout * pl->esize;
+            const size_t rows = (size_t)pl->nsl * pl->rps;
+            for (int s = 0; s < pl->nsl; ++s) {
+                const int lo = pl->h_cover[2 * s], hi = pl->h_cover[2 * s + 1];
+                if (hi <= lo) continue;
+                cudaMemcpy3DParms cp;
+                memset(&cp, 0, sizeof(cp));
+                cp.srcPtr = make_cudaPitchedPtr(sl.d_out, pitch, pitch, rows);
+                cp.dstPtr = make_cudaPitchedPtr(static_cast<char *>(h_out) + (size_t)f0 * out_b,
+                                                pitch, pitch, rows);
+                cp.srcPos = cp.dstPos = make_cudaPos((size_t)lo * pl->esize,
+                                                     (size_t)s * pl->rps, 0);
+                cp.extent = make_cudaExtent((size_t)(hi - lo) * pl->esize, (size_t)pl->rps,
+                                            (size_t)n);
+                cp.kind = cudaMemcpyDeviceToHost;
+                CUDA_TRY(cudaMemcpy3DAsync(&cp, sl.stream));
+            }
+        }
         if (h_jminmax != nullptr)
             CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char *>(h_jminmax) + (size_t)f0 * jmm_b,
                                      sl.d_jmm, jmm_b * n, cudaMemcpyDeviceToHost, sl.stream));

@@ -177,10 +177,20 @@ class RectWavePlan:
                                                      int(threads)))
 
     # -- execution -----------------------------------------------------------
-    def run_host(self, frames, out=None, jminmax=None):
+    def coverage(self):
+        """(55, 2) int32: output columns [lo, hi) of each slitlet that can hold flux."""
+        cover = np.zeros((EMIR_NBARS, 2), dtype=np.int32)
+        _cabi.check(self._lib.emirwv_plan_get_coverage(
+            self._handle, cover.ctypes.data_as(ctypes.c_void_p)))
+        return cover
+
+    def run_host(self, frames, out=None, jminmax=None, out_zeroed=False):
         """Host arrays in, host arrays out (copies pipelined inside the library).
 
         frames: (n, 2048, 2048) C-contiguous array of the plan dtype.
+        out_zeroed: ``out`` already holds zeros outside the wavelength coverage of this
+        plan (zero-initialised, or filled by an earlier call with the same plan): only the
+        covered columns are copied back (EMIRWV_HOST_OUT_ZEROED).
         Returns (out (n, 2090, naxis1_out), jminmax (n, 55, 2) int32, raw 0-based).
         """
         frames = np.ascontiguousarray(frames, dtype=self.np_dtype)
@@ -190,13 +200,15 @@ class RectWavePlan:
         n = frames.shape[0]
         if out is None:
             out = np.empty((n,) + self.out_shape, dtype=self.np_dtype)
+            out_zeroed = False
         if jminmax is None:
             jminmax = np.empty((n, EMIR_NBARS, 2), dtype=np.int32)
         assert out.flags.c_contiguous and out.dtype == self.np_dtype
-        _cabi.check(self._lib.emirwv_run_host(
+        _cabi.check(self._lib.emirwv_run_host_ex(
             self._handle, frames.ctypes.data_as(ctypes.c_void_p),
             out.ctypes.data_as(ctypes.c_void_p), n,
-            jminmax.ctypes.data_as(ctypes.c_void_p)))
+            jminmax.ctypes.data_as(ctypes.c_void_p),
+            _cabi.HOST_OUT_ZEROED if out_zeroed else 0))
         return out, jminmax
 
     def run_device(self, d_in, d_out, nframes, d_jminmax=0, stream=0):

@@ -439,6 +439,57 @@ def test_lr_float32_unaligned_rows():
     assert np.array_equal(out[0] == 0, ref64 == 0)
 
 
+# ------------------------------------------------------------------ kernel variants, host entry
+@pytest.mark.parametrize("number,dtype,mode,frames", [
+    (2, "float32", 2, 5), (2, "float32", 1, 4), ("4b", "float32", 2, 3), (4, "float64", 2, 3),
+    (3, "float64", 2, 2)])
+def test_knot_variants_bit_identical(monkeypatch, number, dtype, mode, frames):
+    """Knots in registers (indexed warp shuffles, default) vs knots through shared memory
+    (EMIRWV_KNOTS=smem): same arithmetic in the same order, so the products and the
+    JMN/JMX scan agree bit for bit (float32 packed and float64, with and without the
+    whole-pixel span loop of the LR grisms)."""
+    coeff = only_slitlets(synthetic.make_config(number), [1, 2, 28, 54, 55])
+    fr = synthetic.make_frames(coeff, frames, seed=77, dtype=np.dtype(dtype).type)
+    res = {}
+    for variant in ("reg", "smem"):
+        monkeypatch.setenv("EMIRWV_KNOTS", variant)
+        plan = RectWavePlan(coeff, mode, dtype, max_order=5)
+        res[variant] = plan.run_host(fr)
+        plan.close()
+    assert np.array_equal(res["reg"][0], res["smem"][0])
+    assert np.array_equal(res["reg"][1], res["smem"][1])
+    assert np.count_nonzero(res["reg"][0]) > 0
+
+
+@pytest.mark.parametrize("number,dtype", [(2, "float32"), ("4b", "float64")])
+def test_run_host_out_zeroed_equals_full_copy(number, dtype):
+    """EMIRWV_HOST_OUT_ZEROED copies back only the covered columns of every slitlet; on a
+    zeroed buffer the result is the full product, and everything outside
+    emirwv_plan_get_coverage is exactly zero in the full copy."""
+    coeff = synthetic.make_config(number)
+    coeff.missing_slitlets = [3, 55]
+    fr = synthetic.make_frames(coeff, 6, seed=5, dtype=np.dtype(dtype).type)
+    plan = RectWavePlan(coeff, 2, dtype)
+    full, jmm_full = plan.run_host(fr)
+    cover = plan.coverage()
+    assert cover.shape == (55, 2) and tuple(cover[2]) == (0, 0) and tuple(cover[54]) == (0, 0)
+    inside = np.zeros(full.shape[1:], dtype=bool)
+    for s, (lo, hi) in enumerate(cover):
+        assert 0 <= lo <= hi <= full.shape[2]
+        inside[s * 38:(s + 1) * 38, lo:hi] = True
+    assert np.all(full[:, ~inside] == 0)
+    assert 0.3 < inside.mean() < 0.9
+    out = np.zeros_like(full)
+    sparse, jmm = plan.run_host(fr, out=out, out_zeroed=True)
+    assert sparse is out
+    assert np.array_equal(sparse, full) and np.array_equal(jmm, jmm_full)
+    # a reused buffer: second call with other frames over the first result
+    fr2 = fr[::-1].copy()
+    plan.run_host(fr2, out=out, out_zeroed=True)
+    assert np.array_equal(out, full[::-1])
+    plan.close()
+
+
 # ---------------------------------------------------------------- median_slitlets_rectified
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
