@@ -234,6 +234,18 @@ int emirwv_abba_finish(const double *d_sum_a, const double *d_sum_b, int count_a
                        int64_t npix, float *d_out, void *cuda_stream);
 
 /*
+ * ABBA combination with method "median" (recipes/spec/abba.py:132-137,579-601; numina's
+ * combine.median restated): per pixel the median over the selected images of a stack, with
+ * numpy.median's semantics (mean of the two middle values, NaN if any sample is NaN).
+ *   d_frames [nframes][npix] plan dtype; h_index [nsel] HOST array: the images that take part
+ *   (the A or the B images of the sequence), 1 <= nsel <= 64; d_out [npix] float64.
+ * emirwv_abba_finish(med_a, med_b, 1, 1, ...) then forms float32(A) - float32(B).  Frames that
+ * are sharded over ranks are first exchanged by row slabs (pyemir_b200/abba.py).
+ */
+int emirwv_stack_median(const void *d_frames, int nframes, const int32_t *h_index, int nsel,
+                        int64_t npix, int dtype, double *d_out, void *cuda_stream);
+
+/*
  * Parity hooks (tests): the plan's geometry for one slitlet, copied to the host.
  *   h_row, h_col [39][bbw]       source pixel of tap (0,0) in bounding-box array
  *                                coordinates (for EMIRWV_NEAREST: the index maps

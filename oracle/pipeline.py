@@ -300,3 +300,20 @@ def combine_abba_mean(frames, full_set):
     data_a = frames[is_a].astype(np.float64).sum(axis=0) / float(is_a.sum())
     data_b = frames[is_b].astype(np.float64).sum(axis=0) / float(is_b.sum())
     return data_a.astype("float32") - data_b.astype("float32")
+
+
+def combine_abba_median(frames, full_set):
+    """Oracle of the ABBA "median" combination (``recipes/spec/abba.py:132-137,579-606``).
+
+    ``combine_imgs(list, method=median)`` is numina code [recalled]: the per-pixel median of
+    the stack in float64 (mean of the two middle samples for an even count); the recipe then
+    casts both medians to float32 and subtracts (``abba.py:604-606``).
+    """
+    frames = np.asarray(frames)
+    is_a = np.array([c == "A" for c in full_set])
+    is_b = np.array([c == "B" for c in full_set])
+    if not (is_a | is_b).all():
+        raise ValueError("Unexpected char value")
+    data_a = np.median(frames[is_a].astype(np.float64), axis=0)
+    data_b = np.median(frames[is_b].astype(np.float64), axis=0)
+    return data_a.astype("float32") - data_b.astype("float32")

@@ -16,8 +16,15 @@ hot path in the ABBA recipe:
   flux-preserving resampling with a pure translation map, i.e. ``rectify2d`` with
   ``aij = [-xoffset, 1, 0]``, ``bij = [-yoffset, 0, 1]`` (GPU, float64).
 
-The median / sigma-clip methods are not covered here (they need ``gather_frames``).  The
-mean of numina's ``combine`` and ``shift_image2d`` are restated (parity unpinned).
+* ``combine_abba_median``: the same with method "median" (``abba.py:132-137``).  A median
+  needs every sample of a pixel on one device, so sharded frames are first exchanged by row
+  slabs (rank r receives rows ``slab_range(H, r, world)`` of every frame: one grouped
+  send/recv, 1/world of each frame per peer), each rank takes the per-pixel medians of the A
+  and of the B images of its slab (``emirwv_stack_median``: samples in registers, bitonic
+  network), forms the difference, and the slabs are gathered on the destination rank.
+
+The sigma-clip method is not covered.  The mean and the median of numina's ``combine`` and
+``shift_image2d`` are restated (parity unpinned).
 """
 
 import ctypes
@@ -152,3 +159,111 @@ def combine_abba_mean(frames_local, labels_local, count_a, count_b, dst=0):
     if sums is None:
         return None
     return finish(sums, count_a, count_b)
+
+
+# ------------------------------------------------------------------ method "median"
+STACK_MAX = 64      # images per nodding position in one emirwv_stack_median call
+
+
+def stack_median(frames, index):
+    """Per-pixel median over ``frames[index]``: a float64 CUDA tensor of the image shape.
+
+    frames: (n, H, W) contiguous float32/float64 CUDA tensor; index: the images that take
+    part (at most 64).  numpy.median semantics (mean of the two middle values, NaN if any
+    sample is NaN); float64 result like numina's ``combine``.
+    """
+    import numpy as np
+    import torch
+    if frames.dim() != 3 or not frames.is_cuda or not frames.is_contiguous() or \
+            frames.dtype not in (torch.float32, torch.float64):
+        raise ValueError("frames must be a contiguous (n, H, W) float32/float64 CUDA tensor")
+    n, height, width = frames.shape
+    idx = np.ascontiguousarray(index, dtype=np.int32)
+    out = torch.empty((height, width), dtype=torch.float64, device=frames.device)
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    vp = ctypes.c_void_p
+    _cabi.check(_cabi.load().emirwv_stack_median(
+        vp(frames.data_ptr()), n, idx.ctypes.data_as(vp), int(idx.size), height * width,
+        _cabi.F32 if frames.dtype == torch.float32 else _cabi.F64, vp(out.data_ptr()),
+        vp(stream) if stream else None))
+    return out
+
+
+def slab_range(height, rank, world):
+    """Rows [start, stop) of every image whose samples end up on ``rank``."""
+    per_rank = -(-height // world)
+    return min(height, rank * per_rank), min(height, (rank + 1) * per_rank)
+
+
+def exchange_row_slabs(frames_local, counts):
+    """(sum(counts), slab rows, W): this rank's row slab of EVERY frame, in frame order.
+
+    frames_local: (counts[rank], H, W); counts: frames owned by every rank (shard_range).
+    One grouped send/recv: each rank sends rows slab_range(H, r, world) of its frames to
+    rank r.  No arithmetic.
+    """
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return frames_local
+    rank, world = dist.get_rank(), dist.get_world_size()
+    height, width = frames_local.shape[1:]
+    r0, r1 = slab_range(height, rank, world)
+    out = torch.empty((sum(counts), r1 - r0, width), dtype=frames_local.dtype,
+                      device=frames_local.device)
+    ops, keep, offset = [], [], 0
+    for peer in range(world):
+        n = counts[peer]
+        if n and r1 > r0:
+            if peer == rank:
+                out[offset:offset + n].copy_(frames_local[:, r0:r1])
+            else:
+                ops.append(dist.P2POp(dist.irecv, out[offset:offset + n], peer))
+        offset += n
+        p0, p1 = slab_range(height, peer, world)
+        if peer != rank and counts[rank] and p1 > p0:
+            keep.append(frames_local[:, p0:p1].contiguous())
+            ops.append(dist.P2POp(dist.isend, keep[-1], peer))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out
+
+
+def median_difference(med_a, med_b):
+    """float32(median A) - float32(median B) (``abba.py:604-606``), emirwv_abba_finish."""
+    import torch
+    return finish(torch.stack([med_a, med_b]), 1, 1)
+
+
+def combine_abba_median(frames_local, labels, counts, dst=0, median=stack_median,
+                        difference=median_difference):
+    """median(A images) - median(B images) of a sequence sharded over the ranks.
+
+    frames_local: this rank's rectified frames; labels: the labels of ALL frames of the
+    sequence (labels_of(full_set)); counts: frames owned by every rank.  Returns the (H, W)
+    float32 image on ``dst`` and None elsewhere.  ``median(stack, index) -> float64 image``
+    and ``difference(med_a, med_b) -> float32 image`` are the CUDA entry points; the CPU
+    (gloo) tests of the exchange pass torch stand-ins.
+    """
+    import torch
+    from .distributed import gather_frames
+    import torch.distributed as dist
+    index_a = [i for i, lab in enumerate(labels) if lab > 0]
+    index_b = [i for i, lab in enumerate(labels) if lab < 0]
+    if not index_a or not index_b:
+        raise ValueError("both A and B images are needed")
+    if len(labels) != sum(counts):
+        raise ValueError("one label per frame of the sequence is needed")
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    slabs = exchange_row_slabs(frames_local, counts)
+    if slabs.shape[1]:
+        diff = difference(median(slabs, index_a), median(slabs, index_b))
+    else:
+        diff = torch.empty((0, slabs.shape[2]), dtype=torch.float32, device=slabs.device)
+    if world == 1:
+        return diff
+    height = frames_local.shape[1]
+    rows = [slab_range(height, r, world)[1] - slab_range(height, r, world)[0]
+            for r in range(world)]
+    return gather_frames(diff, rows, dst)

@@ -726,6 +726,79 @@ __global__ void __launch_bounds__(256) k_abba_finish(const double *__restrict__ 
     }
 }
 
+// ABBA combination, method "median" (abba.py:579-601 with numina's combine.median, restated):
+// per pixel the median over the selected frames of a stack (numpy.median semantics: mean of
+// the two middle values, NaN if any sample is NaN), float64 result like numina's combine.
+// One thread per pixel: its samples sit in registers (N = stack size rounded up to a power of
+// two, padded with +inf) and go through a bitonic sorting network, fully unrolled; all N
+// loads of a thread are in flight together and a warp reads 32 consecutive pixels of a frame.
+constexpr int STACK_MAX = 64;
+struct StackSel {
+    int n;
+    int idx[STACK_MAX];
+};
+
+template <typename T, int N>
+__global__ void __launch_bounds__(256) k_stack_median(const T *__restrict__ frames,
+                                                      const StackSel sel, size_t npix,
+                                                      double *__restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const T inf = (T)INFINITY;
+    const int lo = (sel.n - 1) >> 1, hi = sel.n >> 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        T v[N];
+#pragma unroll
+        for (int u = 0; u < N; ++u)
+            v[u] = u < sel.n ? __ldcs(frames + (size_t)sel.idx[u] * npix + i) : inf;
+        bool has_nan = false;
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            has_nan |= v[u] != v[u];
+            v[u] = v[u] != v[u] ? inf : v[u];
+        }
+        // bitonic network: every index is a compile-time constant after unrolling, so the
+        // samples never leave the registers
+#pragma unroll
+        for (int kk = 2; kk <= N; kk <<= 1)
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1)
+#pragma unroll
+                for (int q = 0; q < N; ++q) {
+                    const int l = q ^ j;
+                    if (l > q) {
+                        const bool up = (q & kk) == 0;
+                        const T x = v[q], y = v[l];
+                        const T mn = x < y ? x : y, mx = x < y ? y : x;
+                        v[q] = up ? mn : mx;
+                        v[l] = up ? mx : mn;
+                    }
+                }
+        T a = v[0], b = v[0];
+#pragma unroll
+        for (int u = 1; u < N; ++u) {
+            a = u == lo ? v[u] : a;
+            b = u == hi ? v[u] : b;
+        }
+        const double med = __dmul_rn(__dadd_rn((double)a, (double)b), 0.5);
+        out[i] = has_nan ? __longlong_as_double(0x7ff8000000000000LL) : med;
+    }
+}
+
+template <typename T>
+void launch_stack_median(const T *frames, const StackSel &sel, size_t npix, double *out, int grid,
+                         cudaStream_t st) {
+    if (sel.n <= 4)
+        k_stack_median<T, 4><<<grid, 256, 0, st>>>(frames, sel, npix, out);
+    else if (sel.n <= 8)
+        k_stack_median<T, 8><<<grid, 256, 0, st>>>(frames, sel, npix, out);
+    else if (sel.n <= 16)
+        k_stack_median<T, 16><<<grid, 256, 0, st>>>(frames, sel, npix, out);
+    else if (sel.n <= 32)
+        k_stack_median<T, 32><<<grid, 256, 0, st>>>(frames, sel, npix, out);
+    else
+        k_stack_median<T, 64><<<grid, 256, 0, st>>>(frames, sel, npix, out);
+}
+
 // Weighted gather of KT x KT taps for the G frames of an item: rowp[a] points at tap (a, 0)
 // of frame 0 in the rolling window, frame g lies g * FRAME elements further.  float32 with
 // an even G runs two frames per instruction.  Taps are accumulated row by row, left to right.
@@ -796,7 +869,7 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 // Shared memory: [tile descriptor ring: 3][mbarriers][G windows: WIN_ROWS x WIN_PITCH]
 //                [per warp: 2 x (rect | ya | yb) x 32 pixels x G][3 table rows]
 // ---------------------------------------------------------------------------------
-template <typename T, int K, int G, bool SPANLOOP, bool KREG>
+template <typename T, int K, int G, bool SPANLOOP>
 __global__ void __launch_bounds__(NTHREADS, 2)
     k_rectwv(const RunParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -898,14 +971,6 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         unsigned nzb[G];                                       // OR of the value bits seen
 #pragma unroll
         for (int g = 0; g < G; ++g) nzb[g] = 0;
-        // KREG: the knots of the row in flight stay in the registers of the lane that owns
-        // the pixel (flux, left-knot slope); the border phase fetches them with indexed warp
-        // shuffles instead of a round trip through shared memory.
-        KV kvr, kva;
-#pragma unroll
-        for (int g = 0; g < G; ++g) kvr.v[g] = kva.v[g] = T(0);
-        const bool any2 = KREG && __any_sync(0xffffffffu, has2);
-        const int wspan = (KREG && SPANLOOP) ? __reduce_max_sync(0xffffffffu, ibn - ibl) : 0;
 
         // ---- the copy pipeline of the item (TMA bulk copies completing on mbarriers):
         //   the new source rows that rectified row y needs, one copy per row and frame into
@@ -989,31 +1054,15 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         //      difference = output pixel; store; remember non-zero values
         auto phase_d = [&](auto store_row) {                   // the 39th row is only scanned
             constexpr bool store = decltype(store_row)::value;
-            [[maybe_unused]] const KV *kb_rect = reinterpret_cast<const KV *>(knots) + kl;
-            [[maybe_unused]] const KV *kb_ya = kb_rect + 32;
+            const KV *kbase = reinterpret_cast<const KV *>(knots) + kl;
+            const KV *kb_rect = kbase, *kb_ya = kbase + 32;
             // flux and left-knot slope of the border's pixel; its right-knot slope is the
             // next pixel's left-knot slope rescaled by the ratio of the pixel widths
-            KV kr, ka, kn, k1;
+            const KV kr = kb_rect[0], ka = kb_ya[0], kn = kb_ya[1];
+            KV k1;
 #pragma unroll
             for (int g = 0; g < G; ++g) k1.v[g] = T(0);
-            if constexpr (KREG) {
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    kr.v[g] = __shfl_sync(0xffffffffu, kvr.v[g], kl);
-                    ka.v[g] = __shfl_sync(0xffffffffu, kva.v[g], kl);
-                    kn.v[g] = __shfl_sync(0xffffffffu, kva.v[g], kl + 1);
-                }
-                if (any2) {
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const T t = __shfl_sync(0xffffffffu, kvr.v[g], kl + 1);
-                        k1.v[g] = has2 ? t : T(0);
-                    }
-                }
-            } else {
-                kr = kb_rect[0], ka = kb_ya[0], kn = kb_ya[1];
-                if (has2) k1 = kb_rect[1];
-            }
+            if (has2) k1 = kb_rect[1];
             T o[G];
             if constexpr (PACKED) {
                 const float2 tau2 = dup2(bd.tau);
@@ -1030,19 +1079,11 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                                                   __shfl_down_sync(0xffffffffu, P.y, 1));
                     float2 whole = make_float2(has1 ? r.x : 0.0f, has1 ? r.y : 0.0f);
                     if (has2) whole = add2(whole, make_float2(k1.v[2 * h], k1.v[2 * h + 1]));
-                    if constexpr (SPANLOOP && KREG) {
-                        for (int i = 2; i < wspan; ++i) {       // warp-uniform trip count
-                            const float2 ki =
-                                make_float2(__shfl_sync(0xffffffffu, kvr.v[2 * h], kl + i),
-                                            __shfl_sync(0xffffffffu, kvr.v[2 * h + 1], kl + i));
-                            if (i < ibn - ibl) whole = add2(whole, ki);
-                        }
-                    } else if constexpr (SPANLOOP) {
+                    if (SPANLOOP)
                         for (int i = 2; i < ibn - ibl; ++i) {
                             const KV ki = kb_rect[i];
                             whole = add2(whole, make_float2(ki.v[2 * h], ki.v[2 * h + 1]));
                         }
-                    }
                     const float2 o2 = add2(whole, sub2(Pn, P));
                     o[2 * h] = o2.x;
                     o[2 * h + 1] = o2.y;
@@ -1054,14 +1095,8 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                     const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
                     T whole = has1 ? kr.v[g] : T(0);
                     if (has2) whole += k1.v[g];
-                    if constexpr (SPANLOOP && KREG) {
-                        for (int i = 2; i < wspan; ++i) {       // warp-uniform trip count
-                            const T ki = __shfl_sync(0xffffffffu, kvr.v[g], kl + i);
-                            if (i < ibn - ibl) whole += ki;
-                        }
-                    } else if constexpr (SPANLOOP) {
+                    if (SPANLOOP)
                         for (int i = 2; i < ibn - ibl; ++i) whole += kb_rect[i].v[g];
-                    }
                     o[g] = whole + (Pn - P);
                 }
             }
@@ -1178,14 +1213,9 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             // the warp's own knot rows (lane 0 holds an incomplete slope, never read)
             // (one buffer is enough: the warp's border phase of the previous row comes first
             // in program order)
-            if constexpr (KREG) {
-                kvr = vr;
-                kva = va;
-            } else {
-                KV *kdst = reinterpret_cast<KV *>(knots) + lane;
-                kdst[0] = vr;
-                kdst[32] = va;
-            }
+            KV *kdst = reinterpret_cast<KV *>(knots) + lane;
+            kdst[0] = vr;
+            kdst[32] = va;
         };
 
         // Row loop without block barriers.  A warp waits for the data of row y, evaluates
@@ -1269,7 +1299,6 @@ struct emirwv_plan {
     int ntiles = 0, ntiles_empty = 0;
     int tile_k = 0, tile_rows = 0;
     int wrows_max = 0, wcols_max = 0, npx_max = 0, max_span = 0;
-    int knots_reg = 1;
     std::vector<int32_t> h_cover;      // [nsl][2]: live output columns [lo, hi) of a slitlet
     int tune_G = 0;
     int num_sms = 148;
@@ -1324,9 +1353,9 @@ LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
     return cfg;
 }
 
-template <typename T, int K, int G, bool SPANLOOP, bool KREG>
+template <typename T, int K, int G, bool SPANLOOP>
 int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, cudaStream_t st) {
-    auto kern = k_rectwv<T, K, G, SPANLOOP, KREG>;
+    auto kern = k_rectwv<T, K, G, SPANLOOP>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)cfg.smem));
     int per_sm = 0;
@@ -1346,14 +1375,8 @@ int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, c
 template <typename T, int K, int G>
 int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
                cudaStream_t st) {
-    // knots of the row in flight: registers + indexed shuffles (default) or the warp's
-    // shared-memory knot rows (EMIRWV_KNOTS=smem)
-    if (pl->knots_reg) {
-        if (pl->max_span > 2) return launch_final<T, K, G, true, true>(pl, rp, cfg, st);
-        return launch_final<T, K, G, false, true>(pl, rp, cfg, st);
-    }
-    if (pl->max_span > 2) return launch_final<T, K, G, true, false>(pl, rp, cfg, st);
-    return launch_final<T, K, G, false, false>(pl, rp, cfg, st);
+    if (pl->max_span > 2) return launch_final<T, K, G, true>(pl, rp, cfg, st);
+    return launch_final<T, K, G, false>(pl, rp, cfg, st);
 }
 
 template <typename T, int K>
@@ -1742,10 +1765,6 @@ int build_plan(emirwv_plan *pl) {
     pl->NB = d.naxis1_out + 1;
     pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", TILE_K_MAX);
     pl->tile_rows = NROWS;       // a tile always spans the 39 scanned rows
-    {
-        const char *kn = getenv("EMIRWV_KNOTS");       // "smem": knots through shared memory
-        pl->knots_reg = !(kn != nullptr && strcmp(kn, "smem") == 0);
-    }
     pl->tile_k = std::max(32, std::min(pl->tile_k, TILE_K_MAX));
 
     pl->h_slit.resize(pl->nsl);
@@ -2000,7 +2019,9 @@ int emirwv_run_host_ex(emirwv_plan *pl, const void *h_in, void *h_out, int nfram
     const bool sparse = (flags & EMIRWV_HOST_OUT_ZEROED) != 0;
     DeviceGuard guard(pl->device);
     std::lock_guard<std::mutex> lock(pl->mu);
-    const int chunk = std::max(1, std::min(nframes, env_int("EMIRWV_HOST_CHUNK", 4)));
+    // frames per pipeline slot: 4 keeps the ramp over PCIe short; the sparse copy-back issues
+    // one strided copy per slitlet and slot, so it takes 8 (measured: 2.08 k vs 1.87 k frames/s)
+    const int chunk = std::max(1, std::min(nframes, env_int("EMIRWV_HOST_CHUNK", sparse ? 8 : 4)));
     int rc = ensure_workspace(pl, chunk);
     if (rc) return rc;
     const size_t in_b = (size_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
@@ -2201,6 +2222,36 @@ int emirwv_abba_partial(const void *d_frames, const int8_t *d_labels, int nframe
         k_abba_partial<double><<<grid, 256, (size_t)nframes, st>>>(static_cast<const double *>(d_frames), d_labels,
                                                      nframes, (size_t)npix, d_sum_a, d_sum_b,
                                                      accumulate);
+    CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+int emirwv_stack_median(const void *d_frames, int nframes, const int32_t *h_index, int nsel,
+                        int64_t npix, int dtype, double *d_out, void *cuda_stream) {
+    if (d_frames == nullptr || h_index == nullptr || d_out == nullptr)
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (nsel < 1) return fail(EMIRWV_E_VALUE, "no image selected");
+    if (nsel > STACK_MAX)
+        return fail(EMIRWV_E_LIMIT, "median of more than %d images per call", STACK_MAX);
+    if (npix < 1 || nframes < 1) return fail(EMIRWV_E_VALUE, "size out of range");
+    if (dtype != EMIRWV_F32 && dtype != EMIRWV_F64) return fail(EMIRWV_E_VALUE, "unknown dtype");
+    StackSel sel;
+    memset(&sel, 0, sizeof(sel));
+    sel.n = nsel;
+    for (int u = 0; u < nsel; ++u) {
+        if (h_index[u] < 0 || h_index[u] >= nframes)
+            return fail(EMIRWV_E_VALUE, "image index %d outside the stack", h_index[u]);
+        sel.idx[u] = h_index[u];
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)sms * 8);
+    if (dtype == EMIRWV_F32)
+        launch_stack_median(static_cast<const float *>(d_frames), sel, (size_t)npix, d_out, grid, st);
+    else
+        launch_stack_median(static_cast<const double *>(d_frames), sel, (size_t)npix, d_out, grid, st);
     CUDA_TRY(cudaGetLastError());
     return EMIRWV_OK;
 }

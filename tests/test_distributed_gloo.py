@@ -99,3 +99,52 @@ def test_abba_reduce_world2(tmp_path):
     port = _free_port()
     mp.spawn(_abba_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "abba_ok.npy")
+
+
+def _abba_median_worker(rank, world, port, nframes, height, result_dir):
+    """ABBA "median" combination over two ranks: row-slab exchange, per-slab medians (torch
+    stand-ins here; emirwv_stack_median / emirwv_abba_finish on a GPU box), slab gather."""
+    from pyemir_b200 import abba
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full_set = abba.build_full_set("ABBA", 1, -(-nframes // 4))[:nframes]
+        labels = abba.labels_of(full_set)
+        counts = [shard_range(nframes, r, world)[1] - shard_range(nframes, r, world)[0]
+                  for r in range(world)]
+        start, stop = shard_range(nframes, rank, world)
+        rng = np.random.default_rng(9)
+        stack = torch.from_numpy(rng.normal(size=(nframes, height, 7)).astype(np.float32))
+        local = stack[start:stop].clone()
+
+        slabs = abba.exchange_row_slabs(local, counts)
+        r0, r1 = abba.slab_range(height, rank, world)
+        assert torch.equal(slabs, stack[:, r0:r1])
+
+        def median(frames, index):
+            return torch.from_numpy(np.median(frames[index].numpy().astype(np.float64), axis=0))
+
+        def difference(a, b):
+            return a.to(torch.float32) - b.to(torch.float32)
+
+        got = abba.combine_abba_median(local, labels, counts, dst=0, median=median,
+                                       difference=difference)
+        if rank == 0:
+            from oracle.pipeline import combine_abba_median as oracle_abba
+            want = oracle_abba(stack.numpy(), full_set)
+            assert np.array_equal(got.numpy(), want)
+            np.save(os.path.join(result_dir, "median_ok.npy"), np.array([1]))
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nframes,height", [(12, 9), (8, 1), (3, 6)])
+def test_abba_median_world2(tmp_path, nframes, height):
+    """(8, 1): one rank gets an empty slab; (3, 6): one rank owns no frame."""
+    port = _free_port()
+    mp.spawn(_abba_median_worker, args=(2, port, nframes, height, str(tmp_path)), nprocs=2,
+             join=True)
+    assert os.path.exists(tmp_path / "median_ok.npy")

@@ -440,27 +440,6 @@ def test_lr_float32_unaligned_rows():
 
 
 # ------------------------------------------------------------------ kernel variants, host entry
-@pytest.mark.parametrize("number,dtype,mode,frames", [
-    (2, "float32", 2, 5), (2, "float32", 1, 4), ("4b", "float32", 2, 3), (4, "float64", 2, 3),
-    (3, "float64", 2, 2)])
-def test_knot_variants_bit_identical(monkeypatch, number, dtype, mode, frames):
-    """Knots in registers (indexed warp shuffles, default) vs knots through shared memory
-    (EMIRWV_KNOTS=smem): same arithmetic in the same order, so the products and the
-    JMN/JMX scan agree bit for bit (float32 packed and float64, with and without the
-    whole-pixel span loop of the LR grisms)."""
-    coeff = only_slitlets(synthetic.make_config(number), [1, 2, 28, 54, 55])
-    fr = synthetic.make_frames(coeff, frames, seed=77, dtype=np.dtype(dtype).type)
-    res = {}
-    for variant in ("reg", "smem"):
-        monkeypatch.setenv("EMIRWV_KNOTS", variant)
-        plan = RectWavePlan(coeff, mode, dtype, max_order=5)
-        res[variant] = plan.run_host(fr)
-        plan.close()
-    assert np.array_equal(res["reg"][0], res["smem"][0])
-    assert np.array_equal(res["reg"][1], res["smem"][1])
-    assert np.count_nonzero(res["reg"][0]) > 0
-
-
 @pytest.mark.parametrize("number,dtype", [(2, "float32"), ("4b", "float64")])
 def test_run_host_out_zeroed_equals_full_copy(number, dtype):
     """EMIRWV_HOST_OUT_ZEROED copies back only the covered columns of every slitlet; on a
@@ -560,6 +539,62 @@ def test_abba_mean_matches_oracle(dtype):
         abba.finish(sums, 0, 8)
     with pytest.raises(ValueError):
         abba.partial_sums(frames, labels[:3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("repeat,nseq", [(1, 1), (1, 3), (2, 3), (3, 5), (8, 2), (16, 2)])
+def test_abba_median_matches_oracle(dtype, repeat, nseq):
+    """emirwv_stack_median (+ _finish) against numpy.median per nodding position: 2 .. 64
+    images per position (every register-array size of the kernel), ties, signed zeros,
+    infinities and NaNs; bit exact."""
+    import torch
+    from oracle.pipeline import combine_abba_median as oracle_abba
+    from pyemir_b200 import abba
+    rng = np.random.default_rng(100 * repeat + nseq)
+    full_set = abba.build_full_set("ABBA", repeat, nseq)
+    n = len(full_set)
+    stack = rng.normal(500.0, 200.0, size=(n, 41, 517)).astype(dtype)
+    stack[:, 3, :] = np.round(stack[:, 3, :] / 100.0)                 # many ties
+    stack[::2, 4, :50] = 0.0
+    stack[1::2, 4, :50] = -0.0
+    stack[0, 5, 7] = np.nan
+    stack[n - 1, 5, 8] = np.nan
+    stack[1, 6, 9] = np.inf
+    stack[2, 6, 10] = -np.inf
+    stack[:, 7, 11] = np.inf
+    labels = abba.labels_of(full_set)
+    frames = torch.from_numpy(stack).cuda()
+    index_a = [i for i, c in enumerate(full_set) if c == "A"]
+    med_a = abba.stack_median(frames, index_a)
+    torch.cuda.synchronize()
+    want_a = np.median(stack[index_a].astype(np.float64), axis=0)
+    assert med_a.dtype == torch.float64
+    assert np.array_equal(med_a.cpu().numpy(), want_a, equal_nan=True)
+    got = abba.combine_abba_median(frames, labels, [n])
+    torch.cuda.synchronize()
+    with np.errstate(invalid="ignore"):
+        want = oracle_abba(stack, full_set)
+    assert got.dtype == torch.float32 and tuple(got.shape) == want.shape
+    assert np.array_equal(got.cpu().numpy(), want, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_abba_median_errors():
+    import torch
+    from pyemir_b200 import abba
+    from pyemir_b200._cabi import EmirwvError
+    frames = torch.zeros((70, 4, 8), dtype=torch.float32, device="cuda")
+    with pytest.raises(EmirwvError):
+        abba.stack_median(frames, list(range(65)))                    # more than 64 images
+    with pytest.raises(ValueError):
+        abba.stack_median(frames, [70])                               # outside the stack
+    with pytest.raises(ValueError):
+        abba.stack_median(frames, [])
+    with pytest.raises(ValueError):
+        abba.combine_abba_median(frames[:4].contiguous(), [1, 1, 1, 1], [4])
+    one = abba.stack_median(frames, [3])
+    assert float(one.abs().max()) == 0.0
 
 
 @pytest.mark.gpu
