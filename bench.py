@@ -43,9 +43,11 @@ def parse_args():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--tile-k", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=0)
-    ap.add_argument("--combine", default="none", choices=["none", "mean", "gather", "abba"],
-                    help="combined product per step: mean image (torch sum + reduce), gather, or\n"
-                         "the ABBA A-B mean combination (own kernels + reduce)")
+    ap.add_argument("--combine", default="none", choices=["none", "mean", "gather", "abba", "abba_median"],
+                    help="combined product per step: mean image (torch sum + reduce), gather,\n"
+                         "the ABBA A-B mean combination (own kernels + reduce) or the ABBA\n"
+                         "median combination (row-slab exchange + stack-median kernel; at most\n"
+                         "64 frames per nodding position over all ranks)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=3,
                     help="frames of the CPU-baseline sample (0 disables it)")
@@ -282,6 +284,8 @@ def run_ours(args):
         elif args.combine == "abba":
             abba.combine_abba_mean(d_out, abba_labels, world * abba_labels.count(1),
                                    world * abba_labels.count(-1), 0)
+        elif args.combine == "abba_median":
+            abba.combine_abba_median(d_out, abba_labels * world, counts, 0)
         elif args.combine == "gather":
             gather_frames(d_out, counts, 0)
 
@@ -404,7 +408,9 @@ def run_ours(args):
         "config": workload_config(args, config, info),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         # per step: k_init_jmm + k_zero_fill + k_rectwv (persistent)
-        "gpu_launches": 3 * args.steps, "clocks": clocks,
+        # (+ the combination kernels: abba 2, abba_median 3 per step)
+        "gpu_launches": (3 + {"abba": 2, "abba_median": 3}.get(args.combine, 0)) * args.steps,
+        "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

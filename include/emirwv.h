@@ -234,6 +234,23 @@ int emirwv_abba_finish(const double *d_sum_a, const double *d_sum_b, int count_a
                        int64_t npix, float *d_out, void *cuda_stream);
 
 /*
+ * Pre-reduction in front of the path: the `flow(newimg)` of the recipes (recipes/spec/abba.py:371,
+ * core/recipe.py:25-61) for the element-wise correctors -- bias and dark subtraction (numina
+ * BiasCorrector / DarkCorrector, restated) and pyemir's FlatFieldCorrector
+ * (processing/flatfield.py:27-70: flat values <= 0 count as 1.0; data / flat, cast to float32).
+ *   d_in  [nframes][npix] EMIRWV_F32 / EMIRWV_F64 / EMIRWV_U16 (raw detector counts)
+ *   d_out [nframes][npix] float32 (may alias d_in when in_dtype is EMIRWV_F32)
+ *   d_bias, d_dark, d_flat [npix] of cal_dtype (EMIRWV_F32 / EMIRWV_F64); NULL skips the stage
+ * Stages in the order of the flow (bias, dark, flat), each rounded to float32, with numpy's
+ * type promotion (a float64 operand makes the stage float64).  Asynchronous on the stream.
+ * The bad-pixel interpolation of the flow (numina BadPixelCorrector) is not covered.
+ */
+#define EMIRWV_U16 2
+int emirwv_prereduce(const void *d_in, int in_dtype, float *d_out, int nframes, int64_t npix,
+                     const void *d_bias, const void *d_dark, const void *d_flat, int cal_dtype,
+                     void *cuda_stream);
+
+/*
  * ABBA combination with method "median" (recipes/spec/abba.py:132-137,579-601; numina's
  * combine.median restated): per pixel the median over the selected images of a stack, with
  * numpy.median's semantics (mean of the two middle values, NaN if any sample is NaN).

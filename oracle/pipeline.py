@@ -317,3 +317,32 @@ def combine_abba_median(frames, full_set):
     data_a = np.median(frames[is_a].astype(np.float64), axis=0)
     data_b = np.median(frames[is_b].astype(np.float64), axis=0)
     return data_a.astype("float32") - data_b.astype("float32")
+
+
+def flatfield_correct(data, flatdata, dtype="float32"):
+    """Oracle of pyemir's FlatFieldCorrector arithmetic (``processing/flatfield.py:43,58-59``).
+
+    ``flatdata[flatdata <= 0] = 1.0`` (on a copy here), ``(data / flatdata).astype(dtype)``.
+    Pinned by tests/golden/flatfield.json (produced with the reference's own class).
+    """
+    flat = np.array(flatdata, copy=True)
+    flat[flat <= 0] = 1.0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (np.asarray(data) / flat).astype(dtype)
+
+
+def prereduce(frames, bias=None, dark=None, flat=None):
+    """Oracle of the element-wise part of ``flow(newimg)`` (``recipes/spec/abba.py:371``).
+
+    numina's BiasCorrector and DarkCorrector [recalled]: image minus calibration, result cast
+    to the corrector's dtype (float32); then ``flatfield_correct``.  numpy type promotion.
+    """
+    x = np.asarray(frames)
+    with np.errstate(invalid="ignore"):
+        if bias is not None:
+            x = (x - np.asarray(bias)).astype(np.float32)
+        if dark is not None:
+            x = (x - np.asarray(dark)).astype(np.float32)
+    if flat is not None:
+        x = flatfield_correct(x, flat, "float32")
+    return x.astype(np.float32)

@@ -15,7 +15,7 @@ MAX_COEF = 21
 MAX_WPOLY = 16
 ROWS_SCANNED = 39
 
-F32, F64 = 0, 1
+F32, F64, U16 = 0, 1, 2
 HOST_OUT_ZEROED = 1
 NEAREST, AREA, BILINEAR = 1, 2, 3
 
@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "emirwv_rectify2d_host", "emirwv_debug_geometry", "emirwv_debug_borders",
     "emirwv_median_slitlets", "emirwv_median_slitlets_host",
     "emirwv_abba_partial", "emirwv_abba_finish", "emirwv_stack_median",
+    "emirwv_prereduce",
 )
 
 
@@ -165,6 +166,8 @@ def load():
     lib.emirwv_abba_finish.argtypes = [vp, vp, i32, i32, ctypes.c_int64, vp, vp]
     lib.emirwv_stack_median.restype = i32
     lib.emirwv_stack_median.argtypes = [vp, i32, vp, i32, ctypes.c_int64, i32, vp, vp]
+    lib.emirwv_prereduce.restype = i32
+    lib.emirwv_prereduce.argtypes = [vp, i32, vp, i32, ctypes.c_int64, vp, vp, vp, i32, vp]
     lib.emirwv_debug_geometry.restype = i32
     lib.emirwv_debug_geometry.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.emirwv_debug_borders.restype = i32

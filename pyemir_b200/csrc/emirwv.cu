@@ -726,6 +726,56 @@ __global__ void __launch_bounds__(256) k_abba_finish(const double *__restrict__ 
     }
 }
 
+// Pre-reduction in front of the path (recipes/spec/abba.py:371 `flow(newimg)`, core/recipe.py:25-61):
+// bias subtraction, dark subtraction (numina BiasCorrector / DarkCorrector, restated: image
+// minus calibration) and the flat field of pyemir's own FlatFieldCorrector
+// (processing/flatfield.py:43,58-59: flat values <= 0 count as 1.0, result = data / flat cast to
+// float32).  One pass over the frames, calibrations (L2 resident: 3 x 16.8 MB) shared by all
+// frames; every stage rounds to float32 like the correctors' dtype="float32".  numpy's type
+// promotion is kept: float32 image with float32 calibrations computes in float32, any float64
+// operand makes the stage float64.
+template <typename TIn, typename TCal>
+__global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, float *__restrict__ out,
+                                                   int nframes, size_t npix,
+                                                   const TCal *__restrict__ bias,
+                                                   const TCal *__restrict__ dark,
+                                                   const TCal *__restrict__ flat) {
+    // float32 unless an operand is float64 (uint16 raw frames promote like numpy: with
+    // float32 calibrations the arithmetic is float32)
+    using A = typename std::conditional<sizeof(TIn) == 8 || sizeof(TCal) == 8, double, float>::type;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        const bool hb = bias != nullptr, hd = dark != nullptr, hf = flat != nullptr;
+        const A b = hb ? (A)bias[i] : A(0), d = hd ? (A)dark[i] : A(0);
+        A f = hf ? (A)flat[i] : A(1);
+        f = f <= A(0) ? A(1) : f;               // flatfield.py:43 (NaN stays NaN, like numpy)
+        for (int n = 0; n < nframes; ++n) {
+            const TIn raw = __ldcs(in + (size_t)n * npix + i);
+            if constexpr (sizeof(TIn) == 8) {
+                double x = raw;
+                if (hb) x = (double)(float)(x - (double)b);
+                if (hd) x = (double)(float)(x - (double)d);
+                if (hf) x = (double)(float)(x / (double)f);
+                __stcs(out + (size_t)n * npix + i, (float)x);
+            } else {
+                float x = (float)raw;
+                if (hb) x = (float)((A)x - b);
+                if (hd) x = (float)((A)x - d);
+                if (hf) x = (float)((A)x / f);
+                __stcs(out + (size_t)n * npix + i, x);
+            }
+        }
+    }
+}
+
+template <typename TIn, typename TCal>
+void launch_prereduce(const void *in, float *out, int nframes, size_t npix, const void *bias,
+                      const void *dark, const void *flat, int grid, cudaStream_t st) {
+    k_prereduce<TIn, TCal><<<grid, 256, 0, st>>>(
+        static_cast<const TIn *>(in), out, nframes, npix, static_cast<const TCal *>(bias),
+        static_cast<const TCal *>(dark), static_cast<const TCal *>(flat));
+}
+
 // ABBA combination, method "median" (abba.py:579-601 with numina's combine.median, restated):
 // per pixel the median over the selected frames of a stack (numpy.median semantics: mean of
 // the two middle values, NaN if any sample is NaN), float64 result like numina's combine.
@@ -2222,6 +2272,37 @@ int emirwv_abba_partial(const void *d_frames, const int8_t *d_labels, int nframe
         k_abba_partial<double><<<grid, 256, (size_t)nframes, st>>>(static_cast<const double *>(d_frames), d_labels,
                                                      nframes, (size_t)npix, d_sum_a, d_sum_b,
                                                      accumulate);
+    CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+int emirwv_prereduce(const void *d_in, int in_dtype, float *d_out, int nframes, int64_t npix,
+                     const void *d_bias, const void *d_dark, const void *d_flat, int cal_dtype,
+                     void *cuda_stream) {
+    if (d_in == nullptr || d_out == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (nframes < 0 || npix < 1) return fail(EMIRWV_E_VALUE, "size out of range");
+    if (in_dtype != EMIRWV_F32 && in_dtype != EMIRWV_F64 && in_dtype != EMIRWV_U16)
+        return fail(EMIRWV_E_VALUE, "unknown image dtype");
+    if (cal_dtype != EMIRWV_F32 && cal_dtype != EMIRWV_F64)
+        return fail(EMIRWV_E_VALUE, "unknown calibration dtype");
+    if (nframes == 0) return EMIRWV_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)sms * 16);
+    const size_t np = (size_t)npix;
+    const bool c64 = cal_dtype == EMIRWV_F64;
+    if (in_dtype == EMIRWV_F32) {
+        if (c64) launch_prereduce<float, double>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
+        else launch_prereduce<float, float>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
+    } else if (in_dtype == EMIRWV_F64) {
+        if (c64) launch_prereduce<double, double>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
+        else launch_prereduce<double, float>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
+    } else {
+        if (c64) launch_prereduce<uint16_t, double>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
+        else launch_prereduce<uint16_t, float>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
+    }
     CUDA_TRY(cudaGetLastError());
     return EMIRWV_OK;
 }
