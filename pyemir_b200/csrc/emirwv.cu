@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -76,6 +77,7 @@ constexpr int BAR_BYTES = ((2 * NSTAGE * 8) + 63) / 64 * 64;   // "full" and "do
 // (int32 bits), padded to a multiple of 4 elements so that records are 16-byte aligned.
 __host__ __device__ constexpr int rec_size(int K) { return (K * K + 1 + 3) & ~3; }
 constexpr int HOST_SLOTS = 3;                // pipeline depth of emirwv_run_host
+constexpr int SCHED_POOL = 1024;             // item counters: launches of one plan in flight
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 thread_local std::string g_error;
@@ -177,6 +179,7 @@ struct RunParams {
     int nlive_tiles;        // tiles [0, nlive_tiles) have wavelength coverage
     int ndead_tiles;        // the tiles after them are exactly zero
     int ngroups;            // ceil(nframes / G)
+    int *sched;             // dynamic work distribution: item counter of this launch (or NULL)
 };
 
 // flags in the top byte of a table record's slot word
@@ -943,8 +946,20 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     constexpr bool PACKED = sizeof(T) == 4 && (G % 2) == 0;
     using KV = KnotVec<T, G>;
 
+    // Work distribution: the first two items of a CTA are b and b + gridDim.x; with p.sched the
+    // following ones come from a counter shared by the CTAs (items differ in cost: tiles at the
+    // ends of a slitlet are narrower), else the stride continues.  wq[] holds the item numbers
+    // of iterations it .. it+2 (thread 0 draws the number of iteration it+3 before the barrier
+    // that ends iteration it).
+    __shared__ int wq[4];
     int w = blockIdx.x;
     if (w >= nwork) return;
+    if (tid == 0) {
+        wq[0] = w;
+        wq[1] = w + (int)gridDim.x;
+        wq[2] = p.sched != nullptr ? 2 * (int)gridDim.x + atomicAdd(p.sched, 1)
+                                   : w + 2 * (int)gridDim.x;
+    }
 
     // descriptors of the first two items
     constexpr int TCH = sizeof(Tile) / 16;
@@ -978,12 +993,12 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 
     for (int it = 0;; ++it) {
         const Tile &tile = ring[it % 3];
-        const int wnext = w + gridDim.x;
+        const int wnext = wq[(it + 1) & 3], wnn = wq[(it + 2) & 3];
         // descriptor of the item after the next one rides along with this item's copies
-        if (wnext + (int)gridDim.x < nwork && tid < TCH)
+        if (wnn < nwork && tid < TCH)
             cp_async_16(reinterpret_cast<char *>(&ring[(it + 2) % 3]) + tid * 16,
-                        reinterpret_cast<const char *>(p.tiles + (wnext + gridDim.x) / p.ngroups) +
-                            tid * 16, true);
+                        reinterpret_cast<const char *>(p.tiles + wnn / p.ngroups) + tid * 16,
+                        true);
 
         const int grp = w % p.ngroups;
         const int g0 = grp * G;
@@ -1319,6 +1334,9 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 
         if (wnext >= nwork) break;
         w = wnext;
+        if (tid == 0)
+            wq[(it + 3) & 3] = p.sched != nullptr ? 2 * (int)gridDim.x + atomicAdd(p.sched, 1)
+                                                  : wnn + (int)gridDim.x;
         cp_async_wait_all();
         __syncthreads();          // next descriptor landed; window and table slots are free
     }
@@ -1350,6 +1368,9 @@ struct emirwv_plan {
     int tile_k = 0, tile_rows = 0;
     int wrows_max = 0, wcols_max = 0, npx_max = 0, max_span = 0;
     std::vector<int32_t> h_cover;      // [nsl][2]: live output columns [lo, hi) of a slitlet
+    int *d_sched = nullptr;            // [SCHED_POOL] item counters, one per launch in flight
+    mutable std::atomic<unsigned> sched_next{0};
+    int dynamic_sched = 1;
     int tune_G = 0;
     int num_sms = 148;
     int64_t table_bytes = 0;
@@ -1466,6 +1487,11 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     rp.vec_ok = ((size_t)pl->nout * sizeof(T)) % 16 == 0;
     rp.nlive_tiles = pl->ntiles - pl->ntiles_empty;
     rp.ngroups = 0;
+    rp.sched = nullptr;
+    if (pl->dynamic_sched && pl->d_sched != nullptr) {
+        rp.sched = pl->d_sched + pl->sched_next.fetch_add(1) % SCHED_POOL;
+        CUDA_TRY(cudaMemsetAsync(rp.sched, 0, sizeof(int), st));
+    }
     if (d_jmm != nullptr) {
         const int n = nframes * pl->nsl * 2;
         k_init_jmm<<<(n + 255) / 256, 256, 0, st>>>(d_jmm, n);
@@ -1732,6 +1758,11 @@ int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int BW
         c[0] = std::min(c[0], t.k0);
         c[1] = std::max(c[1], t.k0 + t.nk);
     }
+    // the widest (most expensive) tiles first, the narrow ones at the ends of the slitlets
+    // last: the tail of the launch is made of short items
+    if (env_int("EMIRWV_TILE_ORDER", 1))
+        std::stable_sort(live.begin(), live.end(),
+                         [](const Tile &a, const Tile &b) { return a.nk > b.nk; });
     pl->ntiles_empty = (int)dead.size();
     pl->h_tiles = live;
     pl->h_tiles.insert(pl->h_tiles.end(), dead.begin(), dead.end());
@@ -1753,6 +1784,9 @@ int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
                     "distortion too strong: the source window of a 32-column block does not fit "
                     "(%d rows x %d columns available)", WIN_ROWS, WIN_PITCH);
     if (pl->ntiles_empty > 65535) return fail(EMIRWV_E_LIMIT, "too many tiles");
+    pl->dynamic_sched = env_int("EMIRWV_DYNAMIC", 1);
+    CUDA_TRY(cudaMalloc(&pl->d_sched, SCHED_POOL * sizeof(int)));
+    CUDA_TRY(cudaMemset(pl->d_sched, 0, SCHED_POOL * sizeof(int)));
     CUDA_TRY(cudaMalloc(&pl->d_tiles, pl->h_tiles.size() * sizeof(Tile)));
     CUDA_TRY(cudaMemcpy(pl->d_tiles, pl->h_tiles.data(), pl->h_tiles.size() * sizeof(Tile),
                         cudaMemcpyHostToDevice));
@@ -2001,6 +2035,7 @@ void emirwv_plan_destroy(emirwv_plan *pl) {
     cudaFree(pl->d_border);
     cudaFree(pl->d_pix);
     cudaFree(pl->d_tiles);
+    cudaFree(pl->d_sched);
     delete pl;
 }
 
