@@ -262,6 +262,13 @@ int emirwv_prereduce(const void *d_in, int in_dtype, float *d_out, int nframes, 
 int emirwv_stack_median(const void *d_frames, int nframes, const int32_t *h_index, int nsel,
                         int64_t npix, int dtype, double *d_out, void *cuda_stream);
 
+/* Both medians and the difference in one pass: d_out [npix] float32 =
+ * float32(median of the h_index_a images) - float32(median of the h_index_b images); the stack
+ * is read once and no float64 intermediate is written (1 <= na, nb <= 64). */
+int emirwv_abba_median(const void *d_frames, int nframes, const int32_t *h_index_a, int na,
+                       const int32_t *h_index_b, int nb, int64_t npix, int dtype, float *d_out,
+                       void *cuda_stream);
+
 /*
  * Parity hooks (tests): the plan's geometry for one slitlet, copied to the host.
  *   h_row, h_col [39][bbw]       source pixel of tap (0,0) in bounding-box array

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "emirwv_host_alloc", "emirwv_host_free", "emirwv_rectify_slitlet",
     "emirwv_rectify2d_host", "emirwv_debug_geometry", "emirwv_debug_borders",
     "emirwv_median_slitlets", "emirwv_median_slitlets_host",
-    "emirwv_abba_partial", "emirwv_abba_finish", "emirwv_stack_median",
+    "emirwv_abba_partial", "emirwv_abba_finish", "emirwv_stack_median", "emirwv_abba_median",
     "emirwv_prereduce",
 )
 
@@ -166,6 +166,8 @@ def load():
     lib.emirwv_abba_finish.argtypes = [vp, vp, i32, i32, ctypes.c_int64, vp, vp]
     lib.emirwv_stack_median.restype = i32
     lib.emirwv_stack_median.argtypes = [vp, i32, vp, i32, ctypes.c_int64, i32, vp, vp]
+    lib.emirwv_abba_median.restype = i32
+    lib.emirwv_abba_median.argtypes = [vp, i32, vp, i32, vp, i32, ctypes.c_int64, i32, vp, vp]
     lib.emirwv_prereduce.restype = i32
     lib.emirwv_prereduce.argtypes = [vp, i32, vp, i32, ctypes.c_int64, vp, vp, vp, i32, vp]
     lib.emirwv_debug_geometry.restype = i32

@@ -20,8 +20,8 @@ hot path in the ABBA recipe:
   needs every sample of a pixel on one device, so sharded frames are first exchanged by row
   slabs (rank r receives rows ``slab_range(H, r, world)`` of every frame: one grouped
   send/recv, 1/world of each frame per peer), each rank takes the per-pixel medians of the A
-  and of the B images of its slab (``emirwv_stack_median``: samples in registers, bitonic
-  network), forms the difference, and the slabs are gathered on the destination rank.
+  and of the B images of its slab and their float32 difference in one pass
+  (``emirwv_abba_median``: samples in registers, bitonic network), and the slabs are gathered on the destination rank.
 
 The sigma-clip method is not covered.  The mean and the median of numina's ``combine`` and
 ``shift_image2d`` are restated (parity unpinned).
@@ -230,21 +230,40 @@ def exchange_row_slabs(frames_local, counts):
     return out
 
 
-def median_difference(med_a, med_b):
-    """float32(median A) - float32(median B) (``abba.py:604-606``), emirwv_abba_finish."""
+def abba_median_difference(frames, index_a, index_b):
+    """float32(median of frames[index_a]) - float32(median of frames[index_b]), one pass.
+
+    ``emirwv_abba_median``: both medians of a pixel are taken in registers and only the
+    float32 difference (``abba.py:604-606``) is written.
+    """
+    import numpy as np
     import torch
-    return finish(torch.stack([med_a, med_b]), 1, 1)
+    if frames.dim() != 3 or not frames.is_cuda or not frames.is_contiguous() or \
+            frames.dtype not in (torch.float32, torch.float64):
+        raise ValueError("frames must be a contiguous (n, H, W) float32/float64 CUDA tensor")
+    n, height, width = frames.shape
+    ia = np.ascontiguousarray(index_a, dtype=np.int32)
+    ib = np.ascontiguousarray(index_b, dtype=np.int32)
+    out = torch.empty((height, width), dtype=torch.float32, device=frames.device)
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    vp = ctypes.c_void_p
+    _cabi.check(_cabi.load().emirwv_abba_median(
+        vp(frames.data_ptr()), n, ia.ctypes.data_as(vp), int(ia.size), ib.ctypes.data_as(vp),
+        int(ib.size), height * width,
+        _cabi.F32 if frames.dtype == torch.float32 else _cabi.F64, vp(out.data_ptr()),
+        vp(stream) if stream else None))
+    return out
 
 
-def combine_abba_median(frames_local, labels, counts, dst=0, median=stack_median,
-                        difference=median_difference):
+def combine_abba_median(frames_local, labels, counts, dst=0,
+                        median_difference=abba_median_difference):
     """median(A images) - median(B images) of a sequence sharded over the ranks.
 
     frames_local: this rank's rectified frames; labels: the labels of ALL frames of the
     sequence (labels_of(full_set)); counts: frames owned by every rank.  Returns the (H, W)
-    float32 image on ``dst`` and None elsewhere.  ``median(stack, index) -> float64 image``
-    and ``difference(med_a, med_b) -> float32 image`` are the CUDA entry points; the CPU
-    (gloo) tests of the exchange pass torch stand-ins.
+    float32 image on ``dst`` and None elsewhere.
+    ``median_difference(stack, index_a, index_b) -> float32 image`` is the CUDA entry point
+    (emirwv_abba_median); the CPU (gloo) tests of the exchange pass a torch stand-in.
     """
     import torch
     from .distributed import gather_frames
@@ -258,7 +277,7 @@ def combine_abba_median(frames_local, labels, counts, dst=0, median=stack_median
     world = dist.get_world_size() if dist.is_initialized() else 1
     slabs = exchange_row_slabs(frames_local, counts)
     if slabs.shape[1]:
-        diff = difference(median(slabs, index_a), median(slabs, index_b))
+        diff = median_difference(slabs, index_a, index_b)
     else:
         diff = torch.empty((0, slabs.shape[2]), dtype=torch.float32, device=slabs.device)
     if world == 1:

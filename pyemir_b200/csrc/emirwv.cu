@@ -791,50 +791,102 @@ struct StackSel {
     int idx[STACK_MAX];
 };
 
+// median of the selected samples of pixel i (float64; NaN if any sample is NaN)
+template <typename T, int N>
+__device__ __forceinline__ double stack_median_px(const T *__restrict__ frames,
+                                                  const StackSel &sel, size_t npix, size_t i) {
+    const T inf = (T)INFINITY;
+    const int lo = (sel.n - 1) >> 1, hi = sel.n >> 1;
+    T v[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u)
+        v[u] = u < sel.n ? __ldcs(frames + (size_t)sel.idx[u] * npix + i) : inf;
+    bool has_nan = false;
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        has_nan |= v[u] != v[u];
+        v[u] = v[u] != v[u] ? inf : v[u];
+    }
+    // bitonic network: every index is a compile-time constant after unrolling, so the
+    // samples never leave the registers
+#pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1)
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+                const int l = q ^ j;
+                if (l > q) {
+                    const bool up = (q & kk) == 0;
+                    const T x = v[q], y = v[l];
+                    const T mn = x < y ? x : y, mx = x < y ? y : x;
+                    v[q] = up ? mn : mx;
+                    v[l] = up ? mx : mn;
+                }
+            }
+    T a = v[0], b = v[0];
+#pragma unroll
+    for (int u = 1; u < N; ++u) {
+        a = u == lo ? v[u] : a;
+        b = u == hi ? v[u] : b;
+    }
+    const double med = __dmul_rn(__dadd_rn((double)a, (double)b), 0.5);
+    return has_nan ? __longlong_as_double(0x7ff8000000000000LL) : med;
+}
+
 template <typename T, int N>
 __global__ void __launch_bounds__(256) k_stack_median(const T *__restrict__ frames,
                                                       const StackSel sel, size_t npix,
                                                       double *__restrict__ out) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const T inf = (T)INFINITY;
-    const int lo = (sel.n - 1) >> 1, hi = sel.n >> 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride)
+        out[i] = stack_median_px<T, N>(frames, sel, npix, i);
+}
+
+// median(A images) and median(B images) of a pixel one after the other in the same registers,
+// then float32(A) - float32(B) like abba.py:604-606: the stack is read once and only the
+// float32 difference is written.
+template <typename T, int N>
+__global__ void __launch_bounds__(256) k_abba_median(const T *__restrict__ frames,
+                                                     const StackSel sel_a, const StackSel sel_b,
+                                                     size_t npix, float *__restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        T v[N];
-#pragma unroll
-        for (int u = 0; u < N; ++u)
-            v[u] = u < sel.n ? __ldcs(frames + (size_t)sel.idx[u] * npix + i) : inf;
-        bool has_nan = false;
-#pragma unroll
-        for (int u = 0; u < N; ++u) {
-            has_nan |= v[u] != v[u];
-            v[u] = v[u] != v[u] ? inf : v[u];
-        }
-        // bitonic network: every index is a compile-time constant after unrolling, so the
-        // samples never leave the registers
-#pragma unroll
-        for (int kk = 2; kk <= N; kk <<= 1)
-#pragma unroll
-            for (int j = kk >> 1; j > 0; j >>= 1)
-#pragma unroll
-                for (int q = 0; q < N; ++q) {
-                    const int l = q ^ j;
-                    if (l > q) {
-                        const bool up = (q & kk) == 0;
-                        const T x = v[q], y = v[l];
-                        const T mn = x < y ? x : y, mx = x < y ? y : x;
-                        v[q] = up ? mn : mx;
-                        v[l] = up ? mx : mn;
-                    }
-                }
-        T a = v[0], b = v[0];
-#pragma unroll
-        for (int u = 1; u < N; ++u) {
-            a = u == lo ? v[u] : a;
-            b = u == hi ? v[u] : b;
-        }
-        const double med = __dmul_rn(__dadd_rn((double)a, (double)b), 0.5);
-        out[i] = has_nan ? __longlong_as_double(0x7ff8000000000000LL) : med;
+        const float ma = (float)stack_median_px<T, N>(frames, sel_a, npix, i);
+        const float mb = (float)stack_median_px<T, N>(frames, sel_b, npix, i);
+        out[i] = __fsub_rn(ma, mb);
     }
+}
+
+int fill_stack_sel(StackSel &sel, const int32_t *h_index, int nsel, int nframes) {
+    memset(&sel, 0, sizeof(sel));
+    if (h_index == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (nsel < 1) return fail(EMIRWV_E_VALUE, "no image selected");
+    if (nsel > STACK_MAX)
+        return fail(EMIRWV_E_LIMIT, "median of more than %d images per call", STACK_MAX);
+    sel.n = nsel;
+    for (int u = 0; u < nsel; ++u) {
+        if (h_index[u] < 0 || h_index[u] >= nframes)
+            return fail(EMIRWV_E_VALUE, "image index %d outside the stack", h_index[u]);
+        sel.idx[u] = h_index[u];
+    }
+    return EMIRWV_OK;
+}
+
+template <typename T>
+void launch_abba_median(const T *frames, const StackSel &sa, const StackSel &sb, size_t npix,
+                        float *out, int grid, cudaStream_t st) {
+    const int n = std::max(sa.n, sb.n);
+    if (n <= 4)
+        k_abba_median<T, 4><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
+    else if (n <= 8)
+        k_abba_median<T, 8><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
+    else if (n <= 16)
+        k_abba_median<T, 16><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
+    else if (n <= 32)
+        k_abba_median<T, 32><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
+    else
+        k_abba_median<T, 64><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
 }
 
 template <typename T>
@@ -1043,13 +1095,30 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         //   copy, slot y % NSTAGE.
         constexpr int VN = Vec16<T>::N;
         const int cv0 = max(tile.c0, 0), cv1 = min(tile.c0 + tile.wcols, W);   // valid columns
-        const unsigned row_bytes = (unsigned)((cv1 - cv0) * sizeof(T));
-        const unsigned win_a = smem_addr_of(win) + (unsigned)((cv0 - tile.c0) * sizeof(T)) +
-                               (unsigned)(cg * WSZ * sizeof(T));
-        const T *fin = p.in + ((size_t)g0 + cg) * W * p.naxis2 + cv0;
-        const unsigned trow_bytes = (unsigned)(npx * RS * sizeof(T));
-        const T *trow = p.w + ((size_t)s * NROWS * W + tile.jlo) * RS;
         const unsigned tsm_a = smem_addr_of(tsm);
+        // what the copy warp needs to know about an item (this one, or the next one whose
+        // first rows it requests as soon as this item's last row is through)
+        struct CopyCtx {
+            unsigned row_bytes, win_a, trow_bytes;
+            const T *fin, *trow;
+            int nlive, wcols;
+            bool oob_rows;
+        };
+        auto make_ctx = [&](const Tile &t, int wi) {
+            CopyCtx c;
+            const int g0i = (wi % p.ngroups) * G;
+            const int v0 = max(t.c0, 0), v1 = min(t.c0 + t.wcols, W);
+            c.nlive = min(G, p.nframes - g0i);
+            c.wcols = t.wcols;
+            c.row_bytes = (unsigned)((v1 - v0) * sizeof(T));
+            c.win_a = smem_addr_of(win) + (unsigned)((v0 - t.c0) * sizeof(T)) +
+                      (unsigned)(cg * WSZ * sizeof(T));
+            c.fin = p.in + ((size_t)g0i + cg) * W * p.naxis2 + v0;
+            c.trow_bytes = (unsigned)(t.npx * RS * sizeof(T));
+            c.trow = p.w + ((size_t)t.slit * NROWS * W + t.jlo) * RS;
+            c.oob_rows = span_lo(t.span[0]) < 0 || span_hi(t.span[NROWS - 1]) >= p.naxis2;
+            return c;
+        };
 
         // columns of the window that fall outside the detector stay zero for the item
         // (first and last tile of a slitlet: a handful of columns)
@@ -1067,47 +1136,52 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // arrivals: the source rows it adds and its table row.  Whichever warp issues them
         // does so with all its lanes: lane 0 posts the byte counts, every lane copies one
         // (row, frame); rows outside the detector (rare) are zero-filled instead.
-        const bool oob_rows = span_lo(tile.span[0]) < 0 || span_hi(tile.span[NROWS - 1]) >= p.naxis2;
-        auto copy_window_rows = [&](unsigned seq, int r_from, int r_to) {
+        auto copy_window_rows = [&](const CopyCtx &c, unsigned seq, int r_from, int r_to) {
             const unsigned bar = bars + 8 * (seq % NSTAGE);
             const int lo = max(r_from + 1, 0), hi = min(r_to, p.naxis2 - 1);
-            if (oob_rows) {
+            if (c.oob_rows) {
                 for (int r = r_from + 1; r <= r_to; ++r)
                     if (r < 0 || r >= p.naxis2) {
                         const unsigned slot = (unsigned)(r + RING_BIAS) % WIN_ROWS;
-                        for (int e = lane; e < nlive * tile.wcols; e += 32)
-                            win[(e / tile.wcols) * WSZ + slot * WIN_PITCH + e % tile.wcols] = T(0);
+                        for (int e = lane; e < c.nlive * c.wcols; e += 32)
+                            win[(e / c.wcols) * WSZ + slot * WIN_PITCH + e % c.wcols] = T(0);
                     }
                 __syncwarp();
             }
-            if (lane == 0) mbar_expect_tx(bar, (unsigned)(max(hi - lo + 1, 0) * nlive) * row_bytes);
+            if (lane == 0)
+                mbar_expect_tx(bar, (unsigned)(max(hi - lo + 1, 0) * c.nlive) * c.row_bytes);
             __syncwarp();
-            if (cg < nlive)
+            if (cg < c.nlive)
                 for (int r = lo + cr; r <= hi; r += ROWS_PER_ISSUE)
-                    bulk_g2s(win_a + (unsigned)(((unsigned)(r + RING_BIAS) % WIN_ROWS) *
-                                                (WIN_PITCH * sizeof(T))),
-                             fin + (size_t)r * W, row_bytes, bar);
+                    bulk_g2s(c.win_a + (unsigned)(((unsigned)(r + RING_BIAS) % WIN_ROWS) *
+                                                  (WIN_PITCH * sizeof(T))),
+                             c.fin + (size_t)r * W, c.row_bytes, bar);
         };
         // table row y = npx contiguous records, one bulk copy
-        auto copy_table_row = [&](unsigned seq, int y) {
+        auto copy_table_row = [&](const CopyCtx &c, unsigned seq, int y) {
             if (lane == 0) {
                 const unsigned bar = bars + 8 * (seq % NSTAGE);
-                mbar_expect_tx(bar, trow_bytes);
+                mbar_expect_tx(bar, c.trow_bytes);
                 bulk_g2s(tsm_a + (y % NSTAGE) * (unsigned)(PXCAP * RS * sizeof(T)),
-                         trow + (size_t)y * W * RS, trow_bytes, bar);
+                         c.trow + (size_t)y * W * RS, c.trow_bytes, bar);
+            }
+        };
+        // the first NSTAGE rows of an item and their table rows
+        auto copy_first_rows = [&](const CopyCtx &c, const Tile &t, unsigned seq0) {
+            for (int y = 0; y < NSTAGE; ++y) {
+                copy_window_rows(c, seq0 + y,
+                                 y == 0 ? span_lo(t.span[0]) - 1 : span_hi(t.span[y - 1]),
+                                 span_hi(t.span[y]));
+                copy_table_row(c, seq0 + y, y);
             }
         };
 
-        // the first NSTAGE rows and their table rows are requested up front; once every compute warp
-        // is through row y the copy warp requests the table row and the source rows of row
-        // y+NSTAGE (nobody reads the slots they overwrite any more)
-        if (producer) {
-            for (int y = 0; y < NSTAGE; ++y) {
-                copy_window_rows(rowseq + y, y == 0 ? span_lo(tile.span[0]) - 1 : span_hi(tile.span[y - 1]),
-                                 span_hi(tile.span[y]));
-                copy_table_row(rowseq + y, y);
-            }
-        }
+        // The first NSTAGE rows and their table rows are requested up front -- for the first
+        // item of the CTA here, for every later one by the copy warp at the end of the item
+        // before it (below); once every compute warp is through row y the copy warp requests
+        // the table row and the source rows of row y+NSTAGE (nobody reads the slots they
+        // overwrite any more)
+        if (producer && it == 0) copy_first_rows(make_ctx(tile, w), tile, rowseq);
         // this thread's slot in the staged table rows (lanes without a pixel read a
         // neighbour's entry; their result is discarded)
         const int ppc = min(max(pp, 0), npx - 1);
@@ -1288,15 +1362,26 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // row y (phases A, C: independent instruction streams in one basic block), then
         // reports row y done; warps may drift apart by up to NSTAGE-1 rows.
         if (producer) {
+            const CopyCtx ctx = make_ctx(tile, w);
 #pragma unroll 1
             for (int y = 0; y < NROWS; ++y) {
                 mbar_wait(bars + 8 * NSTAGE + 8 * (rowseq % NSTAGE), (rowseq / NSTAGE) & 1);  // row y is done
                 if (y + NSTAGE < NROWS) {
-                    copy_table_row(rowseq + NSTAGE, y + NSTAGE);
-                    copy_window_rows(rowseq + NSTAGE, span_hi(tile.span[y + NSTAGE - 1]),
+                    copy_table_row(ctx, rowseq + NSTAGE, y + NSTAGE);
+                    copy_window_rows(ctx, rowseq + NSTAGE, span_hi(tile.span[y + NSTAGE - 1]),
                                      span_hi(tile.span[y + NSTAGE]));
                 }
                 ++rowseq;
+            }
+            // Every compute warp has read what the last row needs: the window and the table
+            // slots are free, so the first rows of the CTA's next item are requested now
+            // -- while the compute warps still evaluate the borders of the last row -- and not
+            // after the barrier that ends the item.  (Its descriptor landed one item ago; the
+            // columns outside the detector that the next item zero-fills are not touched by
+            // these copies.)
+            if (wnext < nwork) {
+                const Tile &tn = ring[(it + 1) % 3];
+                copy_first_rows(make_ctx(tn, wnext), tn, rowseq);
             }
         } else {
             mbar_wait(bars + 8 * (rowseq % NSTAGE), (rowseq / NSTAGE) & 1);   // rows + table landed
@@ -2344,21 +2429,12 @@ int emirwv_prereduce(const void *d_in, int in_dtype, float *d_out, int nframes, 
 
 int emirwv_stack_median(const void *d_frames, int nframes, const int32_t *h_index, int nsel,
                         int64_t npix, int dtype, double *d_out, void *cuda_stream) {
-    if (d_frames == nullptr || h_index == nullptr || d_out == nullptr)
-        return fail(EMIRWV_E_VALUE, "null argument");
-    if (nsel < 1) return fail(EMIRWV_E_VALUE, "no image selected");
-    if (nsel > STACK_MAX)
-        return fail(EMIRWV_E_LIMIT, "median of more than %d images per call", STACK_MAX);
+    if (d_frames == nullptr || d_out == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
     if (npix < 1 || nframes < 1) return fail(EMIRWV_E_VALUE, "size out of range");
     if (dtype != EMIRWV_F32 && dtype != EMIRWV_F64) return fail(EMIRWV_E_VALUE, "unknown dtype");
     StackSel sel;
-    memset(&sel, 0, sizeof(sel));
-    sel.n = nsel;
-    for (int u = 0; u < nsel; ++u) {
-        if (h_index[u] < 0 || h_index[u] >= nframes)
-            return fail(EMIRWV_E_VALUE, "image index %d outside the stack", h_index[u]);
-        sel.idx[u] = h_index[u];
-    }
+    const int rc = fill_stack_sel(sel, h_index, nsel, nframes);
+    if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     int dev = 0, sms = 148;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -2368,6 +2444,31 @@ int emirwv_stack_median(const void *d_frames, int nframes, const int32_t *h_inde
         launch_stack_median(static_cast<const float *>(d_frames), sel, (size_t)npix, d_out, grid, st);
     else
         launch_stack_median(static_cast<const double *>(d_frames), sel, (size_t)npix, d_out, grid, st);
+    CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+int emirwv_abba_median(const void *d_frames, int nframes, const int32_t *h_index_a, int na,
+                       const int32_t *h_index_b, int nb, int64_t npix, int dtype, float *d_out,
+                       void *cuda_stream) {
+    if (d_frames == nullptr || d_out == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (npix < 1 || nframes < 1) return fail(EMIRWV_E_VALUE, "size out of range");
+    if (dtype != EMIRWV_F32 && dtype != EMIRWV_F64) return fail(EMIRWV_E_VALUE, "unknown dtype");
+    if (na < 1 || nb < 1) return fail(EMIRWV_E_VALUE, "both A and B images are needed");
+    StackSel sa, sb;
+    int rc = fill_stack_sel(sa, h_index_a, na, nframes);
+    if (rc) return rc;
+    rc = fill_stack_sel(sb, h_index_b, nb, nframes);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)sms * 8);
+    if (dtype == EMIRWV_F32)
+        launch_abba_median(static_cast<const float *>(d_frames), sa, sb, (size_t)npix, d_out, grid, st);
+    else
+        launch_abba_median(static_cast<const double *>(d_frames), sa, sb, (size_t)npix, d_out, grid, st);
     CUDA_TRY(cudaGetLastError());
     return EMIRWV_OK;
 }

@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 from pyemir_b200 import hdu  # noqa: E402
 
 SHAPE = (96, 128)
+RESULTS = {}
 # (name, image dtype, flat dtype)
 CASES = [("f32_f32", "float32", "float32"), ("f32_f64", "float32", "float64"),
          ("u16_f32", "uint16", "float32"), ("f64_f32", "float64", "float32")]
@@ -50,6 +51,15 @@ def make_inputs(name, img_dtype, flat_dtype):
         flat[2, 3] = np.nan             # stays NaN (nan <= 0 is False)
         flat[2, 4] = np.inf
     return data, flat
+
+
+def sha_canonical(arr):
+    """sha256 of the array with every NaN replaced by one bit pattern (numpy keeps the payload
+    of an input NaN, CUDA arithmetic returns its canonical NaN: both are "NaN")."""
+    arr = np.ascontiguousarray(arr).copy()
+    if arr.dtype.kind == "f":
+        arr[np.isnan(arr)] = np.nan
+    return hashlib.sha256(arr.tobytes()).hexdigest()
 
 
 class _Corrector:
@@ -95,16 +105,18 @@ def main():
         res = node.run(img)
         arr = res["primary"].data
         cards = [[c[0], c[1]] for c in res["primary"].header.cards]
+        RESULTS[name] = arr
         out["cases"][name] = {
             "img_dtype": img_dtype, "flat_dtype": flat_dtype,
             "result_dtype": arr.dtype.name,
-            "sha256": hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest(),
+            "sha256": sha_canonical(arr),
             "flat_fixed_sha256": hashlib.sha256(flat_in.tobytes()).hexdigest(),
             "flat_stats": float(node.flat_stats),
             "sample": [float(v) if np.isfinite(v) else repr(float(v))
                        for v in arr[::17, ::23].ravel()[:12]],
             "cards": [c for c in cards if "correction time" not in str(c[1])],
         }
+    np.savez_compressed(os.path.join(HERE, "flatfield_results.npz"), **RESULTS)
     with open(os.path.join(HERE, "flatfield.json"), "w") as fd:
         json.dump(out, fd, indent=1)
     print("wrote", os.path.join(HERE, "flatfield.json"))

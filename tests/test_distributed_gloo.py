@@ -102,8 +102,8 @@ def test_abba_reduce_world2(tmp_path):
 
 
 def _abba_median_worker(rank, world, port, nframes, height, result_dir):
-    """ABBA "median" combination over two ranks: row-slab exchange, per-slab medians (torch
-    stand-ins here; emirwv_stack_median / emirwv_abba_finish on a GPU box), slab gather."""
+    """ABBA "median" combination over two ranks: row-slab exchange, per-slab medians (a numpy
+    stand-in here; emirwv_abba_median on a GPU box), slab gather."""
     from pyemir_b200 import abba
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -122,14 +122,14 @@ def _abba_median_worker(rank, world, port, nframes, height, result_dir):
         r0, r1 = abba.slab_range(height, rank, world)
         assert torch.equal(slabs, stack[:, r0:r1])
 
-        def median(frames, index):
-            return torch.from_numpy(np.median(frames[index].numpy().astype(np.float64), axis=0))
+        def median_difference(frames, index_a, index_b):
+            def med(index):
+                return np.median(frames[index].numpy().astype(np.float64), axis=0)
+            return torch.from_numpy(med(index_a).astype(np.float32) -
+                                    med(index_b).astype(np.float32))
 
-        def difference(a, b):
-            return a.to(torch.float32) - b.to(torch.float32)
-
-        got = abba.combine_abba_median(local, labels, counts, dst=0, median=median,
-                                       difference=difference)
+        got = abba.combine_abba_median(local, labels, counts, dst=0,
+                                       median_difference=median_difference)
         if rank == 0:
             from oracle.pipeline import combine_abba_median as oracle_abba
             want = oracle_abba(stack.numpy(), full_set)

@@ -577,6 +577,14 @@ def test_abba_median_matches_oracle(dtype, repeat, nseq):
         want = oracle_abba(stack, full_set)
     assert got.dtype == torch.float32 and tuple(got.shape) == want.shape
     assert np.array_equal(got.cpu().numpy(), want, equal_nan=True)
+    # unequal numbers of A and B images (one A image dropped)
+    index_b = [i for i, c in enumerate(full_set) if c == "B"]
+    if len(index_a) > 1:
+        got2 = abba.abba_median_difference(frames, index_a[1:], index_b).cpu().numpy()
+        with np.errstate(invalid="ignore"):
+            want2 = (np.median(stack[index_a[1:]].astype(np.float64), axis=0).astype(np.float32)
+                     - np.median(stack[index_b].astype(np.float64), axis=0).astype(np.float32))
+        assert np.array_equal(got2, want2, equal_nan=True)
 
 
 @pytest.mark.gpu

@@ -16,7 +16,9 @@ with open(os.path.join(HERE, "golden", "flatfield.json")) as _fd:
 
 import sys
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from make_golden_flatfield import make_inputs  # noqa: E402  (seeded inputs only; no reference)
+from make_golden_flatfield import make_inputs, sha_canonical  # noqa: E402  (no reference read)
+
+RESULTS = np.load(os.path.join(HERE, "golden", "flatfield_results.npz"))
 
 
 def _sha(arr):
@@ -29,7 +31,8 @@ def test_oracle_flatfield_matches_reference_vectors(name):
     data, flat = make_inputs(name, case["img_dtype"], case["flat_dtype"])
     got = oracle.flatfield_correct(data, flat)
     assert got.dtype.name == case["result_dtype"]
-    assert _sha(got) == case["sha256"]
+    assert np.array_equal(got, RESULTS[name], equal_nan=True)
+    assert sha_canonical(got) == case["sha256"] == sha_canonical(RESULTS[name])
 
 
 @pytest.mark.gpu
@@ -49,7 +52,11 @@ def test_flatfield_corrector_mirror_bit_exact(name):
     res = node.run(img)
     arr = res["primary"].data
     assert arr.dtype.name == case["result_dtype"]
-    assert _sha(arr) == case["sha256"]
+    # bit exact; NaNs compare as NaNs (CUDA returns its canonical NaN, numpy keeps the payload)
+    assert np.array_equal(arr, RESULTS[name], equal_nan=True), \
+        int((~((arr == RESULTS[name]) | (np.isnan(arr) & np.isnan(RESULTS[name])))).sum())
+    assert np.array_equal(np.signbit(arr[arr == 0]), np.signbit(RESULTS[name][RESULTS[name] == 0]))
+    assert sha_canonical(arr) == case["sha256"]
     cards = [[c[0], c[1]] for c in res["primary"].header.cards
              if "correction time" not in str(c[1])]
     assert cards == case["cards"]
