@@ -180,6 +180,7 @@ struct RunParams {
     int ndead_tiles;        // the tiles after them are exactly zero
     int ngroups;            // ceil(nframes / G)
     int *sched;             // dynamic work distribution: item counter of this launch (or NULL)
+    int early;              // first rows of the next item requested at the end of the current one
 };
 
 // flags in the top byte of a table record's slot word
@@ -1181,7 +1182,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         // before it (below); once every compute warp is through row y the copy warp requests
         // the table row and the source rows of row y+NSTAGE (nobody reads the slots they
         // overwrite any more)
-        if (producer && it == 0) copy_first_rows(make_ctx(tile, w), tile, rowseq);
+        if (producer && (it == 0 || !p.early)) copy_first_rows(make_ctx(tile, w), tile, rowseq);
         // this thread's slot in the staged table rows (lanes without a pixel read a
         // neighbour's entry; their result is discarded)
         const int ppc = min(max(pp, 0), npx - 1);
@@ -1379,7 +1380,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             // after the barrier that ends the item.  (Its descriptor landed one item ago; the
             // columns outside the detector that the next item zero-fills are not touched by
             // these copies.)
-            if (wnext < nwork) {
+            if (p.early && wnext < nwork) {
                 const Tile &tn = ring[(it + 1) % 3];
                 copy_first_rows(make_ctx(tn, wnext), tn, rowseq);
             }
@@ -1456,6 +1457,7 @@ struct emirwv_plan {
     int *d_sched = nullptr;            // [SCHED_POOL] item counters, one per launch in flight
     mutable std::atomic<unsigned> sched_next{0};
     int dynamic_sched = 1;
+    int early_rows = 1;
     int tune_G = 0;
     int num_sms = 148;
     int64_t table_bytes = 0;
@@ -1573,6 +1575,7 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     rp.nlive_tiles = pl->ntiles - pl->ntiles_empty;
     rp.ngroups = 0;
     rp.sched = nullptr;
+    rp.early = pl->early_rows;
     if (pl->dynamic_sched && pl->d_sched != nullptr) {
         rp.sched = pl->d_sched + pl->sched_next.fetch_add(1) % SCHED_POOL;
         CUDA_TRY(cudaMemsetAsync(rp.sched, 0, sizeof(int), st));
@@ -1870,6 +1873,7 @@ int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
                     "(%d rows x %d columns available)", WIN_ROWS, WIN_PITCH);
     if (pl->ntiles_empty > 65535) return fail(EMIRWV_E_LIMIT, "too many tiles");
     pl->dynamic_sched = env_int("EMIRWV_DYNAMIC", 1);
+    pl->early_rows = env_int("EMIRWV_EARLY", 1);
     CUDA_TRY(cudaMalloc(&pl->d_sched, SCHED_POOL * sizeof(int)));
     CUDA_TRY(cudaMemset(pl->d_sched, 0, SCHED_POOL * sizeof(int)));
     CUDA_TRY(cudaMalloc(&pl->d_tiles, pl->h_tiles.size() * sizeof(Tile)));
