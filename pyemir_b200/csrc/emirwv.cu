@@ -738,7 +738,51 @@ __global__ void __launch_bounds__(256) k_abba_finish(const double *__restrict__ 
 // frames; every stage rounds to float32 like the correctors' dtype="float32".  numpy's type
 // promotion is kept: float32 image with float32 calibrations computes in float32, any float64
 // operand makes the stage float64.
-template <typename TIn, typename TCal>
+// four consecutive elements with the widest loads the type allows (the streaming variants for
+// the frames, the cached ones for the calibrations that every frame reuses)
+template <bool STREAM>
+__device__ __forceinline__ void load4(const float *p, float (&v)[4]) {
+    const float4 t = STREAM ? __ldcs(reinterpret_cast<const float4 *>(p))
+                            : __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+template <bool STREAM>
+__device__ __forceinline__ void load4(const double *p, double (&v)[4]) {
+    const double2 a = STREAM ? __ldcs(reinterpret_cast<const double2 *>(p))
+                             : __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 b = STREAM ? __ldcs(reinterpret_cast<const double2 *>(p) + 1)
+                             : __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+}
+template <bool STREAM>
+__device__ __forceinline__ void load4(const uint16_t *p, uint16_t (&v)[4]) {
+    const ushort4 t = STREAM ? __ldcs(reinterpret_cast<const ushort4 *>(p))
+                             : __ldg(reinterpret_cast<const ushort4 *>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+
+// one pixel of one frame through the stages
+template <typename TIn, typename A>
+__device__ __forceinline__ float prereduce_px(TIn raw, bool hb, bool hd, bool hf, A b, A d, A f) {
+    if constexpr (sizeof(TIn) == 8) {
+        double x = raw;
+        if (hb) x = (double)(float)(x - (double)b);
+        if (hd) x = (double)(float)(x - (double)d);
+        if (hf) x = (double)(float)(x / (double)f);
+        return (float)x;
+    } else {
+        float x = (float)raw;
+        if (hb) x = (float)((A)x - b);
+        if (hd) x = (float)((A)x - d);
+        if (hf) x = (float)((A)x / f);
+        return x;
+    }
+}
+
+// VEC = 4: a thread owns four consecutive pixels (16-byte loads and stores, npix % 4 == 0 and
+// aligned buffers); VEC = 1: any size and alignment.  Frames are taken four at a time so that
+// four independent loads are in flight per thread.
+template <typename TIn, typename TCal, int VEC>
 __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, float *__restrict__ out,
                                                    int nframes, size_t npix,
                                                    const TCal *__restrict__ bias,
@@ -747,37 +791,91 @@ __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, f
     // float32 unless an operand is float64 (uint16 raw frames promote like numpy: with
     // float32 calibrations the arithmetic is float32)
     using A = typename std::conditional<sizeof(TIn) == 8 || sizeof(TCal) == 8, double, float>::type;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        const bool hb = bias != nullptr, hd = dark != nullptr, hf = flat != nullptr;
-        const A b = hb ? (A)bias[i] : A(0), d = hd ? (A)dark[i] : A(0);
-        A f = hf ? (A)flat[i] : A(1);
-        f = f <= A(0) ? A(1) : f;               // flatfield.py:43 (NaN stays NaN, like numpy)
-        for (int n = 0; n < nframes; ++n) {
-            const TIn raw = __ldcs(in + (size_t)n * npix + i);
-            if constexpr (sizeof(TIn) == 8) {
-                double x = raw;
-                if (hb) x = (double)(float)(x - (double)b);
-                if (hd) x = (double)(float)(x - (double)d);
-                if (hf) x = (double)(float)(x / (double)f);
-                __stcs(out + (size_t)n * npix + i, (float)x);
-            } else {
-                float x = (float)raw;
-                if (hb) x = (float)((A)x - b);
-                if (hd) x = (float)((A)x - d);
-                if (hf) x = (float)((A)x / f);
-                __stcs(out + (size_t)n * npix + i, x);
+    constexpr int U = 4;
+    const bool hb = bias != nullptr, hd = dark != nullptr, hf = flat != nullptr;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * VEC;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < npix; i += stride) {
+        A b[VEC], d[VEC], f[VEC];
+        if constexpr (VEC == 4) {
+            TCal t[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) b[e] = d[e] = A(0), f[e] = A(1);
+            if (hb) {
+                load4<false>(bias + i, t);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) b[e] = (A)t[e];
             }
+            if (hd) {
+                load4<false>(dark + i, t);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) d[e] = (A)t[e];
+            }
+            if (hf) {
+                load4<false>(flat + i, t);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) f[e] = (A)t[e];
+            }
+        } else {
+            b[0] = hb ? (A)bias[i] : A(0);
+            d[0] = hd ? (A)dark[i] : A(0);
+            f[0] = hf ? (A)flat[i] : A(1);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+            f[e] = f[e] <= A(0) ? A(1) : f[e];   // flatfield.py:43 (NaN stays NaN, like numpy)
+        int n = 0;
+        for (; n + U <= nframes; n += U) {
+            TIn raw[U][VEC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if constexpr (VEC == 4) load4<true>(in + (size_t)(n + u) * npix + i, raw[u]);
+                else raw[u][0] = __ldcs(in + (size_t)(n + u) * npix + i);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float r[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    r[e] = prereduce_px<TIn, A>(raw[u][e], hb, hd, hf, b[e], d[e], f[e]);
+                float *dst = out + (size_t)(n + u) * npix + i;
+                if constexpr (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(r[0], r[1], r[2], r[3]));
+                else __stcs(dst, r[0]);
+            }
+        }
+        for (; n < nframes; ++n) {
+            TIn raw[VEC];
+            if constexpr (VEC == 4) load4<true>(in + (size_t)n * npix + i, raw);
+            else raw[0] = __ldcs(in + (size_t)n * npix + i);
+            float r[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                r[e] = prereduce_px<TIn, A>(raw[e], hb, hd, hf, b[e], d[e], f[e]);
+            float *dst = out + (size_t)n * npix + i;
+            if constexpr (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(r[0], r[1], r[2], r[3]));
+            else __stcs(dst, r[0]);
         }
     }
 }
 
 template <typename TIn, typename TCal>
 void launch_prereduce(const void *in, float *out, int nframes, size_t npix, const void *bias,
-                      const void *dark, const void *flat, int grid, cudaStream_t st) {
-    k_prereduce<TIn, TCal><<<grid, 256, 0, st>>>(
-        static_cast<const TIn *>(in), out, nframes, npix, static_cast<const TCal *>(bias),
-        static_cast<const TCal *>(dark), static_cast<const TCal *>(flat));
+                      const void *dark, const void *flat, int sms, cudaStream_t st) {
+    auto aligned = [](const void *ptr, size_t a) {
+        return ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) == 0;
+    };
+    const bool vec = npix % 4 == 0 && aligned(in, 4 * sizeof(TIn) > 16 ? 16 : 4 * sizeof(TIn)) &&
+                     aligned(out, 16) && aligned(bias, 16) && aligned(dark, 16) &&
+                     aligned(flat, 16);
+    const TIn *tin = static_cast<const TIn *>(in);
+    const TCal *tb = static_cast<const TCal *>(bias), *td = static_cast<const TCal *>(dark),
+               *tf = static_cast<const TCal *>(flat);
+    if (vec) {
+        const int grid = (int)std::min<size_t>((npix / 4 + 255) / 256, (size_t)sms * 16);
+        k_prereduce<TIn, TCal, 4><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf);
+    } else {
+        const int grid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sms * 16);
+        k_prereduce<TIn, TCal, 1><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf);
+    }
 }
 
 // ABBA combination, method "median" (abba.py:579-601 with numina's combine.median, restated):
@@ -2414,7 +2512,7 @@ int emirwv_prereduce(const void *d_in, int in_dtype, float *d_out, int nframes, 
     int dev = 0, sms = 148;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)sms * 16);
+    const int grid = sms;            // the launcher sizes the grid (scalar or 4-pixel threads)
     const size_t np = (size_t)npix;
     const bool c64 = cal_dtype == EMIRWV_F64;
     if (in_dtype == EMIRWV_F32) {

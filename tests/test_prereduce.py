@@ -67,11 +67,13 @@ def test_flatfield_corrector_mirror_bit_exact(name):
 @pytest.mark.parametrize("img_dtype,cal_dtype", [("float32", "float32"), ("uint16", "float32"),
                                                  ("float32", "float64"), ("float64", "float32"),
                                                  ("uint16", "float64")])
-def test_prereduce_stack_bit_exact(img_dtype, cal_dtype):
+@pytest.mark.parametrize("shape", [(5, 64, 200), (6, 21, 33)])
+def test_prereduce_stack_bit_exact(img_dtype, cal_dtype, shape):
+    """(5, 64, 200): 16-byte loads, a batch of four frames and a tail; (6, 21, 33): odd size,
+    scalar path."""
     import torch
     from pyemir_b200.prereduce import prereduce_torch
     rng = np.random.default_rng(3)
-    shape = (5, 64, 200)
     if img_dtype == "uint16":
         frames = rng.integers(0, 65535, size=shape).astype(np.uint16)
     else:
