@@ -890,16 +890,12 @@ struct StackSel {
     int idx[STACK_MAX];
 };
 
-// median of the selected samples of pixel i (float64; NaN if any sample is NaN)
+// median of the n samples held in v[0..n) (v[n..N) must be +inf): float64, NaN if any sample
+// is NaN
 template <typename T, int N>
-__device__ __forceinline__ double stack_median_px(const T *__restrict__ frames,
-                                                  const StackSel &sel, size_t npix, size_t i) {
+__device__ __forceinline__ double median_of_registers(T (&v)[N], int n) {
     const T inf = (T)INFINITY;
-    const int lo = (sel.n - 1) >> 1, hi = sel.n >> 1;
-    T v[N];
-#pragma unroll
-    for (int u = 0; u < N; ++u)
-        v[u] = u < sel.n ? __ldcs(frames + (size_t)sel.idx[u] * npix + i) : inf;
+    const int lo = (n - 1) >> 1, hi = n >> 1;
     bool has_nan = false;
 #pragma unroll
     for (int u = 0; u < N; ++u) {
@@ -933,28 +929,99 @@ __device__ __forceinline__ double stack_median_px(const T *__restrict__ frames,
     return has_nan ? __longlong_as_double(0x7ff8000000000000LL) : med;
 }
 
-template <typename T, int N>
+// medians of VEC consecutive pixels starting at i over the selected images (VEC = 4: 16-byte
+// loads, npix % 4 == 0 and aligned frames)
+template <typename T, int N, int VEC>
+__device__ __forceinline__ void stack_median_px(const T *__restrict__ frames, const StackSel &sel,
+                                                size_t npix, size_t i, double (&med)[VEC]) {
+    const T inf = (T)INFINITY;
+    T v[VEC][N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        if (u < sel.n) {
+            const T *src = frames + (size_t)sel.idx[u] * npix + i;
+            if constexpr (VEC == 4) {
+                T t[4];
+                load4<true>(src, t);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e][u] = t[e];
+            } else {
+                v[0][u] = __ldcs(src);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[e][u] = inf;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) med[e] = median_of_registers<T, N>(v[e], sel.n);
+}
+
+template <typename T, int N, int VEC>
 __global__ void __launch_bounds__(256) k_stack_median(const T *__restrict__ frames,
                                                       const StackSel sel, size_t npix,
                                                       double *__restrict__ out) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride)
-        out[i] = stack_median_px<T, N>(frames, sel, npix, i);
+    const size_t stride = (size_t)gridDim.x * blockDim.x * VEC;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < npix; i += stride) {
+        double med[VEC];
+        stack_median_px<T, N, VEC>(frames, sel, npix, i, med);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) out[i + e] = med[e];
+    }
 }
 
 // median(A images) and median(B images) of a pixel one after the other in the same registers,
 // then float32(A) - float32(B) like abba.py:604-606: the stack is read once and only the
 // float32 difference is written.
-template <typename T, int N>
+template <typename T, int N, int VEC>
 __global__ void __launch_bounds__(256) k_abba_median(const T *__restrict__ frames,
                                                      const StackSel sel_a, const StackSel sel_b,
                                                      size_t npix, float *__restrict__ out) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        const float ma = (float)stack_median_px<T, N>(frames, sel_a, npix, i);
-        const float mb = (float)stack_median_px<T, N>(frames, sel_b, npix, i);
-        out[i] = __fsub_rn(ma, mb);
+    const size_t stride = (size_t)gridDim.x * blockDim.x * VEC;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < npix; i += stride) {
+        double ma[VEC], mb[VEC];
+        stack_median_px<T, N, VEC>(frames, sel_a, npix, i, ma);
+        stack_median_px<T, N, VEC>(frames, sel_b, npix, i, mb);
+        float r[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) r[e] = __fsub_rn((float)ma[e], (float)mb[e]);
+        if constexpr (VEC == 4)
+            __stcs(reinterpret_cast<float4 *>(out + i), make_float4(r[0], r[1], r[2], r[3]));
+        else
+            out[i] = r[0];
     }
+}
+
+// four pixels per thread while the samples of four pixels fit comfortably in registers
+template <typename T, int N>
+constexpr bool stack_vec4() { return N * sizeof(T) <= 64; }
+
+template <typename T, int N>
+void launch_abba_median_n(const T *frames, const StackSel &sa, const StackSel &sb, size_t npix,
+                          float *out, int sms, bool vec_ok, cudaStream_t st) {
+    if constexpr (stack_vec4<T, N>()) {
+        if (vec_ok) {
+            const int grid = (int)std::min<size_t>((npix / 4 + 255) / 256, (size_t)sms * 8);
+            k_abba_median<T, N, 4><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
+            return;
+        }
+    }
+    const int grid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sms * 8);
+    k_abba_median<T, N, 1><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
+}
+
+template <typename T, int N>
+void launch_stack_median_n(const T *frames, const StackSel &sel, size_t npix, double *out,
+                           int sms, bool vec_ok, cudaStream_t st) {
+    if constexpr (stack_vec4<T, N>()) {
+        if (vec_ok) {
+            const int grid = (int)std::min<size_t>((npix / 4 + 255) / 256, (size_t)sms * 8);
+            k_stack_median<T, N, 4><<<grid, 256, 0, st>>>(frames, sel, npix, out);
+            return;
+        }
+    }
+    const int grid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sms * 8);
+    k_stack_median<T, N, 1><<<grid, 256, 0, st>>>(frames, sel, npix, out);
 }
 
 int fill_stack_sel(StackSel &sel, const int32_t *h_index, int nsel, int nframes) {
@@ -974,33 +1041,27 @@ int fill_stack_sel(StackSel &sel, const int32_t *h_index, int nsel, int nframes)
 
 template <typename T>
 void launch_abba_median(const T *frames, const StackSel &sa, const StackSel &sb, size_t npix,
-                        float *out, int grid, cudaStream_t st) {
+                        float *out, int sms, cudaStream_t st) {
     const int n = std::max(sa.n, sb.n);
-    if (n <= 4)
-        k_abba_median<T, 4><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
-    else if (n <= 8)
-        k_abba_median<T, 8><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
-    else if (n <= 16)
-        k_abba_median<T, 16><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
-    else if (n <= 32)
-        k_abba_median<T, 32><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
-    else
-        k_abba_median<T, 64><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
+    const bool vec_ok = npix % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0 &&
+                        (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    if (n <= 4) launch_abba_median_n<T, 4>(frames, sa, sb, npix, out, sms, vec_ok, st);
+    else if (n <= 8) launch_abba_median_n<T, 8>(frames, sa, sb, npix, out, sms, vec_ok, st);
+    else if (n <= 16) launch_abba_median_n<T, 16>(frames, sa, sb, npix, out, sms, vec_ok, st);
+    else if (n <= 32) launch_abba_median_n<T, 32>(frames, sa, sb, npix, out, sms, vec_ok, st);
+    else launch_abba_median_n<T, 64>(frames, sa, sb, npix, out, sms, vec_ok, st);
 }
 
 template <typename T>
-void launch_stack_median(const T *frames, const StackSel &sel, size_t npix, double *out, int grid,
+void launch_stack_median(const T *frames, const StackSel &sel, size_t npix, double *out, int sms,
                          cudaStream_t st) {
-    if (sel.n <= 4)
-        k_stack_median<T, 4><<<grid, 256, 0, st>>>(frames, sel, npix, out);
-    else if (sel.n <= 8)
-        k_stack_median<T, 8><<<grid, 256, 0, st>>>(frames, sel, npix, out);
-    else if (sel.n <= 16)
-        k_stack_median<T, 16><<<grid, 256, 0, st>>>(frames, sel, npix, out);
-    else if (sel.n <= 32)
-        k_stack_median<T, 32><<<grid, 256, 0, st>>>(frames, sel, npix, out);
-    else
-        k_stack_median<T, 64><<<grid, 256, 0, st>>>(frames, sel, npix, out);
+    const bool vec_ok = npix % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0 &&
+                        (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    if (sel.n <= 4) launch_stack_median_n<T, 4>(frames, sel, npix, out, sms, vec_ok, st);
+    else if (sel.n <= 8) launch_stack_median_n<T, 8>(frames, sel, npix, out, sms, vec_ok, st);
+    else if (sel.n <= 16) launch_stack_median_n<T, 16>(frames, sel, npix, out, sms, vec_ok, st);
+    else if (sel.n <= 32) launch_stack_median_n<T, 32>(frames, sel, npix, out, sms, vec_ok, st);
+    else launch_stack_median_n<T, 64>(frames, sel, npix, out, sms, vec_ok, st);
 }
 
 // Weighted gather of KT x KT taps for the G frames of an item: rowp[a] points at tap (a, 0)
@@ -2541,11 +2602,10 @@ int emirwv_stack_median(const void *d_frames, int nframes, const int32_t *h_inde
     int dev = 0, sms = 148;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)sms * 8);
     if (dtype == EMIRWV_F32)
-        launch_stack_median(static_cast<const float *>(d_frames), sel, (size_t)npix, d_out, grid, st);
+        launch_stack_median(static_cast<const float *>(d_frames), sel, (size_t)npix, d_out, sms, st);
     else
-        launch_stack_median(static_cast<const double *>(d_frames), sel, (size_t)npix, d_out, grid, st);
+        launch_stack_median(static_cast<const double *>(d_frames), sel, (size_t)npix, d_out, sms, st);
     CUDA_TRY(cudaGetLastError());
     return EMIRWV_OK;
 }
@@ -2566,11 +2626,10 @@ int emirwv_abba_median(const void *d_frames, int nframes, const int32_t *h_index
     int dev = 0, sms = 148;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)sms * 8);
     if (dtype == EMIRWV_F32)
-        launch_abba_median(static_cast<const float *>(d_frames), sa, sb, (size_t)npix, d_out, grid, st);
+        launch_abba_median(static_cast<const float *>(d_frames), sa, sb, (size_t)npix, d_out, sms, st);
     else
-        launch_abba_median(static_cast<const double *>(d_frames), sa, sb, (size_t)npix, d_out, grid, st);
+        launch_abba_median(static_cast<const double *>(d_frames), sa, sb, (size_t)npix, d_out, sms, st);
     CUDA_TRY(cudaGetLastError());
     return EMIRWV_OK;
 }

@@ -543,8 +543,9 @@ def test_abba_mean_matches_oracle(dtype):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("repeat,nseq", [(1, 1), (1, 3), (2, 3), (3, 5), (8, 2), (16, 2)])
-def test_abba_median_matches_oracle(dtype, repeat, nseq):
+@pytest.mark.parametrize("repeat,nseq,width", [(1, 1, 517), (1, 1, 516), (1, 3, 516), (2, 3, 517),
+                                               (2, 4, 516), (3, 5, 517), (8, 2, 516), (16, 2, 517)])
+def test_abba_median_matches_oracle(dtype, repeat, nseq, width):
     """emirwv_stack_median (+ _finish) against numpy.median per nodding position: 2 .. 64
     images per position (every register-array size of the kernel), ties, signed zeros,
     infinities and NaNs; bit exact."""
@@ -554,7 +555,8 @@ def test_abba_median_matches_oracle(dtype, repeat, nseq):
     rng = np.random.default_rng(100 * repeat + nseq)
     full_set = abba.build_full_set("ABBA", repeat, nseq)
     n = len(full_set)
-    stack = rng.normal(500.0, 200.0, size=(n, 41, 517)).astype(dtype)
+    # width 516: 16-byte loads, four pixels per thread; 517: scalar path
+    stack = rng.normal(500.0, 200.0, size=(n, 40, width)).astype(dtype)
     stack[:, 3, :] = np.round(stack[:, 3, :] / 100.0)                 # many ties
     stack[::2, 4, :50] = 0.0
     stack[1::2, 4, :50] = -0.0
