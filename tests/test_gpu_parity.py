@@ -440,6 +440,30 @@ def test_lr_float32_unaligned_rows():
 
 
 # ------------------------------------------------------------------ kernel variants, host entry
+def test_item_distribution_variants_bit_identical(monkeypatch):
+    """Which CTA takes which item (per-launch counter vs fixed stride), the order of the tiles
+    and the moment the copy warp requests an item's first rows do not change a single bit of
+    the product or of the JMN/JMX scan."""
+    coeff = only_slitlets(synthetic.make_config(2), list(range(1, 56, 3)))
+    fr = synthetic.make_frames(coeff, 9, seed=21)
+    res = []
+    for env in ({}, {"EMIRWV_DYNAMIC": "0"}, {"EMIRWV_TILE_ORDER": "0", "EMIRWV_EARLY": "0"},
+                {"EMIRWV_DYNAMIC": "0", "EMIRWV_TILE_ORDER": "0", "EMIRWV_EARLY": "0"}):
+        for key in ("EMIRWV_DYNAMIC", "EMIRWV_TILE_ORDER", "EMIRWV_EARLY"):
+            monkeypatch.delenv(key, raising=False)
+        for key, value in env.items():
+            monkeypatch.setenv(key, value)
+        plan = RectWavePlan(coeff, 2, "float32")
+        out, jmm = plan.run_host(fr)
+        out2, jmm2 = plan.run_host(fr)                       # counters are per launch
+        assert np.array_equal(out, out2) and np.array_equal(jmm, jmm2)
+        res.append((out, jmm))
+        plan.close()
+    for out, jmm in res[1:]:
+        assert np.array_equal(out, res[0][0]) and np.array_equal(jmm, res[0][1])
+    assert np.count_nonzero(res[0][0]) > 0
+
+
 @pytest.mark.parametrize("number,dtype", [(2, "float32"), ("4b", "float64")])
 def test_run_host_out_zeroed_equals_full_copy(number, dtype):
     """EMIRWV_HOST_OUT_ZEROED copies back only the covered columns of every slitlet; on a
