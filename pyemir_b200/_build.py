@@ -25,7 +25,8 @@ def _stale(target, sources):
 def build_library(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a … -> pyemir_b200/libemirwv.so"""
     sources = [os.path.join(CSRC, "emirwv.cu"), os.path.join(CSRC, "geom.cuh"),
-               os.path.join(CSRC, "median_net38.inc"), os.path.join(ROOT, "include", "emirwv.h")]
+               os.path.join(CSRC, "median_net38.inc"), os.path.join(CSRC, "stack_median_nets.inc"),
+               os.path.join(ROOT, "include", "emirwv.h")]
     if not force and not _stale(LIB_PATH, sources):
         return LIB_PATH
     cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"),

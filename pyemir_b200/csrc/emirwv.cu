@@ -881,50 +881,47 @@ void launch_prereduce(const void *in, float *out, int nframes, size_t npix, cons
 // ABBA combination, method "median" (abba.py:579-601 with numina's combine.median, restated):
 // per pixel the median over the selected frames of a stack (numpy.median semantics: mean of
 // the two middle values, NaN if any sample is NaN), float64 result like numina's combine.
-// One thread per pixel: its samples sit in registers (N = stack size rounded up to a power of
-// two, padded with +inf) and go through a bitonic sorting network, fully unrolled; all N
-// loads of a thread are in flight together and a warp reads 32 consecutive pixels of a frame.
+// One thread per pixel (or four): its samples sit in registers (N = stack size rounded up to a
+// power of two, padded with -inf / +inf) and go through a selection network, fully unrolled;
+// all N loads of a thread are in flight together.
 constexpr int STACK_MAX = 64;
 struct StackSel {
     int n;
     int idx[STACK_MAX];
 };
 
-// median of the n samples held in v[0..n) (v[n..N) must be +inf): float64, NaN if any sample
-// is NaN
+#include "stack_median_nets.inc"
+
+// Median of the n samples held in v[0..n), float64, NaN if any sample is NaN.  The padding
+// v[n..N) -- floor((N-n)/2) times -inf, then +inf -- puts the median of the samples on the
+// wires N/2-1 and N/2 for every n (odd n: wire N/2-1 alone), so the network only has to bring
+// the two middle values of N wires home: Batcher's odd-even merge sort pruned to those two
+// outputs (scripts/gen_stack_median_nets.py), two min/max instructions per exchange, every
+// index a compile-time constant: the samples never leave the registers.
 template <typename T, int N>
 __device__ __forceinline__ double median_of_registers(T (&v)[N], int n) {
     const T inf = (T)INFINITY;
-    const int lo = (n - 1) >> 1, hi = n >> 1;
     bool has_nan = false;
 #pragma unroll
     for (int u = 0; u < N; ++u) {
         has_nan |= v[u] != v[u];
         v[u] = v[u] != v[u] ? inf : v[u];
     }
-    // bitonic network: every index is a compile-time constant after unrolling, so the
-    // samples never leave the registers
-#pragma unroll
-    for (int kk = 2; kk <= N; kk <<= 1)
-#pragma unroll
-        for (int j = kk >> 1; j > 0; j >>= 1)
-#pragma unroll
-            for (int q = 0; q < N; ++q) {
-                const int l = q ^ j;
-                if (l > q) {
-                    const bool up = (q & kk) == 0;
-                    const T x = v[q], y = v[l];
-                    const T mn = x < y ? x : y, mx = x < y ? y : x;
-                    v[q] = up ? mn : mx;
-                    v[l] = up ? mx : mn;
-                }
-            }
-    T a = v[0], b = v[0];
-#pragma unroll
-    for (int u = 1; u < N; ++u) {
-        a = u == lo ? v[u] : a;
-        b = u == hi ? v[u] : b;
+#define CE(a, b) order2(v[a], v[b]);
+    if constexpr (N == 4) {
+        STACK_NET_4(CE)
+    } else if constexpr (N == 8) {
+        STACK_NET_8(CE)
+    } else if constexpr (N == 16) {
+        STACK_NET_16(CE)
+    } else if constexpr (N == 32) {
+        STACK_NET_32(CE)
+    } else {
+        static_assert(N == 4 || N == 8 || N == 16 || N == 32 || N == 64, "stack size bucket");
+        STACK_NET_64(CE)
     }
+#undef CE
+    const T a = v[N / 2 - 1], b = (n & 1) ? a : v[N / 2];
     const double med = __dmul_rn(__dadd_rn((double)a, (double)b), 0.5);
     return has_nan ? __longlong_as_double(0x7ff8000000000000LL) : med;
 }
@@ -935,6 +932,7 @@ template <typename T, int N, int VEC>
 __device__ __forceinline__ void stack_median_px(const T *__restrict__ frames, const StackSel &sel,
                                                 size_t npix, size_t i, double (&med)[VEC]) {
     const T inf = (T)INFINITY;
+    const int nneg = (N - sel.n) >> 1;                          // pads below the samples
     T v[VEC][N];
 #pragma unroll
     for (int u = 0; u < N; ++u) {
@@ -949,8 +947,9 @@ __device__ __forceinline__ void stack_median_px(const T *__restrict__ frames, co
                 v[0][u] = __ldcs(src);
             }
         } else {
+            const T pad = u < sel.n + nneg ? -inf : inf;
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) v[e][u] = inf;
+            for (int e = 0; e < VEC; ++e) v[e][u] = pad;
         }
     }
 #pragma unroll
