@@ -150,6 +150,8 @@ int emirwv_plan_set_tuning(emirwv_plan *plan, int frames_per_cta, int threads);
  *             non-zero value over the 39 scanned rows of each slitlet, or
  *             (INT32_MAX, -1) when there is none; may be NULL.
  * Replaces the slitlet loop of apply_rectwv_coeff.py:136-204.
+ * One call enqueues a 4-byte memset (the item counter of this launch, taken from a pool of
+ * 1024 so that launches on different streams never share one) and three kernels.
  */
 int emirwv_run(const emirwv_plan *plan, const void *d_in, void *d_out, int nframes,
                int32_t *d_jminmax, void *cuda_stream);
