@@ -138,3 +138,66 @@ def test_synthetic_product_is_well_formed(coeff_j):
         bbh = entry["bb_ns2_orig"] - entry["bb_ns1_orig"] + 1
         assert entry["max_row_rectified"] + 1 < bbh
         assert len(entry["ttd_aij"]) == 6 and len(entry["wpoly_coeff"]) >= 4
+
+
+# ------------------------------------------------------------------ ABBA / pre-reduction host logic
+def test_slab_range_partitions_rows():
+    from pyemir_b200.abba import slab_range
+    for height in (0, 1, 5, 38, 2090):
+        for world in (1, 2, 3, 8):
+            spans = [slab_range(height, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == height
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1
+    assert slab_range(2090, 7, 8) == (1834, 2090)
+
+
+def test_combine_abba_median_argument_checks():
+    """Bookkeeping errors are raised before any device work (no GPU needed)."""
+    import torch
+    from pyemir_b200 import abba
+    frames = torch.zeros((4, 3, 5))
+
+    def never(*args):
+        raise AssertionError("the combination must not start")
+
+    with pytest.raises(ValueError, match="both A and B"):
+        abba.combine_abba_median(frames, [1, 1, 1, 1], [4], median_difference=never)
+    with pytest.raises(ValueError, match="one label per frame"):
+        abba.combine_abba_median(frames, [1, -1, -1, 1, 1], [4], median_difference=never)
+    # single process: the stand-in sees the whole stack and the A / B index lists
+    seen = {}
+
+    def fake(stack, index_a, index_b):
+        seen["shape"], seen["a"], seen["b"] = tuple(stack.shape), index_a, index_b
+        return torch.ones(stack.shape[1:], dtype=torch.float32)
+
+    out = abba.combine_abba_median(frames, abba.labels_of("ABBA"), [4], median_difference=fake)
+    assert seen == {"shape": (4, 3, 5), "a": [0, 3], "b": [1, 2]} and out.shape == (3, 5)
+
+
+def test_device_entry_points_reject_host_tensors():
+    """The CUDA entry points take device tensors only: no silent CPU path."""
+    import torch
+    from pyemir_b200 import abba
+    from pyemir_b200.prereduce import prereduce_torch
+    cpu = torch.zeros((2, 4, 8))
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        abba.stack_median(cpu, [0, 1])
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        abba.abba_median_difference(cpu, [0], [1])
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        abba.partial_sums(cpu, [1, -1])
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        prereduce_torch(cpu, flat=np.ones((4, 8), dtype=np.float32))
+
+
+def test_flatfield_corrector_constructor_mirrors_reference():
+    """`processing/flatfield.py:33-45`: the flat is fixed in place, its mean kept."""
+    from pyemir_b200.prereduce import FlatFieldCorrector
+    flat = np.array([[1.0, 0.0, -2.0], [0.5, 2.0, 1.5]], dtype=np.float32)
+    node = FlatFieldCorrector(flat, calibid="uuid:x")
+    assert node.flatdata is flat
+    assert np.array_equal(flat, np.array([[1.0, 1.0, 1.0], [0.5, 2.0, 1.5]], dtype=np.float32))
+    assert node.flat_stats == flat.mean() and node.calibid == "uuid:x" and node.dtype == "float32"
+    assert node.update_variance is False
