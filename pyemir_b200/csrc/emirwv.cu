@@ -69,10 +69,11 @@ constexpr int WIN_PITCH = EMIRWV_WIN_PITCH;                // source window colu
                                               // 32 banks, so lanes on two ring rows never collide
 constexpr int WARP_PX = 30;                   // rectified columns a warp owns
 constexpr int WARP_BORDERS = 31;              // output columns a warp evaluates
-constexpr int NSTAGE = EMIRWV_NSTAGE;                     // rectified rows in flight: a row's copies are
-                                              // requested NSTAGE rows ahead of its use
-constexpr int PREFETCH = NSTAGE - 1;          // rows that share the ring with the current one
-constexpr int BAR_BYTES = ((2 * NSTAGE * 8) + 63) / 64 * 64;   // "full" and "done" mbarriers
+constexpr int NSTAGE_MAX = EMIRWV_NSTAGE;                 // rectified rows in flight: a row's copies are
+                                              // requested NSTAGE rows ahead of its use (a kernel
+                                              // template parameter: NSTAGE_MAX, or 2 for float64
+                                              // plans on request -- 96-byte records, see smem_bytes)
+constexpr int BAR_BYTES = ((2 * NSTAGE_MAX * 8) + 63) / 64 * 64;   // "full" and "done" mbarriers
 // Per output pixel table record: K*K weights followed by the packed source coordinates
 // (int32 bits), padded to a multiple of 4 elements so that records are 16-byte aligned.
 __host__ __device__ constexpr int rec_size(int K) { return (K * K + 1 + 3) & ~3; }
@@ -1133,9 +1134,10 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 // Shared memory: [tile descriptor ring: 3][mbarriers][G windows: WIN_ROWS x WIN_PITCH]
 //                [per warp: 2 x (rect | ya | yb) x 32 pixels x G][3 table rows]
 // ---------------------------------------------------------------------------------
-template <typename T, int K, int G, bool SPANLOOP>
+template <typename T, int K, int G, bool SPANLOOP, int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, 2)
     k_rectwv(const RunParams<T> p) {
+    static_assert(NSTAGE >= 2 && NSTAGE <= NSTAGE_MAX, "stage count");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int WSZ = WIN_ROWS * WIN_PITCH;                  // one frame's window
     constexpr int KNOT_WARP = 2 * 32 * G;                      // knot elements of one warp
@@ -1616,6 +1618,7 @@ struct emirwv_plan {
     mutable std::atomic<unsigned> sched_next{0};
     int dynamic_sched = 1;
     int early_rows = 1;
+    int nstage = NSTAGE_MAX;           // stages of the hot kernel's row pipeline
     int tune_G = 0;
     int num_sms = 148;
     int64_t table_bytes = 0;
@@ -1655,7 +1658,7 @@ struct LaunchCfg {
 size_t smem_bytes(const emirwv_plan *pl, int G) {
     return 3 * sizeof(Tile) + BAR_BYTES +
            (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 2 * 32) * pl->esize +
-           (size_t)NSTAGE * PXCAP * rec_size(pl->K) * pl->esize;
+           (size_t)pl->nstage * PXCAP * rec_size(pl->K) * pl->esize;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
@@ -1669,9 +1672,9 @@ LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
     return cfg;
 }
 
-template <typename T, int K, int G, bool SPANLOOP>
+template <typename T, int K, int G, bool SPANLOOP, int NS>
 int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, cudaStream_t st) {
-    auto kern = k_rectwv<T, K, G, SPANLOOP>;
+    auto kern = k_rectwv<T, K, G, SPANLOOP, NS>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)cfg.smem));
     int per_sm = 0;
@@ -1691,8 +1694,14 @@ int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, c
 template <typename T, int K, int G>
 int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
                cudaStream_t st) {
-    if (pl->max_span > 2) return launch_final<T, K, G, true>(pl, rp, cfg, st);
-    return launch_final<T, K, G, false>(pl, rp, cfg, st);
+    if constexpr (sizeof(T) == 8) {          // float64 plans may ask for two stages
+        if (pl->nstage == 2) {
+            if (pl->max_span > 2) return launch_final<T, K, G, true, 2>(pl, rp, cfg, st);
+            return launch_final<T, K, G, false, 2>(pl, rp, cfg, st);
+        }
+    }
+    if (pl->max_span > 2) return launch_final<T, K, G, true, NSTAGE_MAX>(pl, rp, cfg, st);
+    return launch_final<T, K, G, false, NSTAGE_MAX>(pl, rp, cfg, st);
 }
 
 template <typename T, int K>
@@ -1982,7 +1991,7 @@ int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int BW
             for (int y = 1; y < NROWS; ++y) rhi[y] = std::max(rhi[y], rhi[y - 1]);
             for (int y = NROWS - 2; y >= 0; --y) rlo[y] = std::min(rlo[y], rlo[y + 1]);
             for (int y = 0; y < NROWS; ++y) {
-                const int next_hi = rhi[std::min(y + PREFETCH, NROWS - 1)];
+                const int next_hi = rhi[std::min(y + pl->nstage - 1, NROWS - 1)];
                 span_max = std::max(span_max, next_hi - rlo[y] + 1);
                 t.span[y] = (int32_t)(((uint32_t)(rhi[y] & 0xffff) << 16) | (uint32_t)(rlo[y] & 0xffff));
             }
@@ -2096,6 +2105,10 @@ int build_plan(emirwv_plan *pl) {
     pl->NB = d.naxis1_out + 1;
     pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", TILE_K_MAX);
     pl->tile_rows = NROWS;       // a tile always spans the 39 scanned rows
+    // float64 records are 96 bytes: four staged table rows take 90 KB and leave room for one
+    // CTA per SM only; two stages fit two CTAs (EMIRWV_NSTAGE_F64=2, experimental)
+    pl->nstage = NSTAGE_MAX;
+    if (pl->esize == 8 && env_int("EMIRWV_NSTAGE_F64", NSTAGE_MAX) == 2) pl->nstage = 2;
     pl->tile_k = std::max(32, std::min(pl->tile_k, TILE_K_MAX));
 
     pl->h_slit.resize(pl->nsl);

@@ -464,6 +464,23 @@ def test_item_distribution_variants_bit_identical(monkeypatch):
     assert np.count_nonzero(res[0][0]) > 0
 
 
+@pytest.mark.parametrize("number", [1, 4])
+def test_float64_two_stage_pipeline_bit_identical(monkeypatch, number):
+    """EMIRWV_NSTAGE_F64=2 (two staged table rows instead of four: two CTAs per SM for the
+    96-byte float64 records) changes the depth of the copy pipeline only: same bits."""
+    coeff = only_slitlets(synthetic.make_config(number), [1, 2, 28, 54, 55])
+    fr = synthetic.make_frames(coeff, 5, seed=31, dtype=np.float64)
+    res = []
+    for stages in ("4", "2"):
+        monkeypatch.setenv("EMIRWV_NSTAGE_F64", stages)
+        plan = RectWavePlan(coeff, 2, "float64")
+        res.append(plan.run_host(fr))
+        assert (plan.info()["smem_bytes"] < 116000) == (stages == "2")
+        plan.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.count_nonzero(res[0][0]) > 0
+
+
 @pytest.mark.parametrize("number,dtype", [(2, "float32"), ("4b", "float64")])
 def test_run_host_out_zeroed_equals_full_copy(number, dtype):
     """EMIRWV_HOST_OUT_ZEROED copies back only the covered columns of every slitlet; on a
