@@ -1132,7 +1132,7 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 // The source window is a ring of WIN_ROWS rows per frame.
 //
 // Shared memory: [tile descriptor ring: 3][mbarriers][G windows: WIN_ROWS x WIN_PITCH]
-//                [per warp: 2 x (rect | ya | yb) x 32 pixels x G][3 table rows]
+//                [per warp: (rect | ya) x 32 pixels x G][NSTAGE table rows: PXCAP records]
 // ---------------------------------------------------------------------------------
 template <typename T, int K, int G, bool SPANLOOP, int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, 2)
@@ -1654,7 +1654,7 @@ struct LaunchCfg {
 
 // shared memory of the hot kernel:
 //   [3 tile descriptors][mbarriers, counters][G windows: WIN_ROWS x WIN_PITCH]
-//   [per warp: 2 x (rect | ya) x 32 x G knots][3 table rows: PXCAP records]
+//   [per warp: 2 x (rect | ya) x 32 x G knots][nstage table rows: PXCAP records]
 size_t smem_bytes(const emirwv_plan *pl, int G) {
     return 3 * sizeof(Tile) + BAR_BYTES +
            (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 2 * 32) * pl->esize +
