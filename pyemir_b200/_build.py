@@ -24,9 +24,10 @@ def _stale(target, sources):
 
 def build_library(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a … -> pyemir_b200/libemirwv.so"""
-    sources = [os.path.join(CSRC, "emirwv.cu"), os.path.join(CSRC, "geom.cuh"),
-               os.path.join(CSRC, "median_net38.inc"), os.path.join(CSRC, "stack_median_nets.inc"),
-               os.path.join(ROOT, "include", "emirwv.h")]
+    sources = [os.path.join(CSRC, name) for name in (
+        "emirwv.cu", "geom.cuh", "plan_kernels.cuh", "device_utils.cuh", "side_kernels.cuh",
+        "rectwv_kernel.cuh", "plan_build.inl", "median_net38.inc", "stack_median_nets.inc")]
+    sources.append(os.path.join(ROOT, "include", "emirwv.h"))
     if not force and not _stale(LIB_PATH, sources):
         return LIB_PATH
     cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"),

@@ -22,6 +22,15 @@
 //            store, first/last non-zero channel per slitlet   (kernel 3)
 //
 // No tensor cores (there is no dense contraction), no CPU fallback.
+//
+// One translation unit; the parts live next to this file and are included below:
+//   geom.cuh            2-D polynomial map and polygon clipping (shared with the CPU hostcheck)
+//   plan_kernels.cuh    k_extent, k_build_geometry, k_rectify2d, parity-hook helpers
+//   device_utils.cuh    TMA bulk copies, mbarriers, packed float32 pairs
+//   side_kernels.cuh    zero fill, median_slitlets_rectified, ABBA mean / median, pre-reduction
+//   rectwv_kernel.cuh   the hot kernel k_rectwv
+//   plan_build.inl      host side of a plan (launch configuration, border tables, tiles)
+// and this file keeps the constants, the device structs, the plan object and the C ABI.
 
 #include <cuda_runtime.h>
 
@@ -223,1370 +232,10 @@ __device__ inline void map_corners(const SlitDev &sd, int j, int row, double *qu
     }
 }
 
-// ---------------------------------------------------------------- plan kernels
-// Largest footprint (in source pixels) of any mapped output pixel, mode 2.
-__global__ void k_extent(GeomParams p) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    const int s = blockIdx.z;
-    const SlitDev &sd = p.slit[s];
-    int need = 1;
-    if (sd.valid && j < sd.bbw) {
-        double qu[4], qv[4];
-        map_corners(sd, j, sd.min_row + y, qu, qv);
-        int lo, hi;
-        quad_extent(qu, lo, hi);
-        need = hi - lo + 1;
-        quad_extent(qv, lo, hi);
-        need = max(need, hi - lo + 1);
-    }
-    need = __reduce_max_sync(0xffffffffu, need);
-    if ((threadIdx.x & 31) == 0) atomicMax(p.kmax, need);
-}
-
-// base[s][y][j] (frame coordinates of tap (0,0)) and w[s][y][tap][j].
-template <typename T>
-__global__ void k_build_geometry(GeomParams p, T *w) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    const int s = blockIdx.z;
-    const SlitDev &sd = p.slit[s];
-    if (j >= W) return;
-    const int K = p.K, KK = K * K;
-    const size_t rowtab = (size_t)s * NROWS + y;
-    const int RS = rec_size(K);
-    T *wp = w + (rowtab * W + j) * RS;
-    if (!sd.valid || j >= sd.bbw) {
-        p.base[rowtab * W + j] = pack_base(0, 0);
-        for (int tap = 0; tap < RS; ++tap) wp[tap] = T(0);
-        *reinterpret_cast<int32_t *>(wp + KK) = pack_base(0, 0);
-        return;
-    }
-    const int row = sd.min_row + y;
-    double wt[MAXK * MAXK];
-    int br, bc;
-    if (p.mode == EMIRWV_AREA) {
-        double qu[4], qv[4];
-        map_corners(sd, j, row, qu, qv);
-        int hr, hc;
-        quad_extent(qu, bc, hc);
-        quad_extent(qv, br, hr);
-        // absolute bounding-box coordinates, like the reference's clipping
-        for (int a = 0; a < K; ++a)
-            for (int b = 0; b < K; ++b) {
-                double area = 0.0;
-                if (br + a <= hr && bc + b <= hc)
-                    area = quad_box_area(qu, qv, (double)(bc + b) - 0.5, (double)(bc + b) + 0.5,
-                                         (double)(br + a) - 0.5, (double)(br + a) + 0.5);
-                wt[a * K + b] = area;
-            }
-    } else {
-        double u, v;
-        fmap(sd.order, sd.a, sd.b, (double)j, (double)row, u, v);
-        u = clampd(u);
-        v = clampd(v);
-        if (p.mode == EMIRWV_NEAREST) {
-            bc = (int)rint(u);     // round half to even, like numpy.rint
-            br = (int)rint(v);
-            wt[0] = 1.0;
-        } else {                   // bilinear extension
-            const double fu0 = floor(u), fv0 = floor(v);
-            bc = (int)fu0;
-            br = (int)fv0;
-            const double fu = u - fu0, fv = v - fv0;
-            wt[0] = (1.0 - fv) * (1.0 - fu);
-            wt[1] = (1.0 - fv) * fu;
-            wt[2] = fv * (1.0 - fu);
-            wt[3] = fv * fu;
-        }
-    }
-    // frame coordinates: bounding-box crop (slitlet2d.py:366-369) and the global
-    // integer offsets (apply_rectwv_coeff.py:74-78) folded into the address
-    const int fr0 = br + sd.ns1 - 1 - p.offy;
-    const int fc0 = bc + sd.nc1 - 1 - p.offx;
-    for (int a = 0; a < K; ++a)
-        for (int b = 0; b < K; ++b) {
-            const int r = br + a, c = bc + b;
-            const int fr = fr0 + a, fc = fc0 + b;
-            const bool inside = r >= 0 && r < sd.bbh && c >= 0 && c < sd.bbw && fr >= 0 &&
-                                fr < p.naxis2 && fc >= 0 && fc < p.naxis1;
-            wp[a * K + b] = inside ? (T)wt[a * K + b] : T(0);
-        }
-    for (int tap = KK; tap < RS; ++tap) wp[tap] = T(0);
-    // Compact form (K >= 3): almost every footprint fits a 2 x 2 block of source pixels.
-    // Such a record holds the block's four weights in words 0..3 (zeros elsewhere) and the
-    // coordinates of the block; the hot kernel then gathers 4 taps instead of K*K, with the
-    // same result (the skipped taps have weight zero).
-    int a0 = 0, b0 = 0;
-    uint32_t flags = 0;
-    if (K >= 3) {
-        int alo = K, ahi = -1, blo = K, bhi = -1;
-        for (int a = 0; a < K; ++a)
-            for (int b = 0; b < K; ++b)
-                if (wp[a * K + b] != T(0)) {
-                    alo = min(alo, a), ahi = max(ahi, a);
-                    blo = min(blo, b), bhi = max(bhi, b);
-                }
-        if (ahi < 0) alo = ahi = blo = bhi = 0;                // no contribution at all
-        if (ahi - alo <= 1 && bhi - blo <= 1) {
-            a0 = min(alo, K - 2);
-            b0 = min(blo, K - 2);
-            const T c00 = wp[a0 * K + b0], c01 = wp[a0 * K + b0 + 1];
-            const T c10 = wp[(a0 + 1) * K + b0], c11 = wp[(a0 + 1) * K + b0 + 1];
-            for (int tap = 0; tap < KK; ++tap) wp[tap] = T(0);
-            wp[0] = c00, wp[1] = c01, wp[2] = c10, wp[3] = c11;
-            flags = REC_COMPACT | ((uint32_t)a0 << 1) | ((uint32_t)b0 << 3);
-        }
-    }
-    *reinterpret_cast<int32_t *>(wp + KK) = pack_base(fr0 + a0, fc0 + b0);
-    // ring slot of each of the K source rows in the hot kernel's rolling window
-    uint32_t slots = flags << 24;
-    for (int a = 0; a < K && a < 3; ++a)
-        slots |= (uint32_t)((fr0 + a0 + a + RING_BIAS) % WIN_ROWS) << (8 * a);
-    *reinterpret_cast<uint32_t *>(wp + KK + 1) = slots;
-    if (K == 4)          // the fourth row of a 4 x 4 footprint has its own word
-        *reinterpret_cast<uint32_t *>(wp + KK + 2) = (uint32_t)((fr0 + a0 + 3 + RING_BIAS) % WIN_ROWS);
-    p.base[rowtab * W + j] = pack_base(fr0, fc0);
-}
-
-// General rectify2d on an arbitrary image (numina.array.distortion.rectify2d as called
-// by Slitlet2D.rectify, slitlet2d.py:421-423, direct or inverse map): one thread per
-// output pixel, geometry evaluated on the fly, float64, accumulation in the reference's
-// order.  Not the streaming path: it serves the per-slitlet API of the reference.
-__global__ void k_rectify2d(const double *img, int naxis2, int naxis1, SlitDev sd, int mode,
-                            double *out, int naxis2out, int naxis1out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= naxis1out || i >= naxis2out) return;
-    double acc = 0.0;
-    if (mode == EMIRWV_AREA) {
-        double qu[4], qv[4];
-        map_corners(sd, j, i, qu, qv);
-        int c0, c1, r0, r1;
-        quad_extent(qu, c0, c1);
-        quad_extent(qv, r0, r1);
-        for (int ii = max(r0, 0); ii <= min(r1, naxis2 - 1); ++ii)
-            for (int jj = max(c0, 0); jj <= min(c1, naxis1 - 1); ++jj) {
-                const double area = quad_box_area(qu, qv, (double)jj - 0.5, (double)jj + 0.5,
-                                                  (double)ii - 0.5, (double)ii + 0.5);
-                if (area != 0.0) acc = add_rn(acc, mul_rn(area, img[(size_t)ii * naxis1 + jj]));
-            }
-    } else {
-        double u, v;
-        fmap(sd.order, sd.a, sd.b, (double)j, (double)i, u, v);
-        u = clampd(u);
-        v = clampd(v);
-        if (mode == EMIRWV_NEAREST) {
-            const int ju = (int)rint(u), iv = (int)rint(v);
-            if (ju >= 0 && ju < naxis1 && iv >= 0 && iv < naxis2) acc = img[(size_t)iv * naxis1 + ju];
-        } else {
-            const double u0 = floor(u), v0 = floor(v);
-            const double fu = u - u0, fv = v - v0;
-            const double wv[2] = {1.0 - fv, fv}, wu[2] = {1.0 - fu, fu};
-            for (int dv = 0; dv < 2; ++dv)
-                for (int du = 0; du < 2; ++du) {
-                    const int cu = (int)u0 + du, cv = (int)v0 + dv;
-                    const double val = (cu >= 0 && cu < naxis1 && cv >= 0 && cv < naxis2)
-                                           ? img[(size_t)cv * naxis1 + cu] : 0.0;
-                    acc = add_rn(acc, mul_rn(mul_rn(wv[dv], wu[du]), val));
-                }
-        }
-    }
-    out[(size_t)i * naxis1out + j] = acc;
-}
-
-__global__ void k_init_jmm(int32_t *jmm, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) jmm[i] = (i & 1) ? -1 : INT_MAX;
-}
-
-// Kernel 1 alone, straight from global memory (parity hook / Slitlet2D.rectify).
-template <typename T>
-__global__ void k_rectify_only(const T *frame, T *rect, const int32_t *base, const T *w,
-                               int s, int K, int bbw, int naxis1, int naxis2) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (j >= bbw) return;
-    const size_t rowtab = (size_t)s * NROWS + y;
-    const int32_t pk = base[rowtab * W + j];
-    const int r0 = base_row(pk), c0 = base_col(pk);
-    const T *wp = w + (rowtab * W + j) * rec_size(K);
-    T acc = T(0);
-    for (int a = 0; a < K; ++a)
-        for (int b = 0; b < K; ++b) {
-            const T wt = record_weight(wp, K, a, b);
-            const int r = min(max(r0 + a, 0), naxis2 - 1);
-            const int c = min(max(c0 + b, 0), naxis1 - 1);
-            acc = fma(wt, frame[(size_t)r * naxis1 + c], acc);
-        }
-    rect[(size_t)y * bbw + j] = acc;
-}
-
-// ---------------------------------------------------------------- the hot kernel
-template <typename T>
-struct Vec16;
-template <>
-struct Vec16<float> {
-    using type = float4;
-    static constexpr int N = 4;
-};
-template <>
-struct Vec16<double> {
-    using type = double2;
-    static constexpr int N = 2;
-};
-
-// 16-byte asynchronous global -> shared copy (LDGSTS); zero fill when !valid
-__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, bool valid) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int src_bytes = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src),
-                 "r"(src_bytes)
-                 : "memory");
-}
-// ---- TMA bulk copies (cp.async.bulk) completed through an mbarrier transaction count
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-// global -> shared, 16-byte aligned addresses and size; completes `bytes` on the barrier
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-        : "memory");
-}
-
-__device__ __forceinline__ unsigned smem_addr_of(const void *p) {
-    return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-}
-
-// 8/16/32-byte table records through the read-only path (ld.global.nc)
-__device__ __forceinline__ PixGeom<float> ldg_struct(const PixGeom<float> *p) {
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
-    return PixGeom<float>{v.x, v.y, v.z, v.w};
-}
-__device__ __forceinline__ PixGeom<double> ldg_struct(const PixGeom<double> *p) {
-    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
-    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-    return PixGeom<double>{a.x, a.y, b.x, b.y};
-}
-__device__ __forceinline__ Border<float> ldg_struct(const Border<float> *p) {
-    const int2 v = __ldg(reinterpret_cast<const int2 *>(p));
-    Border<float> b;
-    b.tau = __int_as_float(v.x);
-    b.idx = v.y;
-    return b;
-}
-__device__ __forceinline__ Border<double> ldg_struct(const Border<double> *p) {
-    const int4 v = __ldg(reinterpret_cast<const int4 *>(p));
-    Border<double> b;
-    b.tau = __hiloint2double(v.y, v.x);
-    b.idx = v.z;
-    return b;
-}
-
-// Make a loop-invariant value opaque so that the compiler keeps it in a register
-// instead of recomputing it from kernel parameters inside the hot loops.
-__device__ __forceinline__ void pin(int &x) { asm volatile("" : "+r"(x)); }
-__device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
-template <typename P>
-__device__ __forceinline__ void pin(P *&x) { asm volatile("" : "+l"(x)); }
-
-// ---- packed float32 pairs (SASS FFMA2 / FADD2 / FMUL2): one issue slot does the same
-// IEEE operation for two frames.  Every packed expression below keeps the operation
-// order and the roundings of its scalar counterpart, so both paths give the same bits.
-__device__ __forceinline__ unsigned long long f2_bits(float2 a) {
-    return *reinterpret_cast<unsigned long long *>(&a);
-}
-__device__ __forceinline__ float2 f2_from(unsigned long long a) {
-    return *reinterpret_cast<float2 *>(&a);
-}
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
-    return f2_from(d);
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return f2_from(d);
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return f2_from(d);
-}
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return f2_from(d);
-}
-__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
-
-// The G values of one knot (one per frame of the item), moved as one vector.
-template <typename T, int G>
-struct alignas((sizeof(T) * G >= 16) ? 16 : sizeof(T) * G) KnotVec {
-    T v[G];
-};
-
-// non-zero test that accumulates with one logic instruction: bits other than the sign
-__device__ __forceinline__ unsigned nz_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
-__device__ __forceinline__ unsigned nz_bits(double v) {
-    return ((unsigned)__double2hiint(v) & 0x7fffffffu) | (unsigned)__double2loint(v);
-}
-
-// Zero-coverage runs (outside the wavelength range of a slitlet, or a missing slitlet):
-// exact zeros.  A small persistent grid: every warp takes rows (dead tile, frame, row) in a
-// grid-stride loop and writes them with 16-byte stores (scalar head and tail where the run
-// is not aligned), so the fill trickles along next to the hot kernel instead of bursting.
-template <typename T>
-__global__ void __launch_bounds__(128) k_zero_fill(const RunParams<T> p, int first_tile) {
-    using V = typename Vec16<T>::type;
-    constexpr int VN = Vec16<T>::N;
-    const int lane = threadIdx.x & 31;
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long units = (long long)p.ndead_tiles * p.nframes * p.rps;
-    V zero;
-    memset(&zero, 0, sizeof(zero));
-    for (long long u = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units;
-         u += nwarps) {
-        const int y = (int)(u % p.rps);
-        const long long tf = u / p.rps;
-        const int f = (int)(tf % p.nframes);
-        const Tile &tile = p.tiles[first_tile + (int)(tf / p.nframes)];
-        const int k0 = tile.k0, k1 = k0 + tile.nk;
-        T *orow = p.out + ((size_t)f * p.nrows_out + (size_t)tile.slit * p.rps + y) * p.nout;
-        if (p.vec_ok) {
-            for (int c = (k0 / VN + lane) * VN; c < k1; c += 32 * VN) {
-                if (c >= k0 && c + VN <= k1) {
-                    __stcs(reinterpret_cast<V *>(orow + c), zero);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < VN; ++j)
-                        if (c + j >= k0 && c + j < k1) __stcs(orow + c + j, T(0));
-                }
-            }
-        } else {
-            for (int c = k0 + lane; c < k1; c += 32) __stcs(orow + c, T(0));
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------
-// median_slitlets_rectified, modes 0 and 1 (median_slitlets_rectified.py:85-97): the
-// consumer right behind the path.  For every slitlet and column the median over the R = 38
-// rows of the rectified product, i.e. numpy.median(axis=0) of an even number of values:
-// the mean of the two middle ones, NaN when any value is NaN.
-//
-// One thread per column holds its 38 values in registers and runs a pruned selection network
-// (compare-exchanges only, no data-dependent branches) that leaves the two middle values on
-// two known wires.  Loads and stores are coalesced along the columns; the kernel reads the
-// product once.
-template <typename T>
-__device__ __forceinline__ void order2(T &a, T &b) {
-    const T lo = fmin(a, b), hi = fmax(a, b);
-    a = lo;
-    b = hi;
-}
-
-template <typename T, int R>
-__global__ void __launch_bounds__(128) k_median_slitlets(const T *__restrict__ in,
-                                                        T *__restrict__ out, int naxis1,
-                                                        int nsl, int mode) {
-    static_assert(R % 2 == 0 && R >= 4, "even number of rows per slitlet");
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int slit = blockIdx.y, f = blockIdx.z;
-    if (j >= naxis1) return;
-    const T *src = in + ((size_t)f * nsl + slit) * R * naxis1 + j;
-    bool anynan = false;
-    T lo_mid, hi_mid;                                          // the two middle values
-    if constexpr (R == 38) {
-        // selection network: 223 compare-exchanges bring the two middle values of the 38
-        // inputs to wires 18 and 19 (scripts/gen_median_net.py)
-        T w[R];
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-            w[i] = __ldcs(src + (size_t)i * naxis1);
-            anynan |= w[i] != w[i];
-        }
-#define CE(a, b) order2(w[a], w[b]);
-#include "median_net38.inc"
-#undef CE
-        lo_mid = w[R / 2 - 1];
-        hi_mid = w[R / 2];
-    } else {
-        // any even R: a working set of R/2 + 2 values; its smallest and largest element
-        // cannot be one of the two middle values of the whole column, so both are dropped
-        // and the next value of the column takes a free place
-        constexpr int M = R / 2 + 2;
-        T w[M];
-#pragma unroll
-        for (int i = 0; i < M; ++i) {
-            w[i] = __ldcs(src + (size_t)i * naxis1);
-            anynan |= w[i] != w[i];
-        }
-#pragma unroll
-        for (int step = 0; step <= R - M; ++step) {
-            const int m = M - step;                            // current working-set size
-#pragma unroll
-            for (int i = 0; i + 1 < m; ++i) order2(w[i], w[i + 1]);      // maximum -> w[m-1]
-#pragma unroll
-            for (int i = m - 2; i >= 1; --i) order2(w[i - 1], w[i]);     // minimum -> w[0]
-            if (step < R - M) {                                // drop both, take the next value
-                w[0] = __ldcs(src + (size_t)(M + step) * naxis1);
-                anynan |= w[0] != w[0];
-            }
-        }
-        lo_mid = w[1];            // 4 values are left: minimum, the two middle ones, maximum
-        hi_mid = w[2];
-    }
-    T med;
-    if (sizeof(T) == 4)
-        med = (T)__fmul_rn(__fadd_rn((float)lo_mid, (float)hi_mid), 0.5f);
-    else
-        med = (T)__dmul_rn(__dadd_rn((double)lo_mid, (double)hi_mid), 0.5);
-    if (anynan) med = (T)NAN;
-    if (mode == 1) {
-        out[((size_t)f * nsl + slit) * naxis1 + j] = med;
-    } else {
-        T *dst = out + ((size_t)f * nsl + slit) * R * naxis1 + j;
-#pragma unroll 2
-        for (int i = 0; i < R; ++i) __stcs(dst + (size_t)i * naxis1, med);
-    }
-}
-
-// ---------------------------------------------------------------------------------
-// ABBA combination, method "mean" (recipes/spec/abba.py:579-606): the rectified frames of a
-// rank are summed per nodding position in float64, in frame order, one pass over the stack
-// (labels: +1 = A, -1 = B, 0 = not used).  The sums of all ranks are added by a collective;
-// k_abba_finish forms mean(A) and mean(B), casts both to float32 as the reference does, and
-// subtracts.
-template <typename T>
-__global__ void __launch_bounds__(256) k_abba_partial(const T *__restrict__ frames,
-                                                      const int8_t *__restrict__ labels, int nframes,
-                                                      size_t npix, double *__restrict__ sum_a,
-                                                      double *__restrict__ sum_b, int accumulate) {
-    constexpr int U = 8;                                       // frames in flight per thread
-    extern __shared__ int8_t lab_s[];
-    for (int f = threadIdx.x; f < nframes; f += blockDim.x) lab_s[f] = labels[f];
-    __syncthreads();
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        double a = accumulate ? sum_a[i] : 0.0, b = accumulate ? sum_b[i] : 0.0;
-        int f0 = 0;
-        for (; f0 + U <= nframes; f0 += U) {                   // branch-free: U loads in flight
-            T v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = __ldcs(frames + (size_t)(f0 + u) * npix + i);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {                      // frame order, one rounding each
-                const int lab = lab_s[f0 + u];                 // (adding +0.0 changes nothing)
-                a = __dadd_rn(a, lab > 0 ? (double)v[u] : 0.0);
-                b = __dadd_rn(b, lab < 0 ? (double)v[u] : 0.0);
-            }
-        }
-        for (; f0 < nframes; ++f0) {
-            const int lab = lab_s[f0];
-            const double v = (double)__ldcs(frames + (size_t)f0 * npix + i);
-            a = __dadd_rn(a, lab > 0 ? v : 0.0);
-            b = __dadd_rn(b, lab < 0 ? v : 0.0);
-        }
-        sum_a[i] = a;
-        sum_b[i] = b;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_abba_finish(const double *__restrict__ sum_a,
-                                                     const double *__restrict__ sum_b, double na,
-                                                     double nb, size_t npix, float *__restrict__ out) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        const float ma = (float)__ddiv_rn(sum_a[i], na), mb = (float)__ddiv_rn(sum_b[i], nb);
-        out[i] = __fsub_rn(ma, mb);
-    }
-}
-
-// Pre-reduction in front of the path (recipes/spec/abba.py:371 `flow(newimg)`, core/recipe.py:25-61):
-// bias subtraction, dark subtraction (numina BiasCorrector / DarkCorrector, restated: image
-// minus calibration) and the flat field of pyemir's own FlatFieldCorrector
-// (processing/flatfield.py:43,58-59: flat values <= 0 count as 1.0, result = data / flat cast to
-// float32).  One pass over the frames, calibrations (L2 resident: 3 x 16.8 MB) shared by all
-// frames; every stage rounds to float32 like the correctors' dtype="float32".  numpy's type
-// promotion is kept: float32 image with float32 calibrations computes in float32, any float64
-// operand makes the stage float64.
-// four consecutive elements with the widest loads the type allows (the streaming variants for
-// the frames, the cached ones for the calibrations that every frame reuses)
-template <bool STREAM>
-__device__ __forceinline__ void load4(const float *p, float (&v)[4]) {
-    const float4 t = STREAM ? __ldcs(reinterpret_cast<const float4 *>(p))
-                            : __ldg(reinterpret_cast<const float4 *>(p));
-    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-}
-template <bool STREAM>
-__device__ __forceinline__ void load4(const double *p, double (&v)[4]) {
-    const double2 a = STREAM ? __ldcs(reinterpret_cast<const double2 *>(p))
-                             : __ldg(reinterpret_cast<const double2 *>(p));
-    const double2 b = STREAM ? __ldcs(reinterpret_cast<const double2 *>(p) + 1)
-                             : __ldg(reinterpret_cast<const double2 *>(p) + 1);
-    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
-}
-template <bool STREAM>
-__device__ __forceinline__ void load4(const uint16_t *p, uint16_t (&v)[4]) {
-    const ushort4 t = STREAM ? __ldcs(reinterpret_cast<const ushort4 *>(p))
-                             : __ldg(reinterpret_cast<const ushort4 *>(p));
-    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-}
-
-// one pixel of one frame through the stages
-template <typename TIn, typename A>
-__device__ __forceinline__ float prereduce_px(TIn raw, bool hb, bool hd, bool hf, A b, A d, A f) {
-    if constexpr (sizeof(TIn) == 8) {
-        double x = raw;
-        if (hb) x = (double)(float)(x - (double)b);
-        if (hd) x = (double)(float)(x - (double)d);
-        if (hf) x = (double)(float)(x / (double)f);
-        return (float)x;
-    } else {
-        float x = (float)raw;
-        if (hb) x = (float)((A)x - b);
-        if (hd) x = (float)((A)x - d);
-        if (hf) x = (float)((A)x / f);
-        return x;
-    }
-}
-
-// VEC = 4: a thread owns four consecutive pixels (16-byte loads and stores, npix % 4 == 0 and
-// aligned buffers); VEC = 1: any size and alignment.  Frames are taken four at a time so that
-// four independent loads are in flight per thread.
-template <typename TIn, typename TCal, int VEC>
-__global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, float *__restrict__ out,
-                                                   int nframes, size_t npix,
-                                                   const TCal *__restrict__ bias,
-                                                   const TCal *__restrict__ dark,
-                                                   const TCal *__restrict__ flat) {
-    // float32 unless an operand is float64 (uint16 raw frames promote like numpy: with
-    // float32 calibrations the arithmetic is float32)
-    using A = typename std::conditional<sizeof(TIn) == 8 || sizeof(TCal) == 8, double, float>::type;
-    constexpr int U = 4;
-    const bool hb = bias != nullptr, hd = dark != nullptr, hf = flat != nullptr;
-    const size_t stride = (size_t)gridDim.x * blockDim.x * VEC;
-    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < npix; i += stride) {
-        A b[VEC], d[VEC], f[VEC];
-        if constexpr (VEC == 4) {
-            TCal t[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) b[e] = d[e] = A(0), f[e] = A(1);
-            if (hb) {
-                load4<false>(bias + i, t);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) b[e] = (A)t[e];
-            }
-            if (hd) {
-                load4<false>(dark + i, t);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) d[e] = (A)t[e];
-            }
-            if (hf) {
-                load4<false>(flat + i, t);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) f[e] = (A)t[e];
-            }
-        } else {
-            b[0] = hb ? (A)bias[i] : A(0);
-            d[0] = hd ? (A)dark[i] : A(0);
-            f[0] = hf ? (A)flat[i] : A(1);
-        }
-#pragma unroll
-        for (int e = 0; e < VEC; ++e)
-            f[e] = f[e] <= A(0) ? A(1) : f[e];   // flatfield.py:43 (NaN stays NaN, like numpy)
-        int n = 0;
-        for (; n + U <= nframes; n += U) {
-            TIn raw[U][VEC];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if constexpr (VEC == 4) load4<true>(in + (size_t)(n + u) * npix + i, raw[u]);
-                else raw[u][0] = __ldcs(in + (size_t)(n + u) * npix + i);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                float r[VEC];
-#pragma unroll
-                for (int e = 0; e < VEC; ++e)
-                    r[e] = prereduce_px<TIn, A>(raw[u][e], hb, hd, hf, b[e], d[e], f[e]);
-                float *dst = out + (size_t)(n + u) * npix + i;
-                if constexpr (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(r[0], r[1], r[2], r[3]));
-                else __stcs(dst, r[0]);
-            }
-        }
-        for (; n < nframes; ++n) {
-            TIn raw[VEC];
-            if constexpr (VEC == 4) load4<true>(in + (size_t)n * npix + i, raw);
-            else raw[0] = __ldcs(in + (size_t)n * npix + i);
-            float r[VEC];
-#pragma unroll
-            for (int e = 0; e < VEC; ++e)
-                r[e] = prereduce_px<TIn, A>(raw[e], hb, hd, hf, b[e], d[e], f[e]);
-            float *dst = out + (size_t)n * npix + i;
-            if constexpr (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(r[0], r[1], r[2], r[3]));
-            else __stcs(dst, r[0]);
-        }
-    }
-}
-
-template <typename TIn, typename TCal>
-void launch_prereduce(const void *in, float *out, int nframes, size_t npix, const void *bias,
-                      const void *dark, const void *flat, int sms, cudaStream_t st) {
-    auto aligned = [](const void *ptr, size_t a) {
-        return ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) == 0;
-    };
-    const bool vec = npix % 4 == 0 && aligned(in, 4 * sizeof(TIn) > 16 ? 16 : 4 * sizeof(TIn)) &&
-                     aligned(out, 16) && aligned(bias, 16) && aligned(dark, 16) &&
-                     aligned(flat, 16);
-    const TIn *tin = static_cast<const TIn *>(in);
-    const TCal *tb = static_cast<const TCal *>(bias), *td = static_cast<const TCal *>(dark),
-               *tf = static_cast<const TCal *>(flat);
-    if (vec) {
-        const int grid = (int)std::min<size_t>((npix / 4 + 255) / 256, (size_t)sms * 16);
-        k_prereduce<TIn, TCal, 4><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf);
-    } else {
-        const int grid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sms * 16);
-        k_prereduce<TIn, TCal, 1><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf);
-    }
-}
-
-// ABBA combination, method "median" (abba.py:579-601 with numina's combine.median, restated):
-// per pixel the median over the selected frames of a stack (numpy.median semantics: mean of
-// the two middle values, NaN if any sample is NaN), float64 result like numina's combine.
-// One thread per pixel (or four): its samples sit in registers (N = stack size rounded up to a
-// power of two, padded with -inf / +inf) and go through a selection network, fully unrolled;
-// all N loads of a thread are in flight together.
-constexpr int STACK_MAX = 64;
-struct StackSel {
-    int n;
-    int idx[STACK_MAX];
-};
-
-#include "stack_median_nets.inc"
-
-// Median of the n samples held in v[0..n), float64, NaN if any sample is NaN.  The padding
-// v[n..N) -- floor((N-n)/2) times -inf, then +inf -- puts the median of the samples on the
-// wires N/2-1 and N/2 for every n (odd n: wire N/2-1 alone), so the network only has to bring
-// the two middle values of N wires home: Batcher's odd-even merge sort pruned to those two
-// outputs (scripts/gen_stack_median_nets.py), two min/max instructions per exchange, every
-// index a compile-time constant: the samples never leave the registers.
-template <typename T, int N>
-__device__ __forceinline__ double median_of_registers(T (&v)[N], int n) {
-    const T inf = (T)INFINITY;
-    bool has_nan = false;
-#pragma unroll
-    for (int u = 0; u < N; ++u) {
-        has_nan |= v[u] != v[u];
-        v[u] = v[u] != v[u] ? inf : v[u];
-    }
-#define CE(a, b) order2(v[a], v[b]);
-    if constexpr (N == 4) {
-        STACK_NET_4(CE)
-    } else if constexpr (N == 8) {
-        STACK_NET_8(CE)
-    } else if constexpr (N == 16) {
-        STACK_NET_16(CE)
-    } else if constexpr (N == 32) {
-        STACK_NET_32(CE)
-    } else {
-        static_assert(N == 4 || N == 8 || N == 16 || N == 32 || N == 64, "stack size bucket");
-        STACK_NET_64(CE)
-    }
-#undef CE
-    const T a = v[N / 2 - 1], b = (n & 1) ? a : v[N / 2];
-    const double med = __dmul_rn(__dadd_rn((double)a, (double)b), 0.5);
-    return has_nan ? __longlong_as_double(0x7ff8000000000000LL) : med;
-}
-
-// medians of VEC consecutive pixels starting at i over the selected images (VEC = 4: 16-byte
-// loads, npix % 4 == 0 and aligned frames)
-template <typename T, int N, int VEC>
-__device__ __forceinline__ void stack_median_px(const T *__restrict__ frames, const StackSel &sel,
-                                                size_t npix, size_t i, double (&med)[VEC]) {
-    const T inf = (T)INFINITY;
-    const int nneg = (N - sel.n) >> 1;                          // pads below the samples
-    T v[VEC][N];
-#pragma unroll
-    for (int u = 0; u < N; ++u) {
-        if (u < sel.n) {
-            const T *src = frames + (size_t)sel.idx[u] * npix + i;
-            if constexpr (VEC == 4) {
-                T t[4];
-                load4<true>(src, t);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[e][u] = t[e];
-            } else {
-                v[0][u] = __ldcs(src);
-            }
-        } else {
-            const T pad = u < sel.n + nneg ? -inf : inf;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) v[e][u] = pad;
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) med[e] = median_of_registers<T, N>(v[e], sel.n);
-}
-
-template <typename T, int N, int VEC>
-__global__ void __launch_bounds__(256) k_stack_median(const T *__restrict__ frames,
-                                                      const StackSel sel, size_t npix,
-                                                      double *__restrict__ out) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x * VEC;
-    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < npix; i += stride) {
-        double med[VEC];
-        stack_median_px<T, N, VEC>(frames, sel, npix, i, med);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) out[i + e] = med[e];
-    }
-}
-
-// median(A images) and median(B images) of a pixel one after the other in the same registers,
-// then float32(A) - float32(B) like abba.py:604-606: the stack is read once and only the
-// float32 difference is written.
-template <typename T, int N, int VEC>
-__global__ void __launch_bounds__(256) k_abba_median(const T *__restrict__ frames,
-                                                     const StackSel sel_a, const StackSel sel_b,
-                                                     size_t npix, float *__restrict__ out) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x * VEC;
-    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < npix; i += stride) {
-        double ma[VEC], mb[VEC];
-        stack_median_px<T, N, VEC>(frames, sel_a, npix, i, ma);
-        stack_median_px<T, N, VEC>(frames, sel_b, npix, i, mb);
-        float r[VEC];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) r[e] = __fsub_rn((float)ma[e], (float)mb[e]);
-        if constexpr (VEC == 4)
-            __stcs(reinterpret_cast<float4 *>(out + i), make_float4(r[0], r[1], r[2], r[3]));
-        else
-            out[i] = r[0];
-    }
-}
-
-// four pixels per thread while the samples of four pixels fit comfortably in registers
-template <typename T, int N>
-constexpr bool stack_vec4() { return N * sizeof(T) <= 64; }
-
-template <typename T, int N>
-void launch_abba_median_n(const T *frames, const StackSel &sa, const StackSel &sb, size_t npix,
-                          float *out, int sms, bool vec_ok, cudaStream_t st) {
-    if constexpr (stack_vec4<T, N>()) {
-        if (vec_ok) {
-            const int grid = (int)std::min<size_t>((npix / 4 + 255) / 256, (size_t)sms * 8);
-            k_abba_median<T, N, 4><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
-            return;
-        }
-    }
-    const int grid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sms * 8);
-    k_abba_median<T, N, 1><<<grid, 256, 0, st>>>(frames, sa, sb, npix, out);
-}
-
-template <typename T, int N>
-void launch_stack_median_n(const T *frames, const StackSel &sel, size_t npix, double *out,
-                           int sms, bool vec_ok, cudaStream_t st) {
-    if constexpr (stack_vec4<T, N>()) {
-        if (vec_ok) {
-            const int grid = (int)std::min<size_t>((npix / 4 + 255) / 256, (size_t)sms * 8);
-            k_stack_median<T, N, 4><<<grid, 256, 0, st>>>(frames, sel, npix, out);
-            return;
-        }
-    }
-    const int grid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sms * 8);
-    k_stack_median<T, N, 1><<<grid, 256, 0, st>>>(frames, sel, npix, out);
-}
-
-int fill_stack_sel(StackSel &sel, const int32_t *h_index, int nsel, int nframes) {
-    memset(&sel, 0, sizeof(sel));
-    if (h_index == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
-    if (nsel < 1) return fail(EMIRWV_E_VALUE, "no image selected");
-    if (nsel > STACK_MAX)
-        return fail(EMIRWV_E_LIMIT, "median of more than %d images per call", STACK_MAX);
-    sel.n = nsel;
-    for (int u = 0; u < nsel; ++u) {
-        if (h_index[u] < 0 || h_index[u] >= nframes)
-            return fail(EMIRWV_E_VALUE, "image index %d outside the stack", h_index[u]);
-        sel.idx[u] = h_index[u];
-    }
-    return EMIRWV_OK;
-}
-
-template <typename T>
-void launch_abba_median(const T *frames, const StackSel &sa, const StackSel &sb, size_t npix,
-                        float *out, int sms, cudaStream_t st) {
-    const int n = std::max(sa.n, sb.n);
-    const bool vec_ok = npix % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0 &&
-                        (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-    if (n <= 4) launch_abba_median_n<T, 4>(frames, sa, sb, npix, out, sms, vec_ok, st);
-    else if (n <= 8) launch_abba_median_n<T, 8>(frames, sa, sb, npix, out, sms, vec_ok, st);
-    else if (n <= 16) launch_abba_median_n<T, 16>(frames, sa, sb, npix, out, sms, vec_ok, st);
-    else if (n <= 32) launch_abba_median_n<T, 32>(frames, sa, sb, npix, out, sms, vec_ok, st);
-    else launch_abba_median_n<T, 64>(frames, sa, sb, npix, out, sms, vec_ok, st);
-}
-
-template <typename T>
-void launch_stack_median(const T *frames, const StackSel &sel, size_t npix, double *out, int sms,
-                         cudaStream_t st) {
-    const bool vec_ok = npix % 4 == 0 && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0 &&
-                        (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-    if (sel.n <= 4) launch_stack_median_n<T, 4>(frames, sel, npix, out, sms, vec_ok, st);
-    else if (sel.n <= 8) launch_stack_median_n<T, 8>(frames, sel, npix, out, sms, vec_ok, st);
-    else if (sel.n <= 16) launch_stack_median_n<T, 16>(frames, sel, npix, out, sms, vec_ok, st);
-    else if (sel.n <= 32) launch_stack_median_n<T, 32>(frames, sel, npix, out, sms, vec_ok, st);
-    else launch_stack_median_n<T, 64>(frames, sel, npix, out, sms, vec_ok, st);
-}
-
-// Weighted gather of KT x KT taps for the G frames of an item: rowp[a] points at tap (a, 0)
-// of frame 0 in the rolling window, frame g lies g * FRAME elements further.  float32 with
-// an even G runs two frames per instruction.  Taps are accumulated row by row, left to right.
-// (Lanes without a pixel of their own gather through a neighbour's record: a finite value
-// that only ever reaches knots nobody reads.)
-template <typename T, int KT, int G, int FRAME>
-__device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T *wv, int wstride,
-                                            T (&rect)[G]) {
-    if constexpr (sizeof(T) == 4 && (G % 2) == 0) {
-        float2 acc[G / 2];
-#pragma unroll
-        for (int h = 0; h < G / 2; ++h) acc[h] = make_float2(0.0f, 0.0f);
-#pragma unroll
-        for (int a = 0; a < KT; ++a)
-#pragma unroll
-            for (int b = 0; b < KT; ++b) {
-                const float2 wgt = dup2(wv[a * wstride + b]);
-#pragma unroll
-                for (int h = 0; h < G / 2; ++h)
-                    acc[h] = fma2(wgt,
-                                  make_float2(rowp[a][(2 * h) * FRAME + b],
-                                              rowp[a][(2 * h + 1) * FRAME + b]),
-                                  acc[h]);
-            }
-#pragma unroll
-        for (int h = 0; h < G / 2; ++h) {
-            rect[2 * h] = acc[h].x;
-            rect[2 * h + 1] = acc[h].y;
-        }
-    } else {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            T acc = T(0);
-#pragma unroll
-            for (int a = 0; a < KT; ++a)
-#pragma unroll
-                for (int b = 0; b < KT; ++b)
-                    acc = fma(wv[a * wstride + b], rowp[a][g * FRAME + b], acc);
-            rect[g] = acc;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------
-// The hot kernel.
-//
-// Persistent: CTA b processes work items b, b + gridDim.x, ...; an item is a live
-// tile (slitlet x block of <= TILE_K output columns) for G consecutive frames, frame
-// group fastest so that CTAs running at the same time share the tile's tables in L2.
-//
-// Inside an item the CTA marches down the 39 scanned rows of the slitlet.  Every
-// compute thread keeps, for the whole item, ONE rectified pixel column (phases A and C)
-// and ONE border of the output grid (phase D), so the per-column tables (pixel widths,
-// border positions) sit in registers and only the per-row table records are loaded.
-// A warp owns the borders of its piece of the tile and every pixel they touch, so the
-// rows need no exchange between warps and no block barrier.  Per row and warp:
-//   wait   full[y]: the source rows and the table row of row y have landed (TMA)
-//   D      (row y-1) cumulative-flux difference at the thread's border and the next one
-//          (shuffle), store, non-zero flag -- from the warp's own knot rows
-//   A      rectified flux of G frames: K*K weighted gather from the rolling window
-//   C      Steffen-limited end slopes from the neighbours' flux (warp shuffles: a warp
-//          covers 32 pixels and produces 30), written to the warp's knot rows
-//   arrive done[y]
-// The copy warp waits for done[y] (all compute warps) and requests the table row and
-// the new source rows of row y+NSTAGE into the slots row y has just released.
-// The source window is a ring of WIN_ROWS rows per frame.
-//
-// Shared memory: [tile descriptor ring: 3][mbarriers][G windows: WIN_ROWS x WIN_PITCH]
-//                [per warp: (rect | ya) x 32 pixels x G][NSTAGE table rows: PXCAP records]
-// ---------------------------------------------------------------------------------
-template <typename T, int K, int G, bool SPANLOOP, int NSTAGE>
-__global__ void __launch_bounds__(NTHREADS, 2)
-    k_rectwv(const RunParams<T> p) {
-    static_assert(NSTAGE >= 2 && NSTAGE <= NSTAGE_MAX, "stage count");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int WSZ = WIN_ROWS * WIN_PITCH;                  // one frame's window
-    constexpr int KNOT_WARP = 2 * 32 * G;                      // knot elements of one warp
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const bool producer = warp == NWARPS;          // the copy warp computes nothing
-    const size_t frame_out = (size_t)p.nrows_out * p.nout;
-    const int nwork = p.nlive_tiles * p.ngroups;
-
-    Tile *ring = reinterpret_cast<Tile *>(smem_raw);                       // [3]
-    // mbarriers: "full" [0..2] and "done" [3..5], one pair per rectified row in flight
-    const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
-    T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + BAR_BYTES);   // [G][WSZ]
-    T *knots = win + G * WSZ + min(warp, NWARPS - 1) * KNOT_WARP;   // this warp: [rect|ya][32][G]
-    constexpr int RS = rec_size(K);
-    T *tsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [NSTAGE][PXCAP][RS]
-    // float32 with an even number of frames: two frames per arithmetic instruction
-    constexpr bool PACKED = sizeof(T) == 4 && (G % 2) == 0;
-    using KV = KnotVec<T, G>;
-
-    // Work distribution: the first two items of a CTA are b and b + gridDim.x; with p.sched the
-    // following ones come from a counter shared by the CTAs (items differ in cost: tiles at the
-    // ends of a slitlet are narrower), else the stride continues.  wq[] holds the item numbers
-    // of iterations it .. it+2 (thread 0 draws the number of iteration it+3 before the barrier
-    // that ends iteration it).
-    __shared__ int wq[4];
-    int w = blockIdx.x;
-    if (w >= nwork) return;
-    if (tid == 0) {
-        wq[0] = w;
-        wq[1] = w + (int)gridDim.x;
-        wq[2] = p.sched != nullptr ? 2 * (int)gridDim.x + atomicAdd(p.sched, 1)
-                                   : w + 2 * (int)gridDim.x;
-    }
-
-    // descriptors of the first two items
-    constexpr int TCH = sizeof(Tile) / 16;
-    if (tid < TCH)
-        cp_async_16(reinterpret_cast<char *>(&ring[0]) + tid * 16,
-                    reinterpret_cast<const char *>(p.tiles + w / p.ngroups) + tid * 16, true);
-    if (w + (int)gridDim.x < nwork && tid >= 32 && tid < 32 + TCH)
-        cp_async_16(reinterpret_cast<char *>(&ring[1]) + (tid - 32) * 16,
-                    reinterpret_cast<const char *>(p.tiles + (w + gridDim.x) / p.ngroups) +
-                        (tid - 32) * 16, true);
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < NSTAGE; ++i) {
-            mbar_init(bars + 8 * i, 2);                 // "full": rows part + table part of a row
-            mbar_init(bars + 8 * NSTAGE + 8 * i, NWARPS);       // "done": every compute warp is through
-        }
-        mbar_fence_init();
-    }
-    // the window starts out finite: taps with weight zero may read slots no copy has filled
-    for (int e = tid; e < G * WSZ; e += NTHREADS) win[e] = T(0);
-    cp_async_wait_all();
-    __syncthreads();
-
-    unsigned fo = (unsigned)frame_out;                         // < 2^32 elements per frame
-    pin(fo);
-    unsigned rowseq = 0;            // rectified rows started so far (same in every thread)
-
-    // copy lanes: one (source row, frame) pair each
-    const int cg = lane % G, cr = lane / G;
-    constexpr int ROWS_PER_ISSUE = 32 / G;
-
-    for (int it = 0;; ++it) {
-        const Tile &tile = ring[it % 3];
-        const int wnext = wq[(it + 1) & 3], wnn = wq[(it + 2) & 3];
-        // descriptor of the item after the next one rides along with this item's copies
-        if (wnn < nwork && tid < TCH)
-            cp_async_16(reinterpret_cast<char *>(&ring[(it + 2) % 3]) + tid * 16,
-                        reinterpret_cast<const char *>(p.tiles + wnn / p.ngroups) + tid * 16,
-                        true);
-
-        const int grp = w % p.ngroups;
-        const int g0 = grp * G;
-        const int nlive = min(G, p.nframes - g0);
-        const int s = tile.slit;
-        const int npx = tile.npx;
-        const int k0 = tile.k0;
-
-        // ---- per-item constants of this thread
-        // The warp owns the borders kw[warp] .. kw[warp+1]-1 of the tile (at most 31) and
-        // every rectified pixel they touch (at most 30, lanes 1..30; lanes 0 and 31 hold the
-        // neighbours the slope limiter needs), so a row needs no exchange between warps.
-        const int wc = min(warp, NWARPS - 1);
-        const int kw0 = tile.kw[wc], nb = tile.kw[wc + 1] - kw0;
-        const bool wwarp = nb > 0 && !producer;                // the warp has work at all
-        const int q = kw0 + min(lane, nb);                     // border, tile relative
-        const Border<T> bd = ldg_struct(p.border + (size_t)s * p.NB + k0 + q);
-        const int ibl = bd.idx - tile.jlo;                     // source pixel, tile relative
-        const int ibn = __shfl_down_sync(0xffffffffu, ibl, 1);
-        const int plo = __shfl_sync(0xffffffffu, ibl, 0);      // first pixel the warp owns
-        const int kl = ibl - plo + 1;                          // lane that holds pixel ibl
-        const bool col_ok = lane < nb;
-        const bool has1 = ibn > ibl, has2 = ibn > ibl + 1;
-        const int kb = k0 + q;
-        const int pp = plo - 1 + lane;                         // pixel column, tile relative
-        const bool px_ok = pp >= 0 && pp < npx;
-        PixGeom<T> pg;
-        pg.qm = pg.qp = pg.r0 = pg.r1 = T(0);
-        if (px_ok) pg = ldg_struct(p.pix + (size_t)s * W + tile.jlo + pp);
-        const float qm2 = (float)(pg.qm + pg.qm), hr0 = (float)(T(0.5) * pg.r0);   // packed path
-        // width ratio that turns the next pixel's left-knot slope into this border's pixel's
-        // right-knot slope (the table holds 0 at the red end of the spectrum)
-        const T qpb = __ldg(&p.pix[(size_t)s * W + bd.idx].qp);
-        const unsigned stmask = col_ok ? (1u << nlive) - 1u : 0u;   // frames this lane stores
-        unsigned nzb[G];                                       // OR of the value bits seen
-#pragma unroll
-        for (int g = 0; g < G; ++g) nzb[g] = 0;
-
-        // ---- the copy pipeline of the item (TMA bulk copies completing on mbarriers):
-        //   the new source rows that rectified row y needs, one copy per row and frame into
-        //   ring slot (row + bias) % WIN_ROWS, and the table row of row y, npx records in one
-        //   copy, slot y % NSTAGE.
-        constexpr int VN = Vec16<T>::N;
-        const int cv0 = max(tile.c0, 0), cv1 = min(tile.c0 + tile.wcols, W);   // valid columns
-        const unsigned tsm_a = smem_addr_of(tsm);
-        // what the copy warp needs to know about an item (this one, or the next one whose
-        // first rows it requests as soon as this item's last row is through)
-        struct CopyCtx {
-            unsigned row_bytes, win_a, trow_bytes;
-            const T *fin, *trow;
-            int nlive, wcols;
-            bool oob_rows;
-        };
-        auto make_ctx = [&](const Tile &t, int wi) {
-            CopyCtx c;
-            const int g0i = (wi % p.ngroups) * G;
-            const int v0 = max(t.c0, 0), v1 = min(t.c0 + t.wcols, W);
-            c.nlive = min(G, p.nframes - g0i);
-            c.wcols = t.wcols;
-            c.row_bytes = (unsigned)((v1 - v0) * sizeof(T));
-            c.win_a = smem_addr_of(win) + (unsigned)((v0 - t.c0) * sizeof(T)) +
-                      (unsigned)(cg * WSZ * sizeof(T));
-            c.fin = p.in + ((size_t)g0i + cg) * W * p.naxis2 + v0;
-            c.trow_bytes = (unsigned)(t.npx * RS * sizeof(T));
-            c.trow = p.w + ((size_t)t.slit * NROWS * W + t.jlo) * RS;
-            c.oob_rows = span_lo(t.span[0]) < 0 || span_hi(t.span[NROWS - 1]) >= p.naxis2;
-            return c;
-        };
-
-        // columns of the window that fall outside the detector stay zero for the item
-        // (first and last tile of a slitlet: a handful of columns)
-        if (cv0 > tile.c0 || cv1 < tile.c0 + tile.wcols) {
-            const int nl = cv0 - tile.c0, nr = tile.c0 + tile.wcols - cv1, nbad = nl + nr;
-            for (int e = tid; e < G * WIN_ROWS * nbad; e += NTHREADS) {
-                const int cb = e % nbad, rg = e / nbad;
-                const int c = cb < nl ? cb : cv1 - tile.c0 + (cb - nl);
-                win[rg * WIN_PITCH + c] = T(0);               // rg = frame * WIN_ROWS + ring row
-            }
-            __syncthreads();
-        }
-
-        // Row number n (counted across items) completes on mbarrier n % NSTAGE with two
-        // arrivals: the source rows it adds and its table row.  Whichever warp issues them
-        // does so with all its lanes: lane 0 posts the byte counts, every lane copies one
-        // (row, frame); rows outside the detector (rare) are zero-filled instead.
-        auto copy_window_rows = [&](const CopyCtx &c, unsigned seq, int r_from, int r_to) {
-            const unsigned bar = bars + 8 * (seq % NSTAGE);
-            const int lo = max(r_from + 1, 0), hi = min(r_to, p.naxis2 - 1);
-            if (c.oob_rows) {
-                for (int r = r_from + 1; r <= r_to; ++r)
-                    if (r < 0 || r >= p.naxis2) {
-                        const unsigned slot = (unsigned)(r + RING_BIAS) % WIN_ROWS;
-                        for (int e = lane; e < c.nlive * c.wcols; e += 32)
-                            win[(e / c.wcols) * WSZ + slot * WIN_PITCH + e % c.wcols] = T(0);
-                    }
-                __syncwarp();
-            }
-            if (lane == 0)
-                mbar_expect_tx(bar, (unsigned)(max(hi - lo + 1, 0) * c.nlive) * c.row_bytes);
-            __syncwarp();
-            if (cg < c.nlive)
-                for (int r = lo + cr; r <= hi; r += ROWS_PER_ISSUE)
-                    bulk_g2s(c.win_a + (unsigned)(((unsigned)(r + RING_BIAS) % WIN_ROWS) *
-                                                  (WIN_PITCH * sizeof(T))),
-                             c.fin + (size_t)r * W, c.row_bytes, bar);
-        };
-        // table row y = npx contiguous records, one bulk copy
-        auto copy_table_row = [&](const CopyCtx &c, unsigned seq, int y) {
-            if (lane == 0) {
-                const unsigned bar = bars + 8 * (seq % NSTAGE);
-                mbar_expect_tx(bar, c.trow_bytes);
-                bulk_g2s(tsm_a + (y % NSTAGE) * (unsigned)(PXCAP * RS * sizeof(T)),
-                         c.trow + (size_t)y * W * RS, c.trow_bytes, bar);
-            }
-        };
-        // the first NSTAGE rows of an item and their table rows
-        auto copy_first_rows = [&](const CopyCtx &c, const Tile &t, unsigned seq0) {
-            for (int y = 0; y < NSTAGE; ++y) {
-                copy_window_rows(c, seq0 + y,
-                                 y == 0 ? span_lo(t.span[0]) - 1 : span_hi(t.span[y - 1]),
-                                 span_hi(t.span[y]));
-                copy_table_row(c, seq0 + y, y);
-            }
-        };
-
-        // The first NSTAGE rows and their table rows are requested up front -- for the first
-        // item of the CTA here, for every later one by the copy warp at the end of the item
-        // before it (below); once every compute warp is through row y the copy warp requests
-        // the table row and the source rows of row y+NSTAGE (nobody reads the slots they
-        // overwrite any more)
-        if (producer && (it == 0 || !p.early)) copy_first_rows(make_ctx(tile, w), tile, rowseq);
-        // this thread's slot in the staged table rows (lanes without a pixel read a
-        // neighbour's entry; their result is discarded)
-        const int ppc = min(max(pp, 0), npx - 1);
-        T *orow = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
-        int wb = -tile.c0;                                     // window addressed by frame coords
-        pin(wb);
-
-        // ---- D (row yr): cumulative flux at this thread's border and at the next one,
-        //      difference = output pixel; store; remember non-zero values
-        auto phase_d = [&](auto store_row) {                   // the 39th row is only scanned
-            constexpr bool store = decltype(store_row)::value;
-            const KV *kbase = reinterpret_cast<const KV *>(knots) + kl;
-            const KV *kb_rect = kbase, *kb_ya = kbase + 32;
-            // flux and left-knot slope of the border's pixel; its right-knot slope is the
-            // next pixel's left-knot slope rescaled by the ratio of the pixel widths
-            const KV kr = kb_rect[0], ka = kb_ya[0], kn = kb_ya[1];
-            KV k1;
-#pragma unroll
-            for (int g = 0; g < G; ++g) k1.v[g] = T(0);
-            if (has2) k1 = kb_rect[1];
-            T o[G];
-            if constexpr (PACKED) {
-                const float2 tau2 = dup2(bd.tau);
-#pragma unroll
-                for (int h = 0; h < G / 2; ++h) {
-                    const float2 r = make_float2(kr.v[2 * h], kr.v[2 * h + 1]);
-                    const float2 a = make_float2(ka.v[2 * h], ka.v[2 * h + 1]);
-                    const float2 c = mul2(make_float2(kn.v[2 * h], kn.v[2 * h + 1]), dup2(qpb));
-                    // steffen_partial_flux, two frames at a time
-                    const float2 A = fma2(r, dup2(-2.0f), add2(a, c));
-                    const float2 B = sub2(sub2(r, a), A);
-                    const float2 P = mul2(tau2, fma2(tau2, fma2(tau2, A, B), a));
-                    const float2 Pn = make_float2(__shfl_down_sync(0xffffffffu, P.x, 1),
-                                                  __shfl_down_sync(0xffffffffu, P.y, 1));
-                    float2 whole = make_float2(has1 ? r.x : 0.0f, has1 ? r.y : 0.0f);
-                    if (has2) whole = add2(whole, make_float2(k1.v[2 * h], k1.v[2 * h + 1]));
-                    if (SPANLOOP)
-                        for (int i = 2; i < ibn - ibl; ++i) {
-                            const KV ki = kb_rect[i];
-                            whole = add2(whole, make_float2(ki.v[2 * h], ki.v[2 * h + 1]));
-                        }
-                    const float2 o2 = add2(whole, sub2(Pn, P));
-                    o[2 * h] = o2.x;
-                    o[2 * h + 1] = o2.y;
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const T P = steffen_partial_flux(kr.v[g], ka.v[g], kn.v[g] * qpb, bd.tau);
-                    const T Pn = __shfl_down_sync(0xffffffffu, P, 1);
-                    T whole = has1 ? kr.v[g] : T(0);
-                    if (has2) whole += k1.v[g];
-                    if (SPANLOOP)
-                        for (int i = 2; i < ibn - ibl; ++i) whole += kb_rect[i].v[g];
-                    o[g] = whole + (Pn - P);
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                T *dst = orow + ((unsigned)kb + (unsigned)g * fo);
-                if (store && ((stmask >> g) & 1u)) __stcs(dst, o[g]);
-                nzb[g] |= nz_bits(o[g]);       // lanes / frames that do not count are masked
-            }                                  // once, after the last row
-            orow += p.nout;
-        };
-
-        // the warp has read everything row y needs from the window and the table slot: the
-        // copy warp may overwrite them
-        auto row_done = [&]() {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 8 * NSTAGE + 8 * (rowseq % NSTAGE));
-            ++rowseq;
-        };
-
-        // ---- A, C (row y)
-        auto phase_ac = [&](int y) {
-            // this pixel's record: K*K weights, packed source column, ring slots of the
-            // K source rows
-            using V = typename Vec16<T>::type;
-            const V *rec = reinterpret_cast<const V *>(tsm + ((y % NSTAGE) * PXCAP + ppc) * RS);
-            T wt[RS];
-            // the vector(s) with the source column, the ring slots and the flags come first
-            constexpr int KK = K * K;
-            constexpr int VM0 = KK / VN;
-            constexpr int VM1 = (KK + 2) / VN < RS / VN - 1 ? (KK + 2) / VN : RS / VN - 1;
-#pragma unroll
-            for (int i = VM0; i <= VM1; ++i) *reinterpret_cast<V *>(wt + i * VN) = rec[i];
-            const int32_t pk = *reinterpret_cast<const int32_t *>(wt + KK);
-            const uint32_t slots = *reinterpret_cast<const uint32_t *>(wt + KK + 1);
-            const int fc = base_col(pk) + wb;
-
-            // ---- A (row y): rectified flux of this pixel column, G frames
-            T rect[G];
-            bool all_compact = false;
-            if constexpr (K >= 3)
-                all_compact = __all_sync(0xffffffffu, (slots >> 24) & REC_COMPACT);
-            if (K >= 3 && all_compact) {
-                // every footprint of the warp fits 2 x 2 source pixels: four taps
-#pragma unroll
-                for (int i = 0; i <= 3 / VN; ++i) *reinterpret_cast<V *>(wt + i * VN) = rec[i];
-                const T *rowp[2];
-#pragma unroll
-                for (int a = 0; a < 2; ++a)
-                    rowp[a] = win + ((slots >> (8 * a)) & 0xffu) * WIN_PITCH + fc;
-                gather_taps<T, 2, G, WSZ>(rowp, wt, 2, rect);
-            } else {
-#pragma unroll
-                for (int i = 0; i < VM0; ++i) *reinterpret_cast<V *>(wt + i * VN) = rec[i];
-                if constexpr (K >= 3) {
-                    if ((slots >> 24) & REC_COMPACT) {         // spread the block over K x K
-                        const T c00 = wt[0], c01 = wt[1], c10 = wt[2], c11 = wt[3];
-#pragma unroll
-                        for (int i = 0; i < KK; ++i) wt[i] = T(0);
-                        wt[0] = c00, wt[1] = c01, wt[K] = c10, wt[K + 1] = c11;
-                    }
-                }
-                const T *rowp[K];
-#pragma unroll
-                for (int a = 0; a < K; ++a) {
-                    const uint32_t slot = a < 3 ? (slots >> (8 * a)) & 0xffu
-                                                : *reinterpret_cast<const uint32_t *>(wt + KK + 2);
-                    rowp[a] = win + slot * WIN_PITCH + fc;
-                }
-                gather_taps<T, K, G, WSZ>(rowp, wt, K, rect);
-            }
-
-            row_done();       // (phase C works on registers and the warp's own knot rows)
-
-            // ---- C (row y): Steffen-limited slopes at both ends of the pixel, scaled
-            //      by the pixel width (flux units).  qm = 0 / qp = 0 in the table give
-            //      the zero slopes at the two ends of the spectrum.
-            KV vr, va;
-            if constexpr (PACKED) {
-                // steffen_slope with everything doubled (exact): 2*min(|sl|,|sr|,|p|/2) =
-                // min(|2 sl|, |2 sr|, |p|); the sign test folds into the minimum by
-                // giving 2 sl the sign it has relative to sr.
-#pragma unroll
-                for (int h = 0; h < G / 2; ++h) {
-                    const float2 r = make_float2(rect[2 * h], rect[2 * h + 1]);
-                    const float2 l = make_float2(__shfl_up_sync(0xffffffffu, r.x, 1),
-                                                 __shfl_up_sync(0xffffffffu, r.y, 1));
-                    const float2 cl2 = mul2(l, dup2(qm2));
-                    const float2 rr = add2(r, r);
-                    const float2 pq = fma2(dup2(hr0), sub2(cl2, rr), r);
-                    float ya[2];
-                    const float clv[2] = {cl2.x, cl2.y}, rv[2] = {r.x, r.y}, rrv[2] = {rr.x, rr.y},
-                                pv[2] = {pq.x, pq.y};
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const unsigned sgn = __float_as_uint(rv[e]) & 0x80000000u;
-                        const float x = __uint_as_float(__float_as_uint(clv[e]) ^ sgn);
-                        const float m = fmaxf(fminf(fminf(x, fabsf(rrv[e])), fabsf(pv[e])), 0.0f);
-                        ya[e] = __uint_as_float(__float_as_uint(m) | sgn);
-                    }
-                    vr.v[2 * h] = r.x, vr.v[2 * h + 1] = r.y;
-                    va.v[2 * h] = ya[0], va.v[2 * h + 1] = ya[1];
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    // slope at the left knot from this pixel and its left neighbour (one
-                    // limiter per pixel)
-                    const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
-                    vr.v[g] = rect[g];
-                    va.v[g] = steffen_slope(cl, rect[g], pg.r0);
-                }
-            }
-            // the warp's own knot rows (lane 0 holds an incomplete slope, never read)
-            // (one buffer is enough: the warp's border phase of the previous row comes first
-            // in program order)
-            KV *kdst = reinterpret_cast<KV *>(knots) + lane;
-            kdst[0] = vr;
-            kdst[32] = va;
-        };
-
-        // Row loop without block barriers.  A warp waits for the data of row y, evaluates
-        // the borders of row y-1 from its own knots (phase D) and the flux and slopes of
-        // row y (phases A, C: independent instruction streams in one basic block), then
-        // reports row y done; warps may drift apart by up to NSTAGE-1 rows.
-        if (producer) {
-            const CopyCtx ctx = make_ctx(tile, w);
-#pragma unroll 1
-            for (int y = 0; y < NROWS; ++y) {
-                mbar_wait(bars + 8 * NSTAGE + 8 * (rowseq % NSTAGE), (rowseq / NSTAGE) & 1);  // row y is done
-                if (y + NSTAGE < NROWS) {
-                    copy_table_row(ctx, rowseq + NSTAGE, y + NSTAGE);
-                    copy_window_rows(ctx, rowseq + NSTAGE, span_hi(tile.span[y + NSTAGE - 1]),
-                                     span_hi(tile.span[y + NSTAGE]));
-                }
-                ++rowseq;
-            }
-            // Every compute warp has read what the last row needs: the window and the table
-            // slots are free, so the first rows of the CTA's next item are requested now
-            // -- while the compute warps still evaluate the borders of the last row -- and not
-            // after the barrier that ends the item.  (Its descriptor landed one item ago; the
-            // columns outside the detector that the next item zero-fills are not touched by
-            // these copies.)
-            if (p.early && wnext < nwork) {
-                const Tile &tn = ring[(it + 1) % 3];
-                copy_first_rows(make_ctx(tn, wnext), tn, rowseq);
-            }
-        } else {
-            mbar_wait(bars + 8 * (rowseq % NSTAGE), (rowseq / NSTAGE) & 1);   // rows + table landed
-            if (wwarp)
-                phase_ac(0);
-            else
-                row_done();
-#pragma unroll 1
-            for (int y = 1; y < NROWS; ++y) {
-                mbar_wait(bars + 8 * (rowseq % NSTAGE), (rowseq / NSTAGE) & 1);
-                if (wwarp) {
-                    phase_d(std::true_type{});
-                    phase_ac(y);                               // reports the row done itself
-                } else {
-                    row_done();
-                }
-            }
-        }
-        if (wwarp) phase_d(std::false_type{});
-
-        // ---- first / last non-zero channel of the slitlet (JMNSLTnn / JMXSLTnn)
-        if (p.jmm != nullptr && wwarp) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const bool nz = col_ok && g < nlive && nzb[g] != 0;
-                const int lo = __reduce_min_sync(0xffffffffu, nz ? kb : INT_MAX);
-                const int hi = __reduce_max_sync(0xffffffffu, nz ? kb : -1);
-                if (lane == 0 && hi >= 0) {
-                    int32_t *dst = p.jmm + ((size_t)(g0 + g) * p.nsl + s) * 2;
-                    atomicMin(dst, lo);
-                    atomicMax(dst + 1, hi);
-                }
-            }
-        }
-
-        if (wnext >= nwork) break;
-        w = wnext;
-        if (tid == 0)
-            wq[(it + 3) & 3] = p.sched != nullptr ? 2 * (int)gridDim.x + atomicAdd(p.sched, 1)
-                                                  : wnn + (int)gridDim.x;
-        cp_async_wait_all();
-        __syncthreads();          // next descriptor landed; window and table slots are free
-    }
-}
+#include "plan_kernels.cuh"
+#include "device_utils.cuh"
+#include "side_kernels.cuh"
+#include "rectwv_kernel.cuh"
 
 }  // namespace
 
@@ -1641,600 +290,7 @@ struct emirwv_plan {
 
 namespace {
 
-int env_int(const char *name, int fallback) {
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : fallback;
-}
-
-// launch configuration for a given number of frames per CTA
-struct LaunchCfg {
-    int G, threads;
-    size_t smem;
-};
-
-// shared memory of the hot kernel:
-//   [3 tile descriptors][mbarriers, counters][G windows: WIN_ROWS x WIN_PITCH]
-//   [per warp: 2 x (rect | ya) x 32 x G knots][nstage table rows: PXCAP records]
-size_t smem_bytes(const emirwv_plan *pl, int G) {
-    return 3 * sizeof(Tile) + BAR_BYTES +
-           (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 2 * 32) * pl->esize +
-           (size_t)pl->nstage * PXCAP * rec_size(pl->K) * pl->esize;
-}
-
-LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
-    LaunchCfg cfg;
-    cfg.threads = NTHREADS;
-    int G = pl->tune_G > 0 ? pl->tune_G : env_int("EMIRWV_G", pl->esize == 4 ? 4 : 2);
-    G = (G >= 4) ? 4 : (G >= 2 ? 2 : 1);
-    while (G > 1 && (G > nframes || smem_bytes(pl, G) > (size_t)SMEM_LIMIT)) G >>= 1;
-    cfg.G = G;
-    cfg.smem = smem_bytes(pl, G);
-    return cfg;
-}
-
-template <typename T, int K, int G, bool SPANLOOP, int NS>
-int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, cudaStream_t st) {
-    auto kern = k_rectwv<T, K, G, SPANLOOP, NS>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)cfg.smem));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cfg.threads, cfg.smem));
-    if (per_sm < 1) return fail(EMIRWV_E_LIMIT, "kernel does not fit on an SM");
-    rp.ngroups = (rp.nframes + G - 1) / G;
-    const long long nwork = (long long)rp.nlive_tiles * rp.ngroups;
-    if (nwork > 0) {
-        if (nwork > INT_MAX) return fail(EMIRWV_E_LIMIT, "too many frames in one call");
-        const int grid = (int)std::min<long long>(nwork, (long long)pl->num_sms * per_sm);
-        kern<<<grid, cfg.threads, cfg.smem, st>>>(rp);
-        CUDA_TRY(cudaGetLastError());
-    }
-    return EMIRWV_OK;
-}
-
-template <typename T, int K, int G>
-int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
-               cudaStream_t st) {
-    if constexpr (sizeof(T) == 8) {          // float64 plans may ask for two stages
-        if (pl->nstage == 2) {
-            if (pl->max_span > 2) return launch_final<T, K, G, true, 2>(pl, rp, cfg, st);
-            return launch_final<T, K, G, false, 2>(pl, rp, cfg, st);
-        }
-    }
-    if (pl->max_span > 2) return launch_final<T, K, G, true, NSTAGE_MAX>(pl, rp, cfg, st);
-    return launch_final<T, K, G, false, NSTAGE_MAX>(pl, rp, cfg, st);
-}
-
-template <typename T, int K>
-int launch_k(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
-             cudaStream_t st) {
-    switch (cfg.G) {
-        case 4: return launch_one<T, K, 4>(pl, rp, cfg, st);
-        case 2: return launch_one<T, K, 2>(pl, rp, cfg, st);
-        default: return launch_one<T, K, 1>(pl, rp, cfg, st);
-    }
-}
-
-template <typename T>
-int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
-             int32_t *d_jmm, cudaStream_t st) {
-    const LaunchCfg cfg = choose_cfg(pl, nframes);
-    if (cfg.smem > (size_t)SMEM_LIMIT)
-        return fail(EMIRWV_E_LIMIT, "kernel needs %zu bytes of shared memory", cfg.smem);
-    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
-        return fail(EMIRWV_E_VALUE, "device buffers must be 16-byte aligned");
-    RunParams<T> rp;
-    rp.in = static_cast<const T *>(d_in);
-    rp.out = static_cast<T *>(d_out);
-    rp.jmm = d_jmm;
-    rp.nframes = nframes;
-    rp.tiles = pl->d_tiles;
-    rp.base = pl->d_base;
-    rp.w = static_cast<const T *>(pl->d_w);
-    rp.border = static_cast<const Border<T> *>(pl->d_border);
-    rp.pix = static_cast<const PixGeom<T> *>(pl->d_pix);
-    rp.naxis2 = pl->desc.naxis2;
-    rp.nout = pl->nout;
-    rp.NB = pl->NB;
-    rp.rps = pl->rps;
-    rp.nrows_out = pl->nsl * pl->rps;
-    rp.nsl = pl->nsl;
-    rp.vec_ok = ((size_t)pl->nout * sizeof(T)) % 16 == 0;
-    rp.nlive_tiles = pl->ntiles - pl->ntiles_empty;
-    rp.ngroups = 0;
-    rp.sched = nullptr;
-    rp.early = pl->early_rows;
-    if (pl->dynamic_sched && pl->d_sched != nullptr) {
-        rp.sched = pl->d_sched + pl->sched_next.fetch_add(1) % SCHED_POOL;
-        CUDA_TRY(cudaMemsetAsync(rp.sched, 0, sizeof(int), st));
-    }
-    if (d_jmm != nullptr) {
-        const int n = nframes * pl->nsl * 2;
-        k_init_jmm<<<(n + 255) / 256, 256, 0, st>>>(d_jmm, n);
-        CUDA_TRY(cudaGetLastError());
-    }
-    // The zero-fill kernel is memory bound and the hot kernel issue bound: when a side
-    // stream is available the hot kernel is enqueued first (it takes its shared memory
-    // and registers on every SM) and the fill blocks run next to it in what is left.
-    const bool forked = pl->ntiles_empty > 0 && pl->aux != nullptr;
-    rp.ndead_tiles = pl->ntiles_empty;
-    const int zgrid = std::max(1, env_int("EMIRWV_FILL_BLOCKS", 4 * pl->num_sms));
-    if (pl->ntiles_empty > 0 && !forked) {
-        k_zero_fill<T><<<zgrid, 128, 0, st>>>(rp, rp.nlive_tiles);
-        CUDA_TRY(cudaGetLastError());
-    }
-    std::unique_lock<std::mutex> lock(pl->aux_mu, std::defer_lock);
-    if (forked) {
-        lock.lock();
-        CUDA_TRY(cudaEventRecord(pl->ev_fork, st));
-    }
-    int rc;
-    switch (pl->K) {
-        case 1: rc = launch_k<T, 1>(pl, rp, cfg, st); break;
-        case 2: rc = launch_k<T, 2>(pl, rp, cfg, st); break;
-        case 3: rc = launch_k<T, 3>(pl, rp, cfg, st); break;
-        case 4: rc = launch_k<T, 4>(pl, rp, cfg, st); break;
-        default: rc = fail(EMIRWV_E_LIMIT, "unsupported footprint %d", pl->K);
-    }
-    if (forked) {
-        // the two kernels write disjoint parts of the output
-        CUDA_TRY(cudaStreamWaitEvent(pl->aux, pl->ev_fork, 0));
-        k_zero_fill<T><<<zgrid, 128, 0, pl->aux>>>(rp, rp.nlive_tiles);
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(pl->ev_join, pl->aux));
-        CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
-    }
-    return rc;
-}
-
-// numpy.polynomial.polynomial.polyval: Horner, one rounding per operation
-double polyval_np(double x, const double *c, int n) {
-    double c0 = c[n - 1];
-    for (int m = n - 2; m >= 0; --m) c0 = add_rn(c[m], mul_rn(c0, x));
-    return c0;
-}
-
-template <typename T>
-int upload_tables(emirwv_plan *pl, const std::vector<double> &tau, const std::vector<double> &h) {
-    const int nsl = pl->nsl, NB = pl->NB;
-    // both tables carry 64 extra entries: the kernel requests the row of its next
-    // pass before it knows whether there is one
-    std::vector<Border<T>> border((size_t)nsl * NB + 64);
-    memset(border.data(), 0, border.size() * sizeof(Border<T>));
-    for (size_t k = 0; k < (size_t)nsl * NB; ++k) {
-        border[k].tau = (T)tau[k];
-        border[k].idx = pl->h_idx[k];
-    }
-    std::vector<PixGeom<T>> pix((size_t)nsl * W + 64);
-    memset(pix.data(), 0, pix.size() * sizeof(PixGeom<T>));
-    for (int s = 0; s < nsl; ++s) {
-        const emirwv_slitlet_desc &sl = pl->desc.slitlet[s];
-        if (!sl.valid) continue;
-        const int nchan = sl.bb_nc2_orig - sl.bb_nc1_orig + 1;
-        const double *hs = h.data() + (size_t)s * W;
-        for (int i = 0; i < nchan; ++i) {
-            PixGeom<T> &pg = pix[(size_t)s * W + i];
-            pg.qm = i > 0 ? (T)(hs[i] / hs[i - 1]) : T(0);
-            pg.qp = i + 1 < nchan ? (T)(hs[i] / hs[i + 1]) : T(0);
-            pg.r0 = i > 0 ? (T)(hs[i] / (hs[i - 1] + hs[i])) : T(0);
-            pg.r1 = i + 1 < nchan ? (T)(hs[i + 1] / (hs[i] + hs[i + 1])) : T(0);
-        }
-    }
-    CUDA_TRY(cudaMalloc(&pl->d_border, border.size() * sizeof(Border<T>)));
-    CUDA_TRY(cudaMemcpy(pl->d_border, border.data(), border.size() * sizeof(Border<T>),
-                        cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&pl->d_pix, pix.size() * sizeof(PixGeom<T>)));
-    CUDA_TRY(cudaMemcpy(pl->d_pix, pix.data(), pix.size() * sizeof(PixGeom<T>),
-                        cudaMemcpyHostToDevice));
-    pl->table_bytes += (int64_t)(border.size() * sizeof(Border<T>) + pix.size() * sizeof(PixGeom<T>));
-    return EMIRWV_OK;
-}
-
-// Border tables of every slitlet; float64 with numpy's operation order so that the
-// interval of every border is the one numpy.searchsorted finds in the reference's
-// resample_image2d_flux / SteffenInterpolator (apply_rectwv_coeff.py:152-159).
-int build_border_tables(emirwv_plan *pl, std::vector<uint8_t> &covered) {
-    const emirwv_plan_desc &d = pl->desc;
-    const int nout = pl->nout, NB = pl->NB, nsl = pl->nsl;
-    std::vector<double> nb(NB), wl(nout);
-    for (int k = 0; k < nout; ++k) wl[k] = add_rn(d.crval1, mul_rn(d.cdelt1, (double)k));
-    for (int k = 1; k < nout; ++k) nb[k] = mul_rn(0.5, add_rn(wl[k], wl[k - 1]));
-    nb[0] = add_rn(mul_rn(2.0, wl[0]), -nb[1]);
-    nb[nout] = add_rn(mul_rn(2.0, wl[nout - 1]), -nb[nout - 1]);
-
-    pl->h_idx.assign((size_t)nsl * NB, 0);
-    pl->h_t.assign((size_t)nsl * NB, 0.0);
-    std::vector<double> h_tau((size_t)nsl * NB, 0.0);
-    std::vector<double> h_h((size_t)nsl * W, 0.0);
-    covered.assign((size_t)nsl * NB, 0);
-    pl->max_span = 0;
-
-    std::vector<double> xw(W + 1);
-    for (int s = 0; s < nsl; ++s) {
-        const emirwv_slitlet_desc &sl = d.slitlet[s];
-        if (!sl.valid) continue;
-        const int nchan = sl.bb_nc2_orig - sl.bb_nc1_orig + 1;
-        double *h = h_h.data() + (size_t)s * W;
-        for (int i = 0; i <= nchan; ++i) {
-            const double xb = add_rn(add_rn(-0.5, (double)i), d.crpix1);
-            xw[i] = polyval_np(xb, sl.wpoly, sl.nwpoly);
-        }
-        for (int i = 0; i < nchan; ++i) {
-            h[i] = xw[i + 1] - xw[i];
-            if (!(h[i] > 0.0))
-                return fail(EMIRWV_E_VALUE,
-                            "slitlet %d: wavelength polynomial is not increasing at pixel %d",
-                            s + 1, i + 1);
-        }
-        int prev = 0;
-        for (int k = 0; k < NB; ++k) {
-            const double x = nb[k];
-            int idx;
-            double t, tau;
-            uint8_t cov = 1;
-            if (x < xw[0]) {                       // extrapolate='border': y_0
-                idx = 0;
-                t = 0.0;
-                tau = 0.0;
-                cov = 0;
-            } else if (x > xw[nchan]) {            // extrapolate='border': y_N
-                idx = nchan - 1;
-                t = h[nchan - 1];
-                tau = 1.0;
-                cov = 0;
-            } else {                               // searchsorted(side='left').clip(1, N) - 1
-                const int pos = (int)(std::lower_bound(xw.begin(), xw.begin() + nchan + 1, x) -
-                                      xw.begin());
-                idx = std::min(std::max(pos, 1), nchan) - 1;
-                t = x - xw[idx];
-                tau = t / h[idx];
-            }
-            pl->h_idx[(size_t)s * NB + k] = idx;
-            pl->h_t[(size_t)s * NB + k] = t;
-            h_tau[(size_t)s * NB + k] = tau;
-            covered[(size_t)s * NB + k] = cov;
-            if (k > 0) pl->max_span = std::max(pl->max_span, idx - prev);
-            prev = idx;
-        }
-    }
-    if (pl->dtype == EMIRWV_F32) return upload_tables<float>(pl, h_tau, h_h);
-    return upload_tables<double>(pl, h_tau, h_h);
-}
-
-// Work items: (slitlet, run of output columns), all 39 scanned rows.  A live tile is cut
-// into at most NWARPS consecutive pieces, one per warp: at most BW output columns whose
-// borders touch at most WARP_PX rectified pixels.  Columns without wavelength coverage
-// (and missing slitlets) become wide runs of zeros for the fill kernel.
-// Returns 1 when a tile does not fit the kernel's fixed shared-memory geometry with this
-// BW (the caller retries with narrower pieces), 0 on success.
-int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int BW) {
-    const emirwv_plan_desc &d = pl->desc;
-    const int nout = pl->nout, NB = pl->NB, K = pl->K;
-    std::vector<Tile> live, dead;
-    int wcols_max = 4, span_max = 1, npx_max = 1, nk_max = 0;
-    for (int s = 0; s < pl->nsl; ++s) {
-        const emirwv_slitlet_desc &sl = d.slitlet[s];
-        const int nchan = sl.valid ? sl.bb_nc2_orig - sl.bb_nc1_orig + 1 : 0;
-        const uint8_t *cov = covered.data() + (size_t)s * NB;
-        const int32_t *idx = pl->h_idx.data() + (size_t)s * NB;
-        // output column k carries flux when one of its borders lies inside the spectrum or
-        // the spectrum lies between them
-        auto is_live = [&](int k) {
-            return sl.valid && (cov[k] != 0 || cov[k + 1] != 0 || idx[k] != idx[k + 1]);
-        };
-        // length of the run of dead columns starting at k
-        auto dead_run = [&](int k) {
-            int n = 0;
-            while (k + n < nout && !is_live(k + n)) ++n;
-            return n;
-        };
-        int k0 = 0;
-        while (k0 < nout) {
-            Tile t;
-            memset(&t, 0, sizeof(t));
-            t.slit = s;
-            t.k0 = k0;
-            t.nchan = nchan;
-            int run = dead_run(k0);
-            if (k0 + run < nout) run &= ~3;        // keep the next tile 16-byte aligned
-            if (run >= 32 || k0 + run == nout) {
-                t.empty = 1;
-                t.nk = std::min(run, 1024);
-                dead.push_back(t);
-                k0 += t.nk;
-                continue;
-            }
-            // live tile: one piece per warp
-            int k = k0, nw = 0;
-            t.kw[0] = 0;
-            while (nw < NWARPS && k < nout) {
-                if (nw > 0 && dead_run(k) >= 32) break;        // a fill run starts here
-                int kend = std::min(k + BW, nout);
-                while (kend > k + 1 && idx[kend] - idx[k] + 1 > WARP_PX) --kend;
-                if (idx[kend] - idx[k] + 1 > WARP_PX) return 1;   // one column spans too much
-                k = kend;
-                t.kw[++nw] = (uint8_t)(k - k0);
-            }
-            if (k < nout && (k & 3)) {
-                // end on a multiple of 4 so that a following fill run stays vectorised:
-                // lengthen the last piece if it stays within its limits, else shorten it
-                const int kprev = k0 + t.kw[nw - 1];
-                const int up = std::min((k + 3) & ~3, nout), down = k & ~3;
-                if (up - kprev <= WARP_BORDERS && idx[up] - idx[kprev] + 1 <= WARP_PX)
-                    k = up;
-                else if (down > kprev)
-                    k = down;
-                t.kw[nw] = (uint8_t)(k - k0);
-            }
-            for (int wq = nw + 1; wq <= NWARPS; ++wq) t.kw[wq] = t.kw[nw];
-            t.nk = k - k0;
-            const int ilo = idx[k0], ihi = idx[k0 + t.nk];
-            t.jlo = std::max(0, ilo - 1);
-            const int jhi = std::min(nchan - 1, ihi + 1);
-            t.npx = jhi - t.jlo + 1;
-            if (t.npx > PXCAP) return 1;
-            int c0 = INT_MAX, c1 = INT_MIN;
-            int rlo[NROWS], rhi[NROWS];
-            for (int y = 0; y < NROWS; ++y) {
-                const int32_t *row = pl->h_base.data() + ((size_t)s * NROWS + y) * W;
-                int r0 = INT_MAX, r1 = INT_MIN;
-                for (int j = t.jlo; j <= jhi; ++j) {
-                    const int br = base_row(row[j]), bc = base_col(row[j]);
-                    r0 = std::min(r0, br);
-                    r1 = std::max(r1, br + K - 1);
-                    c0 = std::min(c0, bc);
-                    c1 = std::max(c1, bc + K - 1);
-                }
-                rlo[y] = r0;
-                rhi[y] = r1;
-            }
-            // rolling window: rows may only be added at the top and dropped at the bottom
-            for (int y = 1; y < NROWS; ++y) rhi[y] = std::max(rhi[y], rhi[y - 1]);
-            for (int y = NROWS - 2; y >= 0; --y) rlo[y] = std::min(rlo[y], rlo[y + 1]);
-            for (int y = 0; y < NROWS; ++y) {
-                const int next_hi = rhi[std::min(y + pl->nstage - 1, NROWS - 1)];
-                span_max = std::max(span_max, next_hi - rlo[y] + 1);
-                t.span[y] = (int32_t)(((uint32_t)(rhi[y] & 0xffff) << 16) | (uint32_t)(rlo[y] & 0xffff));
-            }
-            c0 = (int)(std::floor(c0 / 4.0) * 4.0);        // 16-byte aligned window rows
-            t.c0 = c0;
-            t.wcols = ((c1 - c0 + 1) + 3) & ~3;
-            if (t.wcols > WIN_PITCH || span_max > WIN_ROWS) return 1;
-            wcols_max = std::max(wcols_max, t.wcols);
-            npx_max = std::max(npx_max, t.npx);
-            nk_max = std::max(nk_max, t.nk);
-            live.push_back(t);
-            k0 += t.nk;
-        }
-    }
-    pl->h_cover.assign((size_t)pl->nsl * 2, 0);
-    for (const Tile &t : live) {
-        int32_t *c = pl->h_cover.data() + 2 * t.slit;
-        if (c[1] == 0) c[0] = t.k0;
-        c[0] = std::min(c[0], t.k0);
-        c[1] = std::max(c[1], t.k0 + t.nk);
-    }
-    // the widest (most expensive) tiles first, the narrow ones at the ends of the slitlets
-    // last: the tail of the launch is made of short items
-    if (env_int("EMIRWV_TILE_ORDER", 1))
-        std::stable_sort(live.begin(), live.end(),
-                         [](const Tile &a, const Tile &b) { return a.nk > b.nk; });
-    pl->ntiles_empty = (int)dead.size();
-    pl->h_tiles = live;
-    pl->h_tiles.insert(pl->h_tiles.end(), dead.begin(), dead.end());
-    pl->ntiles = (int)pl->h_tiles.size();
-    pl->tile_k = nk_max;
-    pl->wrows_max = span_max;
-    pl->wcols_max = wcols_max;
-    pl->npx_max = npx_max;
-    return 0;
-}
-
-int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
-    // widest pieces whose source window fits the CTA
-    int BW = std::max(4, std::min(pl->tile_k / NWARPS, WARP_BORDERS));
-    for (; BW >= 4; BW -= (BW > 8 ? 4 : 1))
-        if (try_build_tiles(pl, covered, BW) == 0) break;
-    if (BW < 4)
-        return fail(EMIRWV_E_LIMIT,
-                    "distortion too strong: the source window of a 32-column block does not fit "
-                    "(%d rows x %d columns available)", WIN_ROWS, WIN_PITCH);
-    if (pl->ntiles_empty > 65535) return fail(EMIRWV_E_LIMIT, "too many tiles");
-    pl->dynamic_sched = env_int("EMIRWV_DYNAMIC", 1);
-    pl->early_rows = env_int("EMIRWV_EARLY", 1);
-    CUDA_TRY(cudaMalloc(&pl->d_sched, SCHED_POOL * sizeof(int)));
-    CUDA_TRY(cudaMemset(pl->d_sched, 0, SCHED_POOL * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&pl->d_tiles, pl->h_tiles.size() * sizeof(Tile)));
-    CUDA_TRY(cudaMemcpy(pl->d_tiles, pl->h_tiles.data(), pl->h_tiles.size() * sizeof(Tile),
-                        cudaMemcpyHostToDevice));
-    pl->table_bytes += (int64_t)(pl->h_tiles.size() * sizeof(Tile));
-    return EMIRWV_OK;
-}
-
-int validate(const emirwv_plan_desc *d) {
-    // Slitlet2D.extract_slitlet2d accepts 2048 x 2048 frames only (slitlet2d.py:359-363)
-    if (d->naxis1 != W) return fail(EMIRWV_E_VALUE, "Unexpected naxis1");
-    if (d->naxis2 < 2 || d->naxis2 > 16384) return fail(EMIRWV_E_VALUE, "Unexpected naxis2");
-    if (d->nslitlets < 1 || d->nslitlets > EMIRWV_MAX_SLITLETS)
-        return fail(EMIRWV_E_VALUE, "nslitlets=%d out of range", d->nslitlets);
-    if (d->rows_per_slitlet != NROWS - 1)
-        return fail(EMIRWV_E_VALUE, "rows_per_slitlet must be %d", NROWS - 1);
-    if (d->resampling < 1 || d->resampling > 3)
-        return fail(EMIRWV_E_VALUE, "Unexpected resampling value=%d", d->resampling);
-    if (d->dtype != EMIRWV_F32 && d->dtype != EMIRWV_F64)
-        return fail(EMIRWV_E_VALUE, "unknown dtype %d", d->dtype);
-    if (d->naxis1_out < 2 || d->naxis1_out > 65536)
-        return fail(EMIRWV_E_VALUE, "naxis1_out=%d out of range", d->naxis1_out);
-    if (!(d->cdelt1 > 0.0)) return fail(EMIRWV_E_VALUE, "cdelt1 must be positive");
-    const int cap = d->max_order > 0 ? d->max_order : 4;
-    for (int s = 0; s < d->nslitlets; ++s) {
-        const emirwv_slitlet_desc &sl = d->slitlet[s];
-        if (!sl.valid) continue;
-        const int order = order_from_ncoef(sl.ncoef);
-        if (order < 0 || order > cap)
-            return fail(EMIRWV_E_VALUE, "order > %d not implemented", cap);
-        if (sl.nwpoly < 1 || sl.nwpoly > EMIRWV_MAX_WPOLY)
-            return fail(EMIRWV_E_VALUE, "slitlet %d: %d wavelength coefficients", s + 1, sl.nwpoly);
-        if (sl.bb_nc1_orig < 1 || sl.bb_nc2_orig > d->naxis1 || sl.bb_nc2_orig < sl.bb_nc1_orig + 1 ||
-            sl.bb_ns1_orig < 1 || sl.bb_ns2_orig > d->naxis2 || sl.bb_ns2_orig < sl.bb_ns1_orig)
-            return fail(EMIRWV_E_VALUE, "slitlet %d: bounding box outside the frame", s + 1);
-        const int bbh = sl.bb_ns2_orig - sl.bb_ns1_orig + 1;
-        if (sl.max_row_rectified - sl.min_row_rectified + 1 != d->rows_per_slitlet)
-            return fail(EMIRWV_E_VALUE,
-                        "could not broadcast input array from shape (%d,%d) into shape (%d,%d)",
-                        sl.max_row_rectified - sl.min_row_rectified + 1, d->naxis1_out,
-                        d->rows_per_slitlet, d->naxis1_out);
-        if (sl.min_row_rectified < 0)
-            return fail(EMIRWV_E_VALUE, "slitlet %d: negative min_row_rectified", s + 1);
-        if (sl.max_row_rectified + 1 >= bbh)
-            return fail(EMIRWV_E_INDEX, "index %d is out of bounds for axis 0 with size %d",
-                        sl.max_row_rectified + 1, bbh);
-    }
-    return EMIRWV_OK;
-}
-
-int build_plan(emirwv_plan *pl) {
-    const emirwv_plan_desc &d = pl->desc;
-    CUDA_TRY(cudaGetDevice(&pl->device));
-    CUDA_TRY(cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, pl->device));
-    pl->dtype = d.dtype;
-    pl->mode = d.resampling;
-    pl->esize = d.dtype == EMIRWV_F32 ? 4 : 8;
-    pl->nsl = d.nslitlets;
-    pl->rps = d.rows_per_slitlet;
-    pl->nout = d.naxis1_out;
-    pl->NB = d.naxis1_out + 1;
-    pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", TILE_K_MAX);
-    pl->tile_rows = NROWS;       // a tile always spans the 39 scanned rows
-    // float64 records are 96 bytes: four staged table rows take 90 KB and leave room for one
-    // CTA per SM only; two stages fit two CTAs (EMIRWV_NSTAGE_F64=2, experimental)
-    pl->nstage = NSTAGE_MAX;
-    if (pl->esize == 8 && env_int("EMIRWV_NSTAGE_F64", NSTAGE_MAX) == 2) pl->nstage = 2;
-    pl->tile_k = std::max(32, std::min(pl->tile_k, TILE_K_MAX));
-
-    pl->h_slit.resize(pl->nsl);
-    for (int s = 0; s < pl->nsl; ++s) {
-        const emirwv_slitlet_desc &sl = d.slitlet[s];
-        SlitDev &sd = pl->h_slit[s];
-        memset(&sd, 0, sizeof(sd));
-        sd.valid = sl.valid ? 1 : 0;
-        if (!sl.valid) continue;
-        sd.ns1 = sl.bb_ns1_orig;
-        sd.nc1 = sl.bb_nc1_orig;
-        sd.bbh = sl.bb_ns2_orig - sl.bb_ns1_orig + 1;
-        sd.bbw = sl.bb_nc2_orig - sl.bb_nc1_orig + 1;
-        sd.min_row = sl.min_row_rectified;
-        sd.order = order_from_ncoef(sl.ncoef);
-        memcpy(sd.a, sl.aij, sizeof(double) * sl.ncoef);
-        memcpy(sd.b, sl.bij, sizeof(double) * sl.ncoef);
-    }
-    CUDA_TRY(cudaMalloc(&pl->d_slit, pl->nsl * sizeof(SlitDev)));
-    CUDA_TRY(cudaMemcpy(pl->d_slit, pl->h_slit.data(), pl->nsl * sizeof(SlitDev),
-                        cudaMemcpyHostToDevice));
-
-    GeomParams gp;
-    gp.slit = pl->d_slit;
-    gp.nsl = pl->nsl;
-    gp.naxis1 = d.naxis1;
-    gp.naxis2 = d.naxis2;
-    gp.offx = d.offx;
-    gp.offy = d.offy;
-    gp.mode = pl->mode;
-    gp.kmax = nullptr;
-    const dim3 block(128);
-    const dim3 grid((W + 127) / 128, NROWS, pl->nsl);
-
-    if (pl->mode == EMIRWV_AREA) {
-        int *d_kmax = nullptr;
-        int kmax = 1;
-        CUDA_TRY(cudaMalloc(&d_kmax, sizeof(int)));
-        CUDA_TRY(cudaMemcpy(d_kmax, &kmax, sizeof(int), cudaMemcpyHostToDevice));
-        gp.kmax = d_kmax;
-        gp.K = 0;
-        gp.base = nullptr;
-        k_extent<<<grid, block>>>(gp);
-        cudaError_t err = cudaGetLastError();
-        if (err == cudaSuccess)
-            err = cudaMemcpy(&kmax, d_kmax, sizeof(int), cudaMemcpyDeviceToHost);
-        cudaFree(d_kmax);
-        if (err != cudaSuccess)
-            return fail(EMIRWV_E_CUDA, "k_extent failed: %s", cudaGetErrorString(err));
-        if (kmax > MAXK)
-            return fail(EMIRWV_E_LIMIT,
-                        "distortion too strong: an output pixel covers %d source pixels "
-                        "along one axis (limit %d)", kmax, MAXK);
-        pl->K = kmax;
-    } else {
-        pl->K = pl->mode == EMIRWV_NEAREST ? 1 : 2;
-    }
-
-    const size_t nrowtab = (size_t)pl->nsl * NROWS;
-    // (+64 bytes: the kernel copies table rows in 16-byte chunks)
-    CUDA_TRY(cudaMalloc(&pl->d_base, nrowtab * W * sizeof(int32_t) + 64));
-    CUDA_TRY(cudaMalloc(&pl->d_w, nrowtab * W * rec_size(pl->K) * pl->esize + 64));
-    pl->table_bytes += (int64_t)(nrowtab * W * sizeof(int32_t));
-    pl->table_bytes += (int64_t)(nrowtab * W * rec_size(pl->K) * pl->esize);
-    gp.K = pl->K;
-    gp.base = pl->d_base;
-    gp.kmax = nullptr;
-    if (pl->dtype == EMIRWV_F32)
-        k_build_geometry<float><<<grid, block>>>(gp, static_cast<float *>(pl->d_w));
-    else
-        k_build_geometry<double><<<grid, block>>>(gp, static_cast<double *>(pl->d_w));
-    CUDA_TRY(cudaGetLastError());
-    pl->h_base.resize(nrowtab * W);
-    CUDA_TRY(cudaMemcpy(pl->h_base.data(), pl->d_base, pl->h_base.size() * sizeof(int32_t),
-                        cudaMemcpyDeviceToHost));
-
-    std::vector<uint8_t> covered;
-    int rc = build_border_tables(pl, covered);
-    if (rc) return rc;
-    rc = build_tiles(pl, covered);
-    if (rc) return rc;
-    if (env_int("EMIRWV_NO_AUX", 0) == 0) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&pl->aux, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
-    }
-    return EMIRWV_OK;
-}
-
-void release_workspace(emirwv_plan *pl) {
-    for (auto &sl : pl->slots) {
-        if (sl.d_in) cudaFree(sl.d_in);
-        if (sl.d_out) cudaFree(sl.d_out);
-        if (sl.d_jmm) cudaFree(sl.d_jmm);
-        if (sl.stream) cudaStreamDestroy(sl.stream);
-        sl = emirwv_plan::Slot();
-    }
-    pl->ws_chunk = 0;
-}
-
-int ensure_workspace(emirwv_plan *pl, int chunk) {
-    if (pl->ws_chunk >= chunk) return EMIRWV_OK;
-    release_workspace(pl);
-    const size_t in_b = (size_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
-    const size_t out_b = (size_t)pl->nsl * pl->rps * pl->nout * pl->esize;
-    for (auto &sl : pl->slots) {
-        CUDA_TRY(cudaMalloc(&sl.d_in, in_b * chunk));
-        CUDA_TRY(cudaMalloc(&sl.d_out, out_b * chunk));
-        CUDA_TRY(cudaMalloc(&sl.d_jmm, (size_t)chunk * pl->nsl * 2 * sizeof(int32_t)));
-        CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-    }
-    pl->ws_chunk = chunk;
-    return EMIRWV_OK;
-}
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
+#include "plan_build.inl"
 
 }  // namespace
 
