@@ -25,7 +25,7 @@ def _stale(target, sources):
 def build_library(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a … -> pyemir_b200/libemirwv.so"""
     sources = [os.path.join(CSRC, name) for name in (
-        "emirwv.cu", "geom.cuh", "plan_kernels.cuh", "device_utils.cuh", "side_kernels.cuh",
+        "emirwv.cu", "geom.cuh", "pixel_ops.cuh", "plan_kernels.cuh", "device_utils.cuh", "side_kernels.cuh",
         "rectwv_kernel.cuh", "plan_build.inl", "median_net38.inc", "stack_median_nets.inc")]
     sources.append(os.path.join(ROOT, "include", "emirwv.h"))
     if not force and not _stale(LIB_PATH, sources):
@@ -40,7 +40,8 @@ def build_library(force=False, verbose=False):
 
 def build_hostcheck(force=False):
     """g++ build of the shared geometry header, for CPU-side tests of the math."""
-    sources = [os.path.join(CSRC, "hostcheck.cpp"), os.path.join(CSRC, "geom.cuh")]
+    sources = [os.path.join(CSRC, "hostcheck.cpp"), os.path.join(CSRC, "geom.cuh"),
+               os.path.join(CSRC, "pixel_ops.cuh"), os.path.join(CSRC, "stack_median_nets.inc")]
     if not force and not _stale(HOSTCHECK_PATH, sources):
         return HOSTCHECK_PATH
     cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",

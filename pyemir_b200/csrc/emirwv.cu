@@ -25,6 +25,7 @@
 //
 // One translation unit; the parts live next to this file and are included below:
 //   geom.cuh            2-D polynomial map and polygon clipping (shared with the CPU hostcheck)
+//   pixel_ops.cuh       pre-reduction stages, stack-median networks (shared with the hostcheck)
 //   plan_kernels.cuh    k_extent, k_build_geometry, k_rectify2d, parity-hook helpers
 //   device_utils.cuh    TMA bulk copies, mbarriers, packed float32 pairs
 //   side_kernels.cuh    zero fill, median_slitlets_rectified, ABBA mean / median, pre-reduction
@@ -60,6 +61,7 @@
 #define EMIRWV_PXCAP 240
 #endif
 #include "geom.cuh"
+#include "pixel_ops.cuh"
 
 namespace {
 

@@ -41,3 +41,76 @@ int hostcheck_order_from_ncoef(int ncoef) { return emirwv::order_from_ncoef(ncoe
 extern "C" double hostcheck_steffen_partial_flux(double rect, double ya, double yb, double tau) {
     return emirwv::steffen_partial_flux<double>(rect, ya, yb, tau);
 }
+
+// ---- per-pixel arithmetic of the kernels either side of the hot path (pixel_ops.cuh)
+#include "pixel_ops.cuh"
+
+namespace {
+
+// what k_stack_median does for one pixel: samples into N registers, padding, network
+template <typename T, int N>
+double median_bucket(const T *samples, int n, int64_t stride) {
+    T v[N];
+    for (int u = 0; u < N; ++u)
+        v[u] = u < n ? samples[(int64_t)u * stride] : emirwv::stack_pad<T>(u, n, N);
+    return emirwv::median_of_registers<T, N>(v, n);
+}
+
+template <typename T>
+int stack_median_host(const T *frames, int n, int64_t npix, double *out) {
+    if (n < 1 || n > 64) return -1;
+    for (int64_t i = 0; i < npix; ++i) {
+        const T *s = frames + i;
+        if (n <= 4) out[i] = median_bucket<T, 4>(s, n, npix);
+        else if (n <= 8) out[i] = median_bucket<T, 8>(s, n, npix);
+        else if (n <= 16) out[i] = median_bucket<T, 16>(s, n, npix);
+        else if (n <= 32) out[i] = median_bucket<T, 32>(s, n, npix);
+        else out[i] = median_bucket<T, 64>(s, n, npix);
+    }
+    return 0;
+}
+
+// what k_prereduce does for every pixel of a stack
+template <typename TIn, typename TCal, typename A>
+void prereduce_host(const TIn *in, float *out, int nframes, int64_t npix, const TCal *bias,
+                    const TCal *dark, const TCal *flat) {
+    const bool hb = bias != nullptr, hd = dark != nullptr, hf = flat != nullptr;
+    for (int64_t i = 0; i < npix; ++i) {
+        const A b = hb ? (A)bias[i] : A(0), d = hd ? (A)dark[i] : A(0);
+        A f = hf ? (A)flat[i] : A(1);
+        f = f <= A(0) ? A(1) : f;
+        for (int n = 0; n < nframes; ++n)
+            out[(int64_t)n * npix + i] =
+                emirwv::prereduce_px<TIn, A>(in[(int64_t)n * npix + i], hb, hd, hf, b, d, f);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// frames [n][npix], out [npix]; dtype 0 = float32, 1 = float64
+int hostcheck_stack_median(const void *frames, int dtype, int n, int64_t npix, double *out) {
+    if (dtype == 0) return stack_median_host(static_cast<const float *>(frames), n, npix, out);
+    return stack_median_host(static_cast<const double *>(frames), n, npix, out);
+}
+
+// in_dtype 0 float32, 1 float64, 2 uint16; cal_dtype 0 float32, 1 float64 (NULL skips a stage)
+int hostcheck_prereduce(const void *in, int in_dtype, float *out, int nframes, int64_t npix,
+                        const void *bias, const void *dark, const void *flat, int cal_dtype) {
+#define PRE(TIN, TCAL, A)                                                                   \
+    prereduce_host<TIN, TCAL, A>(static_cast<const TIN *>(in), out, nframes, npix,          \
+                                 static_cast<const TCAL *>(bias),                           \
+                                 static_cast<const TCAL *>(dark), static_cast<const TCAL *>(flat))
+    if (in_dtype == 0 && cal_dtype == 0) PRE(float, float, float);
+    else if (in_dtype == 0) PRE(float, double, double);
+    else if (in_dtype == 1 && cal_dtype == 0) PRE(double, float, double);
+    else if (in_dtype == 1) PRE(double, double, double);
+    else if (in_dtype == 2 && cal_dtype == 0) PRE(uint16_t, float, float);
+    else if (in_dtype == 2) PRE(uint16_t, double, double);
+    else return -1;
+#undef PRE
+    return 0;
+}
+
+}  // extern "C"

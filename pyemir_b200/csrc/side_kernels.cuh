@@ -49,13 +49,6 @@ __global__ void __launch_bounds__(128) k_zero_fill(const RunParams<T> p, int fir
 // (compare-exchanges only, no data-dependent branches) that leaves the two middle values on
 // two known wires.  Loads and stores are coalesced along the columns; the kernel reads the
 // product once.
-template <typename T>
-__device__ __forceinline__ void order2(T &a, T &b) {
-    const T lo = fmin(a, b), hi = fmax(a, b);
-    a = lo;
-    b = hi;
-}
-
 template <typename T, int R>
 __global__ void __launch_bounds__(128) k_median_slitlets(const T *__restrict__ in,
                                                         T *__restrict__ out, int naxis1,
@@ -204,24 +197,6 @@ __device__ __forceinline__ void load4(const uint16_t *p, uint16_t (&v)[4]) {
     v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
 }
 
-// one pixel of one frame through the stages
-template <typename TIn, typename A>
-__device__ __forceinline__ float prereduce_px(TIn raw, bool hb, bool hd, bool hf, A b, A d, A f) {
-    if constexpr (sizeof(TIn) == 8) {
-        double x = raw;
-        if (hb) x = (double)(float)(x - (double)b);
-        if (hd) x = (double)(float)(x - (double)d);
-        if (hf) x = (double)(float)(x / (double)f);
-        return (float)x;
-    } else {
-        float x = (float)raw;
-        if (hb) x = (float)((A)x - b);
-        if (hd) x = (float)((A)x - d);
-        if (hf) x = (float)((A)x / f);
-        return x;
-    }
-}
-
 // VEC = 4: a thread owns four consecutive pixels (16-byte loads and stores, npix % 4 == 0 and
 // aligned buffers); VEC = 1: any size and alignment.  Frames are taken four at a time so that
 // four independent loads are in flight per thread.
@@ -333,41 +308,7 @@ struct StackSel {
     int idx[STACK_MAX];
 };
 
-#include "stack_median_nets.inc"
-
-// Median of the n samples held in v[0..n), float64, NaN if any sample is NaN.  The padding
-// v[n..N) -- floor((N-n)/2) times -inf, then +inf -- puts the median of the samples on the
-// wires N/2-1 and N/2 for every n (odd n: wire N/2-1 alone), so the network only has to bring
-// the two middle values of N wires home: Batcher's odd-even merge sort pruned to those two
-// outputs (scripts/gen_stack_median_nets.py), two min/max instructions per exchange, every
-// index a compile-time constant: the samples never leave the registers.
-template <typename T, int N>
-__device__ __forceinline__ double median_of_registers(T (&v)[N], int n) {
-    const T inf = (T)INFINITY;
-    bool has_nan = false;
-#pragma unroll
-    for (int u = 0; u < N; ++u) {
-        has_nan |= v[u] != v[u];
-        v[u] = v[u] != v[u] ? inf : v[u];
-    }
-#define CE(a, b) order2(v[a], v[b]);
-    if constexpr (N == 4) {
-        STACK_NET_4(CE)
-    } else if constexpr (N == 8) {
-        STACK_NET_8(CE)
-    } else if constexpr (N == 16) {
-        STACK_NET_16(CE)
-    } else if constexpr (N == 32) {
-        STACK_NET_32(CE)
-    } else {
-        static_assert(N == 4 || N == 8 || N == 16 || N == 32 || N == 64, "stack size bucket");
-        STACK_NET_64(CE)
-    }
-#undef CE
-    const T a = v[N / 2 - 1], b = (n & 1) ? a : v[N / 2];
-    const double med = __dmul_rn(__dadd_rn((double)a, (double)b), 0.5);
-    return has_nan ? __longlong_as_double(0x7ff8000000000000LL) : med;
-}
+// (median_of_registers, the padding rule and the selection networks: pixel_ops.cuh)
 
 // medians of VEC consecutive pixels starting at i over the selected images (VEC = 4: 16-byte
 // loads, npix % 4 == 0 and aligned frames)
@@ -390,7 +331,7 @@ __device__ __forceinline__ void stack_median_px(const T *__restrict__ frames, co
                 v[0][u] = __ldcs(src);
             }
         } else {
-            const T pad = u < sel.n + nneg ? -inf : inf;
+            const T pad = u < sel.n + nneg ? -inf : inf;        // (= stack_pad, pixel_ops.cuh)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) v[e][u] = pad;
         }
