@@ -270,7 +270,6 @@ struct emirwv_plan {
     int dynamic_sched = 1;
     int early_rows = 1;
     int nstage = NSTAGE_MAX;           // stages of the hot kernel's row pipeline
-    int aligned_lanes = 0;             // experimental lane mapping of the hot kernel
     int tune_G = 0;
     int num_sms = 148;
     int64_t table_bytes = 0;

@@ -33,9 +33,9 @@ LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
     return cfg;
 }
 
-template <typename T, int K, int G, bool SPANLOOP, int NS, bool ALIGNED = false>
+template <typename T, int K, int G, bool SPANLOOP, int NS>
 int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, cudaStream_t st) {
-    auto kern = k_rectwv<T, K, G, SPANLOOP, NS, ALIGNED>;
+    auto kern = k_rectwv<T, K, G, SPANLOOP, NS>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)cfg.smem));
     int per_sm = 0;
@@ -60,10 +60,6 @@ int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &c
             if (pl->max_span > 2) return launch_final<T, K, G, true, 2>(pl, rp, cfg, st);
             return launch_final<T, K, G, false, 2>(pl, rp, cfg, st);
         }
-    }
-    if (pl->aligned_lanes) {                 // experimental lane mapping (EMIRWV_ALIGNED=1)
-        if (pl->max_span > 2) return launch_final<T, K, G, true, NSTAGE_MAX, true>(pl, rp, cfg, st);
-        return launch_final<T, K, G, false, NSTAGE_MAX, true>(pl, rp, cfg, st);
     }
     if (pl->max_span > 2) return launch_final<T, K, G, true, NSTAGE_MAX>(pl, rp, cfg, st);
     return launch_final<T, K, G, false, NSTAGE_MAX>(pl, rp, cfg, st);
@@ -474,7 +470,6 @@ int build_plan(emirwv_plan *pl) {
     // CTA per SM only; two stages fit two CTAs (EMIRWV_NSTAGE_F64=2, experimental)
     pl->nstage = NSTAGE_MAX;
     if (pl->esize == 8 && env_int("EMIRWV_NSTAGE_F64", NSTAGE_MAX) == 2) pl->nstage = 2;
-    pl->aligned_lanes = env_int("EMIRWV_ALIGNED", 0) != 0 && pl->nstage == NSTAGE_MAX;
     pl->tile_k = std::max(32, std::min(pl->tile_k, TILE_K_MAX));
 
     pl->h_slit.resize(pl->nsl);

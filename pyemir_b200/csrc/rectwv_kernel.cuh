@@ -72,7 +72,7 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 // Shared memory: [tile descriptor ring: 3][mbarriers][G windows: WIN_ROWS x WIN_PITCH]
 //                [per warp: (rect | ya) x 32 pixels x G][NSTAGE table rows: PXCAP records]
 // ---------------------------------------------------------------------------------
-template <typename T, int K, int G, bool SPANLOOP, int NSTAGE, bool ALIGNED>
+template <typename T, int K, int G, bool SPANLOOP, int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, 2)
     k_rectwv(const RunParams<T> p) {
     static_assert(NSTAGE >= 2 && NSTAGE <= NSTAGE_MAX, "stage count");
@@ -170,22 +170,11 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         const int ibl = bd.idx - tile.jlo;                     // source pixel, tile relative
         const int ibn = __shfl_down_sync(0xffffffffu, ibl, 1);
         const int plo = __shfl_sync(0xffffffffu, ibl, 0);      // first pixel the warp owns
-        // lane that holds pixel ibl.  ALIGNED (experimental): lane L holds pixel plo + L (lane 31
-        // the left neighbour plo - 1), so that in the common case of one border per source pixel
-        // every border falls into its own lane's pixel
-        const int kl = ALIGNED ? ibl - plo : ibl - plo + 1;
+        const int kl = ibl - plo + 1;                          // lane that holds pixel ibl
         const bool col_ok = lane < nb;
         const bool has1 = ibn > ibl, has2 = ibn > ibl + 1;
         const int kb = k0 + q;
-        const int pp = ALIGNED ? (lane == 31 ? plo - 1 : plo + lane)
-                               : plo - 1 + lane;                // pixel column, tile relative
-        // every border of the warp lies in the pixel of its own lane: the border phase takes
-        // flux and slope from the lane's registers and the next pixel's slope with one shuffle
-        // per frame; the knots never go through shared memory (warp-uniform, per item)
-        const bool fast = ALIGNED && __all_sync(0xffffffffu, lane > nb || kl == lane);
-        KV kvr, kva;                                            // knots of the row in flight
-#pragma unroll
-        for (int g = 0; g < G; ++g) kvr.v[g] = kva.v[g] = T(0);
+        const int pp = plo - 1 + lane;                         // pixel column, tile relative
         const bool px_ok = pp >= 0 && pp < npx;
         PixGeom<T> pg;
         pg.qm = pg.qp = pg.r0 = pg.r1 = T(0);
@@ -307,18 +296,11 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             const KV *kb_rect = kbase, *kb_ya = kbase + 32;
             // flux and left-knot slope of the border's pixel; its right-knot slope is the
             // next pixel's left-knot slope rescaled by the ratio of the pixel widths
-            KV kr, ka, kn, k1;
+            const KV kr = kb_rect[0], ka = kb_ya[0], kn = kb_ya[1];
+            KV k1;
 #pragma unroll
             for (int g = 0; g < G; ++g) k1.v[g] = T(0);
-            if (ALIGNED && fast) {
-                kr = kvr;
-                ka = kva;
-#pragma unroll
-                for (int g = 0; g < G; ++g) kn.v[g] = __shfl_down_sync(0xffffffffu, kva.v[g], 1);
-            } else {
-                kr = kb_rect[0], ka = kb_ya[0], kn = kb_ya[1];
-                if (has2) k1 = kb_rect[1];
-            }
+            if (has2) k1 = kb_rect[1];
             T o[G];
             if constexpr (PACKED) {
                 const float2 tau2 = dup2(bd.tau);
@@ -438,11 +420,8 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 #pragma unroll
                 for (int h = 0; h < G / 2; ++h) {
                     const float2 r = make_float2(rect[2 * h], rect[2 * h + 1]);
-                    const float2 l = ALIGNED
-                        ? make_float2(__shfl_sync(0xffffffffu, r.x, (lane + 31) & 31),
-                                      __shfl_sync(0xffffffffu, r.y, (lane + 31) & 31))
-                        : make_float2(__shfl_up_sync(0xffffffffu, r.x, 1),
-                                      __shfl_up_sync(0xffffffffu, r.y, 1));
+                    const float2 l = make_float2(__shfl_up_sync(0xffffffffu, r.x, 1),
+                                                 __shfl_up_sync(0xffffffffu, r.y, 1));
                     const float2 cl2 = mul2(l, dup2(qm2));
                     const float2 rr = add2(r, r);
                     const float2 pq = fma2(dup2(hr0), sub2(cl2, rr), r);
@@ -464,8 +443,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                 for (int g = 0; g < G; ++g) {
                     // slope at the left knot from this pixel and its left neighbour (one
                     // limiter per pixel)
-                    const T cl = (ALIGNED ? __shfl_sync(0xffffffffu, rect[g], (lane + 31) & 31)
-                                          : __shfl_up_sync(0xffffffffu, rect[g], 1)) * pg.qm;
+                    const T cl = __shfl_up_sync(0xffffffffu, rect[g], 1) * pg.qm;
                     vr.v[g] = rect[g];
                     va.v[g] = steffen_slope(cl, rect[g], pg.r0);
                 }
@@ -473,15 +451,9 @@ __global__ void __launch_bounds__(NTHREADS, 2)
             // the warp's own knot rows (lane 0 holds an incomplete slope, never read)
             // (one buffer is enough: the warp's border phase of the previous row comes first
             // in program order)
-            if constexpr (ALIGNED) {
-                kvr = vr;
-                kva = va;
-            }
-            if (!(ALIGNED && fast)) {
-                KV *kdst = reinterpret_cast<KV *>(knots) + lane;
-                kdst[0] = vr;
-                kdst[32] = va;
-            }
+            KV *kdst = reinterpret_cast<KV *>(knots) + lane;
+            kdst[0] = vr;
+            kdst[32] = va;
         };
 
         // Row loop without block barriers.  A warp waits for the data of row y, evaluates
