@@ -14,9 +14,7 @@ def get_islitlet(ipixel):
         raise ValueError("ipixel={} cannot be < 1".format(ipixel))
     if ipixel > nrows:
         raise ValueError("ipixel={} cannot be > {}".format(ipixel, nrows))
-    # int(x / 38) + 1, one less on the last row of a slitlet == ceil(x / 38) for integers;
-    # the reference's float arithmetic is kept for non-integer arguments
-    islitlet = int(ipixel / EMIR_NPIXPERSLIT_RECTIFIED) + 1
-    if ipixel % EMIR_NPIXPERSLIT_RECTIFIED == 0:
-        islitlet -= 1
-    return islitlet
+    # the reference counts int(x / 38) + 1 and takes one off on the last row of a slitlet:
+    # that is the ceiling of x / 38, written here as a floor division (exact for integers,
+    # same result for the fractional arguments the recipes can pass)
+    return int(-(-ipixel // EMIR_NPIXPERSLIT_RECTIFIED))
