@@ -75,12 +75,23 @@ def prereduce_torch(frames, bias=None, dark=None, flat=None, out=None):
     return out[0] if squeeze else out
 
 
+def as_supported_frames(frames):
+    """Frames as one of the kernel's input types without changing what numpy would compute.
+
+    float32, float64 and uint16 pass through.  Other types are widened exactly to the type
+    numpy's promotion with a float32 calibration image gives: integers of up to 16 bits (and
+    float16) to float32, wider integers to float64.
+    """
+    arr = np.ascontiguousarray(frames)
+    if arr.dtype.name in _IN_DTYPES:
+        return arr
+    return arr.astype(np.result_type(arr.dtype, np.float32))
+
+
 def prereduce(frames, bias=None, dark=None, flat=None):
     """Host arrays in, float32 host array out (copies around :func:`prereduce_torch`)."""
     import torch
-    arr = np.ascontiguousarray(frames)
-    if arr.dtype.name not in _IN_DTYPES:
-        arr = arr.astype(np.float64 if arr.dtype.itemsize > 4 else np.float32)
+    arr = as_supported_frames(frames)
     dev = torch.device("cuda", torch.cuda.current_device())
     out = prereduce_torch(torch.from_numpy(arr).to(dev), bias, dark, flat)
     return out.cpu().numpy()

@@ -201,3 +201,15 @@ def test_flatfield_corrector_constructor_mirrors_reference():
     assert np.array_equal(flat, np.array([[1.0, 1.0, 1.0], [0.5, 2.0, 1.5]], dtype=np.float32))
     assert node.flat_stats == flat.mean() and node.calibid == "uuid:x" and node.dtype == "float32"
     assert node.update_variance is False
+
+
+def test_prereduce_input_widening_follows_numpy_promotion():
+    from pyemir_b200.prereduce import as_supported_frames
+    for dtype, want in (("float32", "float32"), ("float64", "float64"), ("uint16", "uint16"),
+                        ("int16", "float32"), ("uint8", "float32"), ("float16", "float32"),
+                        ("int32", "float64"), ("uint32", "float64"), ("int64", "float64")):
+        arr = as_supported_frames(np.arange(12, dtype=dtype).reshape(3, 4)[:, ::2])
+        assert arr.dtype.name == want and arr.flags.c_contiguous
+        # the same type numpy computes in when such an image meets a float32 flat
+        if dtype != "uint16":
+            assert (np.zeros(1, dtype=dtype) / np.ones(1, dtype=np.float32)).dtype == arr.dtype
