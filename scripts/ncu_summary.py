@@ -25,6 +25,13 @@ WANT = [
     "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+    # instruction pipes: is any of them saturated, or is the kernel latency bound?
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
 ]
 STALLS = ["stall_long_sb", "stall_short_sb", "stall_wait", "stall_barrier", "stall_mio",
           "stall_lg", "stall_not_selected", "stall_selected", "stall_math",
