@@ -40,9 +40,8 @@ def parse_args():
     ap.add_argument("--resampling", type=int, default=2)
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--g", type=int, default=0, help="frames per CTA (tuning)")
-    ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--tile-k", type=int, default=0)
-    ap.add_argument("--tile-rows", type=int, default=0)
+    ap.add_argument("--stages", type=int, default=0, help="rows in flight per CTA (tuning)")
     ap.add_argument("--combine", default="none", choices=["none", "mean", "gather", "abba", "abba_median"],
                     help="combined product per step: mean image (torch sum + reduce), gather,\n"
                          "the ABBA A-B mean combination (own kernels + reduce) or the ABBA\n"
@@ -206,7 +205,7 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(step_times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, config, None),
+        "config": workload_config(args, config),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
@@ -216,7 +215,7 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, config, info):
+def workload_config(args, config):
     from pyemir_b200 import synthetic
     cfg = synthetic.BASELINE_CONFIGS[config]
     out = {
@@ -231,12 +230,17 @@ def workload_config(args, config, info):
                      % (args.frames * (16.78 + 28.42) / 1e3),
         "combine": args.combine,
     }
-    if info:
-        out.update({"frames_per_cta": info["frames_per_cta"], "threads": info["threads"],
-                    "tile_k": info["tile_k"],
-                    "tile_rows": info["tile_rows"], "footprint": info["footprint"],
-                    "smem_bytes": info["smem_bytes"], "table_MB": info["table_bytes"] / 1e6})
     return out
+
+
+def tuning_of(info):
+    """Launch parameters of the hot kernel (not part of the workload: kept out of `config`)."""
+    return {"frames_per_cta": info["frames_per_cta"], "threads": info["threads"],
+            "tile_k": info["tile_k"], "stages": info["stages"], "footprint": info["footprint"],
+            "smem_bytes": info["smem_bytes"], "ctas_per_sm": info["ctas_per_sm"],
+            "window_rows": info["window_rows"], "window_cols": info["window_cols"],
+            "table_MB": info["table_bytes"] / 1e6,
+            "library": os.environ.get("EMIRWV_LIB", "libemirwv.so")}
 
 
 # --------------------------------------------------------------------- GPU arm
@@ -258,9 +262,12 @@ def run_ours(args):
     cfg = synthetic.BASELINE_CONFIGS[config]
 
     coeff = synthetic.make_config(config)
+    torch.cuda.synchronize()
+    t_plan = time.perf_counter()
     plan = RectWavePlan(coeff, args.resampling, args.dtype, max_order=5,
-                        tile_k=args.tile_k, tile_rows=args.tile_rows, device=local_rank)
-    plan.set_tuning(args.g, args.threads)
+                        tile_k=args.tile_k, stages=args.stages, device=local_rank)
+    plan_first_ms = 1e3 * (time.perf_counter() - t_plan)      # includes CUDA module loading
+    plan.set_tuning(args.g)
     info = plan.info()
     F = args.frames
     npdt = np.float32 if args.dtype == "float32" else np.float64
@@ -320,6 +327,36 @@ def run_ours(args):
     elapsed_ms = float(el.item())
     value = world * F * args.steps / (elapsed_ms / 1e3)
 
+    # ---- k_rectwv alone: the same launches told that d_out already holds the zeros outside
+    # the wavelength coverage (EMIRWV_RUN_OUT_ZEROED: no k_zero_fill beside it)
+    own_events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    for _ in range(3):
+        plan.run_torch(d_in, d_out, d_jmm, out_zeroed=True)
+    barrier()
+    own_events[0].record()
+    for i in range(args.steps):
+        plan.run_torch(d_in, d_out, d_jmm, out_zeroed=True)
+        own_events[i + 1].record()
+    barrier()
+    own_ms = own_events[0].elapsed_time(own_events[-1]) / args.steps
+
+    # ---- cost of a plan: first build of the process (above, with CUDA module loading), a
+    # second build of the same product (what a new product costs), a cache hit
+    from pyemir_b200.plan import clear_plan_cache, get_plan
+    t0p = time.perf_counter()
+    plan2 = RectWavePlan(coeff, args.resampling, args.dtype, max_order=5, device=local_rank)
+    torch.cuda.synchronize()
+    plan_cold_ms = 1e3 * (time.perf_counter() - t0p)
+    plan2.close()
+    clear_plan_cache()
+    get_plan(coeff, args.resampling, args.dtype, max_order=5, device=local_rank)
+    t0p = time.perf_counter()
+    get_plan(coeff, args.resampling, args.dtype, max_order=5, device=local_rank)
+    plan_cached_ms = 1e3 * (time.perf_counter() - t0p)
+    clear_plan_cache()
+    plan_cost = {"first_in_process_ms": plan_first_ms, "new_product_ms": plan_cold_ms,
+                 "cached_ms": plan_cached_ms, "table_MB": info["table_bytes"] / 1e6}
+
     # ---- end to end through the host-buffer C-ABI entry (pinned host in/out)
     e2e = None
     if args.e2e_steps > 0:
@@ -354,13 +391,16 @@ def run_ours(args):
         same = bool(np.array_equal(a_out[F - 1], last_dense) and np.array_equal(a_jmm, jmm_dense))
         cover = plan.coverage().astype(np.int64)
         d2h_sparse = int((cover[:, 1] - cover[:, 0]).sum() * 38 * a_out.itemsize * F + a_jmm.nbytes)
-        e2e = {"value": sparse, "unit": UNIT,
+        e2e = {"value": dense, "unit": UNIT,
                "h2d_bytes_per_step": int(a_in.nbytes),
-               "d2h_bytes_per_step": d2h_sparse,
-               "d2h": "columns with wavelength coverage only (emirwv_run_host_ex, "
-                      "EMIRWV_HOST_OUT_ZEROED); result identical to the full copy: %s" % same,
-               "full_copy": {"value": dense,
-                             "d2h_bytes_per_step": int(a_out.nbytes + a_jmm.nbytes)},
+               "d2h_bytes_per_step": int(a_out.nbytes + a_jmm.nbytes),
+               "call": "emirwv_run_host: pinned host frames in, every byte of the products "
+                       "and the JMN/JMX scan copied back to pinned host memory",
+               "zeroed_buffer": {"value": sparse, "d2h_bytes_per_step": d2h_sparse,
+                                 "call": "emirwv_run_host_ex(EMIRWV_HOST_OUT_ZEROED): the caller's "
+                                         "buffer already holds the zeros outside the wavelength "
+                                         "coverage, only covered columns travel; result identical "
+                                         "to the full copy: %s" % same},
                "steps": args.e2e_steps,
                "checksum": float(a_out[0, 1000:1038].sum())}
         if not same:
@@ -413,10 +453,20 @@ def run_ours(args):
                 traffic = rec["dram_bytes_per_launch"] * F / rec["frames"]
     except (OSError, ValueError):
         pass
+    cover = plan.coverage().astype(np.int64)
+    esize = 4 if args.dtype == "float32" else 8
+    own_bytes = F * (info["in_frame_bytes"] + int((cover[:, 1] - cover[:, 0]).sum()) * 38 * esize)
+    own_gbs = own_bytes / (own_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "k_rectwv", "bytes_per_launch": bytes_per_launch,
-                "launch_ms": statistics.mean(launch_ms)}
+                "kernel": "one emirwv_run = k_rectwv with k_zero_fill beside it on a second "
+                          "stream (+ k_init_jmm): whole frames in, whole products out",
+                "bytes_per_launch": bytes_per_launch,
+                "launch_ms": statistics.mean(launch_ms),
+                "k_rectwv_alone": {"launch_ms": own_ms, "bytes_per_launch": own_bytes,
+                                   "achieved": own_gbs, "frac": own_gbs / peak,
+                                   "what": "k_rectwv without k_zero_fill (EMIRWV_RUN_OUT_ZEROED): "
+                                           "frames in + the covered columns of the products out"}}
 
     cpu = None
     if world == 1 and args.cpu_frames > 0:
@@ -428,7 +478,7 @@ def run_ours(args):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
-        "config": workload_config(args, config, info),
+        "config": workload_config(args, config), "tuning": tuning_of(info), "plan": plan_cost,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "dropin_single_frame": dropin,
         # per step: k_init_jmm + k_zero_fill + k_rectwv (persistent)
         # (+ the combination kernels: abba 2, abba_median 3 per step)

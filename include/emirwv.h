@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EMIRWV_VERSION 100          /* 0.1.0 */
+#define EMIRWV_VERSION 200          /* 0.2.0 */
 
 #define EMIRWV_MAX_SLITLETS 55      /* EMIR_NBARS, core/__init__.py:39 */
 #define EMIRWV_MAX_COEF 21          /* 2-D polynomial of order 5 */
@@ -89,7 +89,9 @@ typedef struct emirwv_plan_desc {
     int32_t tile_k;                 /* tuning, 0 = default (248): output columns per tile,
                                        a multiple of 4; narrowed automatically when the
                                        distortion needs a larger source window           */
-    int32_t tile_rows;              /* reserved (a tile always spans the 39 scanned rows) */
+    int32_t stages;                 /* tuning, 0 = default: rectified rows whose table records and
+                                       source rows are in flight per CTA (2 ... 4; default 4 for
+                                       float32, 2 for float64 plans) */
     emirwv_slitlet_desc slitlet[EMIRWV_MAX_SLITLETS];
 } emirwv_plan_desc;
 
@@ -104,14 +106,14 @@ typedef struct emirwv_plan_info {
     int32_t ntiles;                 /* work items per frame group                  */
     int32_t ntiles_empty;           /* tiles outside the wavelength coverage       */
     int32_t tile_k;
-    int32_t tile_rows;
+    int32_t stages;                 /* rows in flight per CTA (copy pipeline depth) */
     int32_t window_rows;            /* staged source window (max over tiles)       */
     int32_t window_cols;
     int32_t max_span;               /* max whole source pixels inside one output pixel */
     int32_t frames_per_cta;         /* G chosen for the next launch                */
     int32_t threads;                /* threads per CTA of that launch              */
     int32_t smem_bytes;             /* dynamic shared memory of that launch        */
-    int32_t reserved;               /* frame subgroups of the pixel phases (1 or 2) */
+    int32_t ctas_per_sm;            /* resident CTAs per SM of that launch (occupancy API) */
     int64_t table_bytes;            /* device memory held by the plan              */
     int64_t in_frame_bytes;
     int64_t out_frame_bytes;
@@ -137,10 +139,8 @@ int emirwv_plan_create(const emirwv_plan_desc *desc, emirwv_plan **plan);
 void emirwv_plan_destroy(emirwv_plan *plan);
 int emirwv_plan_get_info(const emirwv_plan *plan, emirwv_plan_info *info);
 
-/* Launch tuning for subsequent runs (0 keeps the default): frames per CTA
- * (1, 2 or 4).  `threads` is accepted for compatibility: the hot kernel has a fixed
- * CTA size (288 threads: 8 compute warps + 1 copy warp). */
-int emirwv_plan_set_tuning(emirwv_plan *plan, int frames_per_cta, int threads);
+/* Launch tuning for subsequent runs (0 keeps the default): frames per CTA (1, 2 or 4). */
+int emirwv_plan_set_tuning(emirwv_plan *plan, int frames_per_cta);
 
 /*
  * Rectify + wavelength-calibrate nframes device-resident frames.
@@ -155,6 +155,17 @@ int emirwv_plan_set_tuning(emirwv_plan *plan, int frames_per_cta, int threads);
  */
 int emirwv_run(const emirwv_plan *plan, const void *d_in, void *d_out, int nframes,
                int32_t *d_jminmax, void *cuda_stream);
+
+/*
+ * emirwv_run with options.
+ *   EMIRWV_RUN_OUT_ZEROED: the caller guarantees that d_out already holds zeros wherever the
+ *   plan has no wavelength coverage (cudaMemset once, or a buffer filled by an earlier call
+ *   with the same plan): the zero-fill kernel is skipped, only the hot kernel runs.  The
+ *   result in d_out is the same as without the flag.
+ */
+#define EMIRWV_RUN_OUT_ZEROED 1u
+int emirwv_run_ex(const emirwv_plan *plan, const void *d_in, void *d_out, int nframes,
+                  int32_t *d_jminmax, void *cuda_stream, uint32_t flags);
 
 /*
  * Same from host buffers: host->device copies, kernels and device->host copies are

@@ -22,20 +22,26 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > mtime for s in sources)
 
 
-def build_library(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a … -> pyemir_b200/libemirwv.so"""
-    sources = [os.path.join(CSRC, name) for name in (
-        "emirwv.cu", "geom.cuh", "pixel_ops.cuh", "plan_kernels.cuh", "device_utils.cuh", "side_kernels.cuh",
-        "rectwv_kernel.cuh", "plan_build.inl", "median_net38.inc", "stack_median_nets.inc")]
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """nvcc -gencode arch=compute_100a,code=sm_100a … -> pyemir_b200/libemirwv.so
+
+    ``defines`` / ``out`` build an experiment variant next to the product library
+    (e.g. ``defines=("EMIRWV_MINBLOCKS=3",), out="libemirwv_x.so"``); a process picks one
+    with the environment variable ``EMIRWV_LIB`` (see ``_cabi.library_path``).
+    """
+    sources = [os.path.join(CSRC, name) for name in sorted(os.listdir(CSRC))
+               if name.endswith((".cu", ".cuh", ".inl", ".inc"))]
+    main = os.path.join(CSRC, "emirwv.cu")
     sources.append(os.path.join(ROOT, "include", "emirwv.h"))
-    if not force and not _stale(LIB_PATH, sources):
-        return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"),
-                                   "-o", LIB_PATH, sources[0]]
+    target = LIB_PATH if out is None else os.path.join(_HERE, out)
+    if not force and not _stale(target, sources):
+        return target
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defines] + [
+        "-I", os.path.join(ROOT, "include"), "-o", target, main]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)
-    return LIB_PATH
+    return target
 
 
 def build_hostcheck(force=False):

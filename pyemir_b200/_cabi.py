@@ -17,6 +17,7 @@ ROWS_SCANNED = 39
 
 F32, F64, U16 = 0, 1, 2
 HOST_OUT_ZEROED = 1
+RUN_OUT_ZEROED = 1
 NEAREST, AREA, BILINEAR = 1, 2, 3
 
 E_VALUE, E_INDEX, E_CUDA, E_NOMEM, E_LIMIT = -1, -2, -3, -4, -5
@@ -25,7 +26,7 @@ E_VALUE, E_INDEX, E_CUDA, E_NOMEM, E_LIMIT = -1, -2, -3, -4, -5
 EXPORTED_SYMBOLS = (
     "emirwv_version", "emirwv_last_error", "emirwv_device_count", "emirwv_set_device",
     "emirwv_plan_create", "emirwv_plan_destroy", "emirwv_plan_get_info",
-    "emirwv_plan_set_tuning", "emirwv_run", "emirwv_run_host",
+    "emirwv_plan_set_tuning", "emirwv_run", "emirwv_run_ex", "emirwv_run_host",
     "emirwv_run_host_ex", "emirwv_plan_get_coverage",
     "emirwv_host_alloc", "emirwv_host_free", "emirwv_rectify_slitlet",
     "emirwv_rectify2d_host", "emirwv_debug_geometry", "emirwv_debug_borders",
@@ -69,7 +70,7 @@ class PlanDesc(ctypes.Structure):
         ("crval1", ctypes.c_double),
         ("cdelt1", ctypes.c_double),
         ("tile_k", ctypes.c_int32),
-        ("tile_rows", ctypes.c_int32),
+        ("stages", ctypes.c_int32),
         ("slitlet", SlitletDesc * MAX_SLITLETS),
     ]
 
@@ -84,14 +85,14 @@ class PlanInfo(ctypes.Structure):
         ("ntiles", ctypes.c_int32),
         ("ntiles_empty", ctypes.c_int32),
         ("tile_k", ctypes.c_int32),
-        ("tile_rows", ctypes.c_int32),
+        ("stages", ctypes.c_int32),
         ("window_rows", ctypes.c_int32),
         ("window_cols", ctypes.c_int32),
         ("max_span", ctypes.c_int32),
         ("frames_per_cta", ctypes.c_int32),
         ("threads", ctypes.c_int32),
         ("smem_bytes", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("ctas_per_sm", ctypes.c_int32),
         ("table_bytes", ctypes.c_int64),
         ("in_frame_bytes", ctypes.c_int64),
         ("out_frame_bytes", ctypes.c_int64),
@@ -109,6 +110,12 @@ _lib = None
 
 
 def library_path():
+    """The product library, or the experiment variant named by ``EMIRWV_LIB``
+    (a file name inside the package directory or an absolute path)."""
+    override = os.environ.get("EMIRWV_LIB")
+    if override:
+        return override if os.path.isabs(override) else os.path.join(
+            os.path.dirname(_build.LIB_PATH), override)
     return _build.LIB_PATH
 
 
@@ -139,9 +146,11 @@ def load():
     lib.emirwv_plan_get_info.restype = i32
     lib.emirwv_plan_get_info.argtypes = [vp, ctypes.POINTER(PlanInfo)]
     lib.emirwv_plan_set_tuning.restype = i32
-    lib.emirwv_plan_set_tuning.argtypes = [vp, i32, i32]
+    lib.emirwv_plan_set_tuning.argtypes = [vp, i32]
     lib.emirwv_run.restype = i32
     lib.emirwv_run.argtypes = [vp, vp, vp, i32, vp, vp]
+    lib.emirwv_run_ex.restype = i32
+    lib.emirwv_run_ex.argtypes = [vp, vp, vp, i32, vp, vp, ctypes.c_uint32]
     lib.emirwv_run_host.restype = i32
     lib.emirwv_run_host.argtypes = [vp, vp, vp, i32, vp]
     lib.emirwv_run_host_ex.restype = i32

@@ -58,6 +58,12 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
         : "memory");
 }
 
+// Orders this thread's earlier generic-proxy accesses to shared memory (ordinary st.shared)
+// before later async-proxy accesses (cp.async.bulk writes) to the same locations.
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ unsigned smem_addr_of(const void *p) {
     return (unsigned)__cvta_generic_to_shared(p);
 }

@@ -60,6 +60,12 @@
 #ifndef EMIRWV_PXCAP
 #define EMIRWV_PXCAP 240
 #endif
+#ifndef EMIRWV_WIN_ROWS
+#define EMIRWV_WIN_ROWS 12
+#endif
+#ifndef EMIRWV_MINBLOCKS
+#define EMIRWV_MINBLOCKS 2
+#endif
 #include "geom.cuh"
 #include "pixel_ops.cuh"
 
@@ -73,7 +79,7 @@ constexpr int MAXK = 4;                      // largest supported footprint
 constexpr int NWARPS = 8;                     // compute warps: two per SM sub-partition and CTA
 constexpr int NTHREADS = 32 * (NWARPS + 1);   // threads per CTA: compute warps + one copy warp
 constexpr int TILE_K_MAX = 31 * NWARPS;       // output columns per tile (a warp does 31)
-constexpr int WIN_ROWS = 12;                  // rolling source window: rows per frame
+constexpr int WIN_ROWS = EMIRWV_WIN_ROWS;                  // rolling source window: rows per frame
 constexpr int RING_BIAS = 12 * 1024;          // makes (row + bias) % WIN_ROWS non-negative
 constexpr int PXCAP = EMIRWV_PXCAP;            // rectified columns a CTA can stage (8 x 29 + 3 at most)
 constexpr int WIN_PITCH = EMIRWV_WIN_PITCH;                // source window columns, per frame: a multiple of
@@ -262,7 +268,7 @@ struct emirwv_plan {
     std::vector<Tile> h_tiles;
 
     int ntiles = 0, ntiles_empty = 0;
-    int tile_k = 0, tile_rows = 0;
+    int tile_k = 0;
     int wrows_max = 0, wcols_max = 0, npx_max = 0, max_span = 0;
     std::vector<int32_t> h_cover;      // [nsl][2]: live output columns [lo, hi) of a slitlet
     int *d_sched = nullptr;            // [SCHED_POOL] item counters, one per launch in flight
@@ -369,36 +375,54 @@ int emirwv_plan_get_info(const emirwv_plan *pl, emirwv_plan_info *info) {
     info->ntiles = pl->ntiles;
     info->ntiles_empty = pl->ntiles_empty;
     info->tile_k = pl->tile_k;
-    info->tile_rows = pl->tile_rows;
+    info->stages = pl->nstage;
     info->window_rows = pl->wrows_max;
     info->window_cols = pl->wcols_max;
     info->max_span = pl->max_span;
     info->frames_per_cta = cfg.G;
     info->threads = cfg.threads;
     info->smem_bytes = (int32_t)cfg.smem;
+    {
+        DeviceGuard guard(pl->device);
+        int per_sm = 0;
+        const int rc = pl->dtype == EMIRWV_F32
+                           ? launch_t<float>(pl, pl->d_w, pl->d_w, 1 << 20, nullptr, nullptr, &per_sm)
+                           : launch_t<double>(pl, pl->d_w, pl->d_w, 1 << 20, nullptr, nullptr, &per_sm);
+        if (rc) return rc;
+        info->ctas_per_sm = per_sm;
+    }
     info->table_bytes = pl->table_bytes;
     info->in_frame_bytes = (int64_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
     info->out_frame_bytes = (int64_t)pl->nsl * pl->rps * pl->nout * pl->esize;
     return EMIRWV_OK;
 }
 
-int emirwv_plan_set_tuning(emirwv_plan *pl, int frames_per_cta, int threads) {
+int emirwv_plan_set_tuning(emirwv_plan *pl, int frames_per_cta) {
     if (pl == nullptr) return fail(EMIRWV_E_VALUE, "null plan");
+    if (frames_per_cta < 0 || frames_per_cta > 4)
+        return fail(EMIRWV_E_VALUE, "frames_per_cta must be 0 (default), 1, 2 or 4");
     pl->tune_G = frames_per_cta;
-    (void)threads;               // the hot kernel has a fixed CTA size
     return EMIRWV_OK;
 }
 
 int emirwv_run(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
                int32_t *d_jminmax, void *cuda_stream) {
+    return emirwv_run_ex(pl, d_in, d_out, nframes, d_jminmax, cuda_stream, 0u);
+}
+
+int emirwv_run_ex(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
+                  int32_t *d_jminmax, void *cuda_stream, uint32_t flags) {
     if (pl == nullptr || d_in == nullptr || d_out == nullptr)
         return fail(EMIRWV_E_VALUE, "null argument");
     if (nframes < 0) return fail(EMIRWV_E_VALUE, "negative frame count");
+    if (flags & ~(uint32_t)EMIRWV_RUN_OUT_ZEROED) return fail(EMIRWV_E_VALUE, "unknown flag");
     if (nframes == 0) return EMIRWV_OK;
     DeviceGuard guard(pl->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    if (pl->dtype == EMIRWV_F32) return launch_t<float>(pl, d_in, d_out, nframes, d_jminmax, st);
-    return launch_t<double>(pl, d_in, d_out, nframes, d_jminmax, st);
+    const bool skip_fill = (flags & EMIRWV_RUN_OUT_ZEROED) != 0;
+    if (pl->dtype == EMIRWV_F32)
+        return launch_t<float>(pl, d_in, d_out, nframes, d_jminmax, st, nullptr, skip_fill);
+    return launch_t<double>(pl, d_in, d_out, nframes, d_jminmax, st, nullptr, skip_fill);
 }
 
 int emirwv_plan_get_coverage(const emirwv_plan *pl, int32_t *h_cover) {

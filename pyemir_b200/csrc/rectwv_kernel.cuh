@@ -73,7 +73,7 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 //                [per warp: (rect | ya) x 32 pixels x G][NSTAGE table rows: PXCAP records]
 // ---------------------------------------------------------------------------------
 template <typename T, int K, int G, bool SPANLOOP, int NSTAGE>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
     k_rectwv(const RunParams<T> p) {
     static_assert(NSTAGE >= 2 && NSTAGE <= NSTAGE_MAX, "stage count");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -130,7 +130,10 @@ __global__ void __launch_bounds__(NTHREADS, 2)
         mbar_fence_init();
     }
     // the window starts out finite: taps with weight zero may read slots no copy has filled
+    // (generic stores; the bulk copies that later land on the same addresses belong to the
+    // async proxy, hence the proxy fence before the barrier that releases the copy warp)
     for (int e = tid; e < G * WSZ; e += NTHREADS) win[e] = T(0);
+    fence_proxy_async_smem();
     cp_async_wait_all();
     __syncthreads();
 
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                 const int c = cb < nl ? cb : cv1 - tile.c0 + (cb - nl);
                 win[rg * WIN_PITCH + c] = T(0);               // rg = frame * WIN_ROWS + ring row
             }
+            fence_proxy_async_smem();      // a later item's copies may cover these columns
             __syncthreads();
         }
 
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
                         for (int e = lane; e < c.nlive * c.wcols; e += 32)
                             win[(e / c.wcols) * WSZ + slot * WIN_PITCH + e % c.wcols] = T(0);
                     }
+                fence_proxy_async_smem();      // the slot is reused by bulk copies later on
                 __syncwarp();
             }
             if (lane == 0)

@@ -77,7 +77,7 @@ class RectWavePlan:
     """Device-resident tables for one (RectWaveCoeff, resampling, dtype)."""
 
     def __init__(self, rectwv_coeff, resampling=2, dtype="float32", max_order=4,
-                 grid=None, inverse=False, tile_k=0, tile_rows=0, device=None):
+                 grid=None, inverse=False, tile_k=0, stages=0, device=None):
         self._lib = _cabi.load()
         self._handle = ctypes.c_void_p()
         self.dtype = normalise_dtype(dtype)
@@ -107,7 +107,7 @@ class RectWavePlan:
         desc.crval1 = float(self.crval1)
         desc.cdelt1 = float(self.cdelt1)
         desc.tile_k = int(tile_k)
-        desc.tile_rows = int(tile_rows)
+        desc.stages = int(stages)
         prefix = "tti" if inverse else "ttd"
         self.bbox = {}
         for islitlet in range(1, EMIR_NBARS + 1):
@@ -172,9 +172,8 @@ class RectWavePlan:
         _cabi.check(self._lib.emirwv_plan_get_info(self._handle, ctypes.byref(info)))
         return info.asdict()
 
-    def set_tuning(self, frames_per_cta=0, threads=0):
-        _cabi.check(self._lib.emirwv_plan_set_tuning(self._handle, int(frames_per_cta),
-                                                     int(threads)))
+    def set_tuning(self, frames_per_cta=0):
+        _cabi.check(self._lib.emirwv_plan_set_tuning(self._handle, int(frames_per_cta)))
 
     # -- execution -----------------------------------------------------------
     def coverage(self):
@@ -211,14 +210,16 @@ class RectWavePlan:
             _cabi.HOST_OUT_ZEROED if out_zeroed else 0))
         return out, jminmax
 
-    def run_device(self, d_in, d_out, nframes, d_jminmax=0, stream=0):
-        """Raw device pointers (ints); asynchronous on ``stream``."""
-        _cabi.check(self._lib.emirwv_run(
+    def run_device(self, d_in, d_out, nframes, d_jminmax=0, stream=0, out_zeroed=False):
+        """Raw device pointers (ints); asynchronous on ``stream``.  ``out_zeroed``: the
+        output buffer already holds zeros outside the coverage (EMIRWV_RUN_OUT_ZEROED)."""
+        _cabi.check(self._lib.emirwv_run_ex(
             self._handle, ctypes.c_void_p(d_in), ctypes.c_void_p(d_out), int(nframes),
             ctypes.c_void_p(d_jminmax) if d_jminmax else None,
-            ctypes.c_void_p(stream) if stream else None))
+            ctypes.c_void_p(stream) if stream else None,
+            _cabi.RUN_OUT_ZEROED if out_zeroed else 0))
 
-    def run_torch(self, frames, out=None, jminmax=None):
+    def run_torch(self, frames, out=None, jminmax=None, out_zeroed=False):
         """CUDA tensors in / out on torch's current stream (no host copies)."""
         import torch
         if frames.dim() == 2:
@@ -230,10 +231,12 @@ class RectWavePlan:
         n = frames.shape[0]
         if out is None:
             out = torch.empty((n,) + self.out_shape, dtype=tdtype, device=frames.device)
+            out_zeroed = False
         if jminmax is None:
             jminmax = torch.empty((n, EMIR_NBARS, 2), dtype=torch.int32, device=frames.device)
         stream = torch.cuda.current_stream(frames.device).cuda_stream
-        self.run_device(frames.data_ptr(), out.data_ptr(), n, jminmax.data_ptr(), stream)
+        self.run_device(frames.data_ptr(), out.data_ptr(), n, jminmax.data_ptr(), stream,
+                        out_zeroed)
         return out, jminmax
 
     def rectify_slitlet_torch(self, frame, islitlet):
@@ -285,11 +288,11 @@ _CACHE_SIZE = 2          # a plan holds up to a few hundred MB of device tables
 
 
 def get_plan(rectwv_coeff, resampling=2, dtype="float32", max_order=4, grid=None,
-             inverse=False, tile_k=0, tile_rows=0, device=None):
+             inverse=False, tile_k=0, stages=0, device=None):
     """Cached ``RectWavePlan`` for this product and options."""
     dtype = normalise_dtype(dtype)
     key = _fingerprint(rectwv_coeff, int(resampling), dtype, int(max_order), bool(inverse),
-                       grid if grid is None else tuple(grid), (tile_k, tile_rows), device)
+                       grid if grid is None else tuple(grid), (tile_k, stages), device)
     key += ":" + rectwv_coeff.tags.get("grism", "") + ":" + rectwv_coeff.tags.get("filter", "")
     with _CACHE_LOCK:
         plan = _CACHE.get(key)
@@ -297,7 +300,7 @@ def get_plan(rectwv_coeff, resampling=2, dtype="float32", max_order=4, grid=None
             _CACHE.move_to_end(key)
             return plan
     plan = RectWavePlan(rectwv_coeff, resampling, dtype, max_order, grid, inverse,
-                        tile_k, tile_rows, device)
+                        tile_k, stages, device)
     with _CACHE_LOCK:
         _CACHE[key] = plan
         while len(_CACHE) > _CACHE_SIZE:

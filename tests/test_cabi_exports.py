@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(path)
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert _cabi.load().emirwv_version() == 100
+    assert _cabi.load().emirwv_version() == 200
 
 
 def test_struct_sizes_match_the_header():

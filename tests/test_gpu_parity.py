@@ -3,9 +3,11 @@
 Tolerances (BASELINE.json north_star): bit-exact for index maps, interval indices,
 slitlet masks / zero patterns and header integers; 1e-12 relative for float64
 flux; 1e-5 relative for float32 flux.  "Relative" is applied per pixel with an
-absolute floor tied to the frame's flux scale (stated next to each assert),
-because pixels at the edge of the wavelength coverage are differences of nearly
-equal numbers in the oracle itself.
+absolute floor (tests/parity_util.py): for float64 1e-12 x the frame's flux scale
+(pixels at the edge of the wavelength coverage are differences of nearly equal
+numbers in the oracle itself), for float32 1e-6 x the LOCAL flux (the brightest
+pixel among the output pixel's neighbours); every float32 comparison records how
+many pixels pass the bare 1e-5 relative bound (gpurun_out/parity_stats.jsonl).
 """
 
 import copy
@@ -22,36 +24,10 @@ from pyemir_b200.plan import RectWavePlan, clear_plan_cache, get_plan
 from pyemir_b200.set_wv_parameters import set_wv_parameters
 
 import proto_tables as proto
+from parity_util import (assert_flux_close, assert_flux_close_f32, grid_of, header_cards,
+                         only_slitlets)
 
 pytestmark = pytest.mark.gpu
-
-
-def grid_of(coeff):
-    p = set_wv_parameters(coeff.tags["filter"], coeff.tags["grism"])
-    return dict(naxis1=p["naxis1_enlarged"], cdelt1=p["cdelt1_enlarged"],
-                crval1=p["crval1_enlarged"], crpix1=p["crpix1_enlarged"])
-
-
-def only_slitlets(coeff, keep):
-    c = copy.deepcopy(coeff)
-    c.missing_slitlets = [i for i in range(1, 56) if i not in keep]
-    return c
-
-
-def header_cards(hdul):
-    """All cards except the time-stamped last HISTORY (apply_rectwv_coeff.py:277-279)."""
-    cards = list(hdul[0].header.cards)
-    assert cards[-1][0] == "HISTORY" and "calibration time" in cards[-1][1]
-    return cards[:-1]
-
-
-def assert_flux_close(got, want, rtol, floor, what=""):
-    scale = np.abs(want).max()
-    err = np.abs(got.astype(np.float64) - want)
-    bound = rtol * np.abs(want) + floor * scale
-    worst = np.argmax(err - bound)
-    assert np.all(err <= bound), (what, float(err.ravel()[worst]), float(want.ravel()[worst]),
-                                  float(scale))
 
 
 @pytest.fixture(scope="module")
@@ -166,9 +142,8 @@ def test_float32_parity_full_frame(coeff_j, frame_j, oracle_j, mode):
     out, keywords = rectify_frames(frame_j, coeff_j, mode, dtype="float32")
     got = out[0]
     assert got.dtype == np.float32
-    # float32: 1e-5 relative, floor 2e-7 x frame scale (a few float32 ulps of the
-    # brightest pixel) for pixels that are small differences of large ones
-    assert_flux_close(got, ref64, 1e-5, 2e-7, f"mode {mode}")
+    # float32: 1e-5 relative, floor 1e-6 x local flux (parity_util.assert_flux_close_f32)
+    assert_flux_close_f32(got, ref64, f"mode {mode}")
     assert np.array_equal(got == 0, ref64 == 0)
     hdr = ref_hdul[0].header
     for islitlet, (imn, imx, jmn, jmx) in enumerate(keywords[0], start=1):
@@ -184,7 +159,7 @@ def test_dropin_hdulist_matches_oracle(coeff_j, frame_j, oracle_j):
     assert got[0].data.dtype == np.float32 and got[0].data.shape == (2090, 3400)
     assert "MECS" in got and got["MECS"].header["XDTU"] == hdul["MECS"].header["XDTU"]
     assert header_cards(got) == header_cards(ref_hdul)       # keywords, values, comments, order
-    assert_flux_close(got[0].data, ref_hdul[0].data.astype(np.float64), 1e-5, 2e-7)
+    assert_flux_close_f32(got[0].data, ref_hdul[0].data.astype(np.float64))
     for key in ("CD1_1", "PCD1_1", "PCRPIX1"):
         assert key not in got[0].header
     assert got[0].header["CRVAL1"] == 11200.0 and got[0].header["CTYPE1"] == "WAVE"
@@ -261,7 +236,7 @@ def test_order5_distortion(frame_j):
     assert_flux_close(out[0], ref64, 1e-12, 1e-12)
     assert np.array_equal(out[0] == 0, ref64 == 0)
     out32, _ = rectify_frames(frame_j, coeff, 2, dtype="float32", max_order=5)
-    assert_flux_close(out32[0], ref64, 1e-5, 2e-7)
+    assert_flux_close_f32(out32[0], ref64)
 
 
 @pytest.mark.parametrize("number", [4, "4b"])
@@ -293,7 +268,7 @@ def test_integer_input(coeff_j, frame_j):
     ref = oracle_apply(hdul, coeff, only_needed_rows=True)
     got = apply_rectwv_coeff(hdul, coeff)
     assert header_cards(got) == header_cards(ref)
-    assert_flux_close(got[0].data, ref[0].data.astype(np.float64), 1e-5, 2e-7)
+    assert_flux_close_f32(got[0].data, ref[0].data.astype(np.float64))
 
 
 # ------------------------------------------------------------------ size-independent properties
@@ -310,12 +285,12 @@ def test_batch_properties_64_frames(coeff_j, batch64):
     out, jmm = plan.run_torch(frames)
     torch.cuda.synchronize()
     # determinism and independence of the frame grouping inside a CTA
-    for g, threads in ((1, 128), (2, 256), (4, 192), (1, 512)):
-        plan.set_tuning(g, threads)
+    for g in (1, 2, 4):
+        plan.set_tuning(g)
         out2, jmm2 = plan.run_torch(frames[:7])
         torch.cuda.synchronize()
-        assert torch.equal(out2, out[:7]) and torch.equal(jmm2, jmm[:7]), (g, threads)
-    plan.set_tuning(0, 0)
+        assert torch.equal(out2, out[:7]) and torch.equal(jmm2, jmm[:7]), g
+    plan.set_tuning(0)
     # homogeneity: every stage is positively homogeneous, scaling by 2 is exact in binary
     out3, _ = plan.run_torch(frames[:4] * 2.0)
     assert torch.equal(out3, out[:4] * 2.0)
@@ -406,7 +381,7 @@ def test_config2_hh_float32_full_frame():
     ref, ref64 = oracle_apply(hdul, coeff, only_needed_rows=True, return_float64=True)
     got = apply_rectwv_coeff(hdul, coeff)
     assert header_cards(got) == header_cards(ref)
-    assert_flux_close(got[0].data, ref64, 1e-5, 2e-7)
+    assert_flux_close_f32(got[0].data, ref64)
     assert np.array_equal(got[0].data == 0, ref64 == 0)
 
 
@@ -420,7 +395,7 @@ def test_config3_order5_batch_tail_and_nearest():
             hdul = synthetic.make_hdulist(frames[i], coeff)
             ref, ref64 = oracle_apply(hdul, coeff, args_resampling=mode, only_needed_rows=True,
                                       return_float64=True, nmax_order=5)
-            assert_flux_close(out[i], ref64, 1e-5, 2e-7, f"mode {mode} frame {i}")
+            assert_flux_close_f32(out[i], ref64, f"mode {mode} frame {i}")
             assert np.array_equal(out[i] == 0, ref64 == 0)
             for islitlet, (_, _, jmn, jmx) in enumerate(kw[i], start=1):
                 assert (jmn, jmx) == (ref[0].header[f"JMNSLT{islitlet:02d}"],
@@ -435,7 +410,7 @@ def test_lr_float32_unaligned_rows():
     _, ref64 = oracle_apply(hdul, coeff, only_needed_rows=True, return_float64=True)
     out, _ = rectify_frames(frame, coeff, 2, dtype="float32")
     assert out.shape == (1, 2090, 1435)
-    assert_flux_close(out[0], ref64, 1e-5, 2e-7)
+    assert_flux_close_f32(out[0], ref64)
     assert np.array_equal(out[0] == 0, ref64 == 0)
 
 

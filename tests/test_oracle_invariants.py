@@ -157,3 +157,76 @@ def test_apply_integer_offsets():
         nr.apply_integer_offsets(img, 1.0, 0)
     with pytest.raises(ValueError):
         nr.apply_integer_offsets(img, np.int64(1), 0)
+
+
+# ------------------------------------------------------------------ independent area check
+def _random_map(rng, order):
+    """Near-identity polynomial map of the given order (term order 1, x, y, x², xy, …) with
+    shear, stretch and curvature of the size a strongly distorted slitlet shows."""
+    ncoef = (order + 1) * (order + 2) // 2
+    a = np.zeros(ncoef)
+    b = np.zeros(ncoef)
+    a[0], a[1], a[2] = rng.uniform(-3, 3), rng.uniform(0.8, 1.3), rng.uniform(-0.2, 0.2)
+    b[0], b[1], b[2] = rng.uniform(-3, 3), rng.uniform(-0.1, 0.1), rng.uniform(0.8, 1.3)
+    k = 3
+    for i in range(2, order + 1):
+        for _ in range(i + 1):
+            a[k] = rng.uniform(-1, 1) * 0.3 / 200.0 ** i       # sub-pixel over 200 px
+            b[k] = rng.uniform(-1, 1) * 0.3 / 200.0 ** i
+            k += 1
+    return a.tolist(), b.tolist()
+
+
+@pytest.mark.parametrize("order", [2, 3, 4, 5])
+def test_overlap_areas_match_scanline_integration(order):
+    """oracle/clippix.c (Sutherland-Hodgman + shoelace) against tests/area_scanline.py
+    (integration of the chord length, no clipping) on random maps of order 2 … 5: every
+    overlap area, and their sum against the shoelace area of the mapped pixel, to the rounding
+    of the clipper's shoelace sum in absolute coordinates (a few eps x |x| x |y|: products
+    of coordinates ~1e4 are added and cancel down to an area below 1)."""
+    import area_scanline as scan
+    rng = np.random.default_rng(900 + order)
+    lib = load_clippix()
+    dp = ctypes.POINTER(ctypes.c_double)
+    worst = 0.0
+    for _ in range(6):
+        aij, bij = _random_map(rng, order)
+        for _ in range(25):
+            j, i = rng.integers(5, 195), rng.integers(5, 35)
+            xs = np.array([j - .5, j - .5, j + .5, j + .5])
+            ys = np.array([i - .5, i + .5, i + .5, i - .5])
+            qx, qy = nr.fmap(order, aij, bij, xs, ys)
+            j0 = int(np.floor(qx.min() + 0.5))
+            i0 = int(np.floor(qy.min() + 0.5))
+            nx = int(np.floor(qx.max() + 0.5)) - j0 + 1
+            ny = int(np.floor(qy.max() + 0.5)) - i0 + 1
+            got = np.zeros((ny, nx))
+            qx = np.ascontiguousarray(qx)
+            qy = np.ascontiguousarray(qy)
+            lib.oracle_quad_weights(qx.ctypes.data_as(dp), qy.ctypes.data_as(dp), i0, j0, ny, nx,
+                                    got.ctypes.data_as(dp))
+            want = scan.quad_weights(qx, qy, i0, j0, ny, nx)
+            tol = 8 * np.finfo(float).eps * np.abs(qx).max() * np.abs(qy).max()
+            worst = max(worst, float(np.abs(got - want).max()) / tol)
+            assert np.allclose(got, want, rtol=0, atol=tol)
+            # (the reference sum: shoelace about the quad's own centre, no cancellation)
+            area = scan.shoelace(qx - qx.mean(), qy - qy.mean())
+            assert got.sum() == pytest.approx(area, abs=4 * tol)
+            assert want.sum() == pytest.approx(area, abs=1e-13)
+    assert 0.0 < worst < 1.0
+
+
+def test_scanline_area_known_answers():
+    import area_scanline as scan
+    sq = ([0.0, 0.0, 1.0, 1.0], [0.0, 1.0, 1.0, 0.0])
+    assert scan.quad_box_area(*sq, 0.0, 1.0, 0.0, 1.0) == 1.0
+    assert scan.quad_box_area(*sq, 0.5, 2.0, 0.25, 2.0) == pytest.approx(0.375, abs=1e-15)
+    assert scan.quad_box_area(*sq, 1.0, 2.0, 0.0, 1.0) == 0.0
+    diamond = ([1.0, 0.0, -1.0, 0.0], [0.0, 1.0, 0.0, -1.0])
+    assert scan.quad_box_area(*diamond, 0.0, 1.0, 0.0, 1.0) == pytest.approx(0.5, abs=1e-15)
+    assert scan.quad_box_area(*diamond, -1.0, 1.0, -1.0, 1.0) == pytest.approx(2.0, abs=1e-15)
+    # a sheared parallelogram of area 1 spread over three unit boxes
+    para = ([0.0, 0.5, 1.5, 1.0], [0.0, 1.0, 1.0, 0.0])
+    parts = [scan.quad_box_area(*para, k, k + 1.0, 0.0, 1.0) for k in (-1.0, 0.0, 1.0, 2.0)]
+    assert parts[0] == 0.0 and parts[3] == 0.0
+    assert parts[1] == pytest.approx(0.75, abs=1e-15) and parts[2] == pytest.approx(0.25, abs=1e-15)
