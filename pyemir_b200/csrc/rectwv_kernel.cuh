@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
         //   ring slot (row + bias) % WIN_ROWS, and the table row of row y, npx records in one
         //   copy, slot y % NSTAGE.
         constexpr int VN = Vec16<T>::N;
-        const int cv0 = max(tile.c0, 0), cv1 = min(tile.c0 + tile.wcols, W);   // valid columns
+        // window columns that exist on the detector: [cv0, cv1), empty when the whole tile maps
+        // outside (a strongly stretched map): then every window column stays zero
+        const int cv0 = min(max(tile.c0, 0), tile.c0 + tile.wcols);
+        const int cv1 = max(min(tile.c0 + tile.wcols, W), cv0);
         const unsigned tsm_a = smem_addr_of(tsm);
         // what the copy warp needs to know about an item (this one, or the next one whose
         // first rows it requests as soon as this item's last row is through)
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
         auto make_ctx = [&](const Tile &t, int wi) {
             CopyCtx c;
             const int g0i = (wi % p.ngroups) * G;
-            const int v0 = max(t.c0, 0), v1 = min(t.c0 + t.wcols, W);
+            const int v0 = min(max(t.c0, 0), t.c0 + t.wcols), v1 = max(min(t.c0 + t.wcols, W), v0);
             c.nlive = min(G, p.nframes - g0i);
             c.wcols = t.wcols;
             c.row_bytes = (unsigned)((v1 - v0) * sizeof(T));
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
             if (lane == 0)
                 mbar_expect_tx(bar, (unsigned)(max(hi - lo + 1, 0) * c.nlive) * c.row_bytes);
             __syncwarp();
-            if (cg < c.nlive)
+            if (cg < c.nlive && c.row_bytes != 0)
                 for (int r = lo + cr; r <= hi; r += ROWS_PER_ISSUE)
                     bulk_g2s(c.win_a + (unsigned)(((unsigned)(r + RING_BIAS) % WIN_ROWS) *
                                                   (WIN_PITCH * sizeof(T))),
