@@ -58,7 +58,7 @@
 #define EMIRWV_WIN_PITCH 288
 #endif
 #ifndef EMIRWV_PXCAP
-#define EMIRWV_PXCAP 240
+#define EMIRWV_PXCAP 248
 #endif
 #ifndef EMIRWV_WIN_ROWS
 #define EMIRWV_WIN_ROWS 12
@@ -81,7 +81,8 @@ constexpr int NTHREADS = 32 * (NWARPS + 1);   // threads per CTA: compute warps 
 constexpr int TILE_K_MAX = 31 * NWARPS;       // output columns per tile (a warp does 31)
 constexpr int WIN_ROWS = EMIRWV_WIN_ROWS;                  // rolling source window: rows per frame
 constexpr int RING_BIAS = 12 * 1024;          // makes (row + bias) % WIN_ROWS non-negative
-constexpr int PXCAP = EMIRWV_PXCAP;            // rectified columns a CTA can stage (8 x 29 + 3 at most)
+constexpr int PXCAP = EMIRWV_PXCAP;            // rectified columns a CTA can stage (8 x 29 + 3 at most,
+                                              // rounded out to multiples of 4: 16-byte copies)
 constexpr int WIN_PITCH = EMIRWV_WIN_PITCH;                // source window columns, per frame: a multiple of
                                               // 32 banks, so lanes on two ring rows never collide
 constexpr int WARP_PX = 30;                   // rectified columns a warp owns
@@ -91,9 +92,18 @@ constexpr int NSTAGE_MAX = EMIRWV_NSTAGE;                 // rectified rows in f
                                               // template parameter: NSTAGE_MAX, or 2 for float64
                                               // plans on request -- 96-byte records, see smem_bytes)
 constexpr int BAR_BYTES = ((2 * NSTAGE_MAX * 8) + 63) / 64 * 64;   // "full" and "done" mbarriers
-// Per output pixel table record: K*K weights followed by the packed source coordinates
-// (int32 bits), padded to a multiple of 4 elements so that records are 16-byte aligned.
+// Tables per rectified pixel (s, y, j), frame independent:
+//   quad  [4]   the weights of the 2 x 2 block of source pixels the pixel is made of (K <= 2, and
+//               the footprints of a larger K that fit such a block: ~88 % of them), zeros else
+//   meta        packed uint32: bits 0-15 source column of the block (int16, frame coordinates),
+//               16-19 / 20-23 ring slots of its two source rows in the hot kernel's rolling
+//               window, bit 24 "the 2 x 2 block is the whole footprint"
+//   w [RS]      the full record: K*K weights followed by the packed source coordinates, the ring
+//               slots and the flags, padded to a multiple of 4 elements (16-byte aligned).
+// The hot kernel stages quad + meta (20 / 36 bytes) in shared memory; a warp that holds a pixel
+// whose footprint does not fit 2 x 2 reads the full records from global memory instead.
 __host__ __device__ constexpr int rec_size(int K) { return (K * K + 1 + 3) & ~3; }
+constexpr uint32_t META_COMPACT = 1u << 24;
 constexpr int HOST_SLOTS = 3;                // pipeline depth of emirwv_run_host
 constexpr int SCHED_POOL = 1024;             // item counters: launches of one plan in flight
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -150,6 +160,8 @@ struct GeomParams {
     int offx, offy;
     int mode, K;
     int32_t *base;
+    uint32_t *meta;         // per pixel: packed block column, ring slots, flag
+    uint8_t *blockrow;      // per pixel: first source row with weight, relative to base (host)
     int *kmax;              // k_extent result
 };
 
@@ -186,7 +198,9 @@ struct RunParams {
     int nframes;
     const Tile *tiles;
     const int32_t *base;
-    const T *w;
+    const T *w;             // full records (global memory path)
+    const T *quad;          // 2 x 2 block weights, staged in shared memory
+    const uint32_t *meta;   // staged in shared memory
     const Border<T> *border;
     const PixGeom<T> *pix;
     int naxis2;
@@ -221,6 +235,13 @@ __host__ __device__ inline int32_t pack_base(int r, int c) {
 }
 __host__ __device__ inline int base_row(int32_t p) { return (int)(int16_t)((uint32_t)p >> 16); }
 __host__ __device__ inline int base_col(int32_t p) { return (int)(int16_t)((uint32_t)p & 0xffffu); }
+
+// ring slot of a frame row in the hot kernel's rolling window (rows far outside the detector
+// carry no weight: any valid slot will do)
+__host__ __device__ inline uint32_t ring_slot(int r) {
+    r = max(-RING_BIAS, min(30000, r));
+    return (uint32_t)((r + RING_BIAS) % WIN_ROWS);
+}
 
 __host__ __device__ inline int span_lo(int32_t v) { return (int)(int16_t)((uint32_t)v & 0xffffu); }
 __host__ __device__ inline int span_hi(int32_t v) { return (int)(int16_t)((uint32_t)v >> 16); }
@@ -257,12 +278,14 @@ struct emirwv_plan {
 
     SlitDev *d_slit = nullptr;
     int32_t *d_base = nullptr;
-    void *d_w = nullptr;
+    void *d_w = nullptr, *d_quad = nullptr;
+    uint32_t *d_meta = nullptr;
     void *d_border = nullptr, *d_pix = nullptr;
     Tile *d_tiles = nullptr;
 
     std::vector<SlitDev> h_slit;
     std::vector<int32_t> h_base;
+    std::vector<uint8_t> h_blockrow;   // bits 0-3 first used source row - base row, bit 4 compact
     std::vector<int32_t> h_idx;
     std::vector<double> h_t;
     std::vector<Tile> h_tiles;
@@ -356,6 +379,8 @@ void emirwv_plan_destroy(emirwv_plan *pl) {
     cudaFree(pl->d_slit);
     cudaFree(pl->d_base);
     cudaFree(pl->d_w);
+    cudaFree(pl->d_quad);
+    cudaFree(pl->d_meta);
     cudaFree(pl->d_border);
     cudaFree(pl->d_pix);
     cudaFree(pl->d_tiles);

@@ -16,11 +16,12 @@ struct LaunchCfg {
 
 // shared memory of the hot kernel:
 //   [3 tile descriptors][mbarriers, counters][G windows: WIN_ROWS x WIN_PITCH]
-//   [per warp: 2 x (rect | ya) x 32 x G knots][nstage table rows: PXCAP records]
+//   [per warp: 2 x (rect | ya) x 32 x G knots]
+//   [nstage table rows: PXCAP x (4 block weights + 1 meta word)]
 size_t smem_bytes(const emirwv_plan *pl, int G) {
     return 3 * sizeof(Tile) + BAR_BYTES +
            (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 2 * 32) * pl->esize +
-           (size_t)pl->nstage * PXCAP * rec_size(pl->K) * pl->esize;
+           (size_t)pl->nstage * PXCAP * (4 * pl->esize + sizeof(uint32_t));
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
@@ -57,6 +58,21 @@ int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, c
     return EMIRWV_OK;
 }
 
+// EMIRWV_SLIM (experiment builds, scripts/build_variants.py): only the instantiation the
+// headline configuration uses (float32, K = 3, G = 4, no span loop) is compiled.
+#ifdef EMIRWV_SLIM
+template <typename T, int K, int G>
+int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
+               cudaStream_t st) {
+    if constexpr (sizeof(T) == 4 && K == 3 && G == 4) {
+        if (pl->max_span <= 2) {
+            if (pl->nstage == 2) return launch_final<T, K, G, false, 2>(pl, rp, cfg, st);
+            return launch_final<T, K, G, false, NSTAGE_MAX>(pl, rp, cfg, st);
+        }
+    }
+    return fail(EMIRWV_E_LIMIT, "slim experiment build: float32, K = 3, G = 4 only");
+}
+#else
 template <typename T, int K, int G>
 int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
                cudaStream_t st) {
@@ -67,6 +83,7 @@ int launch_one(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &c
     if (pl->max_span > 2) return launch_final<T, K, G, true, NSTAGE_MAX>(pl, rp, cfg, st);
     return launch_final<T, K, G, false, NSTAGE_MAX>(pl, rp, cfg, st);
 }
+#endif
 
 template <typename T, int K>
 int launch_k(const emirwv_plan *pl, const RunParams<T> &rp, const LaunchCfg &cfg,
@@ -107,6 +124,8 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     rp.tiles = pl->d_tiles;
     rp.base = pl->d_base;
     rp.w = static_cast<const T *>(pl->d_w);
+    rp.quad = static_cast<const T *>(pl->d_quad);
+    rp.meta = pl->d_meta;
     rp.border = static_cast<const Border<T> *>(pl->d_border);
     rp.pix = static_cast<const PixGeom<T> *>(pl->d_pix);
     rp.naxis2 = pl->desc.naxis2;
@@ -350,16 +369,20 @@ int try_build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered, int BW
             t.jlo = std::max(0, ilo - 1);
             const int jhi = std::min(nchan - 1, ihi + 1);
             t.npx = jhi - t.jlo + 1;
-            if (t.npx > PXCAP) return 1;
+            // (the staged table row is rounded out to multiples of 4 pixels)
+            if (((t.jlo & 3) + t.npx + 3 & ~3) > PXCAP) return 1;
             int c0 = INT_MAX, c1 = INT_MIN;
             int rlo[NROWS], rhi[NROWS];
             for (int y = 0; y < NROWS; ++y) {
                 const int32_t *row = pl->h_base.data() + ((size_t)s * NROWS + y) * W;
+                const uint8_t *brow = pl->h_blockrow.data() + ((size_t)s * NROWS + y) * W;
                 int r0 = INT_MAX, r1 = INT_MIN;
                 for (int j = t.jlo; j <= jhi; ++j) {
-                    const int br = base_row(row[j]), bc = base_col(row[j]);
+                    // source rows with weight: the two rows of the 2 x 2 block, or K rows
+                    const bool compact = (brow[j] & 16) != 0;
+                    const int br = base_row(row[j]) + (brow[j] & 15), bc = base_col(row[j]);
                     r0 = std::min(r0, br);
-                    r1 = std::max(r1, br + K - 1);
+                    r1 = std::max(r1, br + (compact ? std::min(K, 2) : K) - 1);
                     c0 = std::min(c0, bc);
                     c1 = std::max(c1, bc + K - 1);
                 }
@@ -522,6 +545,8 @@ int build_plan(emirwv_plan *pl) {
     gp.offy = d.offy;
     gp.mode = pl->mode;
     gp.kmax = nullptr;
+    gp.meta = nullptr;
+    gp.blockrow = nullptr;
     const dim3 block(128);
     const dim3 grid((W + 127) / 128, NROWS, pl->nsl);
 
@@ -553,19 +578,36 @@ int build_plan(emirwv_plan *pl) {
     // (+64 bytes: the kernel copies table rows in 16-byte chunks)
     CUDA_TRY(cudaMalloc(&pl->d_base, nrowtab * W * sizeof(int32_t) + 64));
     CUDA_TRY(cudaMalloc(&pl->d_w, nrowtab * W * rec_size(pl->K) * pl->esize + 64));
+    CUDA_TRY(cudaMalloc(&pl->d_quad, nrowtab * W * 4 * pl->esize + 64));
+    CUDA_TRY(cudaMalloc(&pl->d_meta, nrowtab * W * sizeof(uint32_t) + 64));
+    uint8_t *d_blockrow = nullptr;
+    CUDA_TRY(cudaMalloc(&d_blockrow, nrowtab * W));
     pl->table_bytes += (int64_t)(nrowtab * W * sizeof(int32_t));
     pl->table_bytes += (int64_t)(nrowtab * W * rec_size(pl->K) * pl->esize);
+    pl->table_bytes += (int64_t)(nrowtab * W * (4 * pl->esize + sizeof(uint32_t)));
+    gp.meta = pl->d_meta;
+    gp.blockrow = d_blockrow;
     gp.K = pl->K;
     gp.base = pl->d_base;
     gp.kmax = nullptr;
     if (pl->dtype == EMIRWV_F32)
-        k_build_geometry<float><<<grid, block>>>(gp, static_cast<float *>(pl->d_w));
+        k_build_geometry<float><<<grid, block>>>(gp, static_cast<float *>(pl->d_w),
+                                                 static_cast<float *>(pl->d_quad));
     else
-        k_build_geometry<double><<<grid, block>>>(gp, static_cast<double *>(pl->d_w));
-    CUDA_TRY(cudaGetLastError());
+        k_build_geometry<double><<<grid, block>>>(gp, static_cast<double *>(pl->d_w),
+                                                  static_cast<double *>(pl->d_quad));
+    cudaError_t gerr = cudaGetLastError();
     pl->h_base.resize(nrowtab * W);
-    CUDA_TRY(cudaMemcpy(pl->h_base.data(), pl->d_base, pl->h_base.size() * sizeof(int32_t),
-                        cudaMemcpyDeviceToHost));
+    pl->h_blockrow.resize(nrowtab * W);
+    if (gerr == cudaSuccess)
+        gerr = cudaMemcpy(pl->h_base.data(), pl->d_base, pl->h_base.size() * sizeof(int32_t),
+                          cudaMemcpyDeviceToHost);
+    if (gerr == cudaSuccess)
+        gerr = cudaMemcpy(pl->h_blockrow.data(), d_blockrow, pl->h_blockrow.size(),
+                          cudaMemcpyDeviceToHost);
+    cudaFree(d_blockrow);
+    if (gerr != cudaSuccess)
+        return fail(EMIRWV_E_CUDA, "k_build_geometry failed: %s", cudaGetErrorString(gerr));
 
     std::vector<uint8_t> covered;
     int rc = build_border_tables(pl, covered);

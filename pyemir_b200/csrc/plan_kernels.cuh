@@ -23,9 +23,10 @@ __global__ void k_extent(GeomParams p) {
     if ((threadIdx.x & 31) == 0) atomicMax(p.kmax, need);
 }
 
-// base[s][y][j] (frame coordinates of tap (0,0)) and w[s][y][tap][j].
+// base[s][y][j] (frame coordinates of tap (0,0)), the full records w[s][y][j][RS], the 2 x 2
+// block weights quad[s][y][j][4] and the packed meta[s][y][j].
 template <typename T>
-__global__ void k_build_geometry(GeomParams p, T *w) {
+__global__ void k_build_geometry(GeomParams p, T *w, T *quad) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int s = blockIdx.z;
@@ -35,10 +36,14 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
     const size_t rowtab = (size_t)s * NROWS + y;
     const int RS = rec_size(K);
     T *wp = w + (rowtab * W + j) * RS;
+    T *qp = quad + (rowtab * W + j) * 4;
     if (!sd.valid || j >= sd.bbw) {
         p.base[rowtab * W + j] = pack_base(0, 0);
         for (int tap = 0; tap < RS; ++tap) wp[tap] = T(0);
         *reinterpret_cast<int32_t *>(wp + KK) = pack_base(0, 0);
+        for (int tap = 0; tap < 4; ++tap) qp[tap] = T(0);
+        p.meta[rowtab * W + j] = META_COMPACT;
+        p.blockrow[rowtab * W + j] = 16;
         return;
     }
     const int row = sd.min_row + y;
@@ -92,6 +97,11 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
             wp[a * K + b] = inside ? (T)wt[a * K + b] : T(0);
         }
     for (int tap = KK; tap < RS; ++tap) wp[tap] = T(0);
+    // the 2 x 2 block of K <= 2 is the footprint itself (K = 1: one weight)
+    T q4[4] = {T(0), T(0), T(0), T(0)};
+    bool compact = K <= 2;
+    if (K == 1) q4[0] = wp[0];
+    if (K == 2) q4[0] = wp[0], q4[1] = wp[1], q4[2] = wp[2], q4[3] = wp[3];
     // Compact form (K >= 3): almost every footprint fits a 2 x 2 block of source pixels.
     // Such a record holds the block's four weights in words 0..3 (zeros elsewhere) and the
     // coordinates of the block; the hot kernel then gathers 4 taps instead of K*K, with the
@@ -115,16 +125,23 @@ __global__ void k_build_geometry(GeomParams p, T *w) {
             for (int tap = 0; tap < KK; ++tap) wp[tap] = T(0);
             wp[0] = c00, wp[1] = c01, wp[2] = c10, wp[3] = c11;
             flags = REC_COMPACT | ((uint32_t)a0 << 1) | ((uint32_t)b0 << 3);
+            q4[0] = c00, q4[1] = c01, q4[2] = c10, q4[3] = c11;
+            compact = true;
         }
     }
+    for (int tap = 0; tap < 4; ++tap) qp[tap] = q4[tap];
+    p.meta[rowtab * W + j] =
+        ((uint32_t)pack_base(0, fc0 + b0) & 0xffffu) | (ring_slot(fr0 + a0) << 16) |
+        (ring_slot(fr0 + a0 + 1) << 20) | (compact ? META_COMPACT : 0u);
+    p.blockrow[rowtab * W + j] = (uint8_t)(a0 | (compact ? 16 : 0));
     *reinterpret_cast<int32_t *>(wp + KK) = pack_base(fr0 + a0, fc0 + b0);
     // ring slot of each of the K source rows in the hot kernel's rolling window
     uint32_t slots = flags << 24;
     for (int a = 0; a < K && a < 3; ++a)
-        slots |= (uint32_t)((fr0 + a0 + a + RING_BIAS) % WIN_ROWS) << (8 * a);
+        slots |= ring_slot(fr0 + a0 + a) << (8 * a);
     *reinterpret_cast<uint32_t *>(wp + KK + 1) = slots;
     if (K == 4)          // the fourth row of a 4 x 4 footprint has its own word
-        *reinterpret_cast<uint32_t *>(wp + KK + 2) = (uint32_t)((fr0 + a0 + 3 + RING_BIAS) % WIN_ROWS);
+        *reinterpret_cast<uint32_t *>(wp + KK + 2) = ring_slot(fr0 + a0 + 3);
     p.base[rowtab * W + j] = pack_base(fr0, fc0);
 }
 

@@ -70,7 +70,8 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 // The source window is a ring of WIN_ROWS rows per frame.
 //
 // Shared memory: [tile descriptor ring: 3][mbarriers][G windows: WIN_ROWS x WIN_PITCH]
-//                [per warp: (rect | ya) x 32 pixels x G][NSTAGE table rows: PXCAP records]
+//                [per warp: (rect | ya) x 32 pixels x G]
+//                [NSTAGE table rows: PXCAP x quad (4 weights)][NSTAGE x PXCAP meta words]
 // ---------------------------------------------------------------------------------
 template <typename T, int K, int G, bool SPANLOOP, int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
     T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + BAR_BYTES);   // [G][WSZ]
     T *knots = win + G * WSZ + min(warp, NWARPS - 1) * KNOT_WARP;   // this warp: [rect|ya][32][G]
     constexpr int RS = rec_size(K);
-    T *tsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [NSTAGE][PXCAP][RS]
+    T *qsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [NSTAGE][PXCAP][4]
+    uint32_t *msm = reinterpret_cast<uint32_t *>(qsm + NSTAGE * PXCAP * 4);   // [NSTAGE][PXCAP]
     // float32 with an even number of frames: two frames per arithmetic instruction
     constexpr bool PACKED = sizeof(T) == 4 && (G % 2) == 0;
     using KV = KnotVec<T, G>;
@@ -200,12 +202,13 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
         // outside (a strongly stretched map): then every window column stays zero
         const int cv0 = min(max(tile.c0, 0), tile.c0 + tile.wcols);
         const int cv1 = max(min(tile.c0 + tile.wcols, W), cv0);
-        const unsigned tsm_a = smem_addr_of(tsm);
+        const unsigned qsm_a = smem_addr_of(qsm), msm_a = smem_addr_of(msm);
         // what the copy warp needs to know about an item (this one, or the next one whose
         // first rows it requests as soon as this item's last row is through)
         struct CopyCtx {
-            unsigned row_bytes, win_a, trow_bytes;
-            const T *fin, *trow;
+            unsigned row_bytes, win_a, ncopy;
+            const T *fin, *qrow;
+            const uint32_t *mrow;
             int nlive, wcols;
             bool oob_rows;
         };
@@ -219,8 +222,11 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
             c.win_a = smem_addr_of(win) + (unsigned)((v0 - t.c0) * sizeof(T)) +
                       (unsigned)(cg * WSZ * sizeof(T));
             c.fin = p.in + ((size_t)g0i + cg) * W * p.naxis2 + v0;
-            c.trow_bytes = (unsigned)(t.npx * RS * sizeof(T));
-            c.trow = p.w + ((size_t)t.slit * NROWS * W + t.jlo) * RS;
+            // staged table columns: [jal, jal + ncopy), rounded out to multiples of 4 pixels
+            const int jal = t.jlo & ~3;
+            c.ncopy = (unsigned)((t.jlo + t.npx - jal + 3) & ~3);
+            c.qrow = p.quad + ((size_t)t.slit * NROWS * W + jal) * 4;
+            c.mrow = p.meta + (size_t)t.slit * NROWS * W + jal;
             c.oob_rows = span_lo(t.span[0]) < 0 || span_hi(t.span[NROWS - 1]) >= p.naxis2;
             return c;
         };
@@ -264,13 +270,16 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
                                                   (WIN_PITCH * sizeof(T))),
                              c.fin + (size_t)r * W, c.row_bytes, bar);
         };
-        // table row y = npx contiguous records, one bulk copy
+        // table row y: the block weights and the meta words of the tile's pixels, two bulk copies
         auto copy_table_row = [&](const CopyCtx &c, unsigned seq, int y) {
             if (lane == 0) {
                 const unsigned bar = bars + 8 * (seq % NSTAGE);
-                mbar_expect_tx(bar, c.trow_bytes);
-                bulk_g2s(tsm_a + (y % NSTAGE) * (unsigned)(PXCAP * RS * sizeof(T)),
-                         c.trow + (size_t)y * W * RS, c.trow_bytes, bar);
+                const unsigned qb = c.ncopy * (unsigned)(4 * sizeof(T)), mb = c.ncopy * 4u;
+                mbar_expect_tx(bar, qb + mb);
+                bulk_g2s(qsm_a + (y % NSTAGE) * (unsigned)(PXCAP * 4 * sizeof(T)),
+                         c.qrow + (size_t)y * W * 4, qb, bar);
+                bulk_g2s(msm_a + (y % NSTAGE) * (unsigned)(PXCAP * 4), c.mrow + (size_t)y * W, mb,
+                         bar);
             }
         };
         // the first NSTAGE rows of an item and their table rows
@@ -291,7 +300,9 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
         if (producer && (it == 0 || !p.early)) copy_first_rows(make_ctx(tile, w), tile, rowseq);
         // this thread's slot in the staged table rows (lanes without a pixel read a
         // neighbour's entry; their result is discarded)
-        const int ppc = min(max(pp, 0), npx - 1);
+        const int ppc = min(max(pp, 0), npx - 1) + (tile.jlo & 3);      // column of the staged row
+        const T *grec = p.w + ((size_t)s * NROWS * W + tile.jlo + min(max(pp, 0), npx - 1)) * RS;
+        pin(grec);
         T *orow = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
         int wb = -tile.c0;                                     // window addressed by frame coords
         pin(wb);
@@ -365,52 +376,49 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
 
         // ---- A, C (row y)
         auto phase_ac = [&](int y) {
-            // this pixel's record: K*K weights, packed source column, ring slots of the
-            // K source rows
             using V = typename Vec16<T>::type;
-            const V *rec = reinterpret_cast<const V *>(tsm + ((y % NSTAGE) * PXCAP + ppc) * RS);
-            T wt[RS];
-            // the vector(s) with the source column, the ring slots and the flags come first
             constexpr int KK = K * K;
-            constexpr int VM0 = KK / VN;
-            constexpr int VM1 = (KK + 2) / VN < RS / VN - 1 ? (KK + 2) / VN : RS / VN - 1;
-#pragma unroll
-            for (int i = VM0; i <= VM1; ++i) *reinterpret_cast<V *>(wt + i * VN) = rec[i];
-            const int32_t pk = *reinterpret_cast<const int32_t *>(wt + KK);
-            const uint32_t slots = *reinterpret_cast<const uint32_t *>(wt + KK + 1);
-            const int fc = base_col(pk) + wb;
+            // this pixel's meta word: source column of its 2 x 2 block, ring slots of the
+            // block's two source rows, "the block is the whole footprint"
+            const uint32_t meta = msm[(y % NSTAGE) * PXCAP + ppc];
+            const int fc = (int)(int16_t)(meta & 0xffffu) + wb;
 
             // ---- A (row y): rectified flux of this pixel column, G frames
             T rect[G];
-            bool all_compact = false;
-            if constexpr (K >= 3)
-                all_compact = __all_sync(0xffffffffu, (slots >> 24) & REC_COMPACT);
-            if (K >= 3 && all_compact) {
-                // every footprint of the warp fits 2 x 2 source pixels: four taps
+            bool all_compact = true;
+            if constexpr (K >= 3) all_compact = __all_sync(0xffffffffu, meta & META_COMPACT);
+            if (all_compact) {
+                // every footprint of the warp fits 2 x 2 source pixels: four taps (K = 1: one)
+                T wt[4];
+                const V *q = reinterpret_cast<const V *>(qsm + ((y % NSTAGE) * PXCAP + ppc) * 4);
 #pragma unroll
-                for (int i = 0; i <= 3 / VN; ++i) *reinterpret_cast<V *>(wt + i * VN) = rec[i];
-                const T *rowp[2];
+                for (int i = 0; i < 4 / VN; ++i) *reinterpret_cast<V *>(wt + i * VN) = q[i];
+                constexpr int KB = K == 1 ? 1 : 2;
+                const T *rowp[KB];
+                rowp[0] = win + ((meta >> 16) & 0xfu) * WIN_PITCH + fc;
+                if constexpr (KB == 2) rowp[1] = win + ((meta >> 20) & 0xfu) * WIN_PITCH + fc;
+                gather_taps<T, KB, G, WSZ>(rowp, wt, 2, rect);
+            } else if constexpr (K >= 3) {
+                // (rare: 12 % of the warp rows) the full K x K records, from global memory (L2)
+                const V *rec = reinterpret_cast<const V *>(grec + (size_t)y * W * RS);
+                T wt[RS];
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
-                    rowp[a] = win + ((slots >> (8 * a)) & 0xffu) * WIN_PITCH + fc;
-                gather_taps<T, 2, G, WSZ>(rowp, wt, 2, rect);
-            } else {
+                for (int i = 0; i < RS / VN; ++i) *reinterpret_cast<V *>(wt + i * VN) = __ldg(rec + i);
+                const int32_t pk = *reinterpret_cast<const int32_t *>(wt + KK);
+                const uint32_t slots = *reinterpret_cast<const uint32_t *>(wt + KK + 1);
+                const int fcf = base_col(pk) + wb;
+                if ((slots >> 24) & REC_COMPACT) {             // spread the block over K x K
+                    const T c00 = wt[0], c01 = wt[1], c10 = wt[2], c11 = wt[3];
 #pragma unroll
-                for (int i = 0; i < VM0; ++i) *reinterpret_cast<V *>(wt + i * VN) = rec[i];
-                if constexpr (K >= 3) {
-                    if ((slots >> 24) & REC_COMPACT) {         // spread the block over K x K
-                        const T c00 = wt[0], c01 = wt[1], c10 = wt[2], c11 = wt[3];
-#pragma unroll
-                        for (int i = 0; i < KK; ++i) wt[i] = T(0);
-                        wt[0] = c00, wt[1] = c01, wt[K] = c10, wt[K + 1] = c11;
-                    }
+                    for (int i = 0; i < KK; ++i) wt[i] = T(0);
+                    wt[0] = c00, wt[1] = c01, wt[K] = c10, wt[K + 1] = c11;
                 }
                 const T *rowp[K];
 #pragma unroll
                 for (int a = 0; a < K; ++a) {
                     const uint32_t slot = a < 3 ? (slots >> (8 * a)) & 0xffu
                                                 : *reinterpret_cast<const uint32_t *>(wt + KK + 2);
-                    rowp[a] = win + slot * WIN_PITCH + fc;
+                    rowp[a] = win + slot * WIN_PITCH + fcf;
                 }
                 gather_taps<T, K, G, WSZ>(rowp, wt, K, rect);
             }

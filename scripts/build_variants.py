@@ -13,9 +13,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+SLIM = ("EMIRWV_SLIM=1",)         # float32 / K = 3 / G = 4 only: compiles in half a minute
 VARIANTS = {
-    # three CTAs per SM: 72 registers, two rows in flight, nine-row source window (73 KB)
-    "x3": ("EMIRWV_MINBLOCKS=3", "EMIRWV_NSTAGE=2", "EMIRWV_WIN_ROWS=9"),
+    "slim": SLIM,                                        # the product configuration, slim
+    # three CTAs per SM: 72 registers, four rows in flight, ten-row source window (73 KB)
+    "c3s4": SLIM + ("EMIRWV_MINBLOCKS=3", "EMIRWV_NSTAGE=4", "EMIRWV_WIN_ROWS=10"),
+    "c3s3": SLIM + ("EMIRWV_MINBLOCKS=3", "EMIRWV_NSTAGE=3", "EMIRWV_WIN_ROWS=10"),
+    # two CTAs per SM, deeper pipeline
+    "c2s6": SLIM + ("EMIRWV_NSTAGE=6", "EMIRWV_WIN_ROWS=13"),
+    "c2s5": SLIM + ("EMIRWV_NSTAGE=5", "EMIRWV_WIN_ROWS=12"),
+    "c2s8": SLIM + ("EMIRWV_NSTAGE=8", "EMIRWV_WIN_ROWS=15"),
 }
 
 

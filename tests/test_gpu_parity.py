@@ -441,8 +441,8 @@ def test_item_distribution_variants_bit_identical(monkeypatch):
 
 @pytest.mark.parametrize("number", [1, 4])
 def test_float64_two_stage_pipeline_bit_identical(monkeypatch, number):
-    """EMIRWV_NSTAGE_F64=2 (two staged table rows instead of four: two CTAs per SM for the
-    96-byte float64 records) changes the depth of the copy pipeline only: same bits."""
+    """The depth of the copy pipeline (rows in flight per CTA: EMIRWV_NSTAGE_F64, or the
+    `stages` field of the plan description) does not change a bit of the result."""
     coeff = only_slitlets(synthetic.make_config(number), [1, 2, 28, 54, 55])
     fr = synthetic.make_frames(coeff, 5, seed=31, dtype=np.float64)
     res = []
@@ -450,7 +450,7 @@ def test_float64_two_stage_pipeline_bit_identical(monkeypatch, number):
         monkeypatch.setenv("EMIRWV_NSTAGE_F64", stages)
         plan = RectWavePlan(coeff, 2, "float64")
         res.append(plan.run_host(fr))
-        assert (plan.info()["smem_bytes"] < 116000) == (stages == "2")
+        assert plan.info()["stages"] == int(stages)
         plan.close()
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert np.count_nonzero(res[0][0]) > 0
