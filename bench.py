@@ -240,7 +240,8 @@ def tuning_of(info):
             "smem_bytes": info["smem_bytes"], "ctas_per_sm": info["ctas_per_sm"],
             "window_rows": info["window_rows"], "window_cols": info["window_cols"],
             "table_MB": info["table_bytes"] / 1e6,
-            "library": os.environ.get("EMIRWV_LIB", "libemirwv.so")}
+            "library": os.environ.get("EMIRWV_LIB", "libemirwv.so"),
+            "label": os.environ.get("AB_LABEL")}
 
 
 # --------------------------------------------------------------------- GPU arm

@@ -64,6 +64,20 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// shared -> global bulk store (TMA), 16-byte aligned addresses and size; completion is
+// tracked per thread in bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"(src), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ unsigned smem_addr_of(const void *p) {
     return (unsigned)__cvta_generic_to_shared(p);
 }

@@ -55,16 +55,25 @@
 #define EMIRWV_NSTAGE 4
 #endif
 #ifndef EMIRWV_WIN_PITCH
-#define EMIRWV_WIN_PITCH 288
+#define EMIRWV_WIN_PITCH 256
 #endif
 #ifndef EMIRWV_PXCAP
 #define EMIRWV_PXCAP 248
 #endif
 #ifndef EMIRWV_WIN_ROWS
-#define EMIRWV_WIN_ROWS 12
+#define EMIRWV_WIN_ROWS 11
+#endif
+#ifndef EMIRWV_NOFILL
+#define EMIRWV_NOFILL 0        // 1: the zero runs are always written by k_zero_fill (experiment)
+#endif
+#ifndef EMIRWV_DIAG
+#define EMIRWV_DIAG 0          // timing diagnostics that break the result (scripts/build_variants.py)
 #endif
 #ifndef EMIRWV_MINBLOCKS
-#define EMIRWV_MINBLOCKS 2
+#define EMIRWV_MINBLOCKS 3     // resident CTAs per SM the float32 kernels are compiled for (72 registers)
+#endif
+#ifndef EMIRWV_MINBLOCKS_F64
+#define EMIRWV_MINBLOCKS_F64 3 // the same for the float64 kernels
 #endif
 #include "geom.cuh"
 #include "pixel_ops.cuh"
@@ -78,6 +87,8 @@ constexpr int W = 2048;                      // EMIR_NAXIS1: pitch of per-column
 constexpr int MAXK = 4;                      // largest supported footprint
 constexpr int NWARPS = 8;                     // compute warps: two per SM sub-partition and CTA
 constexpr int NTHREADS = 32 * (NWARPS + 1);   // threads per CTA: compute warps + one copy warp
+constexpr int ZFILL_BYTES = 2048;             // zeros in shared memory: source of the bulk stores that
+                                              // write the runs without wavelength coverage
 constexpr int TILE_K_MAX = 31 * NWARPS;       // output columns per tile (a warp does 31)
 constexpr int WIN_ROWS = EMIRWV_WIN_ROWS;                  // rolling source window: rows per frame
 constexpr int RING_BIAS = 12 * 1024;          // makes (row + bias) % WIN_ROWS non-negative
@@ -211,6 +222,8 @@ struct RunParams {
     int nlive_tiles;        // tiles [0, nlive_tiles) have wavelength coverage
     int ndead_tiles;        // the tiles after them are exactly zero
     int ngroups;            // ceil(nframes / G)
+    const int2 *fillruns;   // zero runs of one frame: {first element, bytes}, or NULL
+    int nfillruns;          // dead tiles x output rows
     int *sched;             // dynamic work distribution: item counter of this launch (or NULL)
     int early;              // first rows of the next item requested at the end of the current one
 };
@@ -282,6 +295,7 @@ struct emirwv_plan {
     uint32_t *d_meta = nullptr;
     void *d_border = nullptr, *d_pix = nullptr;
     Tile *d_tiles = nullptr;
+    int2 *d_fillruns = nullptr;        // [ntiles_empty * rps] zero runs of one frame
 
     std::vector<SlitDev> h_slit;
     std::vector<int32_t> h_base;
@@ -384,6 +398,7 @@ void emirwv_plan_destroy(emirwv_plan *pl) {
     cudaFree(pl->d_border);
     cudaFree(pl->d_pix);
     cudaFree(pl->d_tiles);
+    cudaFree(pl->d_fillruns);
     cudaFree(pl->d_sched);
     delete pl;
 }

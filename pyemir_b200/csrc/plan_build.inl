@@ -21,7 +21,7 @@ struct LaunchCfg {
 size_t smem_bytes(const emirwv_plan *pl, int G) {
     return 3 * sizeof(Tile) + BAR_BYTES +
            (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 2 * 32) * pl->esize +
-           (size_t)pl->nstage * PXCAP * (4 * pl->esize + sizeof(uint32_t));
+           (size_t)pl->nstage * PXCAP * (4 * pl->esize + sizeof(uint32_t)) + ZFILL_BYTES;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
@@ -152,12 +152,21 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     // stream is available the hot kernel is enqueued first (it takes its shared memory
     // and registers on every SM) and the fill blocks run next to it in what is left.
     // (skip_fill: the caller's buffer already holds the zeros outside the coverage)
-    const int nfill = skip_fill ? 0 : pl->ntiles_empty;
+    // The zero runs are written by the copy warps of the hot kernel (TMA bulk stores) when
+    // the output rows are 16-byte aligned and there is a hot kernel to ride on; otherwise by
+    // k_zero_fill beside it (EMIRWV_FILL=kernel forces that).
+    const char *fill_env = getenv("EMIRWV_FILL");
+    const bool fill_in_hot = !skip_fill && pl->d_fillruns != nullptr && rp.vec_ok &&
+                             rp.nlive_tiles > 0 && !(fill_env && strcmp(fill_env, "kernel") == 0);
+    rp.fillruns = fill_in_hot ? pl->d_fillruns : nullptr;
+    rp.nfillruns = pl->ntiles_empty * pl->rps;
+    const int nfill = (skip_fill || fill_in_hot) ? 0 : pl->ntiles_empty;
     const bool forked = nfill > 0 && pl->aux != nullptr;
     rp.ndead_tiles = pl->ntiles_empty;
     const int zgrid = std::max(1, env_int("EMIRWV_FILL_BLOCKS", 4 * pl->num_sms));
+    const int zthreads = std::max(32, std::min(128, env_int("EMIRWV_FILL_THREADS", 128) & ~31));
     if (nfill > 0 && !forked) {
-        k_zero_fill<T><<<zgrid, 128, 0, st>>>(rp, rp.nlive_tiles);
+        k_zero_fill<T><<<zgrid, zthreads, 0, st>>>(rp, rp.nlive_tiles);
         CUDA_TRY(cudaGetLastError());
     }
     std::unique_lock<std::mutex> lock(pl->aux_mu, std::defer_lock);
@@ -176,7 +185,7 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     if (forked) {
         // the two kernels write disjoint parts of the output
         CUDA_TRY(cudaStreamWaitEvent(pl->aux, pl->ev_fork, 0));
-        k_zero_fill<T><<<zgrid, 128, 0, pl->aux>>>(rp, rp.nlive_tiles);
+        k_zero_fill<T><<<zgrid, zthreads, 0, pl->aux>>>(rp, rp.nlive_tiles);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(pl->ev_join, pl->aux));
         CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_join, 0));
@@ -445,6 +454,27 @@ int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
     pl->early_rows = env_int("EMIRWV_EARLY", 1);
     CUDA_TRY(cudaMalloc(&pl->d_sched, SCHED_POOL * sizeof(int)));
     CUDA_TRY(cudaMemset(pl->d_sched, 0, SCHED_POOL * sizeof(int)));
+    if (pl->ntiles_empty > 0) {
+        // the zero runs of one frame, one per dead tile and output row: first element, bytes
+        std::vector<int2> runs;
+        runs.reserve((size_t)pl->ntiles_empty * pl->rps);
+        for (int i = pl->ntiles - pl->ntiles_empty; i < pl->ntiles; ++i) {
+            const Tile &t = pl->h_tiles[i];
+            for (int y = 0; y < pl->rps; ++y)
+                runs.push_back(make_int2((t.slit * pl->rps + y) * pl->nout + t.k0,
+                                         (int)(t.nk * pl->esize)));
+        }
+        // bulk stores need 16-byte aligned runs; a plan with an odd one keeps k_zero_fill
+        bool aligned = true;
+        for (const int2 &r : runs)
+            aligned = aligned && ((size_t)r.x * pl->esize) % 16 == 0 && r.y % 16 == 0;
+        if (aligned) {
+            CUDA_TRY(cudaMalloc(&pl->d_fillruns, runs.size() * sizeof(int2)));
+            CUDA_TRY(cudaMemcpy(pl->d_fillruns, runs.data(), runs.size() * sizeof(int2),
+                                cudaMemcpyHostToDevice));
+            pl->table_bytes += (int64_t)(runs.size() * sizeof(int2));
+        }
+    }
     CUDA_TRY(cudaMalloc(&pl->d_tiles, pl->h_tiles.size() * sizeof(Tile)));
     CUDA_TRY(cudaMemcpy(pl->d_tiles, pl->h_tiles.data(), pl->h_tiles.size() * sizeof(Tile),
                         cudaMemcpyHostToDevice));

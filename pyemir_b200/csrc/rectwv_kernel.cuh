@@ -74,7 +74,7 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 //                [NSTAGE table rows: PXCAP x quad (4 weights)][NSTAGE x PXCAP meta words]
 // ---------------------------------------------------------------------------------
 template <typename T, int K, int G, bool SPANLOOP, int NSTAGE>
-__global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
+__global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : EMIRWV_MINBLOCKS_F64)
     k_rectwv(const RunParams<T> p) {
     static_assert(NSTAGE >= 2 && NSTAGE <= NSTAGE_MAX, "stage count");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
     constexpr int RS = rec_size(K);
     T *qsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [NSTAGE][PXCAP][4]
     uint32_t *msm = reinterpret_cast<uint32_t *>(qsm + NSTAGE * PXCAP * 4);   // [NSTAGE][PXCAP]
+    uint32_t *zbuf = msm + NSTAGE * PXCAP;                                 // ZFILL_BYTES of zeros
     // float32 with an even number of frames: two frames per arithmetic instruction
     constexpr bool PACKED = sizeof(T) == 4 && (G % 2) == 0;
     using KV = KnotVec<T, G>;
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
     // (generic stores; the bulk copies that later land on the same addresses belong to the
     // async proxy, hence the proxy fence before the barrier that releases the copy warp)
     for (int e = tid; e < G * WSZ; e += NTHREADS) win[e] = T(0);
+    for (int e = tid; e < ZFILL_BYTES / 4; e += NTHREADS) zbuf[e] = 0u;
     fence_proxy_async_smem();
     cp_async_wait_all();
     __syncthreads();
@@ -189,6 +191,11 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
         // right-knot slope (the table holds 0 at the red end of the spectrum)
         const T qpb = __ldg(&p.pix[(size_t)s * W + bd.idx].qp);
         const unsigned stmask = col_ok ? (1u << nlive) - 1u : 0u;   // frames this lane stores
+#if EMIRWV_DIAG & 2
+        T dreg[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) dreg[g] = T(0);
+#endif
         unsigned nzb[G];                                       // OR of the value bits seen
 #pragma unroll
         for (int g = 0; g < G; ++g) nzb[g] = 0;
@@ -315,11 +322,18 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
             const KV *kb_rect = kbase, *kb_ya = kbase + 32;
             // flux and left-knot slope of the border's pixel; its right-knot slope is the
             // next pixel's left-knot slope rescaled by the ratio of the pixel widths
+#if EMIRWV_DIAG & 2
+            KV kr, ka, kn, k1;                                 // DIAGNOSTIC: no knot loads
+#pragma unroll
+            for (int g = 0; g < G; ++g) kr.v[g] = dreg[g], ka.v[g] = dreg[g] * T(0.5), kn.v[g] = dreg[g] * T(0.25), k1.v[g] = T(0);
+            (void)kb_rect; (void)kb_ya;
+#else
             const KV kr = kb_rect[0], ka = kb_ya[0], kn = kb_ya[1];
             KV k1;
 #pragma unroll
             for (int g = 0; g < G; ++g) k1.v[g] = T(0);
             if (has2) k1 = kb_rect[1];
+#endif
             T o[G];
             if constexpr (PACKED) {
                 const float2 tau2 = dup2(bd.tau);
@@ -393,7 +407,11 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
                 const V *q = reinterpret_cast<const V *>(qsm + ((y % NSTAGE) * PXCAP + ppc) * 4);
 #pragma unroll
                 for (int i = 0; i < 4 / VN; ++i) *reinterpret_cast<V *>(wt + i * VN) = q[i];
+#if EMIRWV_DIAG & 1
+                constexpr int KB = 1;                          // DIAGNOSTIC: one tap instead of four
+#else
                 constexpr int KB = K == 1 ? 1 : 2;
+#endif
                 const T *rowp[KB];
                 rowp[0] = win + ((meta >> 16) & 0xfu) * WIN_PITCH + fc;
                 if constexpr (KB == 2) rowp[1] = win + ((meta >> 20) & 0xfu) * WIN_PITCH + fc;
@@ -467,9 +485,14 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
             // the warp's own knot rows (lane 0 holds an incomplete slope, never read)
             // (one buffer is enough: the warp's border phase of the previous row comes first
             // in program order)
+#if EMIRWV_DIAG & 2
+#pragma unroll
+            for (int g = 0; g < G; ++g) dreg[g] = vr.v[g] + va.v[g];   // DIAGNOSTIC: no knot stores
+#else
             KV *kdst = reinterpret_cast<KV *>(knots) + lane;
             kdst[0] = vr;
             kdst[32] = va;
+#endif
         };
 
         // Row loop without block barriers.  A warp waits for the data of row y, evaluates
@@ -478,6 +501,45 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
         // reports row y done; warps may drift apart by up to NSTAGE-1 rows.
         if (producer) {
             const CopyCtx ctx = make_ctx(tile, w);
+            // The runs without wavelength coverage (and the missing slitlets) are exact zeros:
+            // the item's share of them -- runs (dead tile x output row) x frames, one per lane
+            // and round -- is written by TMA bulk stores from the zeros in shared memory, a
+            // round every few rows so that the writes trickle along with the item.  The run of
+            // the next round is fetched one round ahead: the stores never wait for a load.
+            // (frem: runs of the item still to be written; fcount: rows until the next round)
+            long long fu = 0;
+            int frem = 0, fevery = NROWS + 1, fcount = NROWS + 1;
+            int2 frun = make_int2(0, 0);
+            T *fdst = p.out;
+            auto fill_fetch = [&]() {
+                if (lane < frem) {
+                    const long long u = fu + lane;
+                    frun = __ldg(p.fillruns + (int)(u % p.nfillruns));
+                    fdst = p.out + (size_t)(u / p.nfillruns) * frame_out + (unsigned)frun.x;
+                }
+            };
+            auto fill_round = [&]() {
+                if (lane < frem) {
+                    char *dst = reinterpret_cast<char *>(fdst);
+                    const unsigned zsrc = smem_addr_of(zbuf);
+                    for (unsigned off = 0; off < (unsigned)frun.y; off += ZFILL_BYTES)
+                        bulk_s2g(dst + off, zsrc, min((unsigned)ZFILL_BYTES, (unsigned)frun.y - off));
+                    bulk_commit();
+                }
+                fu += 32;
+                frem -= 32;
+                fill_fetch();
+            };
+#if !EMIRWV_NOFILL
+            if (p.fillruns != nullptr) {
+                const long long total = (long long)p.nfillruns * p.nframes;
+                fu = (long long)w * total / nwork;
+                frem = (int)((long long)(w + 1) * total / nwork - fu);
+                fevery = max(1, NROWS / min(NROWS, (frem + 31) / 32 + 1));
+                fcount = fevery;
+                fill_fetch();
+            }
+#endif
 #pragma unroll 1
             for (int y = 0; y < NROWS; ++y) {
                 mbar_wait(bars + 8 * NSTAGE + 8 * (rowseq % NSTAGE), (rowseq / NSTAGE) & 1);  // row y is done
@@ -487,7 +549,16 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
                                      span_hi(tile.span[y + NSTAGE]));
                 }
                 ++rowseq;
+#if !EMIRWV_NOFILL
+                if (--fcount == 0) {
+                    fcount = fevery;
+                    if (frem > 0) fill_round();
+                }
+#endif
             }
+#if !EMIRWV_NOFILL
+            while (frem > 0) fill_round();
+#endif
             // Every compute warp has read what the last row needs: the window and the table
             // slots are free, so the first rows of the CTA's next item are requested now
             // -- while the compute warps still evaluate the borders of the last row -- and not
@@ -540,4 +611,5 @@ __global__ void __launch_bounds__(NTHREADS, EMIRWV_MINBLOCKS)
         cp_async_wait_all();
         __syncthreads();          // next descriptor landed; window and table slots are free
     }
+    if (producer) bulk_wait_all();   // the zero runs are written before the CTA retires
 }

@@ -16,13 +16,13 @@ sys.path.insert(0, ROOT)
 SLIM = ("EMIRWV_SLIM=1",)         # float32 / K = 3 / G = 4 only: compiles in half a minute
 VARIANTS = {
     "slim": SLIM,                                        # the product configuration, slim
-    # three CTAs per SM: 72 registers, four rows in flight, ten-row source window (73 KB)
-    "c3s4": SLIM + ("EMIRWV_MINBLOCKS=3", "EMIRWV_NSTAGE=4", "EMIRWV_WIN_ROWS=10"),
-    "c3s3": SLIM + ("EMIRWV_MINBLOCKS=3", "EMIRWV_NSTAGE=3", "EMIRWV_WIN_ROWS=10"),
-    # two CTAs per SM, deeper pipeline
-    "c2s6": SLIM + ("EMIRWV_NSTAGE=6", "EMIRWV_WIN_ROWS=13"),
-    "c2s5": SLIM + ("EMIRWV_NSTAGE=5", "EMIRWV_WIN_ROWS=12"),
-    "c2s8": SLIM + ("EMIRWV_NSTAGE=8", "EMIRWV_WIN_ROWS=15"),
+    # round-1 occupancy: two CTAs per SM (96 registers), 12-row window of 288 columns
+    "c2": SLIM + ("EMIRWV_MINBLOCKS=2", "EMIRWV_WIN_ROWS=12", "EMIRWV_WIN_PITCH=288"),
+    "c3s3": SLIM + ("EMIRWV_NSTAGE=3", "EMIRWV_WIN_ROWS=10"),
+    # float64 kernels compiled for two CTAs per SM (full build: every instantiation)
+    "f64c2": ("EMIRWV_MINBLOCKS_F64=2",),
+    # timing diagnostics (WRONG results): one gather tap instead of four / no knot traffic
+    "diag1": SLIM + ("EMIRWV_DIAG=1",), "diag2": SLIM + ("EMIRWV_DIAG=2",),
 }
 
 
