@@ -78,6 +78,20 @@ __device__ __forceinline__ void bulk_wait_all() {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// TMA tensor copy: one box of a 3-D tensor (column, row, frame) -> shared memory; elements of
+// the box outside the tensor arrive as zeros; completes the box's bytes on the barrier
+__device__ __forceinline__ void tensor_g2s_3d(unsigned dst, const void *tmap, int x, int y, int z,
+                                              unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const void *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 __device__ __forceinline__ unsigned smem_addr_of(const void *p) {
     return (unsigned)__cvta_generic_to_shared(p);
 }

@@ -33,6 +33,7 @@
 //   plan_build.inl      host side of a plan (launch configuration, border tables, tiles)
 // and this file keeps the constants, the device structs, the plan object and the C ABI.
 
+#include <cuda.h>               // CUtensorMap and its enums (types only: libcuda is not linked)
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -65,6 +66,9 @@
 #endif
 #ifndef EMIRWV_NOFILL
 #define EMIRWV_NOFILL 0        // 1: the zero runs are always written by k_zero_fill (experiment)
+#endif
+#ifndef EMIRWV_PREFETCH
+#define EMIRWV_PREFETCH 0      // rows of L2 prefetch ahead of the copy pipeline (0: none)
 #endif
 #ifndef EMIRWV_DIAG
 #define EMIRWV_DIAG 0          // timing diagnostics that break the result (scripts/build_variants.py)
@@ -103,6 +107,8 @@ constexpr int NSTAGE_MAX = EMIRWV_NSTAGE;                 // rectified rows in f
                                               // template parameter: NSTAGE_MAX, or 2 for float64
                                               // plans on request -- 96-byte records, see smem_bytes)
 constexpr int BAR_BYTES = ((2 * NSTAGE_MAX * 8) + 63) / 64 * 64;   // "full" and "done" mbarriers
+// one staged table row of a tile: PXCAP block-weight quadruples, then PXCAP meta words
+__host__ __device__ constexpr int stage_bytes(int esize) { return PXCAP * (4 * esize + 4); }
 // Tables per rectified pixel (s, y, j), frame independent:
 //   quad  [4]   the weights of the 2 x 2 block of source pixels the pixel is made of (K <= 2, and
 //               the footprints of a larger K that fit such a block: ~88 % of them), zeros else
@@ -210,8 +216,7 @@ struct RunParams {
     const Tile *tiles;
     const int32_t *base;
     const T *w;             // full records (global memory path)
-    const T *quad;          // 2 x 2 block weights, staged in shared memory
-    const uint32_t *meta;   // staged in shared memory
+    const char *tilepack;   // per live tile and scanned row: the staged table row (stage_bytes)
     const Border<T> *border;
     const PixGeom<T> *pix;
     int naxis2;
@@ -293,6 +298,7 @@ struct emirwv_plan {
     int32_t *d_base = nullptr;
     void *d_w = nullptr, *d_quad = nullptr;
     uint32_t *d_meta = nullptr;
+    char *d_tilepack = nullptr;        // [live tile][39][stage_bytes]: what the hot kernel stages
     void *d_border = nullptr, *d_pix = nullptr;
     Tile *d_tiles = nullptr;
     int2 *d_fillruns = nullptr;        // [ntiles_empty * rps] zero runs of one frame
@@ -395,6 +401,7 @@ void emirwv_plan_destroy(emirwv_plan *pl) {
     cudaFree(pl->d_w);
     cudaFree(pl->d_quad);
     cudaFree(pl->d_meta);
+    cudaFree(pl->d_tilepack);
     cudaFree(pl->d_border);
     cudaFree(pl->d_pix);
     cudaFree(pl->d_tiles);

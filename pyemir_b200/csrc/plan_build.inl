@@ -19,9 +19,45 @@ struct LaunchCfg {
 //   [per warp: 2 x (rect | ya) x 32 x G knots]
 //   [nstage table rows: PXCAP x (4 block weights + 1 meta word)]
 size_t smem_bytes(const emirwv_plan *pl, int G) {
-    return 3 * sizeof(Tile) + BAR_BYTES +
+    return 128 /* alignment slack */ + 3 * sizeof(Tile) + BAR_BYTES +
            (size_t)G * (WIN_ROWS * WIN_PITCH + NWARPS * 2 * 32) * pl->esize +
-           (size_t)pl->nstage * PXCAP * (4 * pl->esize + sizeof(uint32_t)) + ZFILL_BYTES;
+           (size_t)pl->nstage * stage_bytes((int)pl->esize) + ZFILL_BYTES;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked, so
+// the library still loads on a box without a driver)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) !=
+                cudaSuccess || qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+// The frames of a launch as a 3-D tensor (column, row, frame); a box is WIN_PITCH columns of
+// one row of G consecutive frames -- one ring row of the hot kernel's window.
+int make_frames_tensor_map(CUtensorMap *tm, const void *d_in, int esize, int naxis1, int naxis2,
+                           int nframes, int G) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return fail(EMIRWV_E_CUDA, "cuTensorMapEncodeTiled is not available");
+    const cuuint64_t dims[3] = {(cuuint64_t)naxis1, (cuuint64_t)naxis2, (cuuint64_t)nframes};
+    const cuuint64_t strides[2] = {(cuuint64_t)naxis1 * esize, (cuuint64_t)naxis1 * naxis2 * esize};
+    const cuuint32_t box[3] = {(cuuint32_t)WIN_PITCH, 1u, (cuuint32_t)G};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult rc = fn(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                           3, const_cast<void *>(d_in), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(EMIRWV_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+    return EMIRWV_OK;
 }
 
 LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
@@ -37,6 +73,7 @@ LaunchCfg choose_cfg(const emirwv_plan *pl, int nframes) {
 
 template <typename T, int K, int G, bool SPANLOOP, int NS>
 int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, cudaStream_t st) {
+    static_assert(WIN_PITCH <= 256 && (WIN_PITCH * sizeof(float)) % 16 == 0, "tensor-map box");
     auto kern = k_rectwv<T, K, G, SPANLOOP, NS>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)cfg.smem));
@@ -52,7 +89,11 @@ int launch_final(const emirwv_plan *pl, RunParams<T> rp, const LaunchCfg &cfg, c
     if (nwork > 0) {
         if (nwork > INT_MAX) return fail(EMIRWV_E_LIMIT, "too many frames in one call");
         const int grid = (int)std::min<long long>(nwork, (long long)pl->num_sms * per_sm);
-        kern<<<grid, cfg.threads, cfg.smem, st>>>(rp);
+        alignas(64) CUtensorMap tmap;
+        const int rc = make_frames_tensor_map(&tmap, rp.in, (int)sizeof(T), W, rp.naxis2,
+                                              rp.nframes, G);
+        if (rc) return rc;
+        kern<<<grid, cfg.threads, cfg.smem, st>>>(rp, tmap);
         CUDA_TRY(cudaGetLastError());
     }
     return EMIRWV_OK;
@@ -124,8 +165,7 @@ int launch_t(const emirwv_plan *pl, const void *d_in, void *d_out, int nframes,
     rp.tiles = pl->d_tiles;
     rp.base = pl->d_base;
     rp.w = static_cast<const T *>(pl->d_w);
-    rp.quad = static_cast<const T *>(pl->d_quad);
-    rp.meta = pl->d_meta;
+    rp.tilepack = pl->d_tilepack;
     rp.border = static_cast<const Border<T> *>(pl->d_border);
     rp.pix = static_cast<const PixGeom<T> *>(pl->d_pix);
     rp.naxis2 = pl->desc.naxis2;
@@ -479,6 +519,28 @@ int build_tiles(emirwv_plan *pl, const std::vector<uint8_t> &covered) {
     CUDA_TRY(cudaMemcpy(pl->d_tiles, pl->h_tiles.data(), pl->h_tiles.size() * sizeof(Tile),
                         cudaMemcpyHostToDevice));
     pl->table_bytes += (int64_t)(pl->h_tiles.size() * sizeof(Tile));
+    // the staged tables, tile-major; the pixel-major block weights and meta words are not
+    // needed afterwards
+    const int nlive = pl->ntiles - pl->ntiles_empty;
+    const size_t pack_bytes = (size_t)nlive * NROWS * stage_bytes((int)pl->esize);
+    CUDA_TRY(cudaMalloc(&pl->d_tilepack, pack_bytes + 64));
+    if (nlive > 0) {
+        const dim3 pgrid(nlive, NROWS);
+        if (pl->esize == 4)
+            k_pack_tiles<float><<<pgrid, 256>>>(pl->d_tiles, static_cast<const float *>(pl->d_quad),
+                                                pl->d_meta, pl->d_tilepack);
+        else
+            k_pack_tiles<double><<<pgrid, 256>>>(pl->d_tiles, static_cast<const double *>(pl->d_quad),
+                                                 pl->d_meta, pl->d_tilepack);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    const size_t nrowtab = (size_t)pl->nsl * NROWS;
+    pl->table_bytes += (int64_t)pack_bytes - (int64_t)(nrowtab * W * (4 * pl->esize + sizeof(uint32_t)));
+    cudaFree(pl->d_quad);
+    cudaFree(pl->d_meta);
+    pl->d_quad = nullptr;
+    pl->d_meta = nullptr;
     return EMIRWV_OK;
 }
 

@@ -191,6 +191,28 @@ __global__ void k_rectify2d(const double *img, int naxis2, int naxis1, SlitDev s
     out[(size_t)i * naxis1out + j] = acc;
 }
 
+// Tile-major copy of the staged tables: for every live tile and scanned row the block
+// weights and the meta words of the tile's pixels (rounded out to multiples of 4 pixels,
+// padded to PXCAP), laid out exactly as a stage of the hot kernel's shared memory, so that a
+// row costs the copy warp ONE bulk copy.
+template <typename T>
+__global__ void k_pack_tiles(const Tile *tiles, const T *quad, const uint32_t *meta, char *pack) {
+    const Tile &t = tiles[blockIdx.x];
+    const int y = blockIdx.y;
+    char *dst = pack + ((size_t)blockIdx.x * NROWS + y) * stage_bytes(sizeof(T));
+    T *q = reinterpret_cast<T *>(dst);
+    uint32_t *m = reinterpret_cast<uint32_t *>(dst + PXCAP * 4 * sizeof(T));
+    const int jal = t.jlo & ~3;
+    const size_t row = ((size_t)t.slit * NROWS + y) * W;
+    for (int i = threadIdx.x; i < PXCAP; i += blockDim.x) {
+        const int j = jal + i;
+        const bool ok = j < W;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[i * 4 + e] = ok ? quad[(row + j) * 4 + e] : T(0);
+        m[i] = ok ? meta[row + j] : META_COMPACT;
+    }
+}
+
 __global__ void k_init_jmm(int32_t *jmm, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) jmm[i] = (i & 1) ? -1 : INT_MAX;

@@ -65,21 +65,29 @@ __device__ __forceinline__ void gather_taps(const T *const (&rowp)[KT], const T 
 //   C      Steffen-limited end slopes from the neighbours' flux (warp shuffles: a warp
 //          covers 32 pixels and produces 30), written to the warp's knot rows
 //   arrive done[y]
-// The copy warp waits for done[y] (all compute warps) and requests the table row and
-// the new source rows of row y+NSTAGE into the slots row y has just released.
-// The source window is a ring of WIN_ROWS rows per frame.
+// The copy warp waits for done[y] (all compute warps) and requests the table row (one bulk
+// copy: the plan keeps the tables tile-major) and the new source rows of row y+NSTAGE (one
+// TMA tensor copy per source row: a box of WIN_PITCH columns x G frames, zeros outside the
+// detector) into the slots row y has just released.
+// The source window is a ring of WIN_ROWS rows, each holding the G frames side by side.
 //
-// Shared memory: [tile descriptor ring: 3][mbarriers][G windows: WIN_ROWS x WIN_PITCH]
+// Shared memory (128-byte aligned): [window: WIN_ROWS ring rows x G frames x WIN_PITCH]
 //                [per warp: (rect | ya) x 32 pixels x G]
-//                [NSTAGE table rows: PXCAP x quad (4 weights)][NSTAGE x PXCAP meta words]
+//                [NSTAGE staged table rows: PXCAP x quad (4 weights), PXCAP meta words]
+//                [zeros for the fill stores][tile descriptor ring: 3][mbarriers]
 // ---------------------------------------------------------------------------------
 template <typename T, int K, int G, bool SPANLOOP, int NSTAGE>
 __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : EMIRWV_MINBLOCKS_F64)
-    k_rectwv(const RunParams<T> p) {
+    k_rectwv(const RunParams<T> p, const __grid_constant__ CUtensorMap tmap) {
     static_assert(NSTAGE >= 2 && NSTAGE <= NSTAGE_MAX, "stage count");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int WSZ = WIN_ROWS * WIN_PITCH;                  // one frame's window
+    extern __shared__ unsigned char smem_dyn[];
+    // (tensor copies want a 128-byte aligned destination)
+    unsigned char *smem_raw = smem_dyn + ((128u - (smem_addr_of(smem_dyn) & 127u)) & 127u);
+    constexpr int WROW = G * WIN_PITCH;                        // one ring row: G frames side by side
+    constexpr int WSZ = WIN_ROWS * WROW;                       // the window
     constexpr int KNOT_WARP = 2 * 32 * G;                      // knot elements of one warp
+    constexpr unsigned ROW_BYTES = WROW * sizeof(T);           // one tensor copy
+    constexpr unsigned STAGE_BYTES = stage_bytes(sizeof(T));   // one staged table row
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -87,15 +95,15 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
     const size_t frame_out = (size_t)p.nrows_out * p.nout;
     const int nwork = p.nlive_tiles * p.ngroups;
 
-    Tile *ring = reinterpret_cast<Tile *>(smem_raw);                       // [3]
-    // mbarriers: "full" [0..2] and "done" [3..5], one pair per rectified row in flight
-    const unsigned bars = smem_addr_of(smem_raw + 3 * sizeof(Tile));
-    T *win = reinterpret_cast<T *>(smem_raw + 3 * sizeof(Tile) + BAR_BYTES);   // [G][WSZ]
-    T *knots = win + G * WSZ + min(warp, NWARPS - 1) * KNOT_WARP;   // this warp: [rect|ya][32][G]
+    T *win = reinterpret_cast<T *>(smem_raw);                              // [WIN_ROWS][G][WIN_PITCH]
+    T *knots = win + WSZ + min(warp, NWARPS - 1) * KNOT_WARP;   // this warp: [rect|ya][32][G]
     constexpr int RS = rec_size(K);
-    T *qsm = win + G * WSZ + NWARPS * KNOT_WARP;                           // [NSTAGE][PXCAP][4]
-    uint32_t *msm = reinterpret_cast<uint32_t *>(qsm + NSTAGE * PXCAP * 4);   // [NSTAGE][PXCAP]
-    uint32_t *zbuf = msm + NSTAGE * PXCAP;                                 // ZFILL_BYTES of zeros
+    unsigned char *stg = reinterpret_cast<unsigned char *>(win + WSZ + NWARPS * KNOT_WARP);
+    // staged table row `st`: quad [PXCAP][4] T at stg + st * STAGE_BYTES, then meta [PXCAP]
+    uint32_t *zbuf = reinterpret_cast<uint32_t *>(stg + NSTAGE * STAGE_BYTES);   // ZFILL_BYTES of zeros
+    Tile *ring = reinterpret_cast<Tile *>(reinterpret_cast<unsigned char *>(zbuf) + ZFILL_BYTES);   // [3]
+    // mbarriers: "full" and "done", one pair per rectified row in flight
+    const unsigned bars = smem_addr_of(ring + 3);
     // float32 with an even number of frames: two frames per arithmetic instruction
     constexpr bool PACKED = sizeof(T) == 4 && (G % 2) == 0;
     using KV = KnotVec<T, G>;
@@ -135,7 +143,8 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
     // the window starts out finite: taps with weight zero may read slots no copy has filled
     // (generic stores; the bulk copies that later land on the same addresses belong to the
     // async proxy, hence the proxy fence before the barrier that releases the copy warp)
-    for (int e = tid; e < G * WSZ; e += NTHREADS) win[e] = T(0);
+    for (int e = tid; e < WSZ; e += NTHREADS) win[e] = T(0);
+    if (tid == NTHREADS - 1) prefetch_tensormap(&tmap);
     for (int e = tid; e < ZFILL_BYTES / 4; e += NTHREADS) zbuf[e] = 0u;
     fence_proxy_async_smem();
     cp_async_wait_all();
@@ -145,9 +154,6 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
     pin(fo);
     unsigned rowseq = 0;            // rectified rows started so far (same in every thread)
 
-    // copy lanes: one (source row, frame) pair each
-    const int cg = lane % G, cr = lane / G;
-    constexpr int ROWS_PER_ISSUE = 32 / G;
 
     for (int it = 0;; ++it) {
         const Tile &tile = ring[it % 3];
@@ -200,93 +206,48 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
 #pragma unroll
         for (int g = 0; g < G; ++g) nzb[g] = 0;
 
-        // ---- the copy pipeline of the item (TMA bulk copies completing on mbarriers):
-        //   the new source rows that rectified row y needs, one copy per row and frame into
-        //   ring slot (row + bias) % WIN_ROWS, and the table row of row y, npx records in one
-        //   copy, slot y % NSTAGE.
+        // ---- the copy pipeline of the item (TMA copies completing on mbarriers): the new
+        //   source rows that rectified row y needs, one tensor copy per row (all G frames)
+        //   into the row's ring slot, and the staged table row of row y, one bulk copy into
+        //   stage y % NSTAGE.
         constexpr int VN = Vec16<T>::N;
-        // window columns that exist on the detector: [cv0, cv1), empty when the whole tile maps
-        // outside (a strongly stretched map): then every window column stays zero
-        const int cv0 = min(max(tile.c0, 0), tile.c0 + tile.wcols);
-        const int cv1 = max(min(tile.c0 + tile.wcols, W), cv0);
-        const unsigned qsm_a = smem_addr_of(qsm), msm_a = smem_addr_of(msm);
+        const unsigned stg_a = smem_addr_of(stg), win_a = smem_addr_of(win);
         // what the copy warp needs to know about an item (this one, or the next one whose
         // first rows it requests as soon as this item's last row is through)
         struct CopyCtx {
-            unsigned row_bytes, win_a, ncopy;
-            const T *fin, *qrow;
-            const uint32_t *mrow;
-            int nlive, wcols;
-            bool oob_rows;
+            const char *trow;      // the tile's staged table rows (tile-major, STAGE_BYTES each)
+            int c0, g0;            // first window column on the detector, first frame
         };
         auto make_ctx = [&](const Tile &t, int wi) {
             CopyCtx c;
-            const int g0i = (wi % p.ngroups) * G;
-            const int v0 = min(max(t.c0, 0), t.c0 + t.wcols), v1 = max(min(t.c0 + t.wcols, W), v0);
-            c.nlive = min(G, p.nframes - g0i);
-            c.wcols = t.wcols;
-            c.row_bytes = (unsigned)((v1 - v0) * sizeof(T));
-            c.win_a = smem_addr_of(win) + (unsigned)((v0 - t.c0) * sizeof(T)) +
-                      (unsigned)(cg * WSZ * sizeof(T));
-            c.fin = p.in + ((size_t)g0i + cg) * W * p.naxis2 + v0;
-            // staged table columns: [jal, jal + ncopy), rounded out to multiples of 4 pixels
-            const int jal = t.jlo & ~3;
-            c.ncopy = (unsigned)((t.jlo + t.npx - jal + 3) & ~3);
-            c.qrow = p.quad + ((size_t)t.slit * NROWS * W + jal) * 4;
-            c.mrow = p.meta + (size_t)t.slit * NROWS * W + jal;
-            c.oob_rows = span_lo(t.span[0]) < 0 || span_hi(t.span[NROWS - 1]) >= p.naxis2;
+            c.trow = p.tilepack + (size_t)(wi / p.ngroups) * NROWS * STAGE_BYTES;
+            c.c0 = t.c0;
+            c.g0 = (wi % p.ngroups) * G;
             return c;
         };
 
-        // columns of the window that fall outside the detector stay zero for the item
-        // (first and last tile of a slitlet: a handful of columns)
-        if (cv0 > tile.c0 || cv1 < tile.c0 + tile.wcols) {
-            const int nl = cv0 - tile.c0, nr = tile.c0 + tile.wcols - cv1, nbad = nl + nr;
-            for (int e = tid; e < G * WIN_ROWS * nbad; e += NTHREADS) {
-                const int cb = e % nbad, rg = e / nbad;
-                const int c = cb < nl ? cb : cv1 - tile.c0 + (cb - nl);
-                win[rg * WIN_PITCH + c] = T(0);               // rg = frame * WIN_ROWS + ring row
-            }
-            fence_proxy_async_smem();      // a later item's copies may cover these columns
-            __syncthreads();
-        }
-
         // Row number n (counted across items) completes on mbarrier n % NSTAGE with two
-        // arrivals: the source rows it adds and its table row.  Whichever warp issues them
-        // does so with all its lanes: lane 0 posts the byte counts, every lane copies one
-        // (row, frame); rows outside the detector (rare) are zero-filled instead.
+        // arrivals: the source rows it adds and its table row.  Lane 0 posts the byte count,
+        // lane l requests source row r_from + 1 + l: the box [c0, c0 + WIN_PITCH) x {r} x
+        // [g0, g0 + G) of the (column, row, frame) tensor -- columns, rows and frames that do
+        // not exist arrive as zeros, so detector edges and a short last group need no code.
         auto copy_window_rows = [&](const CopyCtx &c, unsigned seq, int r_from, int r_to) {
             const unsigned bar = bars + 8 * (seq % NSTAGE);
-            const int lo = max(r_from + 1, 0), hi = min(r_to, p.naxis2 - 1);
-            if (c.oob_rows) {
-                for (int r = r_from + 1; r <= r_to; ++r)
-                    if (r < 0 || r >= p.naxis2) {
-                        const unsigned slot = (unsigned)(r + RING_BIAS) % WIN_ROWS;
-                        for (int e = lane; e < c.nlive * c.wcols; e += 32)
-                            win[(e / c.wcols) * WSZ + slot * WIN_PITCH + e % c.wcols] = T(0);
-                    }
-                fence_proxy_async_smem();      // the slot is reused by bulk copies later on
-                __syncwarp();
-            }
-            if (lane == 0)
-                mbar_expect_tx(bar, (unsigned)(max(hi - lo + 1, 0) * c.nlive) * c.row_bytes);
+            const int n = r_to - r_from;
+            if (lane == 0) mbar_expect_tx(bar, (unsigned)max(n, 0) * ROW_BYTES);
             __syncwarp();
-            if (cg < c.nlive && c.row_bytes != 0)
-                for (int r = lo + cr; r <= hi; r += ROWS_PER_ISSUE)
-                    bulk_g2s(c.win_a + (unsigned)(((unsigned)(r + RING_BIAS) % WIN_ROWS) *
-                                                  (WIN_PITCH * sizeof(T))),
-                             c.fin + (size_t)r * W, c.row_bytes, bar);
+            if (lane < n) {
+                const int r = r_from + 1 + lane;
+                tensor_g2s_3d(win_a + ring_slot(r) * ROW_BYTES, &tmap, c.c0, r, c.g0, bar);
+            }
         };
-        // table row y: the block weights and the meta words of the tile's pixels, two bulk copies
+        // table row y of the tile: block weights and meta words, one bulk copy
         auto copy_table_row = [&](const CopyCtx &c, unsigned seq, int y) {
             if (lane == 0) {
                 const unsigned bar = bars + 8 * (seq % NSTAGE);
-                const unsigned qb = c.ncopy * (unsigned)(4 * sizeof(T)), mb = c.ncopy * 4u;
-                mbar_expect_tx(bar, qb + mb);
-                bulk_g2s(qsm_a + (y % NSTAGE) * (unsigned)(PXCAP * 4 * sizeof(T)),
-                         c.qrow + (size_t)y * W * 4, qb, bar);
-                bulk_g2s(msm_a + (y % NSTAGE) * (unsigned)(PXCAP * 4), c.mrow + (size_t)y * W, mb,
-                         bar);
+                mbar_expect_tx(bar, STAGE_BYTES);
+                bulk_g2s(stg_a + (y % NSTAGE) * STAGE_BYTES, c.trow + (size_t)y * STAGE_BYTES,
+                         STAGE_BYTES, bar);
             }
         };
         // the first NSTAGE rows of an item and their table rows
@@ -308,6 +269,8 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
         // this thread's slot in the staged table rows (lanes without a pixel read a
         // neighbour's entry; their result is discarded)
         const int ppc = min(max(pp, 0), npx - 1) + (tile.jlo & 3);      // column of the staged row
+        const T *qsm = reinterpret_cast<const T *>(stg) + ppc * 4;      // this pixel, stage 0
+        const uint32_t *msm = reinterpret_cast<const uint32_t *>(stg + PXCAP * 4 * sizeof(T)) + ppc;
         const T *grec = p.w + ((size_t)s * NROWS * W + tile.jlo + min(max(pp, 0), npx - 1)) * RS;
         pin(grec);
         T *orow = p.out + (size_t)g0 * frame_out + (size_t)s * p.rps * p.nout;
@@ -394,7 +357,9 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
             constexpr int KK = K * K;
             // this pixel's meta word: source column of its 2 x 2 block, ring slots of the
             // block's two source rows, "the block is the whole footprint"
-            const uint32_t meta = msm[(y % NSTAGE) * PXCAP + ppc];
+            const unsigned soff = (unsigned)(y % NSTAGE) * STAGE_BYTES;     // this row's stage
+            const uint32_t meta =
+                *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(msm) + soff);
             const int fc = (int)(int16_t)(meta & 0xffffu) + wb;
 
             // ---- A (row y): rectified flux of this pixel column, G frames
@@ -404,7 +369,7 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
             if (all_compact) {
                 // every footprint of the warp fits 2 x 2 source pixels: four taps (K = 1: one)
                 T wt[4];
-                const V *q = reinterpret_cast<const V *>(qsm + ((y % NSTAGE) * PXCAP + ppc) * 4);
+                const V *q = reinterpret_cast<const V *>(reinterpret_cast<const char *>(qsm) + soff);
 #pragma unroll
                 for (int i = 0; i < 4 / VN; ++i) *reinterpret_cast<V *>(wt + i * VN) = q[i];
 #if EMIRWV_DIAG & 1
@@ -413,9 +378,9 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
                 constexpr int KB = K == 1 ? 1 : 2;
 #endif
                 const T *rowp[KB];
-                rowp[0] = win + ((meta >> 16) & 0xfu) * WIN_PITCH + fc;
-                if constexpr (KB == 2) rowp[1] = win + ((meta >> 20) & 0xfu) * WIN_PITCH + fc;
-                gather_taps<T, KB, G, WSZ>(rowp, wt, 2, rect);
+                rowp[0] = win + ((meta >> 16) & 0xfu) * WROW + fc;
+                if constexpr (KB == 2) rowp[1] = win + ((meta >> 20) & 0xfu) * WROW + fc;
+                gather_taps<T, KB, G, WIN_PITCH>(rowp, wt, 2, rect);
             } else if constexpr (K >= 3) {
                 // (rare: 12 % of the warp rows) the full K x K records, from global memory (L2)
                 const V *rec = reinterpret_cast<const V *>(grec + (size_t)y * W * RS);
@@ -436,9 +401,9 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
                 for (int a = 0; a < K; ++a) {
                     const uint32_t slot = a < 3 ? (slots >> (8 * a)) & 0xffu
                                                 : *reinterpret_cast<const uint32_t *>(wt + KK + 2);
-                    rowp[a] = win + slot * WIN_PITCH + fcf;
+                    rowp[a] = win + slot * WROW + fcf;
                 }
-                gather_taps<T, K, G, WSZ>(rowp, wt, K, rect);
+                gather_taps<T, K, G, WIN_PITCH>(rowp, wt, K, rect);
             }
 
             row_done();       // (phase C works on registers and the warp's own knot rows)

@@ -18,10 +18,13 @@ VARIANTS = {
     "slim": SLIM,                                        # the product configuration, slim
     # round-1 occupancy: two CTAs per SM (96 registers), 12-row window of 288 columns
     "c2": SLIM + ("EMIRWV_MINBLOCKS=2", "EMIRWV_WIN_ROWS=12", "EMIRWV_WIN_PITCH=288"),
+    "pf2": SLIM + ("EMIRWV_PREFETCH=2",), "pf4": SLIM + ("EMIRWV_PREFETCH=4",),
+    "pf8": SLIM + ("EMIRWV_PREFETCH=8",),
     "c3s3": SLIM + ("EMIRWV_NSTAGE=3", "EMIRWV_WIN_ROWS=10"),
     # float64 kernels compiled for two CTAs per SM (full build: every instantiation)
     "f64c2": ("EMIRWV_MINBLOCKS_F64=2",),
     # timing diagnostics (WRONG results): one gather tap instead of four / no knot traffic
+    "diag4": SLIM + ("EMIRWV_DIAG=4",),     # every source-row copy as two requests (same bytes)
     "diag1": SLIM + ("EMIRWV_DIAG=1",), "diag2": SLIM + ("EMIRWV_DIAG=2",),
 }
 
