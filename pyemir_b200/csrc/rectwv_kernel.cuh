@@ -467,13 +467,14 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
         if (producer) {
             const CopyCtx ctx = make_ctx(tile, w);
             // The runs without wavelength coverage (and the missing slitlets) are exact zeros:
-            // the item's share of them -- runs (dead tile x output row) x frames, one per lane
-            // and round -- is written by TMA bulk stores from the zeros in shared memory, a
-            // round every few rows so that the writes trickle along with the item.  The run of
-            // the next round is fetched one round ahead: the stores never wait for a load.
-            // (frem: runs of the item still to be written; fcount: rows until the next round)
+            // the item's share of them -- runs (dead tile x output row) x frames -- is written
+            // by TMA bulk stores from the zeros in shared memory, a few per rectified row so
+            // that the writes trickle along with the item and the copy warp stays responsive.
+            // The lanes fetch 32 runs at a time, a batch ahead of their use: the stores never
+            // wait for a load.  (frem: runs left, fpos: lanes of the batch already used,
+            // fper: runs per row)
             long long fu = 0;
-            int frem = 0, fevery = NROWS + 1, fcount = NROWS + 1;
+            int frem = 0, fpos = 0, fper = 0;
             int2 frun = make_int2(0, 0);
             T *fdst = p.out;
             auto fill_fetch = [&]() {
@@ -483,25 +484,29 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
                     fdst = p.out + (size_t)(u / p.nfillruns) * frame_out + (unsigned)frun.x;
                 }
             };
-            auto fill_round = [&]() {
-                if (lane < frem) {
+            auto fill_some = [&](int want) {
+                const int take = min(want, min(32 - fpos, frem));
+                if (lane >= fpos && lane < fpos + take) {
                     char *dst = reinterpret_cast<char *>(fdst);
                     const unsigned zsrc = smem_addr_of(zbuf);
                     for (unsigned off = 0; off < (unsigned)frun.y; off += ZFILL_BYTES)
                         bulk_s2g(dst + off, zsrc, min((unsigned)ZFILL_BYTES, (unsigned)frun.y - off));
                     bulk_commit();
                 }
-                fu += 32;
-                frem -= 32;
-                fill_fetch();
+                fpos += take;
+                frem -= take;
+                if (fpos == 32 && frem > 0) {
+                    fu += 32;
+                    fpos = 0;
+                    fill_fetch();
+                }
             };
 #if !EMIRWV_NOFILL
             if (p.fillruns != nullptr) {
                 const long long total = (long long)p.nfillruns * p.nframes;
                 fu = (long long)w * total / nwork;
                 frem = (int)((long long)(w + 1) * total / nwork - fu);
-                fevery = max(1, NROWS / min(NROWS, (frem + 31) / 32 + 1));
-                fcount = fevery;
+                fper = (frem + NROWS - 3) / (NROWS - 2);
                 fill_fetch();
             }
 #endif
@@ -515,14 +520,11 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
                 }
                 ++rowseq;
 #if !EMIRWV_NOFILL
-                if (--fcount == 0) {
-                    fcount = fevery;
-                    if (frem > 0) fill_round();
-                }
+                if (frem > 0) fill_some(fper);
 #endif
             }
 #if !EMIRWV_NOFILL
-            while (frem > 0) fill_round();
+            while (frem > 0) fill_some(32);
 #endif
             // Every compute warp has read what the last row needs: the window and the table
             // slots are free, so the first rows of the CTA's next item are requested now
