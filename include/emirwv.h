@@ -256,12 +256,26 @@ int emirwv_abba_finish(const double *d_sum_a, const double *d_sum_b, int count_a
  *   d_bias, d_dark, d_flat [npix] of cal_dtype (EMIRWV_F32 / EMIRWV_F64); NULL skips the stage
  * Stages in the order of the flow (bias, dark, flat), each rounded to float32, with numpy's
  * type promotion (a float64 operand makes the stage float64).  Asynchronous on the stream.
- * The bad-pixel interpolation of the flow (numina BadPixelCorrector) is not covered.
+ * Runs on the device that owns d_in.
  */
 #define EMIRWV_U16 2
 int emirwv_prereduce(const void *d_in, int in_dtype, float *d_out, int nframes, int64_t npix,
                      const void *d_bias, const void *d_dark, const void *d_flat, int cal_dtype,
                      void *cuda_stream);
+
+/*
+ * The same with the first stage of the flow in front: the bad-pixel correction (numina
+ * BadPixelCorrector built by get_corrector_p, core/correctors.py:23-42; restated as
+ * numina.array.bpm.process_bpm_median with its 5 x 5 window).
+ *   d_bpm [naxis2][naxis1] uint8, non-zero = bad pixel, NULL skips the stage: a bad pixel becomes
+ *   the median of the good pixels of the raw frame within +-2 rows and columns (clipped at the
+ *   detector edges; 0 when there is none), then goes through bias, dark and flat like any other.
+ * One pass: a frame is read once (the windows of the bad pixels come from L2).  d_out must not
+ * alias d_in when d_bpm is given.
+ */
+int emirwv_prereduce_ex(const void *d_in, int in_dtype, float *d_out, int nframes, int naxis2,
+                        int naxis1, const uint8_t *d_bpm, const void *d_bias, const void *d_dark,
+                        const void *d_flat, int cal_dtype, void *cuda_stream);
 
 /*
  * ABBA combination with method "median" (recipes/spec/abba.py:132-137,579-601; numina's
@@ -281,6 +295,35 @@ int emirwv_stack_median(const void *d_frames, int nframes, const int32_t *h_inde
 int emirwv_abba_median(const void *d_frames, int nframes, const int32_t *h_index_a, int na,
                        const int32_t *h_index_b, int nb, int64_t npix, int dtype, float *d_out,
                        void *cuda_stream);
+
+/*
+ * ABBA combination with method "sigmaclip" (recipes/spec/abba.py:132-137,579-601; numina's
+ * combine.sigmaclip restated): per pixel, repeat { mean and unbiased standard deviation of the
+ * samples still in; drop the samples outside [mean - low*std, mean + high*std] } until nothing
+ * is dropped; the result is the last mean (float64, sums in frame order).  Same stack layout,
+ * selection arrays and limits (1 <= nsel <= 64) as emirwv_stack_median / emirwv_abba_median.
+ */
+int emirwv_stack_sigmaclip(const void *d_frames, int nframes, const int32_t *h_index, int nsel,
+                           int64_t npix, int dtype, double low, double high, double *d_out,
+                           void *cuda_stream);
+int emirwv_abba_sigmaclip(const void *d_frames, int nframes, const int32_t *h_index_a, int na,
+                          const int32_t *h_index_b, int nb, int64_t npix, int dtype, double low,
+                          double high, float *d_out, void *cuda_stream);
+
+/*
+ * The per-frame vertical offsets of the ABBA recipe (recipes/spec/abba.py:545-558:
+ * `shift_image2d(data, yoffset=-offset).astype("float32")` for every frame whose offset is not
+ * zero; numina's shift_image2d = rectify2d with a translation map, area-overlap resampling):
+ * all frames of a device-resident stack in one launch.
+ *   d_in  [nframes][naxis2][naxis1] in_dtype;  d_out the same shape in out_dtype (not d_in)
+ *   h_yoffset [nframes] HOST array: the yoffset argument of shift_image2d for every frame (the
+ *   pixel at row y of the result covers rows y - yoffset -+ 0.5 of the input); a frame whose
+ *   offset is 0 is copied (cast).
+ * float64 arithmetic with the weights of the general clipping, bit for bit.  Replaces one
+ * emirwv_rectify2d_host call (host image in, two allocations, host image out) per frame.
+ */
+int emirwv_shift_rows(const void *d_in, int in_dtype, void *d_out, int out_dtype, int nframes,
+                      int naxis2, int naxis1, const double *h_yoffset, void *cuda_stream);
 
 /*
  * Parity hooks (tests): the plan's geometry for one slitlet, copied to the host.

@@ -346,3 +346,117 @@ def prereduce(frames, bias=None, dark=None, flat=None):
     if flat is not None:
         x = flatfield_correct(x, flat, "float32")
     return x.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------
+# ABBA combination: method "sigmaclip", per-frame vertical offsets, the whole product
+# (recipes/spec/abba.py:132-137,545-610)                                [numina, recalled]
+# ---------------------------------------------------------------------------
+def sigmaclip_stack(stack, low=3.0, high=3.0):
+    """Oracle of numina ``combine.sigmaclip`` (the third ``method`` of ``abba.py:132-137``).
+
+    [numina, recalled — PARITY UNPINNED] numina's C++ ``sigmaclip`` method: per pixel, repeat
+    { mean and unbiased (n-1) standard deviation of the samples still in; drop the samples
+    outside [mean - low*std, mean + high*std] } until a pass drops nothing; the value is the
+    mean of the last pass (``combine_imgs`` keeps ``out[0]``).  Stated here with the sums in
+    frame order over the samples still in; a pass that would drop every sample ends the loop.
+    Returns the float64 image.
+    """
+    v = np.asarray(stack, dtype=np.float64)
+    v = v.reshape(v.shape[0], -1)
+    n, npix = v.shape
+    keep = np.ones((n, npix), dtype=bool)
+    result = np.zeros(npix)
+    active = np.ones(npix, dtype=bool)
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        while active.any():
+            cnt = keep.sum(axis=0)
+            s = np.zeros(npix)
+            for f in range(n):
+                s = np.where(keep[f], s + v[f], s)
+            mean = s / cnt
+            ss = np.zeros(npix)
+            for f in range(n):
+                d = v[f] - mean
+                ss = np.where(keep[f], ss + d * d, ss)
+            var = np.where(cnt > 1, ss / np.maximum(cnt - 1, 1), 0.0)
+            std = np.sqrt(var)
+            lo = mean - std * low
+            hi = mean + std * high
+            new = keep & (v >= lo) & (v <= hi)
+            ncnt = new.sum(axis=0)
+            result[active] = mean[active]
+            changed = active & (ncnt != cnt) & (ncnt > 0)
+            keep[:, changed] = new[:, changed]
+            active = changed
+    return result.reshape(np.asarray(stack).shape[1:])
+
+
+def combine_abba(frames, full_set, offsets=None, method="mean", low=3.0, high=3.0):
+    """Oracle of ``abba.py:545-610``: per-frame vertical offset, combination of the A and of
+    the B images with ``method``, float32(A) - float32(B).
+
+    ``shifted = shift_image2d(data, yoffset=-offset).astype("float32")`` for every frame whose
+    offset is not zero (``abba.py:554-558``), then numina's ``combine`` method [recalled] in
+    float64, the casts and the difference of ``abba.py:604-606``.
+    """
+    frames = np.asarray(frames)
+    if offsets is None:
+        offsets = [0.0] * len(frames)
+    shifted = []
+    for data, offset in zip(frames, offsets):
+        if offset != 0:
+            data = nr.shift_image2d(data, yoffset=-offset).astype("float32")
+        shifted.append(np.asarray(data))
+    is_a = [c == "A" for c in full_set]
+    is_b = [c == "B" for c in full_set]
+    if not all(a or b for a, b in zip(is_a, is_b)):
+        raise ValueError("Unexpected char value")
+
+    def combine(sel):
+        stack = np.stack([s for s, use in zip(shifted, sel) if use]).astype(np.float64)
+        if method == "mean":
+            return stack.sum(axis=0) / float(len(stack))
+        if method == "median":
+            return np.median(stack, axis=0)
+        if method == "sigmaclip":
+            return sigmaclip_stack(stack, low, high)
+        raise ValueError(f"Unexpected method: {method}")
+
+    return combine(is_a).astype("float32") - combine(is_b).astype("float32")
+
+
+# ---------------------------------------------------------------------------
+# bad-pixel stage of the flow (core/correctors.py:23-42)                 [numina, recalled]
+# ---------------------------------------------------------------------------
+def process_bpm_median(arr, mask, hwin=2, wwin=2, fill=0.0):
+    """Oracle of numina ``BadPixelCorrector`` -> ``array.bpm.process_bpm_median``.
+
+    [numina, recalled — PARITY UNPINNED] every pixel with ``mask != 0`` becomes the median of
+    the unmasked pixels of the input within +-hwin rows and +-wwin columns (window clipped at
+    the edges), ``fill`` when there is none; the other pixels are kept.  float64 result.
+    """
+    arr = np.asarray(arr)
+    mask = np.asarray(mask)
+    out = arr.astype(np.float64).copy()
+    naxis2, naxis1 = arr.shape
+    for r, c in zip(*np.nonzero(mask)):
+        r0, r1 = max(r - hwin, 0), min(r + hwin, naxis2 - 1)
+        c0, c1 = max(c - wwin, 0), min(c + wwin, naxis1 - 1)
+        win = arr[r0:r1 + 1, c0:c1 + 1]
+        good = win[mask[r0:r1 + 1, c0:c1 + 1] == 0].astype(np.float64)
+        with np.errstate(invalid="ignore"):
+            out[r, c] = np.median(good) if good.size else fill
+    return out
+
+
+def prereduce_bpm(frames, bpm=None, bias=None, dark=None, flat=None):
+    """``flow(newimg)`` with the bad-pixel stage in front (``core/recipe.py:26-41``): the
+    corrected frame keeps float64 for float64 input and is float32 otherwise (the window
+    medians of uint16 / float32 data are exact in float32), then ``prereduce``."""
+    frames = np.asarray(frames)
+    if bpm is None:
+        return prereduce(frames, bias, dark, flat)
+    fixed = np.stack([process_bpm_median(f, bpm) for f in frames])
+    fixed = fixed if frames.dtype == np.float64 else fixed.astype(np.float32)
+    return prereduce(fixed, bias, dark, flat)

@@ -32,7 +32,8 @@ EXPORTED_SYMBOLS = (
     "emirwv_rectify2d_host", "emirwv_debug_geometry", "emirwv_debug_borders",
     "emirwv_median_slitlets", "emirwv_median_slitlets_host",
     "emirwv_abba_partial", "emirwv_abba_finish", "emirwv_stack_median", "emirwv_abba_median",
-    "emirwv_prereduce",
+    "emirwv_prereduce", "emirwv_prereduce_ex", "emirwv_stack_sigmaclip",
+    "emirwv_abba_sigmaclip", "emirwv_shift_rows",
 )
 
 
@@ -179,6 +180,16 @@ def load():
     lib.emirwv_abba_median.argtypes = [vp, i32, vp, i32, vp, i32, ctypes.c_int64, i32, vp, vp]
     lib.emirwv_prereduce.restype = i32
     lib.emirwv_prereduce.argtypes = [vp, i32, vp, i32, ctypes.c_int64, vp, vp, vp, i32, vp]
+    lib.emirwv_prereduce_ex.restype = i32
+    lib.emirwv_prereduce_ex.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
+    f64 = ctypes.c_double
+    lib.emirwv_stack_sigmaclip.restype = i32
+    lib.emirwv_stack_sigmaclip.argtypes = [vp, i32, vp, i32, ctypes.c_int64, i32, f64, f64, vp, vp]
+    lib.emirwv_abba_sigmaclip.restype = i32
+    lib.emirwv_abba_sigmaclip.argtypes = [vp, i32, vp, i32, vp, i32, ctypes.c_int64, i32, f64, f64,
+                                          vp, vp]
+    lib.emirwv_shift_rows.restype = i32
+    lib.emirwv_shift_rows.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp]
     lib.emirwv_debug_geometry.restype = i32
     lib.emirwv_debug_geometry.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.emirwv_debug_borders.restype = i32

@@ -21,10 +21,17 @@ hot path in the ABBA recipe:
   slabs (rank r receives rows ``slab_range(H, r, world)`` of every frame: one grouped
   send/recv, 1/world of each frame per peer), each rank takes the per-pixel medians of the A
   and of the B images of its slab and their float32 difference in one pass
-  (``emirwv_abba_median``: samples in registers, bitonic network), and the slabs are gathered on the destination rank.
+  (``emirwv_abba_median``: samples in registers, pruned odd-even merge network), and the slabs
+  are gathered on the destination rank.
 
-The sigma-clip method is not covered.  The mean and the median of numina's ``combine`` and
-``shift_image2d`` are restated (parity unpinned).
+* ``combine_abba_sigmaclip``: the same with method "sigmaclip" (``emirwv_abba_sigmaclip``).
+
+* ``shift_frames``: the vertical offsets of all frames of a device-resident stack in one launch
+  (``emirwv_shift_rows``), and ``combine_abba``: offsets + combination + A - B, i.e.
+  ``abba.py:545-610`` for a stack that is already on the GPU.
+
+The mean, the median and the sigma clipping of numina's ``combine`` and ``shift_image2d`` are
+restated (parity unpinned).
 """
 
 import ctypes
@@ -253,6 +260,114 @@ def abba_median_difference(frames, index_a, index_b):
         _cabi.F32 if frames.dtype == torch.float32 else _cabi.F64, vp(out.data_ptr()),
         vp(stream) if stream else None))
     return out
+
+
+def abba_sigmaclip_difference(frames, index_a, index_b, low=3.0, high=3.0):
+    """float32(clipped mean of frames[index_a]) - float32(clipped mean of frames[index_b])
+    (``emirwv_abba_sigmaclip``; numina ``combine.sigmaclip`` restated, at most 64 images per
+    nodding position)."""
+    import numpy as np
+    import torch
+    if frames.dim() != 3 or not frames.is_cuda or not frames.is_contiguous() or \
+            frames.dtype not in (torch.float32, torch.float64):
+        raise ValueError("frames must be a contiguous (n, H, W) float32/float64 CUDA tensor")
+    n, height, width = frames.shape
+    ia = np.ascontiguousarray(index_a, dtype=np.int32)
+    ib = np.ascontiguousarray(index_b, dtype=np.int32)
+    out = torch.empty((height, width), dtype=torch.float32, device=frames.device)
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    vp = ctypes.c_void_p
+    _cabi.check(_cabi.load().emirwv_abba_sigmaclip(
+        vp(frames.data_ptr()), n, ia.ctypes.data_as(vp), int(ia.size), ib.ctypes.data_as(vp),
+        int(ib.size), height * width,
+        _cabi.F32 if frames.dtype == torch.float32 else _cabi.F64, float(low), float(high),
+        vp(out.data_ptr()), vp(stream) if stream else None))
+    return out
+
+
+def stack_sigmaclip(frames, index, low=3.0, high=3.0):
+    """Per-pixel sigma-clipped mean over ``frames[index]``: a float64 CUDA tensor."""
+    import numpy as np
+    import torch
+    if frames.dim() != 3 or not frames.is_cuda or not frames.is_contiguous() or \
+            frames.dtype not in (torch.float32, torch.float64):
+        raise ValueError("frames must be a contiguous (n, H, W) float32/float64 CUDA tensor")
+    n, height, width = frames.shape
+    idx = np.ascontiguousarray(index, dtype=np.int32)
+    out = torch.empty((height, width), dtype=torch.float64, device=frames.device)
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    vp = ctypes.c_void_p
+    _cabi.check(_cabi.load().emirwv_stack_sigmaclip(
+        vp(frames.data_ptr()), n, idx.ctypes.data_as(vp), int(idx.size), height * width,
+        _cabi.F32 if frames.dtype == torch.float32 else _cabi.F64, float(low), float(high),
+        vp(out.data_ptr()), vp(stream) if stream else None))
+    return out
+
+
+def shift_frames(frames, yoffsets, out=None, out_dtype=None):
+    """``shift_image2d(frame, yoffset=yoffsets[i])`` for every frame of a CUDA stack, one launch.
+
+    frames: (n, H, W) contiguous float32/float64 CUDA tensor; yoffsets: n floats (the recipe
+    passes ``-offset``, ``abba.py:556``); frames whose offset is 0 are copied.  The result is
+    float32 by default, like the recipe's ``.astype("float32")``.
+    """
+    import numpy as np
+    import torch
+    if frames.dim() != 3 or not frames.is_cuda or not frames.is_contiguous() or \
+            frames.dtype not in (torch.float32, torch.float64):
+        raise ValueError("frames must be a contiguous (n, H, W) float32/float64 CUDA tensor")
+    n, height, width = frames.shape
+    off = np.ascontiguousarray(yoffsets, dtype=np.float64)
+    if off.shape != (n,):
+        raise ValueError("one offset per frame is needed")
+    out_dtype = out_dtype or torch.float32
+    if out is None:
+        out = torch.empty((n, height, width), dtype=out_dtype, device=frames.device)
+    code = {torch.float32: _cabi.F32, torch.float64: _cabi.F64}
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    vp = ctypes.c_void_p
+    _cabi.check(_cabi.load().emirwv_shift_rows(
+        vp(frames.data_ptr()), code[frames.dtype], vp(out.data_ptr()), code[out.dtype], n,
+        height, width, off.ctypes.data_as(vp), vp(stream) if stream else None))
+    return out
+
+
+def combine_abba(frames, full_set, offsets=None, method="mean", method_kwargs=None):
+    """``abba.py:545-610`` for a device-resident stack of rectified frames: the per-frame
+    vertical offsets (``shift_image2d(data, yoffset=-offset).astype("float32")`` when the offset
+    is not zero), ``combine_imgs`` of the A and of the B images with ``method`` ("mean",
+    "median" or "sigmaclip", ``abba.py:132-137``), float32(A) - float32(B).
+
+    frames: (n, H, W) CUDA tensor; full_set: "ABBA..." (``build_full_set``); offsets: n floats
+    or None.  Returns the (H, W) float32 CUDA tensor.  Median and sigma clipping take at most
+    64 images per nodding position.
+    """
+    labels = labels_of(full_set)
+    if len(labels) != frames.shape[0]:
+        raise ValueError("one label per frame is needed")
+    kwargs = dict(method_kwargs or {})
+    if offsets is not None and any(float(o) != 0.0 for o in offsets):
+        frames = shift_frames(frames, [-float(o) for o in offsets])
+    index_a = [i for i, lab in enumerate(labels) if lab > 0]
+    index_b = [i for i, lab in enumerate(labels) if lab < 0]
+    if not index_a or not index_b:
+        raise ValueError("both A and B images are needed")
+    if method == "mean":
+        return finish(partial_sums(frames, labels), len(index_a), len(index_b))
+    if method == "median":
+        return abba_median_difference(frames, index_a, index_b)
+    if method == "sigmaclip":
+        return abba_sigmaclip_difference(frames, index_a, index_b, kwargs.get("low", 3.0),
+                                         kwargs.get("high", 3.0))
+    raise ValueError(f"Unexpected method: {method}")
+
+
+def combine_abba_sigmaclip(frames_local, labels, counts, dst=0, low=3.0, high=3.0):
+    """sigmaclip(A images) - sigmaclip(B images) of a sequence sharded over the ranks: the
+    row-slab exchange of :func:`combine_abba_median` with ``emirwv_abba_sigmaclip`` per slab."""
+    def difference(stack, index_a, index_b):
+        return abba_sigmaclip_difference(stack, index_a, index_b, low, high)
+    return combine_abba_median(frames_local, labels, counts, dst, median_difference=difference)
 
 
 def combine_abba_median(frames_local, labels, counts, dst=0,

@@ -343,6 +343,28 @@ namespace {
 
 #include "plan_build.inl"
 
+// The entry points either side of the path take no plan: they run on the device that owns the
+// buffer they are given (not on whatever device happens to be current in the calling thread).
+int device_of(const void *ptr) {
+    cudaPointerAttributes attr;
+    if (ptr != nullptr && cudaPointerGetAttributes(&attr, ptr) == cudaSuccess &&
+        (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged))
+        return attr.device;
+    cudaGetLastError();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
+int sm_count(int dev) {
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        cudaGetLastError();
+        sms = 148;
+    }
+    return sms;
+}
+
 }  // namespace
 
 // ====================================================================== C ABI
@@ -634,6 +656,7 @@ int emirwv_median_slitlets(const void *d_in, void *d_out, int nframes, int nslit
     if (nframes < 0 || nslitlets < 1 || nslitlets > 65535 || naxis1 < 1 || nframes > 65535)
         return fail(EMIRWV_E_VALUE, "size out of range");
     if (nframes == 0) return EMIRWV_OK;
+    DeviceGuard guard(device_of(d_in));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const dim3 grid((naxis1 + 127) / 128, nslitlets, nframes);
     if (dtype == EMIRWV_F32)
@@ -684,9 +707,9 @@ int emirwv_abba_partial(const void *d_frames, const int8_t *d_labels, int nframe
         return fail(EMIRWV_E_VALUE, "null argument");
     if (dtype != EMIRWV_F32 && dtype != EMIRWV_F64) return fail(EMIRWV_E_VALUE, "unknown dtype");
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    int dev = 0, sms = 148;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int dev = device_of(d_sum_a);
+    DeviceGuard guard(dev);
+    const int sms = sm_count(dev);
     const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)sms * 32);
     if (dtype == EMIRWV_F32)
         k_abba_partial<float><<<grid, 256, (size_t)nframes, st>>>(static_cast<const float *>(d_frames), d_labels,
@@ -703,31 +726,130 @@ int emirwv_abba_partial(const void *d_frames, const int8_t *d_labels, int nframe
 int emirwv_prereduce(const void *d_in, int in_dtype, float *d_out, int nframes, int64_t npix,
                      const void *d_bias, const void *d_dark, const void *d_flat, int cal_dtype,
                      void *cuda_stream) {
+    return emirwv_prereduce_ex(d_in, in_dtype, d_out, nframes, 1, npix > INT_MAX ? -1 : (int)npix,
+                               nullptr, d_bias, d_dark, d_flat, cal_dtype, cuda_stream);
+}
+
+int emirwv_prereduce_ex(const void *d_in, int in_dtype, float *d_out, int nframes, int naxis2,
+                        int naxis1, const uint8_t *d_bpm, const void *d_bias, const void *d_dark,
+                        const void *d_flat, int cal_dtype, void *cuda_stream) {
     if (d_in == nullptr || d_out == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
-    if (nframes < 0 || npix < 1) return fail(EMIRWV_E_VALUE, "size out of range");
+    if (nframes < 0 || naxis1 < 1 || naxis2 < 1) return fail(EMIRWV_E_VALUE, "size out of range");
     if (in_dtype != EMIRWV_F32 && in_dtype != EMIRWV_F64 && in_dtype != EMIRWV_U16)
         return fail(EMIRWV_E_VALUE, "unknown image dtype");
     if (cal_dtype != EMIRWV_F32 && cal_dtype != EMIRWV_F64)
         return fail(EMIRWV_E_VALUE, "unknown calibration dtype");
+    if (d_bpm != nullptr && static_cast<const void *>(d_in) == static_cast<const void *>(d_out))
+        return fail(EMIRWV_E_VALUE, "the bad-pixel stage reads neighbours: d_out must not alias d_in");
     if (nframes == 0) return EMIRWV_OK;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    int dev = 0, sms = 148;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = sms;            // the launcher sizes the grid (scalar or 4-pixel threads)
-    const size_t np = (size_t)npix;
+    const int dev = device_of(d_in);
+    DeviceGuard guard(dev);
+    const int grid = sm_count(dev);  // the launcher sizes the grid (scalar or 4-pixel threads)
+    const size_t np = (size_t)naxis1 * naxis2;
+    const BpmArgs bpm{d_bpm, naxis1, naxis2};
     const bool c64 = cal_dtype == EMIRWV_F64;
     if (in_dtype == EMIRWV_F32) {
-        if (c64) launch_prereduce<float, double>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
-        else launch_prereduce<float, float>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
+        if (c64) launch_prereduce<float, double>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st, bpm);
+        else launch_prereduce<float, float>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st, bpm);
     } else if (in_dtype == EMIRWV_F64) {
-        if (c64) launch_prereduce<double, double>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
-        else launch_prereduce<double, float>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
+        if (c64) launch_prereduce<double, double>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st, bpm);
+        else launch_prereduce<double, float>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st, bpm);
     } else {
-        if (c64) launch_prereduce<uint16_t, double>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
-        else launch_prereduce<uint16_t, float>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st);
+        if (c64) launch_prereduce<uint16_t, double>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st, bpm);
+        else launch_prereduce<uint16_t, float>(d_in, d_out, nframes, np, d_bias, d_dark, d_flat, grid, st, bpm);
     }
     CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+int emirwv_stack_sigmaclip(const void *d_frames, int nframes, const int32_t *h_index, int nsel,
+                           int64_t npix, int dtype, double low, double high, double *d_out,
+                           void *cuda_stream) {
+    if (d_frames == nullptr || d_out == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (npix < 1 || nframes < 1) return fail(EMIRWV_E_VALUE, "size out of range");
+    if (dtype != EMIRWV_F32 && dtype != EMIRWV_F64) return fail(EMIRWV_E_VALUE, "unknown dtype");
+    if (!(low >= 0.0) || !(high >= 0.0)) return fail(EMIRWV_E_VALUE, "low and high must be >= 0");
+    StackSel sel;
+    const int rc = fill_stack_sel(sel, h_index, nsel, nframes);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int dev = device_of(d_frames);
+    DeviceGuard guard(dev);
+    const int sms = sm_count(dev);
+    if (dtype == EMIRWV_F32)
+        launch_sigmaclip(static_cast<const float *>(d_frames), sel, nullptr, (size_t)npix, low, high, d_out, sms, st);
+    else
+        launch_sigmaclip(static_cast<const double *>(d_frames), sel, nullptr, (size_t)npix, low, high, d_out, sms, st);
+    CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+int emirwv_abba_sigmaclip(const void *d_frames, int nframes, const int32_t *h_index_a, int na,
+                          const int32_t *h_index_b, int nb, int64_t npix, int dtype, double low,
+                          double high, float *d_out, void *cuda_stream) {
+    if (d_frames == nullptr || d_out == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (npix < 1 || nframes < 1) return fail(EMIRWV_E_VALUE, "size out of range");
+    if (dtype != EMIRWV_F32 && dtype != EMIRWV_F64) return fail(EMIRWV_E_VALUE, "unknown dtype");
+    if (na < 1 || nb < 1) return fail(EMIRWV_E_VALUE, "both A and B images are needed");
+    if (!(low >= 0.0) || !(high >= 0.0)) return fail(EMIRWV_E_VALUE, "low and high must be >= 0");
+    StackSel sa, sb;
+    int rc = fill_stack_sel(sa, h_index_a, na, nframes);
+    if (rc) return rc;
+    rc = fill_stack_sel(sb, h_index_b, nb, nframes);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int dev = device_of(d_frames);
+    DeviceGuard guard(dev);
+    const int sms = sm_count(dev);
+    if (dtype == EMIRWV_F32)
+        launch_sigmaclip(static_cast<const float *>(d_frames), sa, &sb, (size_t)npix, low, high, d_out, sms, st);
+    else
+        launch_sigmaclip(static_cast<const double *>(d_frames), sa, &sb, (size_t)npix, low, high, d_out, sms, st);
+    CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+int emirwv_shift_rows(const void *d_in, int in_dtype, void *d_out, int out_dtype, int nframes,
+                      int naxis2, int naxis1, const double *h_yoffset, void *cuda_stream) {
+    if (d_in == nullptr || d_out == nullptr || h_yoffset == nullptr)
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (d_in == d_out) return fail(EMIRWV_E_VALUE, "d_out must not alias d_in");
+    if (nframes < 0 || nframes > 65535 || naxis1 < 1 || naxis2 < 1)
+        return fail(EMIRWV_E_VALUE, "size out of range");
+    if ((in_dtype != EMIRWV_F32 && in_dtype != EMIRWV_F64) ||
+        (out_dtype != EMIRWV_F32 && out_dtype != EMIRWV_F64))
+        return fail(EMIRWV_E_VALUE, "unknown dtype");
+    for (int f = 0; f < nframes; ++f)
+        if (!std::isfinite(h_yoffset[f]) || std::fabs(h_yoffset[f]) > 1.0e6)
+            return fail(EMIRWV_E_VALUE, "offset of frame %d is not a usable number", f);
+    if (nframes == 0) return EMIRWV_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    DeviceGuard guard(device_of(d_in));
+    // the offsets ride along in stream order (allocated, filled and freed on the stream)
+    double *d_off = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_off, sizeof(double) * nframes, st));
+    cudaError_t err = cudaMemcpyAsync(d_off, h_yoffset, sizeof(double) * nframes,
+                                      cudaMemcpyHostToDevice, st);
+    if (err == cudaSuccess) {
+        const dim3 grid((naxis1 + 255) / 256, (naxis2 + SHIFT_STRIP - 1) / SHIFT_STRIP, nframes);
+        if (grid.y > 65535u) {
+            cudaFreeAsync(d_off, st);
+            return fail(EMIRWV_E_VALUE, "size out of range");
+        }
+#define SHIFT(TI, TO)                                                                          \
+    k_shift_rows<TI, TO><<<grid, 256, 0, st>>>(static_cast<const TI *>(d_in),                  \
+                                               static_cast<TO *>(d_out), naxis2, naxis1, d_off)
+        if (in_dtype == EMIRWV_F32 && out_dtype == EMIRWV_F32) SHIFT(float, float);
+        else if (in_dtype == EMIRWV_F32) SHIFT(float, double);
+        else if (out_dtype == EMIRWV_F32) SHIFT(double, float);
+        else SHIFT(double, double);
+#undef SHIFT
+        err = cudaGetLastError();
+    }
+    cudaFreeAsync(d_off, st);
+    if (err != cudaSuccess)
+        return fail(EMIRWV_E_CUDA, "shift_rows failed: %s", cudaGetErrorString(err));
     return EMIRWV_OK;
 }
 
@@ -740,9 +862,9 @@ int emirwv_stack_median(const void *d_frames, int nframes, const int32_t *h_inde
     const int rc = fill_stack_sel(sel, h_index, nsel, nframes);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    int dev = 0, sms = 148;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int dev = device_of(d_frames);
+    DeviceGuard guard(dev);
+    const int sms = sm_count(dev);
     if (dtype == EMIRWV_F32)
         launch_stack_median(static_cast<const float *>(d_frames), sel, (size_t)npix, d_out, sms, st);
     else
@@ -764,9 +886,9 @@ int emirwv_abba_median(const void *d_frames, int nframes, const int32_t *h_index
     rc = fill_stack_sel(sb, h_index_b, nb, nframes);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    int dev = 0, sms = 148;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int dev = device_of(d_frames);
+    DeviceGuard guard(dev);
+    const int sms = sm_count(dev);
     if (dtype == EMIRWV_F32)
         launch_abba_median(static_cast<const float *>(d_frames), sa, sb, (size_t)npix, d_out, sms, st);
     else
@@ -782,9 +904,9 @@ int emirwv_abba_finish(const double *d_sum_a, const double *d_sum_b, int count_a
     if (count_a < 1 || count_b < 1) return fail(EMIRWV_E_VALUE, "both A and B images are needed");
     if (npix < 1) return fail(EMIRWV_E_VALUE, "size out of range");
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    int dev = 0, sms = 148;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int dev = device_of(d_sum_a);
+    DeviceGuard guard(dev);
+    const int sms = sm_count(dev);
     const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)sms * 16);
     k_abba_finish<<<grid, 256, 0, st>>>(d_sum_a, d_sum_b, (double)count_a, (double)count_b,
                                         (size_t)npix, d_out);

@@ -46,6 +46,25 @@ EMIRWV_HD float prereduce_px(TIn raw, bool hb, bool hd, bool hf, A b, A d, A f) 
     }
 }
 
+// the same stages from a float64 starting value (the window median of the bad-pixel stage:
+// exact in float32 for uint16 and float32 frames, kept in float64 for float64 frames)
+template <typename TIn, typename A>
+EMIRWV_HD float prereduce_from(double x0, bool hb, bool hd, bool hf, A b, A d, A f) {
+    if constexpr (sizeof(TIn) == 8) {
+        double x = x0;
+        if (hb) x = (double)(float)(x - (double)b);
+        if (hd) x = (double)(float)(x - (double)d);
+        if (hf) x = (double)(float)(x / (double)f);
+        return (float)x;
+    } else {
+        float x = (float)x0;
+        if (hb) x = (float)((A)x - b);
+        if (hd) x = (float)((A)x - d);
+        if (hf) x = (float)((A)x / f);
+        return x;
+    }
+}
+
 #include "stack_median_nets.inc"
 
 // padding of a stack of n samples held in N registers: floor((N-n)/2) times -inf right after
@@ -88,6 +107,137 @@ EMIRWV_HD double median_of_registers(T (&v)[N], int n) {
     const T a = v[N / 2 - 1], b = (n & 1) ? a : v[N / 2];
     const double med = mul_rn(add_rn((double)a, (double)b), 0.5);
     return has_nan ? quiet_nan() : med;
+}
+
+}  // namespace emirwv
+
+// ------------------------------------------------------------------------------------------
+// The pieces behind the ABBA combination beyond mean and median (recipes/spec/abba.py:545-610)
+// and the bad-pixel stage of the pre-reduction (core/correctors.py:23-42).
+// ------------------------------------------------------------------------------------------
+namespace emirwv {
+
+EMIRWV_HD double sqrt_rn(double a) {
+#if defined(__CUDA_ARCH__)
+    return __dsqrt_rn(a);
+#else
+    volatile double r = sqrt(a);
+    return r;
+#endif
+}
+
+EMIRWV_HD int popcount64(unsigned long long m) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(m);
+#else
+    return __builtin_popcountll(m);
+#endif
+}
+
+// Sigma-clipped mean of the n samples held in v[0..n) (numina combine.sigmaclip, restated:
+// abba.py:132-137 `method`, used at :579-601).  Repeat { mean and unbiased standard deviation
+// of the samples still in; throw out what lies outside [mean - low*std, mean + high*std] }
+// until nothing is thrown out (or nothing would be left); the mean of the last pass is the
+// result.  float64, sums in frame order over the samples still in, one rounding per
+// operation -- the same sequence as the numpy statement in oracle/pipeline.py.
+template <typename T, int N>
+EMIRWV_HD double sigmaclip_of_registers(const T (&v)[N], int n, double low, double high) {
+    unsigned long long keep = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+    double mean = 0.0;
+    for (;;) {
+        const int cnt = popcount64(keep);
+        double s = 0.0;
+#pragma unroll
+        for (int u = 0; u < N; ++u)
+            if ((keep >> u) & 1ull) s = add_rn(s, (double)v[u]);
+        mean = div_rn(s, (double)cnt);
+        double ss = 0.0;
+#pragma unroll
+        for (int u = 0; u < N; ++u)
+            if ((keep >> u) & 1ull) {
+                const double d = sub_rn((double)v[u], mean);
+                ss = add_rn(ss, mul_rn(d, d));
+            }
+        const double sd = sqrt_rn(cnt > 1 ? div_rn(ss, (double)(cnt - 1)) : 0.0);
+        const double lo = sub_rn(mean, mul_rn(sd, low)), hi = add_rn(mean, mul_rn(sd, high));
+        unsigned long long next = 0ull;
+#pragma unroll
+        for (int u = 0; u < N; ++u)
+            if (((keep >> u) & 1ull) && (double)v[u] >= lo && (double)v[u] <= hi) next |= 1ull << u;
+        const int ncnt = popcount64(next);
+        if (ncnt == cnt || ncnt == 0) break;
+        keep = next;
+    }
+    return mean;
+}
+
+// shift_image2d(data, yoffset=...) of the ABBA recipe (abba.py:556; numina: rectify2d with the
+// translation map aij = [-0, 1, 0], bij = [-yoffset, 0, 1], area-overlap resampling).  With no
+// shift along x the mapped corners of output pixel (x, y) are (x -+ .5, v0 | v1) with
+//     v0 = fl(b0 + (y - .5)),  v1 = fl(b0 + (y + .5)),  b0 = -yoffset
+// and the clipping against source pixel (x, ii) leaves the rectangle [x-.5, x+.5] x [ya, yb],
+// ya = max(v0, ii-.5), yb = min(v1, ii+.5), always as the vertex cycle (xa,ya) (xa,yb) (xb,yb)
+// (xb,ya): the shoelace sum below is that of quad_box_area for this cycle, operation by
+// operation, so the weight has the same bits as the general clipping -- without clipping.
+struct ShiftRow {
+    double v0, v1;
+    int lo, hi;          // source rows with a non-degenerate overlap
+};
+
+EMIRWV_HD ShiftRow shift_row(double yoffset, int y) {
+    ShiftRow r;
+    const double b0 = add_rn(0.0, -yoffset);           // fmap's accumulator starts at 0.0
+    r.v0 = add_rn(b0, (double)y - 0.5);
+    r.v1 = add_rn(b0, (double)y + 0.5);
+    r.lo = (int)floor(r.v0 + 0.5);                     // quad_extent
+    r.hi = (int)ceil(r.v1 - 0.5);
+    if (r.hi < r.lo) r.hi = r.lo;
+    return r;
+}
+
+EMIRWV_HD double shift_area(double xa, double xb, const ShiftRow &r, int ii) {
+    const double y0 = (double)ii - 0.5, y1 = (double)ii + 0.5;
+    const double ya = r.v0 >= y0 ? r.v0 : y0;
+    const double yb = r.v1 <= y1 ? r.v1 : y1;
+    if (!(yb > ya)) return 0.0;
+    const double pa = mul_rn(xa, ya), pb = mul_rn(xa, yb), pc = mul_rn(xb, ya), pd = mul_rn(xb, yb);
+    double twice = sub_rn(pb, pa);
+    twice = add_rn(twice, sub_rn(pb, pd));
+    twice = add_rn(twice, sub_rn(pc, pd));
+    twice = add_rn(twice, sub_rn(pc, pa));
+    return 0.5 * fabs(twice);
+}
+
+// Bad-pixel stage of the flow (numina BadPixelCorrector -> array.bpm.process_bpm_median,
+// restated; built by get_corrector_p, core/correctors.py:23-42): a masked pixel becomes the
+// median of the unmasked pixels of the (2*HW+1)^2 window around it, clipped at the detector
+// edges (values of the INPUT image: corrected pixels are not reused), `fill` when the window
+// holds none.  numpy.median semantics (mean of the two middle values), float64.
+template <typename TIn, int HW>
+EMIRWV_HD double bpm_window_median(const TIn *img, const uint8_t *mask, int naxis1, int naxis2,
+                                   int col, int row, double fill) {
+    double buf[(2 * HW + 1) * (2 * HW + 1)];
+    int n = 0;
+    bool has_nan = false;
+    for (int r = row - HW; r <= row + HW; ++r) {
+        if (r < 0 || r >= naxis2) continue;
+        for (int c = col - HW; c <= col + HW; ++c) {
+            if (c < 0 || c >= naxis1) continue;
+            const long long i = (long long)r * naxis1 + c;
+            if (mask[i] != 0) continue;
+            const double val = (double)img[i];
+            has_nan |= val != val;
+            int k = n++;                               // insertion sort (rare path, n <= 25)
+            while (k > 0 && buf[k - 1] > val) {
+                buf[k] = buf[k - 1];
+                --k;
+            }
+            buf[k] = val;
+        }
+    }
+    if (n == 0) return fill;
+    if (has_nan) return quiet_nan();
+    return (n & 1) ? buf[n / 2] : mul_rn(add_rn(buf[n / 2 - 1], buf[n / 2]), 0.5);
 }
 
 }  // namespace emirwv

@@ -200,12 +200,23 @@ __device__ __forceinline__ void load4(const uint16_t *p, uint16_t (&v)[4]) {
 // VEC = 4: a thread owns four consecutive pixels (16-byte loads and stores, npix % 4 == 0 and
 // aligned buffers); VEC = 1: any size and alignment.  Frames are taken four at a time so that
 // four independent loads are in flight per thread.
+//
+// The bad-pixel stage comes first in the flow (BadPixelCorrector, core/correctors.py:23-42,
+// core/recipe.py:26-41): a thread whose pixel is masked replaces the raw value by the median of
+// the unmasked raw pixels of the 5 x 5 window around it (bpm_window_median, pixel_ops.cuh) and
+// carries on with bias, dark and flat -- the frame is still read once (the window of the few
+// masked pixels comes from L2 / L1).
+struct BpmArgs {
+    const uint8_t *mask;    // [naxis2][naxis1], non-zero = bad; NULL: no bad-pixel stage
+    int naxis1, naxis2;
+};
+
 template <typename TIn, typename TCal, int VEC>
 __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, float *__restrict__ out,
                                                    int nframes, size_t npix,
                                                    const TCal *__restrict__ bias,
                                                    const TCal *__restrict__ dark,
-                                                   const TCal *__restrict__ flat) {
+                                                   const TCal *__restrict__ flat, const BpmArgs bpm) {
     // float32 unless an operand is float64 (uint16 raw frames promote like numpy: with
     // float32 calibrations the arithmetic is float32)
     using A = typename std::conditional<sizeof(TIn) == 8 || sizeof(TCal) == 8, double, float>::type;
@@ -241,6 +252,21 @@ __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, f
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
             f[e] = f[e] <= A(0) ? A(1) : f[e];   // flatfield.py:43 (NaN stays NaN, like numpy)
+        unsigned bad = 0;                        // masked pixels among this thread's VEC
+        if (bpm.mask != nullptr) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) bad |= (bpm.mask[i + e] != 0 ? 1u : 0u) << e;
+        }
+        // one pixel of one frame: the window median first when the pixel is masked
+        auto px = [&](const TIn *frame, TIn raw, int e) -> float {
+            if (bad & (1u << e)) {
+                const size_t ii = i + e;
+                const double m = bpm_window_median<TIn, 2>(frame, bpm.mask, bpm.naxis1, bpm.naxis2,
+                                                          (int)(ii % bpm.naxis1), (int)(ii / bpm.naxis1), 0.0);
+                return prereduce_from<TIn, A>(m, hb, hd, hf, b[e], d[e], f[e]);
+            }
+            return prereduce_px<TIn, A>(raw, hb, hd, hf, b[e], d[e], f[e]);
+        };
         int n = 0;
         for (; n + U <= nframes; n += U) {
             TIn raw[U][VEC];
@@ -253,8 +279,7 @@ __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, f
             for (int u = 0; u < U; ++u) {
                 float r[VEC];
 #pragma unroll
-                for (int e = 0; e < VEC; ++e)
-                    r[e] = prereduce_px<TIn, A>(raw[u][e], hb, hd, hf, b[e], d[e], f[e]);
+                for (int e = 0; e < VEC; ++e) r[e] = px(in + (size_t)(n + u) * npix, raw[u][e], e);
                 float *dst = out + (size_t)(n + u) * npix + i;
                 if constexpr (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(r[0], r[1], r[2], r[3]));
                 else __stcs(dst, r[0]);
@@ -266,8 +291,7 @@ __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, f
             else raw[0] = __ldcs(in + (size_t)n * npix + i);
             float r[VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e)
-                r[e] = prereduce_px<TIn, A>(raw[e], hb, hd, hf, b[e], d[e], f[e]);
+            for (int e = 0; e < VEC; ++e) r[e] = px(in + (size_t)n * npix, raw[e], e);
             float *dst = out + (size_t)n * npix + i;
             if constexpr (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(r[0], r[1], r[2], r[3]));
             else __stcs(dst, r[0]);
@@ -277,7 +301,8 @@ __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, f
 
 template <typename TIn, typename TCal>
 void launch_prereduce(const void *in, float *out, int nframes, size_t npix, const void *bias,
-                      const void *dark, const void *flat, int sms, cudaStream_t st) {
+                      const void *dark, const void *flat, int sms, cudaStream_t st,
+                      const BpmArgs bpm = BpmArgs{nullptr, 0, 0}) {
     auto aligned = [](const void *ptr, size_t a) {
         return ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) == 0;
     };
@@ -289,10 +314,10 @@ void launch_prereduce(const void *in, float *out, int nframes, size_t npix, cons
                *tf = static_cast<const TCal *>(flat);
     if (vec) {
         const int grid = (int)std::min<size_t>((npix / 4 + 255) / 256, (size_t)sms * 16);
-        k_prereduce<TIn, TCal, 4><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf);
+        k_prereduce<TIn, TCal, 4><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf, bpm);
     } else {
         const int grid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sms * 16);
-        k_prereduce<TIn, TCal, 1><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf);
+        k_prereduce<TIn, TCal, 1><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf, bpm);
     }
 }
 
@@ -445,4 +470,111 @@ void launch_stack_median(const T *frames, const StackSel &sel, size_t npix, doub
     else if (sel.n <= 16) launch_stack_median_n<T, 16>(frames, sel, npix, out, sms, vec_ok, st);
     else if (sel.n <= 32) launch_stack_median_n<T, 32>(frames, sel, npix, out, sms, vec_ok, st);
     else launch_stack_median_n<T, 64>(frames, sel, npix, out, sms, vec_ok, st);
+}
+
+// ---------------------------------------------------------------------------------
+// ABBA combination, method "sigmaclip" (abba.py:132-137,579-601 with numina's
+// combine.sigmaclip, restated): per pixel the sigma-clipped mean of the selected frames of a
+// stack (sigmaclip_of_registers, pixel_ops.cuh), the samples of a pixel in registers, all N
+// loads of a thread in flight together; the stack is read once.
+template <typename T, int N>
+__device__ __forceinline__ double stack_sigmaclip_px(const T *__restrict__ frames,
+                                                     const StackSel &sel, size_t npix, size_t i,
+                                                     double low, double high) {
+    T v[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) v[u] = u < sel.n ? __ldcs(frames + (size_t)sel.idx[u] * npix + i) : T(0);
+    return sigmaclip_of_registers<T, N>(v, sel.n, low, high);
+}
+
+template <typename T, int N>
+__global__ void __launch_bounds__(256) k_stack_sigmaclip(const T *__restrict__ frames,
+                                                         const StackSel sel, size_t npix,
+                                                         double low, double high,
+                                                         double *__restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride)
+        out[i] = stack_sigmaclip_px<T, N>(frames, sel, npix, i, low, high);
+}
+
+// float32(clipped mean of the A images) - float32(clipped mean of the B images), abba.py:604-606
+template <typename T, int N>
+__global__ void __launch_bounds__(256) k_abba_sigmaclip(const T *__restrict__ frames,
+                                                        const StackSel sel_a, const StackSel sel_b,
+                                                        size_t npix, double low, double high,
+                                                        float *__restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        const double ma = stack_sigmaclip_px<T, N>(frames, sel_a, npix, i, low, high);
+        const double mb = stack_sigmaclip_px<T, N>(frames, sel_b, npix, i, low, high);
+        __stcs(out + i, __fsub_rn((float)ma, (float)mb));
+    }
+}
+
+template <typename T>
+void launch_sigmaclip(const T *frames, const StackSel &sa, const StackSel *sb, size_t npix,
+                      double low, double high, void *out, int sms, cudaStream_t st) {
+    const int n = sb != nullptr ? std::max(sa.n, sb->n) : sa.n;
+    const int grid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sms * 8);
+#define SIGCLIP_BUCKET(N)                                                                      \
+    do {                                                                                       \
+        if (sb != nullptr)                                                                     \
+            k_abba_sigmaclip<T, N><<<grid, 256, 0, st>>>(frames, sa, *sb, npix, low, high,     \
+                                                         static_cast<float *>(out));           \
+        else                                                                                   \
+            k_stack_sigmaclip<T, N><<<grid, 256, 0, st>>>(frames, sa, npix, low, high,         \
+                                                          static_cast<double *>(out));         \
+    } while (0)
+    if (n <= 4) SIGCLIP_BUCKET(4);
+    else if (n <= 8) SIGCLIP_BUCKET(8);
+    else if (n <= 16) SIGCLIP_BUCKET(16);
+    else if (n <= 32) SIGCLIP_BUCKET(32);
+    else SIGCLIP_BUCKET(64);
+#undef SIGCLIP_BUCKET
+}
+
+// ---------------------------------------------------------------------------------
+// The per-frame vertical offset of the ABBA recipe (abba.py:545-558:
+// `shift_image2d(data, yoffset=-offset).astype("float32")` for every frame whose offset is not
+// zero), all frames of a stack in one launch, device resident.  A thread owns one column of a
+// strip of SHIFT_STRIP output rows of one frame; an output pixel is the sum over the (at most
+// three, normally two) source rows it overlaps of area x value in float64, the areas with the
+// bits of the general clipping (shift_row / shift_area, pixel_ops.cuh); consecutive output rows
+// share a source row, which the thread keeps in a register.  HBM bound: the stack is read once
+// and written once.
+constexpr int SHIFT_STRIP = 8;
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) k_shift_rows(const TIn *__restrict__ in, TOut *__restrict__ out,
+                                                    int naxis2, int naxis1,
+                                                    const double *__restrict__ yoffset) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ys = blockIdx.y * SHIFT_STRIP;
+    const int f = blockIdx.z;
+    if (x >= naxis1) return;
+    const size_t fo = (size_t)f * naxis2 * naxis1;
+    const TIn *img = in + fo;
+    TOut *dst = out + fo;
+    const double yo = yoffset[f];
+    if (yo == 0.0) {                                   // abba.py:554 `if offset != 0`
+        for (int y = ys; y < min(ys + SHIFT_STRIP, naxis2); ++y)
+            __stcs(dst + (size_t)y * naxis1 + x, (TOut)__ldcs(img + (size_t)y * naxis1 + x));
+        return;
+    }
+    const double xa = (double)x - 0.5, xb = (double)x + 0.5;
+    int have = INT_MIN;                                // source row held in `val`
+    double val = 0.0;
+    for (int y = ys; y < min(ys + SHIFT_STRIP, naxis2); ++y) {
+        const ShiftRow r = shift_row(yo, y);
+        double acc = 0.0;
+        for (int ii = max(r.lo, 0); ii <= min(r.hi, naxis2 - 1); ++ii) {
+            const double area = shift_area(xa, xb, r, ii);
+            if (ii != have) {
+                val = (double)__ldg(img + (size_t)ii * naxis1 + x);
+                have = ii;
+            }
+            if (area != 0.0) acc = add_rn(acc, mul_rn(area, val));
+        }
+        __stcs(dst + (size_t)y * naxis1 + x, (TOut)acc);
+    }
 }

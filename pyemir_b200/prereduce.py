@@ -13,7 +13,10 @@ field.  Here:
   (bias / dark subtraction restate numina's BiasCorrector / DarkCorrector: image minus
   calibration, float32 result; parity unpinned for those two stages).
 
-numina's BadPixelCorrector (interpolation over masked pixels) is not covered.
+* ``bpm`` adds the first stage of the flow, numina's BadPixelCorrector
+  (``core/correctors.py:23-42``), restated as ``process_bpm_median`` with its 5 x 5 window
+  (parity unpinned): a masked pixel becomes the median of the unmasked raw pixels around it,
+  in the same pass (``emirwv_prereduce_ex``).  ``BadPixelCorrector`` mirrors the node.
 """
 
 import ctypes
@@ -35,8 +38,11 @@ def _cal_tensor(cal, device, want64):
     return cal.to(device=device, dtype=torch.float64 if want64 else torch.float32).contiguous()
 
 
-def prereduce_torch(frames, bias=None, dark=None, flat=None, out=None):
+def prereduce_torch(frames, bias=None, dark=None, flat=None, out=None, bpm=None):
     """``((frames - bias) - dark) / flat'`` as float32, ``flat' = where(flat <= 0, 1, flat)``.
+
+    bpm: (H, W) mask, non-zero = bad pixel: such a pixel of every frame is first replaced by
+    the median of the good raw pixels within +-2 rows and columns (0 when there is none).
 
     frames: (n, H, W) or (H, W) contiguous CUDA tensor, float32 / float64 / uint16.
     bias, dark, flat: (H, W) arrays or tensors, or None to skip the stage.  If any of them is
@@ -66,10 +72,20 @@ def prereduce_torch(frames, bias=None, dark=None, flat=None, out=None):
     elif out.dtype != torch.float32 or tuple(out.shape) != (n, height, width) or \
             not out.is_contiguous():
         raise ValueError("out must be a contiguous float32 tensor of the shape of frames")
+    mask = None
+    if bpm is not None:
+        if not isinstance(bpm, torch.Tensor):
+            bpm = torch.from_numpy(np.ascontiguousarray(np.asarray(bpm) != 0))
+        mask = (bpm != 0).to(device=frames.device, dtype=torch.uint8).contiguous()
+        if tuple(mask.shape) != (height, width):
+            raise ValueError("the bad-pixel mask must have the shape of the frames")
+        if out.data_ptr() == frames.data_ptr():
+            raise ValueError("out must not be frames when a bad-pixel mask is given")
     stream = torch.cuda.current_stream(frames.device).cuda_stream
     vp = ctypes.c_void_p
-    _cabi.check(_cabi.load().emirwv_prereduce(
-        vp(frames.data_ptr()), _IN_DTYPES[name], vp(out.data_ptr()), n, height * width,
+    _cabi.check(_cabi.load().emirwv_prereduce_ex(
+        vp(frames.data_ptr()), _IN_DTYPES[name], vp(out.data_ptr()), n, height, width,
+        vp(mask.data_ptr()) if mask is not None else None,
         *[vp(c.data_ptr()) if c is not None else None for c in cals],
         _cabi.F64 if want64 else _cabi.F32, vp(stream) if stream else None))
     return out[0] if squeeze else out
@@ -88,13 +104,46 @@ def as_supported_frames(frames):
     return arr.astype(np.result_type(arr.dtype, np.float32))
 
 
-def prereduce(frames, bias=None, dark=None, flat=None):
+def prereduce(frames, bias=None, dark=None, flat=None, bpm=None):
     """Host arrays in, float32 host array out (copies around :func:`prereduce_torch`)."""
     import torch
     arr = as_supported_frames(frames)
     dev = torch.device("cuda", torch.cuda.current_device())
-    out = prereduce_torch(torch.from_numpy(arr).to(dev), bias, dark, flat)
+    out = prereduce_torch(torch.from_numpy(arr).to(dev), bias, dark, flat, bpm=bpm)
     return out.cpu().numpy()
+
+
+class BadPixelCorrector:
+    """A node that replaces the masked pixels of a frame (numina ``BadPixelCorrector`` as built
+    by ``get_corrector_p``, ``core/correctors.py:23-42``; restated, parity unpinned).
+
+    ``BadPixelCorrector(hdul[0].data, datamodel=..., calibid=...)``; ``run(img)`` replaces the
+    primary data by the corrected frame (``dtype``, float32 by default) and records the
+    calibration in the header like numina's correctors do (``NUM-BPM`` + a HISTORY card).
+    """
+
+    def __init__(self, badpixelmask, mark=True, tagger=None, datamodel=None,
+                 calibid="calibid-unknown", dtype="float32"):
+        self.bpm = np.asarray(badpixelmask)
+        self.mark = mark
+        self.datamodel = datamodel
+        self.calibid = calibid
+        self.dtype = dtype
+
+    def __call__(self, img):
+        return self.run(img)
+
+    def run(self, img):
+        data = img["primary"].data if self.datamodel is None else self.datamodel.get_data(img)
+        result = prereduce(data, bpm=self.bpm)
+        img["primary"].data = result if np.dtype(self.dtype) == np.float32 else result.astype(self.dtype)
+        if self.mark:
+            hdr = img["primary"].header
+            hdr["NUM-BPM"] = self.calibid
+            hdr["history"] = "BPM correction with {}".format(self.calibid)
+            hdr["history"] = "BPM correction time {}".format(
+                datetime.datetime.now(datetime.timezone.utc).isoformat())
+        return img
 
 
 class FlatFieldCorrector:
