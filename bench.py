@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=3,
                     help="frames of the CPU-baseline sample (0 disables it)")
     ap.add_argument("--ref-budget-s", type=float, default=200.0)
+    ap.add_argument("--no-collective", action="store_true",
+                    help="N > 1: skip the timed combined products (collective block)")
     return ap.parse_args()
 
 
@@ -244,6 +246,197 @@ def tuning_of(info):
             "label": os.environ.get("AB_LABEL")}
 
 
+def e2e_recipe_entries(args, plan, h_in, a_out, a_jmm, F, world, dev, barrier):
+    """End to end through the entries that follow the recipe further than the path itself:
+    RAW uint16 frames in (half the bytes over PCIe; bad-pixel mask, bias, dark and flat applied
+    on the device in front of the path), and the whole ABBA product (only the combined A - B
+    image comes back).  Same frames/s metric; both results are checked against the
+    device-resident kernels before they are timed."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pyemir_b200 import abba
+    from pyemir_b200.prereduce import prereduce_torch
+
+    rng = np.random.default_rng(77)
+    raw = torch.empty(h_in.shape, dtype=torch.uint16, pin_memory=True)
+    raw_np = raw.numpy()
+    raw_np[...] = np.clip(h_in.numpy() * 8.0 + 1000.0, 0, 65535).astype(np.uint16)
+    bias = rng.normal(1000.0, 2.0, size=raw_np.shape[1:]).astype(np.float32)
+    dark = rng.normal(2.0, 0.5, size=raw_np.shape[1:]).astype(np.float32)
+    flat = rng.normal(8.0, 0.2, size=raw_np.shape[1:]).astype(np.float32)
+    bpm = (rng.random(raw_np.shape[1:]) < 0.005).astype(np.uint8)
+    plan.set_calibration(bpm=bpm, bias=bias, dark=dark, flat=flat)
+    labels = abba.labels_of(abba.build_full_set("ABBA", 1, (F + 3) // 4)[:F])
+    offsets = [0.0 if i % 4 in (0, 3) else 0.3127 for i in range(F)]
+    img = torch.empty(plan.out_shape, dtype=torch.float32, pin_memory=True)
+
+    # -- checks against the device-resident kernels (untimed)
+    d_red = prereduce_torch(raw.to(dev), bias, dark, flat, bpm=bpm)
+    d_prod, d_jm = plan.run_torch(d_red)
+    plan.run_host_raw(raw_np, a_out, a_jmm)
+    ok_raw = bool(torch.equal(torch.from_numpy(a_out[F - 1]), d_prod[F - 1].cpu())
+                  and torch.equal(torch.from_numpy(a_jmm), d_jm.cpu()))
+    want = abba.combine_abba(d_prod, abba.build_full_set("ABBA", 1, (F + 3) // 4)[:F], offsets,
+                             "mean").cpu()
+    plan.abba_host(raw_np, labels, offsets, "mean", raw=True, out=img.numpy())
+    ok_abba = bool(torch.equal(img, want))
+    del d_red, d_prod, want
+    if not (ok_raw and ok_abba):
+        raise SystemExit(f"bench.py: host entries differ from the device path (raw {ok_raw}, abba {ok_abba})")
+
+    def timed(call):
+        call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            call()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * F * args.e2e_steps / float(te.item())
+
+    v_raw = timed(lambda: plan.run_host_raw(raw_np, a_out, a_jmm))
+    v_abba = timed(lambda: plan.abba_host(raw_np, labels, offsets, "mean", raw=True, out=img.numpy()))
+    v_abba_f32 = timed(lambda: plan.abba_host(h_in.numpy(), labels, offsets, "mean", out=img.numpy()))
+    plan.set_calibration()
+    return {
+        "raw_u16": {"value": v_raw, "h2d_bytes_per_step": int(raw_np.nbytes),
+                    "d2h_bytes_per_step": int(a_out.nbytes + a_jmm.nbytes),
+                    "call": "emirwv_run_host_raw: RAW uint16 frames in pinned memory -> bad-pixel "
+                            "mask, bias, dark, flat (k_prereduce) -> k_rectwv -> every byte of the "
+                            "products back; identical to the device-resident kernels: %s" % ok_raw},
+        "abba_product": {"value": v_abba, "h2d_bytes_per_step": int(raw_np.nbytes),
+                         "d2h_bytes_per_step": int(img.numpy().nbytes),
+                         "float32_reduced_frames_in": v_abba_f32,
+                         "call": "emirwv_abba_host(mean, EMIRWV_HOST_RAW): RAW uint16 frames in, flow, "
+                                 "rectification, per-frame vertical offsets (half of the frames "
+                                 "shifted), float64 sums in frame order, float32(A) - float32(B): "
+                                 "only the combined image comes back; identical to the "
+                                 "device-resident kernels: %s" % ok_abba},
+    }
+
+
+def collective_block(args, plan, d_in, d_out, d_jmm, F, world, rank, dev):
+    """N > 1: what a combined product costs (BASELINE config 5: an ABBA sequence sharded over the
+    ranks with an exchange over NVLink at the end), timed per sequence with CUDA events, max over
+    ranks; the headline `value` stays the collective-free rectification."""
+    import statistics as st
+
+    import torch
+    import torch.distributed as dist
+
+    from pyemir_b200 import abba
+    from pyemir_b200.distributed import gather_frames
+
+    npix = plan.out_shape[0] * plan.out_shape[1]
+    esz = d_out.element_size()
+
+    def run(fn, reps=3):
+        fn()
+        times = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+        return st.median(times)
+
+    out = {}
+    # (i) mean: every rank rectifies its share of a >= 1024-frame sequence in rounds of F frames,
+    # adds them to its float64 A and B sums (k_abba_partial), ONE reduce of the two sums, finish
+    rounds = max(1, -(-1024 // (F * world)))
+    labels = abba.labels_of(abba.build_full_set("ABBA", 1, (F + 3) // 4)[:F])
+    na = world * rounds * labels.count(1)
+    nb = world * rounds * labels.count(-1)
+    state = {}
+
+    def local_sums():
+        sums = None
+        for _ in range(rounds):
+            plan.run_torch(d_in, d_out, d_jmm)
+            sums = abba.partial_sums(d_out, labels, sums=sums)
+        state["sums"] = sums
+
+    def mean_all():
+        local_sums()
+        red = abba.reduce_sums(state["sums"], 0)
+        if red is not None:
+            abba.finish(red, na, nb)
+
+    t_local = run(local_sums)
+    t_all = run(mean_all)
+    red_bytes = 2 * npix * 8
+    out["abba_mean"] = {
+        "frames_per_sequence": F * world * rounds, "ms_per_sequence": t_all,
+        "ms_rectify_and_partial_sums": t_local, "ms_reduce_and_finish": max(t_all - t_local, 0.0),
+        "frames_per_s": F * world * rounds / (t_all / 1e3),
+        "bytes_reduced_per_rank": red_bytes,
+        "nvlink_GBs_per_rank": red_bytes / max(t_all - t_local, 1e-6) / 1e6,
+        "nvlink_peak_GBs_per_direction": 900.0,
+        "how": "k_rectwv + k_abba_partial per round of %d frames per rank, one NCCL reduce(sum) of "
+               "the float64 A and B sums (2 x %.1f MB per rank) to rank 0, k_abba_finish" % (F, npix * 8 / 1e6)}
+
+    # (ii) median: 64 images per nodding position over all ranks; row-slab exchange (grouped
+    # send/recv), per-slab k_abba_median, gather of the slabs
+    per_rank = max(4, (128 // world) // 4 * 4)
+    if per_rank <= F:
+        lab_all = abba.labels_of(abba.build_full_set("ABBA", 1, per_rank * world // 4))
+        counts = [per_rank] * world
+        sub = d_out[:per_rank]
+
+        def median_all():
+            plan.run_torch(d_in[:per_rank], sub, d_jmm[:per_rank])
+            abba.combine_abba_median(sub, lab_all, counts, 0)
+
+        def rect_only():
+            plan.run_torch(d_in[:per_rank], sub, d_jmm[:per_rank])
+
+        t_rect = run(rect_only)
+        t_med = run(median_all)
+        sent = per_rank * npix * esz * (world - 1) / world
+        out["abba_median"] = {
+            "frames_per_sequence": per_rank * world, "ms_per_sequence": t_med,
+            "ms_rectify": t_rect, "ms_exchange_median_gather": max(t_med - t_rect, 0.0),
+            "frames_per_s": per_rank * world / (t_med / 1e3),
+            "bytes_sent_per_rank": int(sent + npix * 4 / world),
+            "nvlink_GBs_per_rank": sent / max(t_med - t_rect, 1e-6) / 1e6,
+            "nvlink_peak_GBs_per_direction": 900.0,
+            "how": "row-slab exchange (every rank sends 1/world of each of its frames to every "
+                   "peer), k_abba_median on the slab, gather of the float32 slabs on rank 0; the "
+                   "stack-median kernels take at most 64 images per nodding position"}
+
+    # (iii) plain gather of the rectified products on rank 0
+    counts = [F] * world
+
+    def gather_all():
+        gather_frames(d_out, counts, 0)
+
+    try:
+        t_g = run(gather_all, reps=2)
+        into_root = (world - 1) * F * npix * esz
+        out["gather"] = {"frames": F * world, "ms": t_g, "bytes_into_root": into_root,
+                         "nvlink_GBs_into_root": into_root / t_g / 1e6,
+                         "nvlink_peak_GBs_per_direction": 900.0,
+                         "how": "grouped NCCL send/recv of every rank's %d products to rank 0" % F}
+    except RuntimeError as exc:           # root out of memory for the gathered stack
+        out["gather"] = {"error": repr(exc)[:200]}
+    limiter = ("mean: the per-rank k_abba_partial pass over the products (HBM) and the float64 "
+               "reduce; median: the exchange moves (world-1)/world of every product once; gather: "
+               "the root's NVLink ingest (900 GB/s per direction)")
+    out["limiter"] = limiter
+    return out
+
+
 # --------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import numpy as np
@@ -251,12 +444,15 @@ def run_ours(args):
     import torch.distributed as dist
 
     from pyemir_b200 import abba, synthetic
-    from pyemir_b200.distributed import gather_frames, init_from_env, reduce_mean
+    from pyemir_b200.distributed import (bind_to_gpu_numa, gather_frames, init_from_env,
+                                         reduce_mean)
     from pyemir_b200.plan import RectWavePlan
 
-    rank, world, local_rank = init_from_env("nccl")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: pyemir_b200 has no CPU fallback")
+    # before anything is allocated: this rank's CPUs and page-locked buffers next to its GPU
+    numa = bind_to_gpu_numa(int(os.environ.get("LOCAL_RANK", "0")))
+    rank, world, local_rank = init_from_env("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     config = config_key(args.config)
@@ -406,6 +602,12 @@ def run_ours(args):
                "checksum": float(a_out[0, 1000:1038].sum())}
         if not same:
             raise SystemExit("bench.py: sparse device->host copy differs from the full copy")
+        if args.dtype == "float32":
+            e2e.update(e2e_recipe_entries(args, plan, h_in, a_out, a_jmm, F, world, dev, barrier))
+
+    collective = None
+    if world > 1 and args.dtype == "float32" and not args.no_collective:
+        collective = collective_block(args, plan, d_in, d_out, d_jmm, F, world, rank, dev)
 
     if rank != 0:
         if world > 1:
@@ -460,14 +662,16 @@ def run_ours(args):
     own_gbs = own_bytes / (own_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "one emirwv_run = k_rectwv with k_zero_fill beside it on a second "
-                          "stream (+ k_init_jmm): whole frames in, whole products out",
+                "kernel": "one emirwv_run = k_rectwv (its copy warps also write the zero runs "
+                          "outside the wavelength coverage) + k_init_jmm: whole frames in, whole "
+                          "products out; the STEP, identical to k_rectwv's own launch",
                 "bytes_per_launch": bytes_per_launch,
                 "launch_ms": statistics.mean(launch_ms),
                 "k_rectwv_alone": {"launch_ms": own_ms, "bytes_per_launch": own_bytes,
                                    "achieved": own_gbs, "frac": own_gbs / peak,
-                                   "what": "k_rectwv without k_zero_fill (EMIRWV_RUN_OUT_ZEROED): "
-                                           "frames in + the covered columns of the products out"}}
+                                   "what": "k_rectwv told that the output already holds the zeros "
+                                           "(EMIRWV_RUN_OUT_ZEROED): frames in + only the covered "
+                                           "columns of the products out, fewer bytes in less time"}}
 
     cpu = None
     if world == 1 and args.cpu_frames > 0:
@@ -481,10 +685,11 @@ def run_ours(args):
         "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
         "config": workload_config(args, config), "tuning": tuning_of(info), "plan": plan_cost,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "dropin_single_frame": dropin,
-        # per step: k_init_jmm + k_zero_fill + k_rectwv (persistent)
-        # (+ the combination kernels: abba 2, abba_median 3 per step)
-        "gpu_launches": (3 + {"abba": 2, "abba_median": 3}.get(args.combine, 0)) * args.steps,
-        "clocks": clocks,
+        # per step: k_init_jmm + k_rectwv (persistent; + k_zero_fill when the output rows are
+        # not 16-byte aligned) (+ the combination kernels: abba 2, abba_median 3 per step)
+        "gpu_launches": (2 + (0 if (info["out_frame_bytes"] // (55 * 38)) % 16 == 0 else 1)
+                         + {"abba": 2, "abba_median": 3}.get(args.combine, 0)) * args.steps,
+        "clocks": clocks, "host_placement": numa, "collective": collective,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

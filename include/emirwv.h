@@ -129,6 +129,9 @@ int emirwv_device_count(void);
  * (one process per GPU: pass LOCAL_RANK). */
 int emirwv_set_device(int device);
 
+/* The calling thread's current CUDA device, or a negative error code. */
+int emirwv_get_device(void);
+
 /*
  * Build the frame-independent tables of a RectWaveCoeff on the current device.
  * Replaces the per-frame work of Slitlet2D.__init__ (slitlet2d.py:145-218), fmap /
@@ -182,11 +185,54 @@ int emirwv_run_host(emirwv_plan *plan, const void *h_in, void *h_out, int nframe
  *   plan has no wavelength coverage (a zero-initialised buffer, or one filled by an earlier
  *   call with the same plan -- the usual loop over exposures).  Only the covered columns of
  *   every slitlet (emirwv_plan_get_coverage) are copied back: about 62 % of the product for
- *   the J/H/K grisms.  The result in h_out is the same as without the flag.
+ *   the J/H/K grisms -- by one kernel per pipeline chunk that writes them straight into a pinned
+ *   h_out, by one strided copy per slitlet into a pageable one.  The result in h_out is the
+ *   same as without the flag.
  */
 #define EMIRWV_HOST_OUT_ZEROED 1u
 int emirwv_run_host_ex(emirwv_plan *plan, const void *h_in, void *h_out, int nframes,
                        int32_t *h_jminmax, uint32_t flags);
+
+/*
+ * The recipes run `flow(newimg)` on every raw frame before the path (recipes/spec/abba.py:371,
+ * core/recipe.py:25-61: bad-pixel mask, bias, dark, flat).  A plan can hold the calibration
+ * images of that flow (copied to its device; NULL skips a stage, all NULL clears them):
+ *   h_bpm [naxis2][naxis1] uint8 (non-zero = bad); h_bias, h_dark, h_flat [naxis2][naxis1] of
+ *   cal_dtype (EMIRWV_F32 / EMIRWV_F64).
+ * emirwv_run_host_raw is emirwv_run_host_ex for RAW frames (raw_dtype EMIRWV_U16 -- detector
+ * counts, half the bytes over PCIe --, EMIRWV_F32 or EMIRWV_F64): every pipeline chunk goes
+ * host -> device, through emirwv_prereduce_ex with the plan's calibration and through the hot
+ * kernel.  The plan must be float32 (the flow rounds to float32).
+ */
+int emirwv_plan_set_calibration(emirwv_plan *plan, const uint8_t *h_bpm, const void *h_bias,
+                                const void *h_dark, const void *h_flat, int cal_dtype);
+int emirwv_run_host_raw(emirwv_plan *plan, const void *h_raw, int raw_dtype, void *h_out,
+                        int nframes, int32_t *h_jminmax, uint32_t flags);
+
+/*
+ * The ABBA product from host frames in one call (recipes/spec/abba.py:351-381 rectification of
+ * every frame, :545-558 per-frame vertical offsets, :579-606 combination of the A and of the B
+ * images and their float32 difference): only the combined image travels back.
+ *   h_in      [nframes][naxis2][naxis1]: reduced frames of the plan dtype, or raw frames of
+ *             in_dtype with EMIRWV_HOST_RAW (the plan's calibration flow runs first)
+ *   h_labels  [nframes] int8: +1 = A, -1 = B, 0 = not used
+ *   h_offset  [nframes] the recipe's list_offsets (a frame is shifted by
+ *             shift_image2d(data, yoffset=-offset).astype("float32") when its offset is not 0),
+ *             or NULL
+ *   method    EMIRWV_MEAN / EMIRWV_MEDIAN / EMIRWV_SIGMACLIP (low, high: clipping limits);
+ *             median and sigma clipping keep the products on the device: at most 64 images per
+ *             nodding position
+ *   h_out     [naxis2_out][naxis1_out] float32
+ * Copies and kernels are pipelined over internal streams; the float64 sums of the mean run in
+ * frame order.  Returns when h_out is complete.
+ */
+#define EMIRWV_MEAN 0
+#define EMIRWV_MEDIAN 1
+#define EMIRWV_SIGMACLIP 2
+#define EMIRWV_HOST_RAW 2u
+int emirwv_abba_host(emirwv_plan *plan, const void *h_in, int in_dtype, int nframes,
+                     const int8_t *h_labels, const double *h_offset, int method, double low,
+                     double high, float *h_out, uint32_t flags);
 
 /* h_cover [nslitlets][2] int32: output columns [lo, hi) of each slitlet that can hold flux
  * (0, 0 for a missing slitlet); everything outside is exactly zero in every product. */

@@ -17,14 +17,16 @@ ROWS_SCANNED = 39
 
 F32, F64, U16 = 0, 1, 2
 HOST_OUT_ZEROED = 1
+HOST_RAW = 2
 RUN_OUT_ZEROED = 1
+MEAN, MEDIAN, SIGMACLIP = 0, 1, 2
 NEAREST, AREA, BILINEAR = 1, 2, 3
 
 E_VALUE, E_INDEX, E_CUDA, E_NOMEM, E_LIMIT = -1, -2, -3, -4, -5
 
 # every symbol include/emirwv.h declares
 EXPORTED_SYMBOLS = (
-    "emirwv_version", "emirwv_last_error", "emirwv_device_count", "emirwv_set_device",
+    "emirwv_version", "emirwv_last_error", "emirwv_device_count", "emirwv_set_device", "emirwv_get_device",
     "emirwv_plan_create", "emirwv_plan_destroy", "emirwv_plan_get_info",
     "emirwv_plan_set_tuning", "emirwv_run", "emirwv_run_ex", "emirwv_run_host",
     "emirwv_run_host_ex", "emirwv_plan_get_coverage",
@@ -33,7 +35,8 @@ EXPORTED_SYMBOLS = (
     "emirwv_median_slitlets", "emirwv_median_slitlets_host",
     "emirwv_abba_partial", "emirwv_abba_finish", "emirwv_stack_median", "emirwv_abba_median",
     "emirwv_prereduce", "emirwv_prereduce_ex", "emirwv_stack_sigmaclip",
-    "emirwv_abba_sigmaclip", "emirwv_shift_rows",
+    "emirwv_abba_sigmaclip", "emirwv_shift_rows", "emirwv_plan_set_calibration",
+    "emirwv_run_host_raw", "emirwv_abba_host",
 )
 
 
@@ -138,6 +141,8 @@ def load():
     lib.emirwv_last_error.argtypes = []
     lib.emirwv_device_count.restype = i32
     lib.emirwv_device_count.argtypes = []
+    lib.emirwv_get_device.restype = i32
+    lib.emirwv_get_device.argtypes = []
     lib.emirwv_set_device.restype = i32
     lib.emirwv_set_device.argtypes = [i32]
     lib.emirwv_plan_create.restype = i32
@@ -190,6 +195,12 @@ def load():
                                           vp, vp]
     lib.emirwv_shift_rows.restype = i32
     lib.emirwv_shift_rows.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp]
+    lib.emirwv_plan_set_calibration.restype = i32
+    lib.emirwv_plan_set_calibration.argtypes = [vp, vp, vp, vp, vp, i32]
+    lib.emirwv_run_host_raw.restype = i32
+    lib.emirwv_run_host_raw.argtypes = [vp, vp, i32, vp, i32, vp, ctypes.c_uint32]
+    lib.emirwv_abba_host.restype = i32
+    lib.emirwv_abba_host.argtypes = [vp, vp, i32, i32, vp, vp, i32, f64, f64, vp, ctypes.c_uint32]
     lib.emirwv_debug_geometry.restype = i32
     lib.emirwv_debug_geometry.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.emirwv_debug_borders.restype = i32

@@ -14,7 +14,8 @@ import numpy as np
 
 from .core import EMIR_NAXIS1, EMIR_NAXIS2, EMIR_NBARS, EMIR_NPIXPERSLIT_RECTIFIED
 from .dtu import DtuConf
-from .hdu import copy_img
+from . import _pinned
+from .hdu import ImageHDU, copy_img
 from .plan import get_plan
 from .set_wv_parameters import set_wv_parameters
 
@@ -34,6 +35,21 @@ def _auto_dtype(array):
     if (kind == "f" and size <= 4) or (kind in "iu" and size <= 2) or kind == "b":
         return "float32"
     return "float64"
+
+
+def _copy_for_result(img):
+    """``copy_img`` (apply_rectwv_coeff.py:69) without duplicating pixels that are replaced.
+
+    The reference deep-copies the input and later replaces the primary data by the rectified
+    image; the primary pixels of the copy are never used.  For this package's own HDU classes
+    the copy therefore shares the (never modified) primary array with the input -- headers and
+    extension HDUs are copied as before; unknown HDU classes (astropy) take the deep copy.
+    """
+    primary = img[0]
+    if not isinstance(primary, ImageHDU):
+        return copy_img(img)
+    light = type(primary)(data=primary.data, header=primary.header.copy())
+    return type(img)([light] + [hdu.copy() for hdu in img[1:]])
 
 
 def _check_tags(header, rectwv_coeff, logger):
@@ -156,7 +172,7 @@ def apply_rectwv_coeff(reduced_image, rectwv_coeff, args_resampling=2,
     """
     logger = logging.getLogger(__name__)
 
-    rectwv_image = copy_img(reduced_image)
+    rectwv_image = _copy_for_result(reduced_image)
     header = rectwv_image[0].header
     image2d = rectwv_image[0].data
 
@@ -187,7 +203,10 @@ def apply_rectwv_coeff(reduced_image, rectwv_coeff, args_resampling=2,
             raise ValueError("Unexpected naxis1")
         if image2d.shape[0] != EMIR_NAXIS2:
             raise ValueError("Unexpected naxis2")
-        out, jminmax = plan.run_host(image2d)
+        # the result lands in page-locked memory (a pooled buffer: _pinned.py): the copy back
+        # runs at PCIe speed instead of at the speed of page faults
+        out = _pinned.empty((1,) + plan.out_shape, plan.np_dtype)
+        out, jminmax = plan.run_host(image2d, out=out)
         image2d_rectwv = out[0].astype(np.float32, copy=False)
         jminmax = jminmax[0]
     else:

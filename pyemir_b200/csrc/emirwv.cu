@@ -35,6 +35,7 @@
 
 #include <cuda.h>               // CUtensorMap and its enums (types only: libcuda is not linked)
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: nothing is linked
 
 #include <algorithm>
 #include <atomic>
@@ -302,6 +303,7 @@ struct emirwv_plan {
     void *d_border = nullptr, *d_pix = nullptr;
     Tile *d_tiles = nullptr;
     int2 *d_fillruns = nullptr;        // [ntiles_empty * rps] zero runs of one frame
+    int2 *d_cover = nullptr;           // [nsl] covered output columns (sparse copy-back kernel)
 
     std::vector<SlitDev> h_slit;
     std::vector<int32_t> h_base;
@@ -329,14 +331,32 @@ struct emirwv_plan {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     mutable std::mutex aux_mu;
 
+    // calibration images of the flow in front of the path (emirwv_plan_set_calibration)
+    uint8_t *d_bpm = nullptr;
+    void *d_bias = nullptr, *d_dark = nullptr, *d_flat = nullptr;
+    int cal_dtype = EMIRWV_F32;
+
     std::mutex mu;
     struct Slot {
         void *d_in = nullptr;
         void *d_out = nullptr;
+        void *d_raw = nullptr;         // raw frames before the flow (allocated on first use)
         int32_t *d_jmm = nullptr;
         cudaStream_t stream = nullptr;
+        cudaEvent_t ev_ready = nullptr;   // the slot's products are complete
+        cudaEvent_t ev_free = nullptr;    // the consumer stream is through with them
     } slots[HOST_SLOTS];
     int ws_chunk = 0;
+    size_t ws_raw_bytes = 0;           // bytes per frame the d_raw buffers were sized for
+    // ABBA host entry: consumer stream, float64 sums, result image, frame stack (median /
+    // sigma clipping), shifted chunk
+    cudaStream_t acc = nullptr;
+    double *d_sums = nullptr;
+    float *d_image = nullptr;
+    void *d_stack = nullptr;
+    size_t stack_bytes = 0;
+    void *d_shift = nullptr;
+    int shift_chunk = 0;
 };
 
 namespace {
@@ -380,6 +400,14 @@ int emirwv_device_count(void) {
     if (err != cudaSuccess)
         return fail(EMIRWV_E_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(err));
     return n;
+}
+
+int emirwv_get_device(void) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess)
+        return fail(EMIRWV_E_CUDA, "cudaGetDevice failed: %s", cudaGetErrorString(err));
+    return dev;
 }
 
 int emirwv_set_device(int device) {
@@ -428,7 +456,17 @@ void emirwv_plan_destroy(emirwv_plan *pl) {
     cudaFree(pl->d_pix);
     cudaFree(pl->d_tiles);
     cudaFree(pl->d_fillruns);
+    cudaFree(pl->d_cover);
     cudaFree(pl->d_sched);
+    cudaFree(pl->d_bpm);
+    cudaFree(pl->d_bias);
+    cudaFree(pl->d_dark);
+    cudaFree(pl->d_flat);
+    cudaFree(pl->d_sums);
+    cudaFree(pl->d_image);
+    cudaFree(pl->d_stack);
+    cudaFree(pl->d_shift);
+    if (pl->acc) cudaStreamDestroy(pl->acc);
     delete pl;
 }
 
@@ -500,6 +538,211 @@ int emirwv_plan_get_coverage(const emirwv_plan *pl, int32_t *h_cover) {
     return EMIRWV_OK;
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------ host-buffer entries
+namespace {
+
+// NVTX ranges around plan build / copies / kernels of the host entries (header-only NVTX 3: no
+// library is linked, the calls are no-ops unless a tool is attached)
+struct nvtx_range {
+    bool open = true;
+    explicit nvtx_range(const char *name) { nvtxRangePushA(name); }
+    void end() {
+        if (open) nvtxRangePop();
+        open = false;
+    }
+    ~nvtx_range() { end(); }
+};
+
+// The covered columns of every slitlet of n products, device -> the caller's pinned output
+// buffer through its device alias: a warp per (frame, output row) writes the row's covered run
+// with 16-byte stores that go out over PCIe; ONE launch per chunk instead of one strided copy
+// per slitlet (55 per chunk).
+template <typename T>
+__global__ void __launch_bounds__(256) k_copy_cover(const T *__restrict__ src, T *__restrict__ dst,
+                                                    const int2 *__restrict__ cover, int nsl, int rps,
+                                                    int nout, int nframes, int vec_ok) {
+    using V = typename Vec16<T>::type;
+    constexpr int VN = Vec16<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long units = (long long)nframes * nsl * rps;
+    for (long long u = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units;
+         u += nwarps) {
+        const int2 cv = cover[(int)((u / rps) % nsl)];
+        const size_t row = (size_t)u * nout;
+        if (vec_ok) {
+            for (int c = (cv.x / VN + lane) * VN; c < cv.y; c += 32 * VN) {
+                if (c >= cv.x && c + VN <= cv.y) {
+                    *reinterpret_cast<V *>(dst + row + c) = __ldcs(reinterpret_cast<const V *>(src + row + c));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j)
+                        if (c + j >= cv.x && c + j < cv.y) dst[row + c + j] = src[row + c + j];
+                }
+            }
+        } else {
+            for (int c = cv.x + lane; c < cv.y; c += 32) dst[row + c] = src[row + c];
+        }
+    }
+}
+
+int launch_copy_cover(emirwv_plan *pl, const void *d_src, void *d_host_alias, int n, cudaStream_t st) {
+    if (pl->d_cover == nullptr) {
+        CUDA_TRY(cudaMalloc(&pl->d_cover, pl->h_cover.size() * sizeof(int32_t)));
+        CUDA_TRY(cudaMemcpy(pl->d_cover, pl->h_cover.data(), pl->h_cover.size() * sizeof(int32_t),
+                            cudaMemcpyHostToDevice));
+    }
+    const int vec_ok = ((size_t)pl->nout * pl->esize) % 16 == 0 &&
+                       (reinterpret_cast<uintptr_t>(d_host_alias) & 15u) == 0;
+    const int grid = std::max(1, env_int("EMIRWV_PACK_BLOCKS", pl->num_sms));
+    if (pl->dtype == EMIRWV_F32)
+        k_copy_cover<float><<<grid, 256, 0, st>>>(static_cast<const float *>(d_src),
+                                                  static_cast<float *>(d_host_alias), pl->d_cover,
+                                                  pl->nsl, pl->rps, pl->nout, n, vec_ok);
+    else
+        k_copy_cover<double><<<grid, 256, 0, st>>>(static_cast<const double *>(d_src),
+                                                   static_cast<double *>(d_host_alias), pl->d_cover,
+                                                   pl->nsl, pl->rps, pl->nout, n, vec_ok);
+    CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+size_t dtype_size(int dtype) { return dtype == EMIRWV_F64 ? 8 : (dtype == EMIRWV_U16 ? 2 : 4); }
+
+// device address of a pinned host buffer the GPU can write to directly, or NULL
+void *mapped_alias(void *h_ptr) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, h_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
+}
+
+// one chunk of frames into a slot and through the kernels: host -> device, the flow of the
+// recipes when the frames are raw (bad pixels, bias, dark, flat: one pass), the hot kernel.
+// The products land in d_dst (the slot's own buffer or a place in a stack).
+int enqueue_chunk(emirwv_plan *pl, emirwv_plan::Slot &sl, const void *h_src, int in_dtype,
+                  bool raw, int n, void *d_dst, int32_t *d_jmm) {
+    const size_t npix = (size_t)pl->desc.naxis1 * pl->desc.naxis2;
+    nvtx_range r_h2d("emirwv: host -> device");
+    if (!raw) {
+        CUDA_TRY(cudaMemcpyAsync(sl.d_in, h_src, npix * pl->esize * n, cudaMemcpyHostToDevice,
+                                 sl.stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(sl.d_raw, h_src, npix * dtype_size(in_dtype) * n,
+                                 cudaMemcpyHostToDevice, sl.stream));
+        const int rc = emirwv_prereduce_ex(sl.d_raw, in_dtype, static_cast<float *>(sl.d_in), n,
+                                           pl->desc.naxis2, pl->desc.naxis1, pl->d_bpm, pl->d_bias,
+                                           pl->d_dark, pl->d_flat, pl->cal_dtype, sl.stream);
+        if (rc) return rc;
+    }
+    r_h2d.end();
+    nvtx_range r_k("emirwv: k_rectwv");
+    if (pl->dtype == EMIRWV_F32) return launch_t<float>(pl, sl.d_in, d_dst, n, d_jmm, sl.stream);
+    return launch_t<double>(pl, sl.d_in, d_dst, n, d_jmm, sl.stream);
+}
+
+int ensure_raw(emirwv_plan *pl, int chunk, int in_dtype) {
+    const size_t per_frame = (size_t)pl->desc.naxis1 * pl->desc.naxis2 * dtype_size(in_dtype);
+    if (pl->ws_raw_bytes >= per_frame && pl->slots[0].d_raw != nullptr) return EMIRWV_OK;
+    for (auto &sl : pl->slots) {
+        if (sl.d_raw) cudaFree(sl.d_raw);
+        sl.d_raw = nullptr;
+        CUDA_TRY(cudaMalloc(&sl.d_raw, per_frame * pl->ws_chunk));
+    }
+    pl->ws_raw_bytes = per_frame;
+    (void)chunk;
+    return EMIRWV_OK;
+}
+
+int check_raw(const emirwv_plan *pl, int in_dtype, bool raw) {
+    if (!raw) {
+        if (in_dtype != pl->dtype)
+            return fail(EMIRWV_E_VALUE, "reduced frames must have the dtype of the plan");
+        return EMIRWV_OK;
+    }
+    if (in_dtype != EMIRWV_F32 && in_dtype != EMIRWV_F64 && in_dtype != EMIRWV_U16)
+        return fail(EMIRWV_E_VALUE, "unknown image dtype");
+    if (pl->dtype != EMIRWV_F32)
+        return fail(EMIRWV_E_VALUE, "raw frames need a float32 plan (the flow rounds to float32)");
+    return EMIRWV_OK;
+}
+
+int run_host_impl(emirwv_plan *pl, const void *h_in, int in_dtype, bool raw, void *h_out,
+                  int nframes, int32_t *h_jminmax, bool sparse) {
+    DeviceGuard guard(pl->device);
+    std::lock_guard<std::mutex> lock(pl->mu);
+    nvtx_range r_all("emirwv_run_host");
+    // frames per pipeline slot: 4 keeps the ramp over PCIe short; the sparse copy-back takes 8
+    const int chunk = std::max(1, std::min(nframes, env_int("EMIRWV_HOST_CHUNK", sparse ? 8 : 4)));
+    int rc = ensure_workspace(pl, chunk);
+    if (rc == EMIRWV_OK && raw) rc = ensure_raw(pl, chunk, in_dtype);
+    if (rc) return rc;
+    const size_t in_b = (size_t)pl->desc.naxis1 * pl->desc.naxis2 * (raw ? dtype_size(in_dtype) : pl->esize);
+    const size_t out_b = (size_t)pl->nsl * pl->rps * pl->nout * pl->esize;
+    const size_t jmm_b = (size_t)pl->nsl * 2 * sizeof(int32_t);
+    // the covered columns can be written straight into a pinned output buffer by a kernel (one
+    // launch per chunk); a pageable buffer takes one strided copy per slitlet
+    char *alias = sparse && env_int("EMIRWV_HOST_PACK", 1) ? static_cast<char *>(mapped_alias(h_out))
+                                                           : nullptr;
+    int slot = 0;
+    // (an error inside the loop must not return while other slots still copy from / into the
+    // caller's buffers: break, then wait for every stream below)
+    auto step = [&](int f0, emirwv_plan::Slot &sl) -> int {
+        const int n = std::min(chunk, nframes - f0);
+        int rc2 = enqueue_chunk(pl, sl, static_cast<const char *>(h_in) + (size_t)f0 * in_b,
+                                in_dtype, raw, n, sl.d_out, sl.d_jmm);
+        if (rc2) return rc2;
+        nvtx_range r_d2h("emirwv: device -> host");
+        char *dst = static_cast<char *>(h_out) + (size_t)f0 * out_b;
+        if (!sparse) {
+            CUDA_TRY(cudaMemcpyAsync(dst, sl.d_out, out_b * n, cudaMemcpyDeviceToHost, sl.stream));
+        } else if (alias != nullptr) {
+            rc2 = launch_copy_cover(pl, sl.d_out, alias + (size_t)f0 * out_b, n, sl.stream);
+            if (rc2) return rc2;
+        } else {
+            // only the columns with wavelength coverage travel: one strided copy per slitlet
+            // (its live columns x 38 rows x n frames); the rest of h_out already holds the
+            // zeros the reference writes there
+            const size_t pitch = (size_t)pl->nout * pl->esize;
+            const size_t rows = (size_t)pl->nsl * pl->rps;
+            for (int s = 0; s < pl->nsl; ++s) {
+                const int lo = pl->h_cover[2 * s], hi = pl->h_cover[2 * s + 1];
+                if (hi <= lo) continue;
+                cudaMemcpy3DParms cp;
+                memset(&cp, 0, sizeof(cp));
+                cp.srcPtr = make_cudaPitchedPtr(sl.d_out, pitch, pitch, rows);
+                cp.dstPtr = make_cudaPitchedPtr(dst, pitch, pitch, rows);
+                cp.srcPos = cp.dstPos = make_cudaPos((size_t)lo * pl->esize, (size_t)s * pl->rps, 0);
+                cp.extent = make_cudaExtent((size_t)(hi - lo) * pl->esize, (size_t)pl->rps, (size_t)n);
+                cp.kind = cudaMemcpyDeviceToHost;
+                CUDA_TRY(cudaMemcpy3DAsync(&cp, sl.stream));
+            }
+        }
+        if (h_jminmax != nullptr)
+            CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char *>(h_jminmax) + (size_t)f0 * jmm_b,
+                                     sl.d_jmm, jmm_b * n, cudaMemcpyDeviceToHost, sl.stream));
+        return EMIRWV_OK;
+    };
+    for (int f0 = 0; f0 < nframes && rc == EMIRWV_OK; f0 += chunk, slot = (slot + 1) % HOST_SLOTS)
+        rc = step(f0, pl->slots[slot]);
+    const std::string keep = g_error;
+    for (auto &sl : pl->slots) {
+        cudaError_t err = cudaStreamSynchronize(sl.stream);
+        if (err != cudaSuccess && rc == EMIRWV_OK)
+            rc = fail(EMIRWV_E_CUDA, "stream failed: %s", cudaGetErrorString(err));
+    }
+    if (rc != EMIRWV_OK && !keep.empty()) g_error = keep;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
 int emirwv_run_host(emirwv_plan *pl, const void *h_in, void *h_out, int nframes,
                     int32_t *h_jminmax) {
     return emirwv_run_host_ex(pl, h_in, h_out, nframes, h_jminmax, 0u);
@@ -512,62 +755,185 @@ int emirwv_run_host_ex(emirwv_plan *pl, const void *h_in, void *h_out, int nfram
     if (nframes < 0) return fail(EMIRWV_E_VALUE, "negative frame count");
     if (flags & ~(uint32_t)EMIRWV_HOST_OUT_ZEROED) return fail(EMIRWV_E_VALUE, "unknown flag");
     if (nframes == 0) return EMIRWV_OK;
-    const bool sparse = (flags & EMIRWV_HOST_OUT_ZEROED) != 0;
+    return run_host_impl(pl, h_in, pl->dtype, false, h_out, nframes, h_jminmax,
+                         (flags & EMIRWV_HOST_OUT_ZEROED) != 0);
+}
+
+int emirwv_plan_set_calibration(emirwv_plan *pl, const uint8_t *h_bpm, const void *h_bias,
+                                const void *h_dark, const void *h_flat, int cal_dtype) {
+    if (pl == nullptr) return fail(EMIRWV_E_VALUE, "null plan");
+    if (cal_dtype != EMIRWV_F32 && cal_dtype != EMIRWV_F64)
+        return fail(EMIRWV_E_VALUE, "unknown calibration dtype");
     DeviceGuard guard(pl->device);
     std::lock_guard<std::mutex> lock(pl->mu);
-    // frames per pipeline slot: 4 keeps the ramp over PCIe short; the sparse copy-back issues
-    // one strided copy per slitlet and slot, so it takes 8 (measured: 2.08 k vs 1.87 k frames/s)
-    const int chunk = std::max(1, std::min(nframes, env_int("EMIRWV_HOST_CHUNK", sparse ? 8 : 4)));
-    int rc = ensure_workspace(pl, chunk);
-    if (rc) return rc;
-    const size_t in_b = (size_t)pl->desc.naxis1 * pl->desc.naxis2 * pl->esize;
-    const size_t out_b = (size_t)pl->nsl * pl->rps * pl->nout * pl->esize;
-    const size_t jmm_b = (size_t)pl->nsl * 2 * sizeof(int32_t);
-    int slot = 0;
-    for (int f0 = 0; f0 < nframes; f0 += chunk, slot = (slot + 1) % HOST_SLOTS) {
-        const int n = std::min(chunk, nframes - f0);
-        emirwv_plan::Slot &sl = pl->slots[slot];
-        CUDA_TRY(cudaMemcpyAsync(sl.d_in, static_cast<const char *>(h_in) + (size_t)f0 * in_b,
-                                 in_b * n, cudaMemcpyHostToDevice, sl.stream));
-        if (pl->dtype == EMIRWV_F32)
-            rc = launch_t<float>(pl, sl.d_in, sl.d_out, n, sl.d_jmm, sl.stream);
-        else
-            rc = launch_t<double>(pl, sl.d_in, sl.d_out, n, sl.d_jmm, sl.stream);
-        if (rc) break;
-        if (!sparse) {
-            CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(h_out) + (size_t)f0 * out_b, sl.d_out,
-                                     out_b * n, cudaMemcpyDeviceToHost, sl.stream));
-        } else {
-            // only the columns with wavelength coverage travel: one strided copy per
-            // slitlet (its live columns x 38 rows x n frames); the rest of h_out already
-            // holds the zeros the reference writes there
-            const size_t pitch = (size_t)pl->nout * pl->esize;
-            const size_t rows = (size_t)pl->nsl * pl->rps;
-            for (int s = 0; s < pl->nsl; ++s) {
-                const int lo = pl->h_cover[2 * s], hi = pl->h_cover[2 * s + 1];
-                if (hi <= lo) continue;
-                cudaMemcpy3DParms cp;
-                memset(&cp, 0, sizeof(cp));
-                cp.srcPtr = make_cudaPitchedPtr(sl.d_out, pitch, pitch, rows);
-                cp.dstPtr = make_cudaPitchedPtr(static_cast<char *>(h_out) + (size_t)f0 * out_b,
-                                                pitch, pitch, rows);
-                cp.srcPos = cp.dstPos = make_cudaPos((size_t)lo * pl->esize,
-                                                     (size_t)s * pl->rps, 0);
-                cp.extent = make_cudaExtent((size_t)(hi - lo) * pl->esize, (size_t)pl->rps,
-                                            (size_t)n);
-                cp.kind = cudaMemcpyDeviceToHost;
-                CUDA_TRY(cudaMemcpy3DAsync(&cp, sl.stream));
-            }
+    const size_t npix = (size_t)pl->desc.naxis1 * pl->desc.naxis2;
+    const size_t csize = cal_dtype == EMIRWV_F64 ? 8 : 4;
+    auto put = [&](void **d_ptr, const void *h_ptr, size_t nbytes) -> int {
+        if (*d_ptr) cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        if (h_ptr == nullptr) return EMIRWV_OK;
+        if (cudaMalloc(d_ptr, nbytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(EMIRWV_E_NOMEM, "out of device memory");
         }
-        if (h_jminmax != nullptr)
-            CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char *>(h_jminmax) + (size_t)f0 * jmm_b,
-                                     sl.d_jmm, jmm_b * n, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(cudaMemcpy(*d_ptr, h_ptr, nbytes, cudaMemcpyHostToDevice));
+        return EMIRWV_OK;
+    };
+    for (auto &sl : pl->slots) cudaStreamSynchronize(sl.stream);
+    int rc = put(reinterpret_cast<void **>(&pl->d_bpm), h_bpm, npix);
+    if (rc == EMIRWV_OK) rc = put(&pl->d_bias, h_bias, npix * csize);
+    if (rc == EMIRWV_OK) rc = put(&pl->d_dark, h_dark, npix * csize);
+    if (rc == EMIRWV_OK) rc = put(&pl->d_flat, h_flat, npix * csize);
+    pl->cal_dtype = cal_dtype;
+    return rc;
+}
+
+int emirwv_run_host_raw(emirwv_plan *pl, const void *h_raw, int raw_dtype, void *h_out,
+                        int nframes, int32_t *h_jminmax, uint32_t flags) {
+    if (pl == nullptr || h_raw == nullptr || h_out == nullptr)
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (nframes < 0) return fail(EMIRWV_E_VALUE, "negative frame count");
+    if (flags & ~(uint32_t)EMIRWV_HOST_OUT_ZEROED) return fail(EMIRWV_E_VALUE, "unknown flag");
+    const int rc = check_raw(pl, raw_dtype, true);
+    if (rc) return rc;
+    if (nframes == 0) return EMIRWV_OK;
+    return run_host_impl(pl, h_raw, raw_dtype, true, h_out, nframes, h_jminmax,
+                         (flags & EMIRWV_HOST_OUT_ZEROED) != 0);
+}
+
+int emirwv_abba_host(emirwv_plan *pl, const void *h_in, int in_dtype, int nframes,
+                     const int8_t *h_labels, const double *h_offset, int method, double low,
+                     double high, float *h_out, uint32_t flags) {
+    if (pl == nullptr || h_in == nullptr || h_labels == nullptr || h_out == nullptr)
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (nframes < 1 || nframes > 32768) return fail(EMIRWV_E_VALUE, "size out of range");
+    if (flags & ~(uint32_t)EMIRWV_HOST_RAW) return fail(EMIRWV_E_VALUE, "unknown flag");
+    if (method != EMIRWV_MEAN && method != EMIRWV_MEDIAN && method != EMIRWV_SIGMACLIP)
+        return fail(EMIRWV_E_VALUE, "Unexpected method");
+    const bool raw = (flags & EMIRWV_HOST_RAW) != 0;
+    int rc = check_raw(pl, in_dtype, raw);
+    if (rc) return rc;
+    std::vector<int32_t> ia, ib;
+    for (int f = 0; f < nframes; ++f) {
+        if (h_labels[f] > 0) ia.push_back(f);
+        else if (h_labels[f] < 0) ib.push_back(f);
     }
+    if (ia.empty() || ib.empty()) return fail(EMIRWV_E_VALUE, "both A and B images are needed");
+    const bool stacked = method != EMIRWV_MEAN;
+    if (stacked && (ia.size() > (size_t)STACK_MAX || ib.size() > (size_t)STACK_MAX))
+        return fail(EMIRWV_E_LIMIT, "median / sigmaclip of more than %d images per position", STACK_MAX);
+    // the recipe passes yoffset = -offset and leaves frames with a zero offset alone (abba.py:554-556)
+    std::vector<double> yoff(nframes, 0.0);
+    bool any_shift = false;
+    if (h_offset != nullptr)
+        for (int f = 0; f < nframes; ++f) {
+            if (!std::isfinite(h_offset[f])) return fail(EMIRWV_E_VALUE, "offset of frame %d is not finite", f);
+            yoff[f] = h_offset[f] != 0.0 ? -h_offset[f] : 0.0;
+            any_shift |= h_offset[f] != 0.0;
+        }
+
+    DeviceGuard guard(pl->device);
+    std::lock_guard<std::mutex> lock(pl->mu);
+    nvtx_range r_all("emirwv_abba_host");
+    const int chunk = std::max(1, std::min(nframes, env_int("EMIRWV_HOST_CHUNK", 8)));
+    rc = ensure_workspace(pl, chunk);
+    if (rc == EMIRWV_OK && raw) rc = ensure_raw(pl, chunk, in_dtype);
+    if (rc) return rc;
+    const size_t npix_out = (size_t)pl->nsl * pl->rps * pl->nout;
+    const size_t in_b = (size_t)pl->desc.naxis1 * pl->desc.naxis2 * (raw ? dtype_size(in_dtype) : pl->esize);
+    // the shifted frames are float32 like the recipe's `.astype("float32")`
+    const size_t shift_esize = 4;
+    const int comb_dtype = any_shift ? EMIRWV_F32 : pl->dtype;
+    const size_t comb_esize = any_shift ? shift_esize : pl->esize;
+    if (pl->acc == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&pl->acc, cudaStreamNonBlocking));
+    if (pl->d_image == nullptr) CUDA_TRY(cudaMalloc(&pl->d_image, npix_out * sizeof(float)));
+    if (!stacked && pl->d_sums == nullptr) CUDA_TRY(cudaMalloc(&pl->d_sums, 2 * npix_out * sizeof(double)));
+    if (stacked && pl->stack_bytes < (size_t)nframes * npix_out * comb_esize) {
+        cudaFree(pl->d_stack);
+        pl->d_stack = nullptr;
+        pl->stack_bytes = 0;
+        if (cudaMalloc(&pl->d_stack, (size_t)nframes * npix_out * comb_esize) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(EMIRWV_E_NOMEM, "out of device memory for the stack of %d products", nframes);
+        }
+        pl->stack_bytes = (size_t)nframes * npix_out * comb_esize;
+    }
+    if (any_shift && !stacked && pl->shift_chunk < chunk) {
+        cudaFree(pl->d_shift);
+        pl->d_shift = nullptr;
+        CUDA_TRY(cudaMalloc(&pl->d_shift, (size_t)chunk * npix_out * shift_esize));
+        pl->shift_chunk = chunk;
+    }
+    int8_t *d_labels = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_labels, (size_t)nframes, pl->acc));
+
+    // Slot streams: host -> device, flow, hot kernel.  Consumer stream `acc`, chunk after chunk
+    // in frame order: the offsets of the chunk's frames, then the float64 sums (mean) -- so the
+    // sums run in frame order whatever the slots do -- or nothing (stack: the frames are
+    // rectified or shifted straight into their place).
+    // (an error must not return while streams still read the caller's buffers: the steps are
+    // lambdas, the streams are drained below whatever happened)
+    auto step = [&](int f0, int nchunk, emirwv_plan::Slot &sl) -> int {
+        const int n = std::min(chunk, nframes - f0);
+        if (nchunk >= HOST_SLOTS) CUDA_TRY(cudaStreamWaitEvent(sl.stream, sl.ev_free, 0));
+        char *place = stacked ? static_cast<char *>(pl->d_stack) + (size_t)f0 * npix_out * comb_esize : nullptr;
+        void *d_dst = (stacked && !any_shift) ? static_cast<void *>(place) : sl.d_out;
+        int rc2 = enqueue_chunk(pl, sl, static_cast<const char *>(h_in) + (size_t)f0 * in_b, in_dtype,
+                                raw, n, d_dst, nullptr);
+        if (rc2) return rc2;
+        CUDA_TRY(cudaEventRecord(sl.ev_ready, sl.stream));
+        CUDA_TRY(cudaStreamWaitEvent(pl->acc, sl.ev_ready, 0));
+        const void *d_comb = d_dst;
+        if (any_shift) {
+            void *d_sh = stacked ? static_cast<void *>(place) : pl->d_shift;
+            rc2 = emirwv_shift_rows(sl.d_out, pl->dtype, d_sh, EMIRWV_F32, n, pl->nsl * pl->rps,
+                                    pl->nout, yoff.data() + f0, pl->acc);
+            if (rc2) return rc2;
+            d_comb = d_sh;
+        }
+        if (!stacked) {
+            rc2 = emirwv_abba_partial(d_comb, d_labels + f0, n, (int64_t)npix_out, comb_dtype,
+                                      pl->d_sums, pl->d_sums + npix_out, f0 > 0 ? 1 : 0, pl->acc);
+            if (rc2) return rc2;
+        }
+        CUDA_TRY(cudaEventRecord(sl.ev_free, pl->acc));
+        return EMIRWV_OK;
+    };
+    {
+        cudaError_t e0 = cudaMemcpyAsync(d_labels, h_labels, (size_t)nframes, cudaMemcpyHostToDevice, pl->acc);
+        if (e0 != cudaSuccess) rc = fail(EMIRWV_E_CUDA, "copy failed: %s", cudaGetErrorString(e0));
+    }
+    int slot = 0, nchunk = 0;
+    for (int f0 = 0; f0 < nframes && rc == EMIRWV_OK; f0 += chunk, slot = (slot + 1) % HOST_SLOTS, ++nchunk)
+        rc = step(f0, nchunk, pl->slots[slot]);
+    if (rc == EMIRWV_OK) {
+        if (method == EMIRWV_MEAN)
+            rc = emirwv_abba_finish(pl->d_sums, pl->d_sums + npix_out, (int)ia.size(), (int)ib.size(),
+                                    (int64_t)npix_out, pl->d_image, pl->acc);
+        else if (method == EMIRWV_MEDIAN)
+            rc = emirwv_abba_median(pl->d_stack, nframes, ia.data(), (int)ia.size(), ib.data(),
+                                    (int)ib.size(), (int64_t)npix_out, comb_dtype, pl->d_image, pl->acc);
+        else
+            rc = emirwv_abba_sigmaclip(pl->d_stack, nframes, ia.data(), (int)ia.size(), ib.data(),
+                                       (int)ib.size(), (int64_t)npix_out, comb_dtype, low, high,
+                                       pl->d_image, pl->acc);
+    }
+    if (rc == EMIRWV_OK) {
+        cudaError_t err = cudaMemcpyAsync(h_out, pl->d_image, npix_out * sizeof(float),
+                                          cudaMemcpyDeviceToHost, pl->acc);
+        if (err != cudaSuccess) rc = fail(EMIRWV_E_CUDA, "copy failed: %s", cudaGetErrorString(err));
+    }
+    cudaFreeAsync(d_labels, pl->acc);
+    const std::string keep = g_error;
     for (auto &sl : pl->slots) {
         cudaError_t err = cudaStreamSynchronize(sl.stream);
         if (err != cudaSuccess && rc == EMIRWV_OK)
             rc = fail(EMIRWV_E_CUDA, "stream failed: %s", cudaGetErrorString(err));
     }
+    cudaError_t err = cudaStreamSynchronize(pl->acc);
+    if (err != cudaSuccess && rc == EMIRWV_OK)
+        rc = fail(EMIRWV_E_CUDA, "stream failed: %s", cudaGetErrorString(err));
+    if (rc != EMIRWV_OK && !keep.empty()) g_error = keep;
     return rc;
 }
 

@@ -724,10 +724,14 @@ void release_workspace(emirwv_plan *pl) {
         if (sl.d_in) cudaFree(sl.d_in);
         if (sl.d_out) cudaFree(sl.d_out);
         if (sl.d_jmm) cudaFree(sl.d_jmm);
+        if (sl.d_raw) cudaFree(sl.d_raw);
+        if (sl.ev_ready) cudaEventDestroy(sl.ev_ready);
+        if (sl.ev_free) cudaEventDestroy(sl.ev_free);
         if (sl.stream) cudaStreamDestroy(sl.stream);
         sl = emirwv_plan::Slot();
     }
     pl->ws_chunk = 0;
+    pl->ws_raw_bytes = 0;
 }
 
 int ensure_workspace(emirwv_plan *pl, int chunk) {
@@ -740,6 +744,8 @@ int ensure_workspace(emirwv_plan *pl, int chunk) {
         CUDA_TRY(cudaMalloc(&sl.d_out, out_b * chunk));
         CUDA_TRY(cudaMalloc(&sl.d_jmm, (size_t)chunk * pl->nsl * 2 * sizeof(int32_t)));
         CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_ready, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_free, cudaEventDisableTiming));
     }
     pl->ws_chunk = chunk;
     return EMIRWV_OK;

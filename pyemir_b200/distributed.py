@@ -15,6 +15,7 @@ functions are backend-agnostic and never touch pixel arithmetic themselves.
 """
 
 import os
+import subprocess
 
 import torch
 import torch.distributed as dist
@@ -126,3 +127,83 @@ def rectify_sharded(frames_local, rectwv_coeff, args_resampling=2, dtype="float3
     elif combine is not None:
         raise ValueError("combine must be None, 'mean' or 'gather'")
     return out, jmm, combined
+
+
+# --------------------------------------------------------------------------- host placement
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(index):
+    """NUMA node the GPU ``index`` hangs off (sysfs, then ``nvidia-smi topo``), or None."""
+    try:
+        props = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fd:
+            node = int(fd.read().strip())
+        if node >= 0:
+            return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    try:
+        text = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True,
+                              timeout=20).stdout
+        header = None
+        for line in text.splitlines():
+            cells = [c.strip() for c in line.split("\t") if c.strip()]
+            if not cells:
+                continue
+            if header is None and any("NUMA Affinity" in c for c in cells):
+                header = cells
+                continue
+            if header is not None and cells[0] == f"GPU{index}":
+                # the header has no cell above the row labels
+                col = [i for i, c in enumerate(header) if "NUMA Affinity" in c][0] + 1
+                if col < len(cells):
+                    return int(cells[col].split("-")[0].split(",")[0])
+    except (OSError, ValueError, IndexError, subprocess.SubprocessError):
+        pass
+    return None
+
+
+def bind_to_gpu_numa(index):
+    """Run this process on the CPUs of the NUMA node of GPU ``index`` and prefer that node's
+    memory, so that the page-locked buffers it allocates AFTERWARDS sit next to the PCIe root
+    the GPU hangs off (one process per GPU: without it every rank's buffers may land on the node
+    the launcher started on, and all copies of all GPUs go through one node's memory and the
+    socket interconnect).  Returns what was done, for the record.  ``EMIRWV_NUMA_BIND=0`` skips it.
+    """
+    info = {"numa_node": None, "cpus": None, "mempolicy": None}
+    if os.environ.get("EMIRWV_NUMA_BIND", "1") == "0":
+        info["skipped"] = "EMIRWV_NUMA_BIND=0"
+        return info
+    node = gpu_numa_node(index)
+    info["numa_node"] = node
+    if node is None:
+        return info
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fd:
+            cpus = _parse_cpulist(fd.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        info["cpus"] = len(cpus)
+    except (OSError, ValueError):
+        pass
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        mpol_preferred, nr_set_mempolicy = 1, 238            # x86-64
+        mask = ctypes.c_ulong(1 << node)
+        rc = libc.syscall(nr_set_mempolicy, mpol_preferred, ctypes.byref(mask),
+                          ctypes.c_ulong(8 * ctypes.sizeof(mask)))
+        info["mempolicy"] = "preferred" if rc == 0 else f"errno {ctypes.get_errno()}"
+    except (OSError, AttributeError):
+        pass
+    return info

@@ -140,11 +140,18 @@ class RectWavePlan:
                 sl.wpoly[k] = float(c)
             self.bbox[islitlet] = (sl.bb_ns2_orig - sl.bb_ns1_orig + 1,
                                    sl.bb_nc2_orig - sl.bb_nc1_orig + 1)
-        if device is not None:
-            _cabi.check(self._lib.emirwv_set_device(int(device)))
-        self.device = device
-        _cabi.check(self._lib.emirwv_plan_create(ctypes.byref(desc),
-                                                 ctypes.byref(self._handle)))
+        # the plan lives on `device` (default: the thread's current one); the thread's current
+        # device is the same after the call as before
+        previous = _cabi.check(self._lib.emirwv_get_device())
+        self.device = previous if device is None else int(device)
+        if self.device != previous:
+            _cabi.check(self._lib.emirwv_set_device(self.device))
+        try:
+            _cabi.check(self._lib.emirwv_plan_create(ctypes.byref(desc),
+                                                     ctypes.byref(self._handle)))
+        finally:
+            if self.device != previous:
+                self._lib.emirwv_set_device(previous)
         self.naxis2_out = EMIR_NBARS * EMIR_NPIXPERSLIT_RECTIFIED
 
     # -- lifetime ----------------------------------------------------------
@@ -209,6 +216,88 @@ class RectWavePlan:
             jminmax.ctypes.data_as(ctypes.c_void_p),
             _cabi.HOST_OUT_ZEROED if out_zeroed else 0))
         return out, jminmax
+
+    # -- the recipes' flow in front of the path, and the ABBA product behind it -------------
+    _RAW_DTYPES = {"float32": _cabi.F32, "float64": _cabi.F64, "uint16": _cabi.U16}
+
+    def set_calibration(self, bpm=None, bias=None, dark=None, flat=None):
+        """Calibration images of ``flow(newimg)`` (``recipes/spec/abba.py:371``,
+        ``core/recipe.py:25-61``) for :meth:`run_host_raw` / ``abba_host(raw=True)``: (2048, 2048)
+        arrays or None; float64 if any of bias / dark / flat is float64 (numpy's promotion),
+        else float32; ``flat`` values <= 0 count as 1.0 (``flatfield.py:43``)."""
+        cals = [None if c is None else np.asarray(c) for c in (bias, dark, flat)]
+        want64 = any(c is not None and c.dtype == np.float64 for c in cals)
+        cdt = np.float64 if want64 else np.float32
+        cals = [None if c is None else np.ascontiguousarray(c, dtype=cdt) for c in cals]
+        mask = None if bpm is None else np.ascontiguousarray(np.asarray(bpm) != 0, dtype=np.uint8)
+        for c in cals + [mask]:
+            if c is not None and c.shape != (EMIR_NAXIS2, EMIR_NAXIS1):
+                raise ValueError("calibration images must be 2048 x 2048")
+        vp = ctypes.c_void_p
+        ptr = [None if c is None else c.ctypes.data_as(vp) for c in [mask] + cals]
+        _cabi.check(self._lib.emirwv_plan_set_calibration(
+            self._handle, *ptr, _cabi.F64 if want64 else _cabi.F32))
+
+    def run_host_raw(self, raw, out=None, jminmax=None, out_zeroed=False):
+        """RAW frames (uint16 / float32 / float64 host array) through the plan's calibration
+        flow and the path: ``(out, jminmax)`` like :meth:`run_host`.  float32 plans only."""
+        raw = np.ascontiguousarray(raw)
+        if raw.ndim == 2:
+            raw = raw[None]
+        if raw.dtype.name not in self._RAW_DTYPES:
+            raise ValueError("raw frames must be uint16, float32 or float64")
+        self._check_frames(raw.shape)
+        n = raw.shape[0]
+        if out is None:
+            out = np.empty((n,) + self.out_shape, dtype=self.np_dtype)
+            out_zeroed = False
+        if jminmax is None:
+            jminmax = np.empty((n, EMIR_NBARS, 2), dtype=np.int32)
+        assert out.flags.c_contiguous and out.dtype == self.np_dtype
+        vp = ctypes.c_void_p
+        _cabi.check(self._lib.emirwv_run_host_raw(
+            self._handle, raw.ctypes.data_as(vp), self._RAW_DTYPES[raw.dtype.name],
+            out.ctypes.data_as(vp), n, jminmax.ctypes.data_as(vp),
+            _cabi.HOST_OUT_ZEROED if out_zeroed else 0))
+        return out, jminmax
+
+    def abba_host(self, frames, labels, offsets=None, method="mean", low=3.0, high=3.0,
+                  raw=False, out=None):
+        """The ABBA product of host frames in one call (``abba.py:351-381,545-606``): every
+        frame rectified, shifted by its vertical offset, A and B images combined with
+        ``method`` ("mean", "median", "sigmaclip"), float32(A) - float32(B).  Only the
+        (2090, naxis1) float32 image comes back.  ``raw``: the frames are raw and go through
+        the plan's calibration flow first."""
+        frames = np.ascontiguousarray(frames)
+        self._check_frames(frames.shape)
+        n = frames.shape[0]
+        if raw:
+            if frames.dtype.name not in self._RAW_DTYPES:
+                raise ValueError("raw frames must be uint16, float32 or float64")
+            code = self._RAW_DTYPES[frames.dtype.name]
+        else:
+            frames = np.ascontiguousarray(frames, dtype=self.np_dtype)
+            code = _DTYPES[self.dtype][0]
+        lab = np.ascontiguousarray(labels, dtype=np.int8)
+        if lab.shape != (n,):
+            raise ValueError("one label per frame is needed")
+        off = None
+        if offsets is not None:
+            off = np.ascontiguousarray(offsets, dtype=np.float64)
+            if off.shape != (n,):
+                raise ValueError("one offset per frame is needed")
+        methods = {"mean": _cabi.MEAN, "median": _cabi.MEDIAN, "sigmaclip": _cabi.SIGMACLIP}
+        if method not in methods:
+            raise ValueError(f"Unexpected method: {method}")
+        if out is None:
+            out = np.empty(self.out_shape, dtype=np.float32)
+        assert out.flags.c_contiguous and out.dtype == np.float32 and out.shape == self.out_shape
+        vp = ctypes.c_void_p
+        _cabi.check(self._lib.emirwv_abba_host(
+            self._handle, frames.ctypes.data_as(vp), code, n, lab.ctypes.data_as(vp),
+            off.ctypes.data_as(vp) if off is not None else None, methods[method], float(low),
+            float(high), out.ctypes.data_as(vp), _cabi.HOST_RAW if raw else 0))
+        return out
 
     def run_device(self, d_in, d_out, nframes, d_jminmax=0, stream=0, out_zeroed=False):
         """Raw device pointers (ints); asynchronous on ``stream``.  ``out_zeroed``: the
@@ -287,13 +376,43 @@ _CACHE_LOCK = threading.Lock()
 _CACHE_SIZE = 2          # a plan holds up to a few hundred MB of device tables
 
 
+_KEY_MEMO = {}           # quick look -> full fingerprint of the product it was taken from
+
+
+def _quick_look(rectwv_coeff, options):
+    """What changes when a product is edited in place, without serialising all of it: the
+    object, its uuid, offsets, missing slitlets and one coefficient of every table."""
+    prefix = "tti" if options[3] else "ttd"
+    probe = 0.0
+    for entry in rectwv_coeff.contents:
+        coef = entry.get(prefix + "_aij")
+        if coef:
+            probe += float(coef[0]) + float(coef[-1]) + float(entry[prefix + "_bij"][0]) \
+                + float(entry["wpoly_coeff"][0]) + float(entry["wpoly_coeff"][-1])
+    return (id(rectwv_coeff), getattr(rectwv_coeff, "uuid", None),
+            rectwv_coeff.global_integer_offset_x_pix, rectwv_coeff.global_integer_offset_y_pix,
+            tuple(rectwv_coeff.missing_slitlets), len(rectwv_coeff.contents), probe,
+            rectwv_coeff.tags.get("grism", ""), rectwv_coeff.tags.get("filter", "")) + options
+
+
 def get_plan(rectwv_coeff, resampling=2, dtype="float32", max_order=4, grid=None,
              inverse=False, tile_k=0, stages=0, device=None):
     """Cached ``RectWavePlan`` for this product and options."""
     dtype = normalise_dtype(dtype)
-    key = _fingerprint(rectwv_coeff, int(resampling), dtype, int(max_order), bool(inverse),
-                       grid if grid is None else tuple(grid), (tile_k, stages), device)
-    key += ":" + rectwv_coeff.tags.get("grism", "") + ":" + rectwv_coeff.tags.get("filter", "")
+    if device is None:          # the key names the device the plan will really live on
+        device = _cabi.check(_cabi.load().emirwv_get_device())
+    options = (int(resampling), dtype, int(max_order), bool(inverse),
+               grid if grid is None else tuple(grid), (tile_k, stages), device)
+    # the full fingerprint serialises every coefficient (0.6 ms): the loop over exposures of a
+    # recipe passes the same object again and again, so it is remembered per quick look
+    look = _quick_look(rectwv_coeff, options)
+    key = _KEY_MEMO.get(look)
+    if key is None:
+        key = _fingerprint(rectwv_coeff, *options)
+        key += ":" + rectwv_coeff.tags.get("grism", "") + ":" + rectwv_coeff.tags.get("filter", "")
+        if len(_KEY_MEMO) > 64:
+            _KEY_MEMO.clear()
+        _KEY_MEMO[look] = key
     with _CACHE_LOCK:
         plan = _CACHE.get(key)
         if plan is not None:
@@ -311,3 +430,4 @@ def get_plan(rectwv_coeff, resampling=2, dtype="float32", max_order=4, grid=None
 def clear_plan_cache():
     with _CACHE_LOCK:
         _CACHE.clear()
+    _KEY_MEMO.clear()

@@ -172,3 +172,107 @@ def test_bad_pixel_corrector_node_full_frame():
     assert out[0].header["NUM-BPM"] == "ID-BPM"
     good = mask == 0
     assert np.array_equal(out[0].data[good], raw[good].astype(np.float32))
+
+
+# ------------------------------------------------------------------ host-buffer entries
+def _raw_case(coeff_j, frame_j, n):
+    rng = np.random.default_rng(31)
+    scale = rng.uniform(0.5, 1.5, size=n)
+    raw = np.clip(frame_j[None] * scale[:, None, None] * 8.0 + 1000.0, 0, 65535).astype(np.uint16)
+    bias = rng.normal(1000.0, 2.0, size=frame_j.shape).astype(np.float32)
+    dark = rng.normal(2.0, 0.5, size=frame_j.shape).astype(np.float32)
+    flat = rng.normal(8.0, 0.2, size=frame_j.shape).astype(np.float32)
+    bpm = (rng.random(frame_j.shape) < 0.004).astype(np.uint8)
+    return raw, bias, dark, flat, bpm
+
+
+def test_run_host_raw_equals_flow_then_path(coeff_j, frame_j):
+    """emirwv_run_host_raw (uint16 frames + the plan's calibration) = prereduce kernel + path,
+    bit for bit, dense and sparse copy-back, pageable and page-locked output."""
+    import torch
+    from pyemir_b200 import _pinned
+    from pyemir_b200.plan import RectWavePlan
+    from pyemir_b200.prereduce import prereduce_torch
+    n = 11                                       # three pipeline slots, a short last chunk
+    raw, bias, dark, flat, bpm = _raw_case(coeff_j, frame_j, n)
+    plan = RectWavePlan(coeff_j, 2, "float32")
+    plan.set_calibration(bpm=bpm, bias=bias, dark=dark, flat=flat)
+    red = prereduce_torch(torch.from_numpy(raw).cuda(), bias, dark, flat, bpm=bpm)
+    want, want_jm = plan.run_torch(red)
+    want, want_jm = want.cpu().numpy(), want_jm.cpu().numpy()
+    got, jm = plan.run_host_raw(raw)
+    assert np.array_equal(got, want) and np.array_equal(jm, want_jm)
+    # sparse copy-back: page-locked buffer (one kernel per chunk writes the covered columns
+    # straight into it) and pageable buffer (strided copies)
+    for out in (_pinned.empty(want.shape, np.float32), np.empty(want.shape, np.float32)):
+        out[...] = 0
+        got, jm = plan.run_host_raw(raw, out=out, out_zeroed=True)
+        assert np.array_equal(got, want) and np.array_equal(jm, want_jm)
+    # float32 "raw" frames, no bad-pixel mask
+    plan.set_calibration(flat=flat)
+    rawf = raw[:3].astype(np.float32)
+    got, _ = plan.run_host_raw(rawf)
+    red = prereduce_torch(torch.from_numpy(rawf).cuda(), flat=flat)
+    assert np.array_equal(got, plan.run_torch(red)[0].cpu().numpy())
+    with pytest.raises(ValueError):
+        RectWavePlan(coeff_j, 2, "float64").run_host_raw(raw[:1])
+    plan.close()
+
+
+@pytest.mark.parametrize("method", ["mean", "median", "sigmaclip"])
+@pytest.mark.parametrize("shifted", [False, True])
+def test_abba_host_equals_device_pipeline(coeff_j, frame_j, method, shifted):
+    """emirwv_abba_host: frames in, one combined image out = path + shift + combination run
+    kernel by kernel on device tensors, bit for bit (the sums of the mean run in frame order
+    although three pipeline slots work concurrently)."""
+    import torch
+    from pyemir_b200 import abba
+    from pyemir_b200.plan import RectWavePlan
+    from pyemir_b200.prereduce import prereduce_torch
+    n = 12
+    raw, bias, dark, flat, bpm = _raw_case(coeff_j, frame_j, n)
+    full_set = abba.build_full_set("ABBA", 1, 3)
+    labels = abba.labels_of(full_set)
+    offsets = [0.0, 0.7312, -0.7312, 0.0, 1.25, 0.0, 0.0, -2.0, 0.0005, 0.0, 0.0, 3.3333] \
+        if shifted else None
+    plan = RectWavePlan(coeff_j, 2, "float32")
+    plan.set_calibration(bpm=bpm, bias=bias, dark=dark, flat=flat)
+    red = prereduce_torch(torch.from_numpy(raw).cuda(), bias, dark, flat, bpm=bpm)
+    prod, _ = plan.run_torch(red)
+    want = abba.combine_abba(prod, full_set, offsets, method).cpu().numpy()
+    got = plan.abba_host(raw, labels, offsets, method, raw=True)
+    assert got.dtype == np.float32 and got.shape == plan.out_shape
+    assert np.array_equal(got, want, equal_nan=True)
+    # reduced float32 frames in (no flow), an unused frame in the sequence
+    lab2 = list(labels)
+    lab2[5] = 0
+    got = plan.abba_host(red.cpu().numpy(), lab2, offsets, method)
+    fs2 = [i for i in range(n) if i != 5]
+    want = abba.combine_abba(prod[fs2].contiguous(), "".join(full_set[i] for i in fs2),
+                             None if offsets is None else [offsets[i] for i in fs2], method)
+    assert np.array_equal(got, want.cpu().numpy(), equal_nan=True)
+    with pytest.raises(ValueError):
+        plan.abba_host(raw, [1] * n, None, method, raw=True)       # no B image
+    plan.close()
+
+
+def test_abba_host_mean_against_oracle_small(coeff_j, frame_j):
+    """The whole chain against the CPU oracle for three slitlets: rectification (float32
+    tolerance), shift + mean combination on the oracle's own products (bit exact)."""
+    import copy
+    from oracle.pipeline import apply_rectwv_coeff as oracle_apply
+    from pyemir_b200 import abba, synthetic
+    from pyemir_b200.plan import RectWavePlan
+    coeff = copy.deepcopy(coeff_j)
+    coeff.missing_slitlets = [i for i in range(1, 56) if i not in (3, 27, 50)]
+    frames = np.stack([frame_j, frame_j * 0.5, frame_j * 0.25, frame_j * 2.0]).astype(np.float32)
+    offsets = [0.0, 0.4, -0.4, 0.0]
+    plan = RectWavePlan(coeff, 2, "float32")
+    got = plan.abba_host(frames, abba.labels_of("ABBA"), offsets, "mean")
+    prods = [oracle_apply(synthetic.make_hdulist(f, coeff), coeff, only_needed_rows=True)[0].data
+             for f in frames]
+    want = oracle.combine_abba(np.stack(prods), "ABBA", offsets, "mean")
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() < 2e-5 * scale
+    assert np.array_equal(got == 0, want == 0) or np.abs(got - want).max() < 2e-5 * scale
+    plan.close()
