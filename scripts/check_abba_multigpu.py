@@ -4,9 +4,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 scripts/check_abba_multigpu.py
 
-Every rank holds a contiguous shard of a seeded stack of "rectified products"; the mean and the
-median combination (partial sums + reduce; row-slab exchange + emirwv_abba_median + slab
-gather) must reproduce the single-process numpy result bit for bit on rank 0.
+Every rank holds a contiguous shard of a seeded stack of "rectified products"; the mean, the
+median and the sigma-clip combination (partial sums + reduce; row-slab exchange +
+emirwv_abba_median / emirwv_abba_sigmaclip + slab gather) must reproduce the single-process
+numpy result bit for bit on rank 0.
 """
 import json
 import os
@@ -18,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle.pipeline import combine_abba_mean, combine_abba_median  # noqa: E402  (checker)
+from oracle.pipeline import combine_abba, combine_abba_mean, combine_abba_median  # noqa: E402  (checker)
 from pyemir_b200 import abba  # noqa: E402
 from pyemir_b200.distributed import init_from_env, shard_range  # noqa: E402
 
@@ -33,6 +34,8 @@ def main():
         labels = abba.labels_of(full_set)
         rng = np.random.default_rng(1234 + nseq)
         stack = rng.normal(300.0, 100.0, size=(n,) + shape).astype(np.float32)
+        hits = rng.integers(0, [n, shape[0], shape[1]], size=(200, 3))
+        stack[hits[:, 0], hits[:, 1], hits[:, 2]] += 5000.0        # cosmic rays
         counts = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
         start, stop = shard_range(n, rank, world)
         local = torch.from_numpy(stack[start:stop]).cuda()
@@ -43,18 +46,23 @@ def main():
         t1 = time.perf_counter()
         mean = abba.combine_abba_mean(local, labels[start:stop], full_set.count("A"),
                                       full_set.count("B"), dst=0)
+        clip = abba.combine_abba_sigmaclip(local, labels, counts, dst=0, low=3.0, high=2.5)
         torch.cuda.synchronize()
         if rank == 0:
+            ok_clip = bool(np.array_equal(
+                clip.cpu().numpy(), combine_abba(stack, full_set, None, "sigmaclip", 3.0, 2.5)))
             ok_med = bool(np.array_equal(med.cpu().numpy(), combine_abba_median(stack, full_set)))
             ok_mean = bool(np.array_equal(mean.cpu().numpy(), combine_abba_mean(stack, full_set)))
             results.append({"frames": n, "shape": list(shape), "world": world,
                             "median_bit_exact": ok_med, "mean_bit_exact": ok_mean,
+                            "sigmaclip_bit_exact": ok_clip,
                             "median_first_call_ms": 1e3 * (t1 - t0)})
         else:
-            assert med is None and mean is None
+            assert med is None and mean is None and clip is None
     if rank == 0:
         print(json.dumps(results), flush=True)
-        if not all(r["median_bit_exact"] and r["mean_bit_exact"] for r in results):
+        if not all(r["median_bit_exact"] and r["mean_bit_exact"] and r["sigmaclip_bit_exact"]
+                   for r in results):
             raise SystemExit("ABBA combination over NCCL differs from the single-process result")
     if world > 1:
         dist.barrier()
