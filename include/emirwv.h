@@ -316,8 +316,9 @@ int emirwv_prereduce(const void *d_in, int in_dtype, float *d_out, int nframes, 
  *   d_bpm [naxis2][naxis1] uint8, non-zero = bad pixel, NULL skips the stage: a bad pixel becomes
  *   the median of the good pixels of the raw frame within +-2 rows and columns (clipped at the
  *   detector edges; 0 when there is none), then goes through bias, dark and flat like any other.
- * One pass: a frame is read once (the windows of the bad pixels come from L2).  d_out must not
- * alias d_in when d_bpm is given.
+ * The element-wise pass reads every frame once; a second small kernel looks at the mask only and
+ * rewrites the bad pixels (their windows come from L2).  d_out must not alias d_in when d_bpm is
+ * given.
  */
 int emirwv_prereduce_ex(const void *d_in, int in_dtype, float *d_out, int nframes, int naxis2,
                         int naxis1, const uint8_t *d_bpm, const void *d_bias, const void *d_dark,

@@ -140,7 +140,7 @@ def write_header(header, rectwv_coeff, wv_parameters, keywords):
 
 def apply_rectwv_coeff(reduced_image, rectwv_coeff, args_resampling=2,
                        args_ignore_dtu_configuration=True, debugplot=0, *,
-                       dtype=None, max_order=4, device=None):
+                       dtype=None, max_order=4, device=None, allow_extensions=False):
     """Rectify and wavelength-calibrate one reduced EMIR frame on the GPU.
 
     Parameters (first five as in the reference)
@@ -150,8 +150,10 @@ def apply_rectwv_coeff(reduced_image, rectwv_coeff, args_resampling=2,
     rectwv_coeff : RectWaveCoeff
         Rectification and wavelength calibration coefficients.
     args_resampling : int
-        1: nearest neighbour, 2: flux preserving interpolation
-        (3: bilinear — extension, not in the reference).
+        1: nearest neighbour, 2: flux preserving interpolation.  Any other value raises
+        ``ValueError("Unexpected resampling value=...")`` like the reference
+        (slitlet2d.py:403-404) -- unless ``allow_extensions`` admits 3 (true bilinear
+        sampling, not in the reference).
     args_ignore_dtu_configuration : bool
         If True, only warn about DTU configuration differences.
     debugplot : int
@@ -164,6 +166,13 @@ def apply_rectwv_coeff(reduced_image, rectwv_coeff, args_resampling=2,
         Cap on the distortion polynomial order (numina: 4).
     device : int, keyword only
         CUDA device ordinal (default: the current one).
+    allow_extensions : bool, keyword only
+        Admit ``args_resampling=3`` (bilinear; BASELINE.json names it, the reference has none).
+
+    Known deviations from the reference ("Known deviations"): float32 input runs
+    float32 kernels (the JMNSLT/JMXSLT scan then tests float32 values for != 0; pass
+    ``dtype="float64"`` for the reference's arithmetic), and a NaN / Inf pixel stays local
+    instead of poisoning every redder column of its row through the cumulative sum.
 
     Returns
     -------
@@ -192,7 +201,7 @@ def apply_rectwv_coeff(reduced_image, rectwv_coeff, args_resampling=2,
     logger.info("Applying rectification and wavelength calibration")
     logger.info("RectWaveCoeff uuid={}".format(rectwv_coeff.uuid))
 
-    if args_resampling not in (1, 2, 3):
+    if args_resampling not in ((1, 2, 3) if allow_extensions else (1, 2)):
         raise ValueError("Unexpected resampling value=" + str(args_resampling))
     plan = get_plan(rectwv_coeff, args_resampling, dtype, max_order, device=device)
     naxis1_enlarged = wv_parameters["naxis1_enlarged"]
@@ -244,7 +253,7 @@ def rectify_frames(frames, rectwv_coeff, args_resampling=2, *, dtype=None, max_o
 
 def apply_rectwv_coeff_batch(reduced_images, rectwv_coeff, args_resampling=2,
                              args_ignore_dtu_configuration=True, debugplot=0, *,
-                             dtype=None, max_order=4, device=None):
+                             dtype=None, max_order=4, device=None, allow_extensions=False):
     """``apply_rectwv_coeff`` for a list of HDULists sharing one RectWaveCoeff.
 
     One plan, one pipelined pass over all frames; returns a list of HDULists
@@ -264,7 +273,7 @@ def apply_rectwv_coeff_batch(reduced_images, rectwv_coeff, args_resampling=2,
         results.append(rectwv_image)
     if not results:
         return results
-    if args_resampling not in (1, 2, 3):
+    if args_resampling not in ((1, 2, 3) if allow_extensions else (1, 2)):
         raise ValueError("Unexpected resampling value=" + str(args_resampling))
     if dtype is None:
         kinds = {_auto_dtype(a) for a in arrays}

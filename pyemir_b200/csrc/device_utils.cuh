@@ -92,6 +92,9 @@ __device__ __forceinline__ void prefetch_tensormap(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ unsigned smem_addr_of(const void *p) {
     return (unsigned)__cvta_generic_to_shared(p);
 }

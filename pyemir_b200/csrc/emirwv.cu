@@ -71,6 +71,9 @@
 #ifndef EMIRWV_PREFETCH
 #define EMIRWV_PREFETCH 0      // rows of L2 prefetch ahead of the copy pipeline (0: none)
 #endif
+#ifndef EMIRWV_RECPF
+#define EMIRWV_RECPF 0         // 1: prefetch the next row's full records in the rare-footprint path
+#endif
 #ifndef EMIRWV_DIAG
 #define EMIRWV_DIAG 0          // timing diagnostics that break the result (scripts/build_variants.py)
 #endif
@@ -1100,7 +1103,8 @@ int emirwv_prereduce_ex(const void *d_in, int in_dtype, float *d_out, int nframe
                         int naxis1, const uint8_t *d_bpm, const void *d_bias, const void *d_dark,
                         const void *d_flat, int cal_dtype, void *cuda_stream) {
     if (d_in == nullptr || d_out == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
-    if (nframes < 0 || naxis1 < 1 || naxis2 < 1) return fail(EMIRWV_E_VALUE, "size out of range");
+    if (nframes < 0 || naxis1 < 1 || naxis2 < 1 || (d_bpm != nullptr && nframes > 65535))
+        return fail(EMIRWV_E_VALUE, "size out of range");
     if (in_dtype != EMIRWV_F32 && in_dtype != EMIRWV_F64 && in_dtype != EMIRWV_U16)
         return fail(EMIRWV_E_VALUE, "unknown image dtype");
     if (cal_dtype != EMIRWV_F32 && cal_dtype != EMIRWV_F64)

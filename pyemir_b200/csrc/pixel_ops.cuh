@@ -216,28 +216,43 @@ EMIRWV_HD double shift_area(double xa, double xb, const ShiftRow &r, int ii) {
 template <typename TIn, int HW>
 EMIRWV_HD double bpm_window_median(const TIn *img, const uint8_t *mask, int naxis1, int naxis2,
                                    int col, int row, double fill) {
-    double buf[(2 * HW + 1) * (2 * HW + 1)];
+    // the window in registers (every index below is a compile-time constant once unrolled):
+    // pixels that do not count -- masked, or outside the detector -- hold +inf
+    constexpr int S = 2 * HW + 1, M = S * S;
+    double w[M];
     int n = 0;
     bool has_nan = false;
-    for (int r = row - HW; r <= row + HW; ++r) {
-        if (r < 0 || r >= naxis2) continue;
-        for (int c = col - HW; c <= col + HW; ++c) {
-            if (c < 0 || c >= naxis1) continue;
-            const long long i = (long long)r * naxis1 + c;
-            if (mask[i] != 0) continue;
-            const double val = (double)img[i];
-            has_nan |= val != val;
-            int k = n++;                               // insertion sort (rare path, n <= 25)
-            while (k > 0 && buf[k - 1] > val) {
-                buf[k] = buf[k - 1];
-                --k;
+#pragma unroll
+    for (int a = 0; a < S; ++a)
+#pragma unroll
+        for (int b = 0; b < S; ++b) {
+            const int r = row - HW + a, c = col - HW + b;
+            double val = (double)INFINITY;
+            if (r >= 0 && r < naxis2 && c >= 0 && c < naxis1) {
+                const long long i = (long long)r * naxis1 + c;
+                if (mask[i] == 0) {
+                    val = (double)img[i];
+                    has_nan |= val != val;
+                    ++n;
+                }
             }
-            buf[k] = val;
+            w[a * S + b] = val != val ? (double)INFINITY : val;
         }
-    }
     if (n == 0) return fill;
     if (has_nan) return quiet_nan();
-    return (n & 1) ? buf[n / 2] : mul_rn(add_rn(buf[n / 2 - 1], buf[n / 2]), 0.5);
+    // selection by rank (ties broken by position): no sort, no indexed array
+    const int klo = (n - 1) >> 1, khi = n >> 1;
+    double lo = 0.0, hi = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+            rank += (w[j] < w[i] || (j < i && w[j] == w[i])) ? 1 : 0;
+        lo = rank == klo ? w[i] : lo;
+        hi = rank == khi ? w[i] : hi;
+    }
+    return (n & 1) ? lo : mul_rn(add_rn(lo, hi), 0.5);
 }
 
 }  // namespace emirwv

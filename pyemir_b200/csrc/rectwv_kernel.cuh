@@ -387,6 +387,17 @@ __global__ void __launch_bounds__(NTHREADS, sizeof(T) == 4 ? EMIRWV_MINBLOCKS : 
                 T wt[RS];
 #pragma unroll
                 for (int i = 0; i < RS / VN; ++i) *reinterpret_cast<V *>(wt + i * VN) = __ldg(rec + i);
+#if EMIRWV_RECPF
+                // a warp that needs the full records in this row mostly needs them in the next
+                // one too: ask for them now (L2 -> L1), so that the next row does not stand
+                // still for an L2 round trip -- and with it the row's "done" barrier, the copy
+                // warp and every other warp of the CTA
+                if (y + 1 < NROWS) {
+                    const char *nx = reinterpret_cast<const char *>(rec) + (size_t)W * RS * sizeof(T);
+                    prefetch_l1(nx);
+                    prefetch_l1(nx + RS * sizeof(T) - 4);
+                }
+#endif
                 const int32_t pk = *reinterpret_cast<const int32_t *>(wt + KK);
                 const uint32_t slots = *reinterpret_cast<const uint32_t *>(wt + KK + 1);
                 const int fcf = base_col(pk) + wb;

@@ -202,21 +202,57 @@ __device__ __forceinline__ void load4(const uint16_t *p, uint16_t (&v)[4]) {
 // four independent loads are in flight per thread.
 //
 // The bad-pixel stage comes first in the flow (BadPixelCorrector, core/correctors.py:23-42,
-// core/recipe.py:26-41): a thread whose pixel is masked replaces the raw value by the median of
-// the unmasked raw pixels of the 5 x 5 window around it (bpm_window_median, pixel_ops.cuh) and
-// carries on with bias, dark and flat -- the frame is still read once (the window of the few
-// masked pixels comes from L2 / L1).
+// core/recipe.py:26-41).  It touches a fraction of a per cent of the pixels, so it does not ride
+// in k_prereduce (whose threads would all pay for the registers of the window median): a second
+// small kernel, k_bpm_fix, looks at the mask only and, for a masked pixel of a frame, replaces
+// what k_prereduce wrote by the value that starts from the median of the unmasked RAW pixels of
+// the 5 x 5 window (bpm_window_median, pixel_ops.cuh) and goes through the same bias / dark /
+// flat stages.  The frames are still read once (the windows come from L2).
 struct BpmArgs {
     const uint8_t *mask;    // [naxis2][naxis1], non-zero = bad; NULL: no bad-pixel stage
     int naxis1, naxis2;
 };
+
+// grid: x over groups of 4 pixels (one mask word per thread), y over frames
+template <typename TIn, typename TCal>
+__global__ void __launch_bounds__(128) k_bpm_fix(const TIn *__restrict__ in, float *__restrict__ out,
+                                                 size_t npix, const TCal *__restrict__ bias,
+                                                 const TCal *__restrict__ dark,
+                                                 const TCal *__restrict__ flat, const BpmArgs bpm,
+                                                 int words_ok) {
+    using A = typename std::conditional<sizeof(TIn) == 8 || sizeof(TCal) == 8, double, float>::type;
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= npix) return;
+    uint32_t m4 = 0;
+    if (words_ok && i0 + 4 <= npix) {
+        m4 = __ldg(reinterpret_cast<const uint32_t *>(bpm.mask + i0));
+    } else {
+        for (int e = 0; e < 4 && i0 + e < npix; ++e) m4 |= (uint32_t)(bpm.mask[i0 + e] != 0) << (8 * e);
+    }
+    if (m4 == 0) return;
+    const TIn *frame = in + (size_t)blockIdx.y * npix;
+    float *dst = out + (size_t)blockIdx.y * npix;
+    const bool hb = bias != nullptr, hd = dark != nullptr, hf = flat != nullptr;
+#pragma unroll 1
+    for (int e = 0; e < 4; ++e) {
+        if (!((m4 >> (8 * e)) & 0xffu)) continue;
+        const size_t i = i0 + e;
+        const A b = hb ? (A)bias[i] : A(0), d = hd ? (A)dark[i] : A(0);
+        A f = hf ? (A)flat[i] : A(1);
+        f = f <= A(0) ? A(1) : f;
+        const double med = bpm_window_median<TIn, 2>(frame, bpm.mask, bpm.naxis1, bpm.naxis2,
+                                                     (int)(i % (size_t)bpm.naxis1),
+                                                     (int)(i / (size_t)bpm.naxis1), 0.0);
+        dst[i] = prereduce_from<TIn, A>(med, hb, hd, hf, b, d, f);
+    }
+}
 
 template <typename TIn, typename TCal, int VEC>
 __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, float *__restrict__ out,
                                                    int nframes, size_t npix,
                                                    const TCal *__restrict__ bias,
                                                    const TCal *__restrict__ dark,
-                                                   const TCal *__restrict__ flat, const BpmArgs bpm) {
+                                                   const TCal *__restrict__ flat) {
     // float32 unless an operand is float64 (uint16 raw frames promote like numpy: with
     // float32 calibrations the arithmetic is float32)
     using A = typename std::conditional<sizeof(TIn) == 8 || sizeof(TCal) == 8, double, float>::type;
@@ -252,21 +288,6 @@ __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, f
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
             f[e] = f[e] <= A(0) ? A(1) : f[e];   // flatfield.py:43 (NaN stays NaN, like numpy)
-        unsigned bad = 0;                        // masked pixels among this thread's VEC
-        if (bpm.mask != nullptr) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) bad |= (bpm.mask[i + e] != 0 ? 1u : 0u) << e;
-        }
-        // one pixel of one frame: the window median first when the pixel is masked
-        auto px = [&](const TIn *frame, TIn raw, int e) -> float {
-            if (bad & (1u << e)) {
-                const size_t ii = i + e;
-                const double m = bpm_window_median<TIn, 2>(frame, bpm.mask, bpm.naxis1, bpm.naxis2,
-                                                          (int)(ii % bpm.naxis1), (int)(ii / bpm.naxis1), 0.0);
-                return prereduce_from<TIn, A>(m, hb, hd, hf, b[e], d[e], f[e]);
-            }
-            return prereduce_px<TIn, A>(raw, hb, hd, hf, b[e], d[e], f[e]);
-        };
         int n = 0;
         for (; n + U <= nframes; n += U) {
             TIn raw[U][VEC];
@@ -279,7 +300,8 @@ __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, f
             for (int u = 0; u < U; ++u) {
                 float r[VEC];
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) r[e] = px(in + (size_t)(n + u) * npix, raw[u][e], e);
+                for (int e = 0; e < VEC; ++e)
+                    r[e] = prereduce_px<TIn, A>(raw[u][e], hb, hd, hf, b[e], d[e], f[e]);
                 float *dst = out + (size_t)(n + u) * npix + i;
                 if constexpr (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(r[0], r[1], r[2], r[3]));
                 else __stcs(dst, r[0]);
@@ -291,7 +313,8 @@ __global__ void __launch_bounds__(256) k_prereduce(const TIn *__restrict__ in, f
             else raw[0] = __ldcs(in + (size_t)n * npix + i);
             float r[VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) r[e] = px(in + (size_t)n * npix, raw[e], e);
+            for (int e = 0; e < VEC; ++e)
+                r[e] = prereduce_px<TIn, A>(raw[e], hb, hd, hf, b[e], d[e], f[e]);
             float *dst = out + (size_t)n * npix + i;
             if constexpr (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(r[0], r[1], r[2], r[3]));
             else __stcs(dst, r[0]);
@@ -314,10 +337,15 @@ void launch_prereduce(const void *in, float *out, int nframes, size_t npix, cons
                *tf = static_cast<const TCal *>(flat);
     if (vec) {
         const int grid = (int)std::min<size_t>((npix / 4 + 255) / 256, (size_t)sms * 16);
-        k_prereduce<TIn, TCal, 4><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf, bpm);
+        k_prereduce<TIn, TCal, 4><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf);
     } else {
         const int grid = (int)std::min<size_t>((npix + 255) / 256, (size_t)sms * 16);
-        k_prereduce<TIn, TCal, 1><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf, bpm);
+        k_prereduce<TIn, TCal, 1><<<grid, 256, 0, st>>>(tin, out, nframes, npix, tb, td, tf);
+    }
+    if (bpm.mask != nullptr) {
+        const dim3 grid((unsigned)((npix / 4 + 128) / 128), (unsigned)nframes);
+        k_bpm_fix<TIn, TCal><<<grid, 128, 0, st>>>(tin, out, npix, tb, td, tf, bpm,
+                                                  (int)aligned(bpm.mask, 4));
     }
 }
 

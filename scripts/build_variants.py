@@ -20,6 +20,7 @@ VARIANTS = {
     "c2": SLIM + ("EMIRWV_MINBLOCKS=2", "EMIRWV_WIN_ROWS=12", "EMIRWV_WIN_PITCH=288"),
     "pf2": SLIM + ("EMIRWV_PREFETCH=2",), "pf4": SLIM + ("EMIRWV_PREFETCH=4",),
     "pf8": SLIM + ("EMIRWV_PREFETCH=8",),
+    "recpf": SLIM + ("EMIRWV_RECPF=1",),
     "c3s3": SLIM + ("EMIRWV_NSTAGE=3", "EMIRWV_WIN_ROWS=10"),
     # float64 kernels compiled for two CTAs per SM (full build: every instantiation)
     "f64c2": ("EMIRWV_MINBLOCKS_F64=2",),

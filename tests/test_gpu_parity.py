@@ -193,6 +193,11 @@ def test_error_behaviour(coeff_j, frame_j):
         apply_rectwv_coeff(bad, coeff_j, args_ignore_dtu_configuration=False)
     with pytest.raises(ValueError, match="Unexpected resampling value=7"):
         apply_rectwv_coeff(hdul, coeff_j, args_resampling=7)
+    # 3 is the bilinear extension: refused like in the reference unless asked for by name
+    with pytest.raises(ValueError, match="Unexpected resampling value=3"):
+        apply_rectwv_coeff(hdul, coeff_j, args_resampling=3)
+    assert apply_rectwv_coeff(hdul, coeff_j, args_resampling=3,
+                              allow_extensions=True)[0].data.shape == (2090, 3400)
     small = synthetic.make_hdulist(frame_j[:100], coeff_j)
     with pytest.raises(ValueError, match="Unexpected naxis2"):
         apply_rectwv_coeff(small, coeff_j)
