@@ -213,7 +213,11 @@ struct BpmArgs {
     int naxis1, naxis2;
 };
 
-// grid: x over groups of 4 pixels (one mask word per thread), y over frames
+// grid: x over groups of 4 pixels (one mask word per thread), y over frames.  A warp looks at
+// 128 pixels of the mask; for every masked one among them ALL its lanes work on the fix: lane
+// l < 25 holds window pixel (l / 5, l % 5), the rank of every value among the others comes from
+// 25 shuffles, the two middle values from two ballots -- about a hundred warp instructions per
+// bad pixel instead of a few thousand in one lane of a divergent warp.
 template <typename TIn, typename TCal>
 __global__ void __launch_bounds__(128) k_bpm_fix(const TIn *__restrict__ in, float *__restrict__ out,
                                                  size_t npix, const TCal *__restrict__ bias,
@@ -221,29 +225,69 @@ __global__ void __launch_bounds__(128) k_bpm_fix(const TIn *__restrict__ in, flo
                                                  const TCal *__restrict__ flat, const BpmArgs bpm,
                                                  int words_ok) {
     using A = typename std::conditional<sizeof(TIn) == 8 || sizeof(TCal) == 8, double, float>::type;
+    // uint16 and float32 pixels compare exactly as float32
+    using Key = typename std::conditional<sizeof(TIn) == 8, double, float>::type;
+    constexpr int HW = 2, S = 2 * HW + 1;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i0 >= npix) return;
     uint32_t m4 = 0;
-    if (words_ok && i0 + 4 <= npix) {
-        m4 = __ldg(reinterpret_cast<const uint32_t *>(bpm.mask + i0));
-    } else {
-        for (int e = 0; e < 4 && i0 + e < npix; ++e) m4 |= (uint32_t)(bpm.mask[i0 + e] != 0) << (8 * e);
+    if (i0 < npix) {
+        if (words_ok && i0 + 4 <= npix) {
+            m4 = __ldg(reinterpret_cast<const uint32_t *>(bpm.mask + i0));
+        } else {
+            for (int e = 0; e < 4 && i0 + e < npix; ++e)
+                m4 |= (uint32_t)(bpm.mask[i0 + e] != 0) << (8 * e);
+        }
     }
-    if (m4 == 0) return;
+    if (__ballot_sync(full, m4 != 0) == 0) return;
     const TIn *frame = in + (size_t)blockIdx.y * npix;
     float *dst = out + (size_t)blockIdx.y * npix;
     const bool hb = bias != nullptr, hd = dark != nullptr, hf = flat != nullptr;
+    const int wa = lane / S - HW, wb = lane % S - HW;          // this lane's place in the window
 #pragma unroll 1
     for (int e = 0; e < 4; ++e) {
-        if (!((m4 >> (8 * e)) & 0xffu)) continue;
-        const size_t i = i0 + e;
-        const A b = hb ? (A)bias[i] : A(0), d = hd ? (A)dark[i] : A(0);
-        A f = hf ? (A)flat[i] : A(1);
-        f = f <= A(0) ? A(1) : f;
-        const double med = bpm_window_median<TIn, 2>(frame, bpm.mask, bpm.naxis1, bpm.naxis2,
-                                                     (int)(i % (size_t)bpm.naxis1),
-                                                     (int)(i / (size_t)bpm.naxis1), 0.0);
-        dst[i] = prereduce_from<TIn, A>(med, hb, hd, hf, b, d, f);
+        unsigned todo = __ballot_sync(full, (m4 >> (8 * e)) & 0xffu);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const size_t i = ((size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31) + src) * 4 + e;
+            const int col = (int)(i % (size_t)bpm.naxis1), row = (int)(i / (size_t)bpm.naxis1);
+            const int r = row + wa, c = col + wb;
+            bool ok = lane < S * S && r >= 0 && r < bpm.naxis2 && c >= 0 && c < bpm.naxis1;
+            Key val = (Key)INFINITY;
+            if (ok) {
+                const size_t k = (size_t)r * bpm.naxis1 + c;
+                ok = bpm.mask[k] == 0;
+                if (ok) val = (Key)frame[k];
+            }
+            const unsigned good = __ballot_sync(full, ok);
+            const bool has_nan = __ballot_sync(full, ok && val != val) != 0;
+            val = val != val ? (Key)INFINITY : val;
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < S * S; ++j) {
+                const Key vj = __shfl_sync(full, val, j);
+                rank += (vj < val || (j < lane && vj == val)) ? 1 : 0;
+            }
+            const int n = __popc(good);
+            double med = 0.0;                                  // `fill` when the window is empty
+            if (n > 0) {
+                const unsigned in_win = (1u << (S * S)) - 1u;
+                const unsigned at_lo = __ballot_sync(full, rank == ((n - 1) >> 1)) & in_win;
+                const unsigned at_hi = __ballot_sync(full, rank == (n >> 1)) & in_win;
+                const double lo = (double)__shfl_sync(full, val, __ffs(at_lo) - 1);
+                const double hi = (double)__shfl_sync(full, val, __ffs(at_hi) - 1);
+                med = (n & 1) ? lo : mul_rn(add_rn(lo, hi), 0.5);
+                if (has_nan) med = quiet_nan();
+            }
+            if (lane == 0) {
+                const A b = hb ? (A)bias[i] : A(0), d = hd ? (A)dark[i] : A(0);
+                A f = hf ? (A)flat[i] : A(1);
+                f = f <= A(0) ? A(1) : f;
+                dst[i] = prereduce_from<TIn, A>(med, hb, hd, hf, b, d, f);
+            }
+        }
     }
 }
 
