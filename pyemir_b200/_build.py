@@ -11,7 +11,7 @@ HOSTCHECK_PATH = os.path.join(_HERE, "libemirwv_hostcheck.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC,-ffp-contract=off", "-cudart", "static",
+    "--shared", "-Xcompiler", "-fPIC,-ffp-contract=off,-pthread", "-cudart", "static",
 ]
 
 

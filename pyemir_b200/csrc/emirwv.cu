@@ -48,6 +48,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -674,11 +675,54 @@ int check_raw(const emirwv_plan *pl, int in_dtype, bool raw) {
     return EMIRWV_OK;
 }
 
+// The zeros outside the wavelength coverage (38 % of a J/H/K product) written where they are
+// needed instead of shipped: host threads of the library fill the uncovered columns of the
+// caller's buffer while the covered ones arrive over PCIe.  The device -> host direction is the
+// narrow one (one GPU: the link; eight GPUs of one box: the host's ingest, ~80 GB/s in all,
+// profiles/r02_pcie_probe_8gpu.json), so every byte that does not travel counts.
+void host_zero_fill(const emirwv_plan *pl, char *h_out, int f_begin, int f_end, int f_step) {
+    const size_t pitch = (size_t)pl->nout * pl->esize;
+    const size_t out_b = (size_t)pl->nsl * pl->rps * pitch;
+    for (int f = f_begin; f < f_end; f += f_step)
+        for (int s = 0; s < pl->nsl; ++s) {
+            const size_t lo = (size_t)pl->h_cover[2 * s] * pl->esize;
+            const size_t hi = (size_t)pl->h_cover[2 * s + 1] * pl->esize;
+            char *row = h_out + (size_t)f * out_b + (size_t)s * pl->rps * pitch;
+            for (int y = 0; y < pl->rps; ++y, row += pitch) {
+                if (hi <= lo) {
+                    memset(row, 0, pitch);
+                } else {
+                    if (lo > 0) memset(row, 0, lo);
+                    if (hi < pitch) memset(row + hi, 0, pitch - hi);
+                }
+            }
+        }
+}
+
 int run_host_impl(emirwv_plan *pl, const void *h_in, int in_dtype, bool raw, void *h_out,
                   int nframes, int32_t *h_jminmax, bool sparse) {
     DeviceGuard guard(pl->device);
     std::lock_guard<std::mutex> lock(pl->mu);
     nvtx_range r_all("emirwv_run_host");
+    // A batch into a page-locked buffer without the caller's promise: ship the covered columns
+    // only and let host threads write the zeros (EMIRWV_HOST_ZERO_THREADS, default 3; 0: every
+    // byte travels).  Single frames and pageable buffers take the plain copy.
+    std::vector<std::thread> zero_team;
+    if (!sparse && nframes >= 8 && mapped_alias(h_out) != nullptr) {
+        const int nthreads = std::min(env_int("EMIRWV_HOST_ZERO_THREADS", 3), nframes);
+        if (nthreads > 0) {
+            sparse = true;
+            for (int t = 0; t < nthreads; ++t)
+                zero_team.emplace_back(host_zero_fill, pl, static_cast<char *>(h_out), t, nframes,
+                                       nthreads);
+        }
+    }
+    struct Joiner {
+        std::vector<std::thread> &team;
+        ~Joiner() {
+            for (auto &th : team) th.join();
+        }
+    } joiner{zero_team};
     // frames per pipeline slot: 4 keeps the ramp over PCIe short; the sparse copy-back takes 8
     const int chunk = std::max(1, std::min(nframes, env_int("EMIRWV_HOST_CHUNK", sparse ? 8 : 4)));
     int rc = ensure_workspace(pl, chunk);

@@ -383,12 +383,13 @@ def _quick_look(rectwv_coeff, options):
     """What changes when a product is edited in place, without serialising all of it: the
     object, its uuid, offsets, missing slitlets and one coefficient of every table."""
     prefix = "tti" if options[3] else "ttd"
-    probe = 0.0
+    probe = []
     for entry in rectwv_coeff.contents:
         coef = entry.get(prefix + "_aij")
         if coef:
-            probe += float(coef[0]) + float(coef[-1]) + float(entry[prefix + "_bij"][0]) \
-                + float(entry["wpoly_coeff"][0]) + float(entry["wpoly_coeff"][-1])
+            wpoly = entry["wpoly_coeff"]
+            probe += [coef[0], coef[-1], entry[prefix + "_bij"][0], wpoly[0], wpoly[-1]]
+    probe = hash(tuple(probe))
     return (id(rectwv_coeff), getattr(rectwv_coeff, "uuid", None),
             rectwv_coeff.global_integer_offset_x_pix, rectwv_coeff.global_integer_offset_y_pix,
             tuple(rectwv_coeff.missing_slitlets), len(rectwv_coeff.contents), probe,

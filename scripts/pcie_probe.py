@@ -22,15 +22,16 @@ from pyemir_b200.distributed import bind_to_gpu_numa, gpu_numa_node, init_from_e
 NBYTES = 1 << 30
 
 
-def measure(dev, h_in, h_out, d_in, d_out, both):
+def measure(dev, h_in, h_out, d_in, d_out, both, h2d=True):
     s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     reps = 4
     for _ in range(reps):
-        with torch.cuda.stream(s1):
-            d_in.copy_(h_in, non_blocking=True)
-        if both:
+        if h2d:
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+        if both or not h2d:
             with torch.cuda.stream(s2):
                 h_out.copy_(d_out, non_blocking=True)
     torch.cuda.synchronize()
@@ -65,10 +66,12 @@ def main():
         dist.all_reduce(alone)
         rows["alone_GBs_each_direction"] = [round(v, 1) for v in alone.tolist()]
         # all ranks at once: both directions, then host -> device only
-        for name, both in (("together_GBs_each_direction", True), ("together_h2d_only_GBs", False)):
+        for name, both, h2d in (("together_GBs_each_direction", True, True),
+                                ("together_h2d_only_GBs", False, True),
+                                ("together_d2h_only_GBs", False, False)):
             dist.barrier()
             val = torch.zeros(world, dtype=torch.float64, device=dev)
-            val[rank] = measure(dev, h_in, h_out, d_in, d_out, both)
+            val[rank] = measure(dev, h_in, h_out, d_in, d_out, both, h2d)
             dist.all_reduce(val)
             rows[name] = [round(v, 1) for v in val.tolist()]
             rows[name + "_sum"] = round(float(val.sum()), 1)

@@ -3,7 +3,9 @@
 (scripts/sanitize.sh): BASELINE config 2 geometry restricted to a few slitlets (the first and
 the last one touch the detector edge: zero-filled window columns and rows), 4 + 3 frames
 (a full frame group and an odd tail), float32 and float64, nearest and area resampling,
-device and host entries, and the side kernels (median, ABBA, pre-reduction)."""
+device and host entries (reduced and raw frames, dense and sparse copy-back, the ABBA product),
+and the side kernels (median, ABBA mean / median / sigma clipping, vertical offsets,
+pre-reduction with the bad-pixel stage)."""
 
 import copy
 import os
@@ -41,9 +43,26 @@ def main():
             dmed = abba.combine_abba_median(out[:4].contiguous(), abba.labels_of("ABBA"), [4])
             torch.cuda.synchronize()
             checks.append(("median", tuple(med.shape), "abba", tuple(diff.shape), tuple(dmed.shape)))
+            # the rest of the ABBA product and the flow in front of the path
+            offs = [0.0, 0.37, -1.2, 0.0]
+            for method in ("mean", "median", "sigmaclip"):
+                abba.combine_abba(out[:4].contiguous(), "ABBA", offs, method)
+            rng = np.random.default_rng(2)
+            raw = np.clip(frames * 8.0 + 1000.0, 0, 65535).astype(np.uint16)
+            bpm = (rng.random(raw.shape[1:]) < 0.003).astype(np.uint8)
+            bpm[0, 0] = bpm[2047, 2047] = 1
+            flat = rng.normal(8.0, 0.2, size=raw.shape[1:]).astype(np.float32)
+            plan.set_calibration(bpm=bpm, bias=flat * 100.0, flat=flat)
+            raw_out, _ = plan.run_host_raw(raw)
+            zeroed = np.zeros_like(raw_out)
+            plan.run_host_raw(raw, out=zeroed, out_zeroed=True)
+            img = plan.abba_host(raw[:4], abba.labels_of("ABBA"), offs, "sigmaclip", raw=True)
+            torch.cuda.synchronize()
+            checks.append(("raw", bool(np.array_equal(raw_out, zeroed)), tuple(img.shape)))
         plan.close()
     print("sanitize_case ok:", checks, flush=True)
     assert all(c[2] for c in checks if isinstance(c[2], bool))
+    assert all(c[1] for c in checks if c[0] == "raw")
 
 
 if __name__ == "__main__":

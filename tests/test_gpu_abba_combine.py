@@ -219,6 +219,28 @@ def test_run_host_raw_equals_flow_then_path(coeff_j, frame_j):
     plan.close()
 
 
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_run_host_batch_into_pinned_buffer_zeros_written_on_the_host(coeff_j, frame_j, dtype,
+                                                                     monkeypatch):
+    """A batch into a page-locked buffer: the covered columns travel, host threads write the
+    zeros; the buffer starts out full of NaNs and must come back identical to the plain copy
+    (pageable buffer) and to the all-bytes-over-PCIe variant."""
+    from pyemir_b200 import _pinned
+    from pyemir_b200.plan import RectWavePlan
+    n = 9
+    rng = np.random.default_rng(5)
+    frames = (frame_j[None] * rng.uniform(0.5, 1.5, size=(n, 1, 1))).astype(dtype)
+    plan = RectWavePlan(coeff_j, 2, dtype)
+    want, want_jm = plan.run_host(frames)                    # pageable: plain copies
+    out = _pinned.empty(want.shape, want.dtype)
+    for threads in ("3", "1", "0"):
+        monkeypatch.setenv("EMIRWV_HOST_ZERO_THREADS", threads)
+        out[...] = np.nan
+        got, jm = plan.run_host(frames, out=out)
+        assert np.array_equal(got, want) and np.array_equal(jm, want_jm), threads
+    plan.close()
+
+
 @pytest.mark.parametrize("method", ["mean", "median", "sigmaclip"])
 @pytest.mark.parametrize("shifted", [False, True])
 def test_abba_host_equals_device_pipeline(coeff_j, frame_j, method, shifted):
