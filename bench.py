@@ -246,7 +246,7 @@ def tuning_of(info):
             "label": os.environ.get("AB_LABEL")}
 
 
-def e2e_recipe_entries(args, plan, h_in, a_out, a_jmm, F, world, dev, barrier):
+def e2e_recipe_entries(args, plan, h_in, a_out, a_jmm, F, world, dev, barrier, d2h_sparse):
     """End to end through the entries that follow the recipe further than the path itself:
     RAW uint16 frames in (half the bytes over PCIe; bad-pixel mask, bias, dark and flat applied
     on the device in front of the path), and the whole ABBA product (only the combined A - B
@@ -304,10 +304,11 @@ def e2e_recipe_entries(args, plan, h_in, a_out, a_jmm, F, world, dev, barrier):
     plan.set_calibration()
     return {
         "raw_u16": {"value": v_raw, "h2d_bytes_per_step": int(raw_np.nbytes),
-                    "d2h_bytes_per_step": int(a_out.nbytes + a_jmm.nbytes),
+                    "d2h_bytes_per_step": d2h_sparse,
                     "call": "emirwv_run_host_raw: RAW uint16 frames in pinned memory -> bad-pixel "
-                            "mask, bias, dark, flat (k_prereduce) -> k_rectwv -> every byte of the "
-                            "products back; identical to the device-resident kernels: %s" % ok_raw},
+                            "mask, bias, dark, flat (k_prereduce, k_bpm_fix) -> k_rectwv -> the whole "
+                            "products delivered like e2e.value (zeros written by host threads); "
+                            "identical to the device-resident kernels: %s" % ok_raw},
         "abba_product": {"value": v_abba, "h2d_bytes_per_step": int(raw_np.nbytes),
                          "d2h_bytes_per_step": int(img.numpy().nbytes),
                          "float32_reduced_frames_in": v_abba_f32,
@@ -619,7 +620,8 @@ def run_ours(args):
         if not same:
             raise SystemExit("bench.py: sparse device->host copy differs from the full copy")
         if args.dtype == "float32":
-            e2e.update(e2e_recipe_entries(args, plan, h_in, a_out, a_jmm, F, world, dev, barrier))
+            e2e.update(e2e_recipe_entries(args, plan, h_in, a_out, a_jmm, F, world, dev, barrier,
+                                          d2h_sparse))
 
     collective = None
     if world > 1 and args.dtype == "float32" and not args.no_collective:
