@@ -49,6 +49,9 @@
 #include <new>
 #include <string>
 #include <thread>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <type_traits>
 #include <vector>
 
@@ -680,6 +683,26 @@ int check_raw(const emirwv_plan *pl, int in_dtype, bool raw) {
 // caller's buffer while the covered ones arrive over PCIe.  The device -> host direction is the
 // narrow one (one GPU: the link; eight GPUs of one box: the host's ingest, ~80 GB/s in all,
 // profiles/r02_pcie_probe_8gpu.json), so every byte that does not travel counts.
+// zeros with non-temporal stores: no read-for-ownership of lines that are overwritten whole, no
+// cache pollution next to the DMA traffic into the same buffer
+inline void zero_stream(char *p, size_t n) {
+#if defined(__x86_64__) && defined(__SSE2__)
+    while (n > 0 && (reinterpret_cast<uintptr_t>(p) & 15u)) {
+        *p++ = 0;
+        --n;
+    }
+    const __m128i z = _mm_setzero_si128();
+    for (; n >= 64; n -= 64, p += 64) {
+        _mm_stream_si128(reinterpret_cast<__m128i *>(p), z);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(p + 16), z);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(p + 32), z);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(p + 48), z);
+    }
+    for (; n >= 16; n -= 16, p += 16) _mm_stream_si128(reinterpret_cast<__m128i *>(p), z);
+#endif
+    if (n > 0) memset(p, 0, n);
+}
+
 void host_zero_fill(const emirwv_plan *pl, char *h_out, int f_begin, int f_end, int f_step) {
     const size_t pitch = (size_t)pl->nout * pl->esize;
     const size_t out_b = (size_t)pl->nsl * pl->rps * pitch;
@@ -690,13 +713,16 @@ void host_zero_fill(const emirwv_plan *pl, char *h_out, int f_begin, int f_end, 
             char *row = h_out + (size_t)f * out_b + (size_t)s * pl->rps * pitch;
             for (int y = 0; y < pl->rps; ++y, row += pitch) {
                 if (hi <= lo) {
-                    memset(row, 0, pitch);
+                    zero_stream(row, pitch);
                 } else {
-                    if (lo > 0) memset(row, 0, lo);
-                    if (hi < pitch) memset(row + hi, 0, pitch - hi);
+                    if (lo > 0) zero_stream(row, lo);
+                    if (hi < pitch) zero_stream(row + hi, pitch - hi);
                 }
             }
         }
+#if defined(__x86_64__) && defined(__SSE2__)
+    _mm_sfence();
+#endif
 }
 
 int run_host_impl(emirwv_plan *pl, const void *h_in, int in_dtype, bool raw, void *h_out,
