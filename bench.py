@@ -579,9 +579,13 @@ def run_ours(args):
         # covered columns travel over PCIe, the zeros outside the wavelength coverage are
         # written by host threads of the library while the copies run; before it, the same
         # call with every byte shipped over PCIe (EMIRWV_HOST_ZERO_THREADS=0)
+        keep_env = os.environ.get("EMIRWV_HOST_ZERO_THREADS")
         os.environ["EMIRWV_HOST_ZERO_THREADS"] = "0"
         all_dma = timed_host(False)
-        del os.environ["EMIRWV_HOST_ZERO_THREADS"]
+        if keep_env is None:
+            del os.environ["EMIRWV_HOST_ZERO_THREADS"]
+        else:
+            os.environ["EMIRWV_HOST_ZERO_THREADS"] = keep_env
         a_out[...] = np.float32(7.0) if args.dtype == "float32" else 7.0     # not zeros
         dense = timed_host(False)
         last_dense = a_out[F - 1].copy()
