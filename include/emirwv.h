@@ -373,6 +373,26 @@ int emirwv_shift_rows(const void *d_in, int in_dtype, void *d_out, int out_dtype
                       int naxis2, int naxis1, const double *h_yoffset, void *cuda_stream);
 
 /*
+ * The exchanges of a sharded sequence for a caller that owns an NCCL communicator (one rank per
+ * GPU; recipes/spec/abba.py:351-381 sharded over ranks, :579-606 combined on one).  NCCL is NOT
+ * linked: the entry points (ncclGroupStart/End, ncclSend, ncclRecv, ncclReduce) are looked up in
+ * the calling process, else in libnccl.so.2 (EMIRWV_NCCL_LIB names another file);
+ * EMIRWV_E_CUDA when there is none.  `nccl_comm` is the caller's ncclComm_t.  Asynchronous on
+ * the stream; every rank of the communicator must make the call.
+ *
+ * emirwv_gather: the products of all ranks on `root`, in rank order.
+ *   d_local [counts[rank]] frames of frame_bytes bytes each (this rank's products)
+ *   d_root  [sum(counts)] frames on `root` (ignored elsewhere)
+ * emirwv_abba_reduce: method "mean" -- the float64 sums of emirwv_abba_partial of every rank
+ *   added in place on `root` (emirwv_abba_finish then forms float32(mean A) - float32(mean B)).
+ */
+int emirwv_gather(const void *d_local, const int32_t *counts, int world, int rank,
+                  int64_t frame_bytes, void *d_root, void *nccl_comm, int root,
+                  void *cuda_stream);
+int emirwv_abba_reduce(double *d_sum_a, double *d_sum_b, int64_t npix, void *nccl_comm, int root,
+                       void *cuda_stream);
+
+/*
  * Parity hooks (tests): the plan's geometry for one slitlet, copied to the host.
  *   h_row, h_col [39][bbw]       source pixel of tap (0,0) in bounding-box array
  *                                coordinates (for EMIRWV_NEAREST: the index maps

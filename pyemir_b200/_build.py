@@ -37,7 +37,7 @@ def build_library(force=False, verbose=False, defines=(), out=None):
     if not force and not _stale(target, sources):
         return target
     cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defines] + [
-        "-I", os.path.join(ROOT, "include"), "-o", target, main]
+        "-I", os.path.join(ROOT, "include"), "-o", target, main, "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

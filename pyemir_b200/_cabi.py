@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = (
     "emirwv_abba_partial", "emirwv_abba_finish", "emirwv_stack_median", "emirwv_abba_median",
     "emirwv_prereduce", "emirwv_prereduce_ex", "emirwv_stack_sigmaclip",
     "emirwv_abba_sigmaclip", "emirwv_shift_rows", "emirwv_plan_set_calibration",
-    "emirwv_run_host_raw", "emirwv_abba_host",
+    "emirwv_run_host_raw", "emirwv_abba_host", "emirwv_gather", "emirwv_abba_reduce",
 )
 
 
@@ -201,6 +201,10 @@ def load():
     lib.emirwv_run_host_raw.argtypes = [vp, vp, i32, vp, i32, vp, ctypes.c_uint32]
     lib.emirwv_abba_host.restype = i32
     lib.emirwv_abba_host.argtypes = [vp, vp, i32, i32, vp, vp, i32, f64, f64, vp, ctypes.c_uint32]
+    lib.emirwv_gather.restype = i32
+    lib.emirwv_gather.argtypes = [vp, vp, i32, i32, ctypes.c_int64, vp, vp, i32, vp]
+    lib.emirwv_abba_reduce.restype = i32
+    lib.emirwv_abba_reduce.argtypes = [vp, vp, ctypes.c_int64, vp, i32, vp]
     lib.emirwv_debug_geometry.restype = i32
     lib.emirwv_debug_geometry.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.emirwv_debug_borders.restype = i32

@@ -47,6 +47,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <dlfcn.h>
 #include <string>
 #include <thread>
 #if defined(__x86_64__)
@@ -1351,6 +1352,118 @@ int emirwv_abba_finish(const double *d_sum_a, const double *d_sum_b, int count_a
     k_abba_finish<<<grid, 256, 0, st>>>(d_sum_a, d_sum_b, (double)count_a, (double)count_b,
                                         (size_t)npix, d_out);
     CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+// ------------------------------------------------------------------ NCCL exchanges
+}  // extern "C"
+
+namespace {
+
+// NCCL is not linked: the library must load on a box without it.  A caller that owns an
+// ncclComm_t has NCCL in its process already; the few entry points used here are looked up in
+// it (or in libnccl.so.2) on first use.  Enum values are NCCL's stable ABI.
+struct NcclApi {
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+constexpr int NCCL_UINT8 = 1, NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+const NcclApi &nccl_api() {
+    static NcclApi api = []() {
+        NcclApi a;
+        void *h = dlopen(nullptr, RTLD_NOW);                       // already in the process?
+        if (h == nullptr || dlsym(h, "ncclSend") == nullptr) {
+            const char *name = getenv("EMIRWV_NCCL_LIB");
+            h = dlopen(name && *name ? name : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        }
+        if (h == nullptr) return a;
+        a.GroupStart = reinterpret_cast<int (*)()>(dlsym(h, "ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<int (*)()>(dlsym(h, "ncclGroupEnd"));
+        a.Send = reinterpret_cast<decltype(a.Send)>(dlsym(h, "ncclSend"));
+        a.Recv = reinterpret_cast<decltype(a.Recv)>(dlsym(h, "ncclRecv"));
+        a.Reduce = reinterpret_cast<decltype(a.Reduce)>(dlsym(h, "ncclReduce"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+        a.ok = a.GroupStart && a.GroupEnd && a.Send && a.Recv && a.Reduce;
+        return a;
+    }();
+    return api;
+}
+
+int nccl_fail(const NcclApi &api, int rc, const char *what) {
+    return fail(EMIRWV_E_CUDA, "%s failed: %s", what,
+                api.GetErrorString ? api.GetErrorString(rc) : "NCCL error");
+}
+
+}  // namespace
+
+extern "C" {
+
+int emirwv_gather(const void *d_local, const int32_t *counts, int world, int rank,
+                  int64_t frame_bytes, void *d_root, void *nccl_comm, int root,
+                  void *cuda_stream) {
+    if (counts == nullptr || nccl_comm == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (world < 1 || rank < 0 || rank >= world || root < 0 || root >= world || frame_bytes < 1)
+        return fail(EMIRWV_E_VALUE, "invalid rank / world size");
+    for (int r = 0; r < world; ++r)
+        if (counts[r] < 0) return fail(EMIRWV_E_VALUE, "negative frame count");
+    if (counts[rank] > 0 && d_local == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (rank == root && d_root == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    const NcclApi &api = nccl_api();
+    if (!api.ok) return fail(EMIRWV_E_CUDA, "NCCL is not available in this process (libnccl.so.2)");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    DeviceGuard guard(device_of(rank == root ? d_root : d_local));
+    if (rank == root && counts[rank] > 0) {        // the root's own products: a local copy
+        size_t off = 0;
+        for (int r = 0; r < rank; ++r) off += (size_t)counts[r] * (size_t)frame_bytes;
+        char *dst = static_cast<char *>(d_root) + off;
+        if (dst != d_local)
+            CUDA_TRY(cudaMemcpyAsync(dst, d_local, (size_t)counts[rank] * (size_t)frame_bytes,
+                                     cudaMemcpyDeviceToDevice, st));
+    }
+    int rc = api.GroupStart();
+    if (rc) return nccl_fail(api, rc, "ncclGroupStart");
+    if (rank == root) {
+        size_t off = 0;
+        for (int r = 0; r < world && rc == 0; ++r) {
+            const size_t nbytes = (size_t)counts[r] * (size_t)frame_bytes;
+            char *dst = static_cast<char *>(d_root) + off;
+            off += nbytes;
+            if (nbytes == 0 || r == rank) continue;
+            rc = api.Recv(dst, nbytes, NCCL_UINT8, r, nccl_comm, st);
+        }
+    } else if (counts[rank] > 0) {
+        rc = api.Send(d_local, (size_t)counts[rank] * (size_t)frame_bytes, NCCL_UINT8, root,
+                      nccl_comm, st);
+    }
+    const int rc_end = api.GroupEnd();
+    if (rc) return nccl_fail(api, rc, "ncclSend / ncclRecv");
+    if (rc_end) return nccl_fail(api, rc_end, "ncclGroupEnd");
+    return EMIRWV_OK;
+}
+
+int emirwv_abba_reduce(double *d_sum_a, double *d_sum_b, int64_t npix, void *nccl_comm, int root,
+                       void *cuda_stream) {
+    if (d_sum_a == nullptr || d_sum_b == nullptr || nccl_comm == nullptr)
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if (npix < 1 || root < 0) return fail(EMIRWV_E_VALUE, "size out of range");
+    const NcclApi &api = nccl_api();
+    if (!api.ok) return fail(EMIRWV_E_CUDA, "NCCL is not available in this process (libnccl.so.2)");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    DeviceGuard guard(device_of(d_sum_a));
+    int rc = api.GroupStart();
+    if (rc) return nccl_fail(api, rc, "ncclGroupStart");
+    rc = api.Reduce(d_sum_a, d_sum_a, (size_t)npix, NCCL_FLOAT64, NCCL_SUM, root, nccl_comm, st);
+    if (rc == 0)
+        rc = api.Reduce(d_sum_b, d_sum_b, (size_t)npix, NCCL_FLOAT64, NCCL_SUM, root, nccl_comm, st);
+    const int rc_end = api.GroupEnd();
+    if (rc) return nccl_fail(api, rc, "ncclReduce");
+    if (rc_end) return nccl_fail(api, rc_end, "ncclGroupEnd");
     return EMIRWV_OK;
 }
 
