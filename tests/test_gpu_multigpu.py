@@ -42,7 +42,8 @@ def _load_nccl():
     names = []
     try:
         import nvidia.nccl
-        names += glob.glob(os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so*"))
+        for base in list(getattr(nvidia.nccl, "__path__", [])):
+            names += glob.glob(os.path.join(base, "lib", "libnccl.so*"))
     except ImportError:
         pass
     for name in names + ["libnccl.so.2"]:
