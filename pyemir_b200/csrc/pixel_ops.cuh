@@ -146,18 +146,18 @@ EMIRWV_HD double sigmaclip_of_registers(const T (&v)[N], int n, double low, doub
     double mean = 0.0;
     for (;;) {
         const int cnt = popcount64(keep);
+        // (a dropped sample enters as +0.0: the select sits in front of the addition, off the
+        // chain of dependent additions, and changes nothing but the sign of a zero sum)
         double s = 0.0;
 #pragma unroll
-        for (int u = 0; u < N; ++u)
-            if ((keep >> u) & 1ull) s = add_rn(s, (double)v[u]);
+        for (int u = 0; u < N; ++u) s = add_rn(s, ((keep >> u) & 1ull) ? (double)v[u] : 0.0);
         mean = div_rn(s, (double)cnt);
         double ss = 0.0;
 #pragma unroll
-        for (int u = 0; u < N; ++u)
-            if ((keep >> u) & 1ull) {
-                const double d = sub_rn((double)v[u], mean);
-                ss = add_rn(ss, mul_rn(d, d));
-            }
+        for (int u = 0; u < N; ++u) {
+            const double d = sub_rn((double)v[u], mean);
+            ss = add_rn(ss, ((keep >> u) & 1ull) ? mul_rn(d, d) : 0.0);
+        }
         const double sd = sqrt_rn(cnt > 1 ? div_rn(ss, (double)(cnt - 1)) : 0.0);
         const double lo = sub_rn(mean, mul_rn(sd, low)), hi = add_rn(mean, mul_rn(sd, high));
         unsigned long long next = 0ull;
