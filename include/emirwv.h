@@ -393,6 +393,32 @@ int emirwv_abba_reduce(double *d_sum_a, double *d_sum_b, int64_t npix, void *ncc
                        void *cuda_stream);
 
 /*
+ * ABBA combination, method "mean", FUSED with its exchange over NVLink peer memory (one process
+ * per GPU on one box; no collective library on the data path).  Every rank creates a workspace
+ * (one device allocation), the 64-byte IPC handles of all ranks are exchanged by the caller (any
+ * channel: MPI, torch.distributed, a file) and connected; then, per sequence:
+ *   earlier passes over a rank's rectified frames: emirwv_abba_partial (local float64 sums);
+ *   the LAST pass: emirwv_abba_mean_push -- the kernel that adds the rank's frames pushes every
+ *   sum straight into the receive buffer of the rank that OWNS the pixel (pixels are dealt out in
+ *   `world` slabs), flags travel with system-scope release / acquire, every owner adds the
+ *   `world` contributions of its slab in rank order, forms float32(mean A) - float32(mean B)
+ *   (abba.py:604-606) and stores it into the image on `root`.
+ *   d_sum_a / d_sum_b: the sums of earlier passes (both NULL: none);  count_a / count_b: A and B
+ *   frames of the WHOLE sequence;  *d_image: on `root` the [npix] float32 result inside the
+ *   workspace (valid in stream order; overwritten by the next call), NULL
+ *   elsewhere.  Every rank must make the call, in the same order.
+ * emirwv_peer_timed_out: 1 when a wait for a peer gave up (a rank missing): synchronises.
+ */
+typedef struct emirwv_peer emirwv_peer;   /* opaque */
+int emirwv_peer_create(int64_t npix, int rank, int world, emirwv_peer **peer, void *h_handle64);
+int emirwv_peer_connect(emirwv_peer *peer, const void *h_handles /* [world][64] */);
+void emirwv_peer_destroy(emirwv_peer *peer);
+int emirwv_peer_timed_out(emirwv_peer *peer);
+int emirwv_abba_mean_push(emirwv_peer *peer, const void *d_frames, const int8_t *d_labels,
+                          int nframes, int dtype, const double *d_sum_a, const double *d_sum_b,
+                          int count_a, int count_b, int root, float **d_image, void *cuda_stream);
+
+/*
  * Parity hooks (tests): the plan's geometry for one slitlet, copied to the host.
  *   h_row, h_col [39][bbw]       source pixel of tap (0,0) in bounding-box array
  *                                coordinates (for EMIRWV_NEAREST: the index maps

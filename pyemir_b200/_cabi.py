@@ -37,6 +37,8 @@ EXPORTED_SYMBOLS = (
     "emirwv_prereduce", "emirwv_prereduce_ex", "emirwv_stack_sigmaclip",
     "emirwv_abba_sigmaclip", "emirwv_shift_rows", "emirwv_plan_set_calibration",
     "emirwv_run_host_raw", "emirwv_abba_host", "emirwv_gather", "emirwv_abba_reduce",
+    "emirwv_peer_create", "emirwv_peer_connect", "emirwv_peer_destroy", "emirwv_peer_timed_out",
+    "emirwv_abba_mean_push",
 )
 
 
@@ -205,6 +207,17 @@ def load():
     lib.emirwv_gather.argtypes = [vp, vp, i32, i32, ctypes.c_int64, vp, vp, i32, vp]
     lib.emirwv_abba_reduce.restype = i32
     lib.emirwv_abba_reduce.argtypes = [vp, vp, ctypes.c_int64, vp, i32, vp]
+    lib.emirwv_peer_create.restype = i32
+    lib.emirwv_peer_create.argtypes = [ctypes.c_int64, i32, i32, ctypes.POINTER(vp), vp]
+    lib.emirwv_peer_connect.restype = i32
+    lib.emirwv_peer_connect.argtypes = [vp, vp]
+    lib.emirwv_peer_destroy.restype = None
+    lib.emirwv_peer_destroy.argtypes = [vp]
+    lib.emirwv_peer_timed_out.restype = i32
+    lib.emirwv_peer_timed_out.argtypes = [vp]
+    lib.emirwv_abba_mean_push.restype = i32
+    lib.emirwv_abba_mean_push.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32, i32, i32,
+                                          ctypes.POINTER(vp), vp]
     lib.emirwv_debug_geometry.restype = i32
     lib.emirwv_debug_geometry.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.emirwv_debug_borders.restype = i32

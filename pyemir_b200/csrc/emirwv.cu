@@ -292,6 +292,7 @@ __device__ inline void map_corners(const SlitDev &sd, int j, int row, double *qu
 #include "device_utils.cuh"
 #include "side_kernels.cuh"
 #include "rectwv_kernel.cuh"
+#include "peer_kernels.cuh"
 
 }  // namespace
 
@@ -1352,6 +1353,154 @@ int emirwv_abba_finish(const double *d_sum_a, const double *d_sum_b, int count_a
     k_abba_finish<<<grid, 256, 0, st>>>(d_sum_a, d_sum_b, (double)count_a, (double)count_b,
                                         (size_t)npix, d_out);
     CUDA_TRY(cudaGetLastError());
+    return EMIRWV_OK;
+}
+
+// ------------------------------------------------------------------ peer-memory exchange
+}  // extern "C"
+
+// Workspace of the fused ABBA mean combination: ONE device allocation per rank, opened by every
+// other rank through CUDA IPC.  Layout (the same on every rank, from npix and world):
+//   recv  [2 parities][world sources][2 (A, B)][slab]  float64
+//   image [npix] float32   (the result; the destination rank's copy is the one that is written)
+//   flags [4][PEER_MAX] int32: pushed (parity 0, 1), slab finished (parity 0, 1);  [1] time-out
+struct emirwv_peer {
+    int device = 0, rank = 0, world = 1;
+    size_t npix = 0, slab = 0;
+    size_t off_image = 0, off_flags = 0, nbytes = 0;
+    char *local = nullptr;
+    char *peer[PEER_MAX] = {};
+    int epoch = 0;
+    bool connected = false;
+};
+
+extern "C" {
+
+int emirwv_peer_create(int64_t npix, int rank, int world, emirwv_peer **out, void *h_handle) {
+    if (out == nullptr || h_handle == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    *out = nullptr;
+    if (npix < 1 || world < 1 || world > PEER_MAX || rank < 0 || rank >= world)
+        return fail(EMIRWV_E_VALUE, "invalid rank / world size (at most %d ranks)", PEER_MAX);
+    emirwv_peer *p = new (std::nothrow) emirwv_peer();
+    if (p == nullptr) return fail(EMIRWV_E_NOMEM, "out of host memory");
+    CUDA_TRY(cudaGetDevice(&p->device));
+    p->rank = rank;
+    p->world = world;
+    p->npix = (size_t)npix;
+    p->slab = ((size_t)npix + world - 1) / world;
+    const size_t recv_b = (size_t)2 * world * 2 * p->slab * sizeof(double);
+    p->off_image = (recv_b + 255) & ~(size_t)255;
+    p->off_flags = (p->off_image + (size_t)npix * sizeof(float) + 255) & ~(size_t)255;
+    p->nbytes = p->off_flags + (4 * PEER_MAX + 4) * sizeof(int);
+    cudaError_t err = cudaMalloc(&p->local, p->nbytes);
+    if (err == cudaSuccess) err = cudaMemset(p->local, 0, p->nbytes);
+    cudaIpcMemHandle_t handle;
+    if (err == cudaSuccess) err = cudaIpcGetMemHandle(&handle, p->local);
+    if (err != cudaSuccess) {
+        cudaFree(p->local);
+        delete p;
+        return fail(EMIRWV_E_CUDA, "peer workspace: %s", cudaGetErrorString(err));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(h_handle, &handle, sizeof(handle));
+    *out = p;
+    return EMIRWV_OK;
+}
+
+int emirwv_peer_connect(emirwv_peer *p, const void *h_handles) {
+    if (p == nullptr || h_handles == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    DeviceGuard guard(p->device);
+    for (int r = 0; r < p->world; ++r) {
+        if (r == p->rank) {
+            p->peer[r] = p->local;
+            continue;
+        }
+        cudaIpcMemHandle_t handle;
+        memcpy(&handle, static_cast<const char *>(h_handles) + (size_t)r * 64, 64);
+        void *ptr = nullptr;
+        cudaError_t err = cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess)
+            return fail(EMIRWV_E_CUDA, "cannot open the workspace of rank %d: %s", r,
+                        cudaGetErrorString(err));
+        p->peer[r] = static_cast<char *>(ptr);
+    }
+    p->connected = true;
+    return EMIRWV_OK;
+}
+
+void emirwv_peer_destroy(emirwv_peer *p) {
+    if (p == nullptr) return;
+    DeviceGuard guard(p->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < p->world; ++r)
+        if (r != p->rank && p->peer[r] != nullptr) cudaIpcCloseMemHandle(p->peer[r]);
+    cudaFree(p->local);
+    delete p;
+}
+
+int emirwv_peer_timed_out(emirwv_peer *p) {
+    if (p == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    DeviceGuard guard(p->device);
+    int flag = 0;
+    CUDA_TRY(cudaMemcpy(&flag, p->local + p->off_flags + 4 * PEER_MAX * sizeof(int), sizeof(int),
+                        cudaMemcpyDeviceToHost));
+    return flag;
+}
+
+int emirwv_abba_mean_push(emirwv_peer *p, const void *d_frames, const int8_t *d_labels,
+                          int nframes, int dtype, const double *d_sum_a, const double *d_sum_b,
+                          int count_a, int count_b, int root, float **d_image, void *cuda_stream) {
+    if (p == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    if (!p->connected) return fail(EMIRWV_E_VALUE, "the peer workspace is not connected");
+    if (nframes < 0 || nframes > 32768) return fail(EMIRWV_E_VALUE, "size out of range");
+    if (nframes > 0 && (d_frames == nullptr || d_labels == nullptr))
+        return fail(EMIRWV_E_VALUE, "null argument");
+    if ((d_sum_a == nullptr) != (d_sum_b == nullptr)) return fail(EMIRWV_E_VALUE, "null argument");
+    if (dtype != EMIRWV_F32 && dtype != EMIRWV_F64) return fail(EMIRWV_E_VALUE, "unknown dtype");
+    if (count_a < 1 || count_b < 1) return fail(EMIRWV_E_VALUE, "both A and B images are needed");
+    if (root < 0 || root >= p->world) return fail(EMIRWV_E_VALUE, "invalid rank / world size");
+    DeviceGuard guard(p->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int epoch = ++p->epoch, parity = epoch & 1;
+    PeerPtrs peers;
+    memset(&peers, 0, sizeof(peers));
+    for (int r = 0; r < p->world; ++r) {
+        peers.recv[r] = reinterpret_cast<double *>(p->peer[r]);
+        peers.flags[r] = reinterpret_cast<int *>(p->peer[r] + p->off_flags);
+    }
+    int *flags = reinterpret_cast<int *>(p->local + p->off_flags);
+    int *timeout = flags + 4 * PEER_MAX;
+    const long long max_spins = 4000000;                       // a few seconds, then give up
+    const int sms = sm_count(p->device);
+    const int grid = (int)std::min<size_t>((p->npix + 255) / 256, (size_t)sms * 32);
+    const int acc = d_sum_a != nullptr ? 1 : 0;
+    // 1. this rank's sums, pushed to the owners of the pixels
+    if (dtype == EMIRWV_F32)
+        k_abba_partial_push<float><<<grid, 256, (size_t)nframes, st>>>(
+            static_cast<const float *>(d_frames), d_labels, nframes, p->npix, d_sum_a, d_sum_b, acc,
+            peers, p->rank, p->world, p->slab, parity);
+    else
+        k_abba_partial_push<double><<<grid, 256, (size_t)nframes, st>>>(
+            static_cast<const double *>(d_frames), d_labels, nframes, p->npix, d_sum_a, d_sum_b, acc,
+            peers, p->rank, p->world, p->slab, parity);
+    // 2. tell every owner; 3. wait for every rank's pushes into this rank's slab
+    k_peer_signal<<<1, PEER_MAX, 0, st>>>(peers, p->rank, p->world, parity, epoch, 0, -1);
+    k_peer_wait<<<1, PEER_MAX, 0, st>>>(flags + parity * PEER_MAX, p->world, epoch, max_spins, timeout);
+    // 4. this rank's slab of the result, stored into the destination rank's image
+    const size_t first = (size_t)p->rank * p->slab;
+    const double *recv = reinterpret_cast<const double *>(p->local) + (size_t)parity * p->world * 2 * p->slab;
+    float *image_root = reinterpret_cast<float *>(p->peer[root] + p->off_image);
+    const int fgrid = (int)std::max<size_t>(1, std::min<size_t>((p->slab + 255) / 256, (size_t)sms * 8));
+    k_abba_finish_slab<<<fgrid, 256, 0, st>>>(recv, p->world, p->slab, first, p->npix, (double)count_a,
+                                              (double)count_b, image_root);
+    k_peer_signal<<<1, PEER_MAX, 0, st>>>(peers, p->rank, p->world, parity, epoch, 2 * PEER_MAX, root);
+    // 5. the destination waits for the slabs of all ranks
+    if (p->rank == root)
+        k_peer_wait<<<1, PEER_MAX, 0, st>>>(flags + (2 + parity) * PEER_MAX, p->world, epoch, max_spins,
+                                            timeout);
+    CUDA_TRY(cudaGetLastError());
+    if (d_image != nullptr)
+        *d_image = p->rank == root ? reinterpret_cast<float *>(p->local + p->off_image) : nullptr;
     return EMIRWV_OK;
 }
 

@@ -47,22 +47,41 @@ def main():
         mean = abba.combine_abba_mean(local, labels[start:stop], full_set.count("A"),
                                       full_set.count("B"), dst=0)
         clip = abba.combine_abba_sigmaclip(local, labels, counts, dst=0, low=3.0, high=2.5)
+        # the mean again, exchange fused into the summing kernel over NVLink peer memory; twice
+        # (buffer parities), the second time in two passes with carried sums
+        from pyemir_b200.peer import PeerWorkspace, combine_abba_mean_fused
+        ws = PeerWorkspace(shape[0] * shape[1])
+        fused = combine_abba_mean_fused(local, labels[start:stop], full_set.count("A"),
+                                        full_set.count("B"), ws, dst=0)
+        fused1 = fused.clone() if fused is not None else None
+        half = (stop - start) // 2
+        carried = abba.partial_sums(local[:half].contiguous(), labels[start:start + half]) if half else None
+        fused = combine_abba_mean_fused(local[half:].contiguous(), labels[start + half:stop],
+                                        full_set.count("A"), full_set.count("B"), ws, dst=0,
+                                        sums=carried)
+        fused2 = fused.clone() if fused is not None else None
         torch.cuda.synchronize()
+        timed_out = ws.timed_out()
+        ws.close()
         if rank == 0:
             ok_clip = bool(np.array_equal(
                 clip.cpu().numpy(), combine_abba(stack, full_set, None, "sigmaclip", 3.0, 2.5)))
+            want_mean = combine_abba_mean(stack, full_set)
+            ok_fused = bool(not timed_out and np.array_equal(fused1.cpu().numpy(), want_mean)
+                            and np.array_equal(fused2.cpu().numpy(), want_mean))
             ok_med = bool(np.array_equal(med.cpu().numpy(), combine_abba_median(stack, full_set)))
             ok_mean = bool(np.array_equal(mean.cpu().numpy(), combine_abba_mean(stack, full_set)))
             results.append({"frames": n, "shape": list(shape), "world": world,
                             "median_bit_exact": ok_med, "mean_bit_exact": ok_mean,
-                            "sigmaclip_bit_exact": ok_clip,
+                            "sigmaclip_bit_exact": ok_clip, "fused_mean_bit_exact": ok_fused,
                             "median_first_call_ms": 1e3 * (t1 - t0)})
         else:
-            assert med is None and mean is None and clip is None
+            assert med is None and mean is None and clip is None and fused is None
+            assert not timed_out
     if rank == 0:
         print(json.dumps(results), flush=True)
         if not all(r["median_bit_exact"] and r["mean_bit_exact"] and r["sigmaclip_bit_exact"]
-                   for r in results):
+                   and r["fused_mean_bit_exact"] for r in results):
             raise SystemExit("ABBA combination over NCCL differs from the single-process result")
     if world > 1:
         dist.barrier()

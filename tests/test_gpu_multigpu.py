@@ -33,6 +33,7 @@ def test_abba_combinations_over_nccl():
     for case in json.loads(line):
         assert case["world"] == world
         assert case["mean_bit_exact"] and case["median_bit_exact"] and case["sigmaclip_bit_exact"]
+        assert case["fused_mean_bit_exact"]          # exchange over NVLink peer memory (peer.py)
 
 
 def _load_nccl():
