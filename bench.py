@@ -387,6 +387,46 @@ def collective_block(args, plan, d_in, d_out, d_jmm, F, world, rank, dev):
         "how": "k_rectwv + k_abba_partial per round of %d frames per rank, one NCCL reduce(sum) of "
                "the float64 A and B sums (2 x %.1f MB per rank) to rank 0, k_abba_finish" % (F, npix * 8 / 1e6)}
 
+    # (i') the same product with the exchange fused into the last summing pass over NVLink peer
+    # memory (pyemir_b200/peer.py): no collective call on the data path
+    try:
+        from pyemir_b200.peer import PeerWorkspace, combine_abba_mean_fused
+        ws = PeerWorkspace(npix)
+
+        def mean_fused():
+            sums = None
+            for _ in range(rounds - 1):
+                plan.run_torch(d_in, d_out, d_jmm)
+                sums = abba.partial_sums(d_out, labels, sums=sums)
+            plan.run_torch(d_in, d_out, d_jmm)
+            state["fused"] = combine_abba_mean_fused(d_out, labels, na, nb, ws, 0, sums=sums)
+
+        t_fused = run(mean_fused)
+        same = None
+        if rank == 0:
+            mean_all()
+            ref_img = abba.finish(abba.reduce_sums(state["sums"], 0), na, nb)
+        else:
+            mean_all()
+        mean_fused()
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = bool(torch.equal(state["fused"], ref_img))
+        timed_out = ws.timed_out()
+        ws.close()
+        out["abba_mean_fused"] = {
+            "frames_per_sequence": F * world * rounds, "ms_per_sequence": t_fused,
+            "ms_exchange_and_finish": max(t_fused - t_local, 0.0),
+            "frames_per_s": F * world * rounds / (t_fused / 1e3),
+            "bytes_pushed_per_rank": int(red_bytes * (world - 1) / world),
+            "identical_to_the_nccl_path": same, "timed_out": timed_out,
+            "how": "the last k_abba_partial pass of every rank pushes its float64 sums straight into "
+                   "the receive buffer of the rank that owns the pixel (stores over NVLink, CUDA IPC "
+                   "peer memory), system-scope flags, every owner finishes its slab and stores it "
+                   "into the image on rank 0: no collective call"}
+    except Exception as exc:                                      # noqa: BLE001
+        out["abba_mean_fused"] = {"error": repr(exc)[:300]}
+
     # (ii) median: 64 images per nodding position over all ranks; row-slab exchange (grouped
     # send/recv), per-slab k_abba_median, gather of the slabs
     per_rank = max(4, (128 // world) // 4 * 4)
