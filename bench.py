@@ -372,7 +372,7 @@ def collective_block(args, plan, d_in, d_out, d_jmm, F, world, rank, dev):
         local_sums()
         red = abba.reduce_sums(state["sums"], 0)
         if red is not None:
-            abba.finish(red, na, nb)
+            state["ref"] = abba.finish(red, na, nb)
 
     t_local = run(local_sums)
     t_all = run(mean_all)
@@ -402,16 +402,8 @@ def collective_block(args, plan, d_in, d_out, d_jmm, F, world, rank, dev):
             state["fused"] = combine_abba_mean_fused(d_out, labels, na, nb, ws, 0, sums=sums)
 
         t_fused = run(mean_fused)
-        same = None
-        if rank == 0:
-            mean_all()
-            ref_img = abba.finish(abba.reduce_sums(state["sums"], 0), na, nb)
-        else:
-            mean_all()
-        mean_fused()
-        torch.cuda.synchronize()
-        if rank == 0:
-            same = bool(torch.equal(state["fused"], ref_img))
+        torch.cuda.synchronize()                 # (every rank made the same calls up to here)
+        same = bool(torch.equal(state["fused"], state["ref"])) if rank == 0 else None
         timed_out = ws.timed_out()
         ws.close()
         out["abba_mean_fused"] = {

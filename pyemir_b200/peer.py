@@ -26,18 +26,38 @@ class PeerWorkspace:
         self.npix = int(npix)
         self.device = torch.cuda.current_device() if device is None else int(device)
         ipc = ctypes.create_string_buffer(64)
+        # every rank goes through the same exchanges whatever happens locally: a rank that failed
+        # must not leave the others waiting in a collective
+        error = None
         with torch.cuda.device(self.device):
-            _cabi.check(self._lib.emirwv_peer_create(self.npix, self.rank, self.world,
-                                                     ctypes.byref(self._handle), ipc))
+            try:
+                _cabi.check(self._lib.emirwv_peer_create(self.npix, self.rank, self.world,
+                                                         ctypes.byref(self._handle), ipc))
+            except Exception as exc:                              # noqa: BLE001
+                error = exc
             handles = [None] * self.world
             if self.world > 1:
-                dist.all_gather_object(handles, ipc.raw)
+                dist.all_gather_object(handles, ipc.raw if error is None else None)
             else:
                 handles[0] = ipc.raw
-            blob = ctypes.create_string_buffer(b"".join(handles), 64 * self.world)
-            _cabi.check(self._lib.emirwv_peer_connect(self._handle, blob))
-        if self.world > 1:
-            dist.barrier()              # every rank has opened every workspace
+            if error is None and all(h is not None for h in handles):
+                try:
+                    blob = ctypes.create_string_buffer(b"".join(handles), 64 * self.world)
+                    _cabi.check(self._lib.emirwv_peer_connect(self._handle, blob))
+                except Exception as exc:                          # noqa: BLE001
+                    error = exc
+            elif error is None:
+                error = RuntimeError("another rank could not create its peer workspace")
+            ok = torch.tensor([0 if error is not None else 1], dtype=torch.int32,
+                              device=torch.device("cuda", self.device))
+            if self.world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)     # (also: every rank has connected)
+        if int(ok.item()) == 0:
+            if self._handle.value:
+                self._lib.emirwv_peer_destroy(self._handle)
+                self._handle = ctypes.c_void_p()
+            raise error if error is not None else RuntimeError(
+                "another rank could not connect its peer workspace")
 
     def close(self):
         if getattr(self, "_handle", None) and self._handle.value:

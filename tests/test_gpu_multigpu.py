@@ -27,7 +27,7 @@ def test_abba_combinations_over_nccl():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "scripts", "check_abba_multigpu.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=200, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     line = [l for l in res.stdout.splitlines() if l.startswith("[{")][-1]
     for case in json.loads(line):
