@@ -464,8 +464,9 @@ def collective_block(args, plan, d_in, d_out, d_jmm, F, world, rank, dev):
     except RuntimeError as exc:           # root out of memory for the gathered stack
         out["gather"] = {"error": repr(exc)[:200]}
     limiter = ("mean: the per-rank k_abba_partial pass over the products (HBM) and the float64 "
-               "reduce; median: the exchange moves (world-1)/world of every product once; gather: "
-               "the root's NVLink ingest (900 GB/s per direction)")
+               "reduce -- with the exchange fused into the last pass over peer memory only the "
+               "HBM pass is left; median: the exchange moves (world-1)/world of every product once; "
+               "gather: the root's NVLink ingest (900 GB/s per direction)")
     out["limiter"] = limiter
     return out
 
