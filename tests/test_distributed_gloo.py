@@ -148,3 +148,47 @@ def test_abba_median_world2(tmp_path, nframes, height):
     mp.spawn(_abba_median_worker, args=(2, port, nframes, height, str(tmp_path)), nprocs=2,
              join=True)
     assert os.path.exists(tmp_path / "median_ok.npy")
+
+
+def _abba_sigmaclip_worker(rank, world, port, result_dir):
+    """ABBA "sigmaclip" combination over two ranks: the row-slab exchange of the median path
+    with the sigma-clip difference per slab (the oracle's restatement stands in for
+    emirwv_abba_sigmaclip on a CPU box)."""
+    from oracle.pipeline import combine_abba, sigmaclip_stack
+    from pyemir_b200 import abba
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        nframes, height = 16, 7
+        full_set = abba.build_full_set("ABBA", 2, 2)
+        labels = abba.labels_of(full_set)
+        counts = [shard_range(nframes, r, world)[1] - shard_range(nframes, r, world)[0]
+                  for r in range(world)]
+        start, stop = shard_range(nframes, rank, world)
+        rng = np.random.default_rng(19)
+        data = rng.normal(100.0, 2.0, size=(nframes, height, 9)).astype(np.float32)
+        data[5, 3, 4] += 900.0                                    # a cosmic ray in an A image
+        stack = torch.from_numpy(data)
+
+        def difference(frames, index_a, index_b):
+            x = frames.numpy()
+            return torch.from_numpy(sigmaclip_stack(x[index_a], 2.0, 2.0).astype(np.float32)
+                                    - sigmaclip_stack(x[index_b], 2.0, 2.0).astype(np.float32))
+
+        got = abba.combine_abba_median(stack[start:stop].clone(), labels, counts, dst=0,
+                                       median_difference=difference)
+        if rank == 0:
+            want = combine_abba(data, full_set, None, "sigmaclip", 2.0, 2.0)
+            assert np.array_equal(got.numpy(), want)
+            np.save(os.path.join(result_dir, "sigmaclip_ok.npy"), np.array([1]))
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_abba_sigmaclip_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_abba_sigmaclip_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "sigmaclip_ok.npy")
