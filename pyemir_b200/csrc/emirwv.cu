@@ -13,9 +13,11 @@
 //         piece per warp) with the source window each one needs
 //
 //   run   (per batch of frames; one fused kernel, nothing intermediate touches HBM)
-//     k_rectwv<T,K,G>: a copy warp streams the source window of G frames and the table
-//       records into shared memory (TMA bulk copies, mbarriers); every compute warp owns a
-//       piece of the tile and marches down its 39 rows:
+//     k_rectwv<T,K,G>: three CTAs per SM; a copy warp streams the source window of G frames
+//       (TMA tensor copies: one box of 256 columns x 1 row x G frames per source row), the
+//       staged table rows (bulk copies) and the zero runs outside the wavelength coverage
+//       (bulk stores) through shared memory, mbarriers; every compute warp owns a piece of
+//       the tile and marches down its 39 rows:
 //         A: rectified flux = K*K weighted gather            (kernel 1 of the spec)
 //         C: Steffen-limited end slopes of every source pixel (kernel 2)
 //         D: cumulative-flux difference at the output borders (kernel 2), coalesced
@@ -28,8 +30,10 @@
 //   pixel_ops.cuh       pre-reduction stages, stack-median networks (shared with the hostcheck)
 //   plan_kernels.cuh    k_extent, k_build_geometry, k_rectify2d, parity-hook helpers
 //   device_utils.cuh    TMA bulk copies, mbarriers, packed float32 pairs
-//   side_kernels.cuh    zero fill, median_slitlets_rectified, ABBA mean / median, pre-reduction
+//   side_kernels.cuh    zero fill, median_slitlets_rectified, ABBA mean / median / sigma clipping,
+//                       per-frame vertical offsets, pre-reduction with its bad-pixel stage
 //   rectwv_kernel.cuh   the hot kernel k_rectwv
+//   peer_kernels.cuh    ABBA mean fused with its exchange over NVLink peer memory
 //   plan_build.inl      host side of a plan (launch configuration, border tables, tiles)
 // and this file keeps the constants, the device structs, the plan object and the C ABI.
 

@@ -600,9 +600,9 @@ int build_plan(emirwv_plan *pl) {
     pl->nout = d.naxis1_out;
     pl->NB = d.naxis1_out + 1;
     pl->tile_k = d.tile_k > 0 ? d.tile_k : env_int("EMIRWV_TILE_K", TILE_K_MAX);
-    // float64 records are 96 bytes: four staged table rows take 90 KB and leave room for one
-    // CTA per SM only; two stages fit two CTAs and are faster (+21 %, bit-identical output),
-    // so they are the default (EMIRWV_NSTAGE_F64=4 brings the deep pipeline back)
+    // float64: two staged table rows (36 bytes per pixel each) keep three CTAs per SM like
+    // float32; measured faster than four stages with fewer CTAs, bit-identical output
+    // (EMIRWV_NSTAGE_F64=4 brings the deep pipeline back)
     pl->nstage = NSTAGE_MAX;
     if (pl->esize == 8 && env_int("EMIRWV_NSTAGE_F64", 2) == 2) pl->nstage = 2;
     if (d.stages != 0) pl->nstage = d.stages;                  // validated: 2 or NSTAGE_MAX

@@ -1,9 +1,11 @@
-// Kernels either side of the hot path: zero fill, median_slitlets_rectified, ABBA mean and
-// median combinations, pre-reduction (bias, dark, flat).
+// Kernels either side of the hot path: zero fill, median_slitlets_rectified, the ABBA product
+// (mean, median and sigma-clip combinations, per-frame vertical offsets), pre-reduction (bad
+// pixels, bias, dark, flat).
 // Included by emirwv.cu inside its anonymous namespace (one translation unit).
 
 // Zero-coverage runs (outside the wavelength range of a slitlet, or a missing slitlet):
-// exact zeros.  A small persistent grid: every warp takes rows (dead tile, frame, row) in a
+// exact zeros.  Only used when the copy warps of the hot kernel cannot write them (output rows
+// that are not 16-byte aligned, or EMIRWV_FILL=kernel).  A small persistent grid: every warp takes rows (dead tile, frame, row) in a
 // grid-stride loop and writes them with 16-byte stores (scalar head and tail where the run
 // is not aligned), so the fill trickles along next to the hot kernel instead of bursting.
 template <typename T>
