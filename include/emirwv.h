@@ -412,6 +412,10 @@ int emirwv_abba_reduce(double *d_sum_a, double *d_sum_b, int64_t npix, void *ncc
 typedef struct emirwv_peer emirwv_peer;   /* opaque */
 int emirwv_peer_create(int64_t npix, int rank, int world, emirwv_peer **peer, void *h_handle64);
 int emirwv_peer_connect(emirwv_peer *peer, const void *h_handles /* [world][64] */);
+/* Shutting down: every rank disconnects (closes the workspaces of the others), the ranks meet at
+ * a barrier of the caller's, then every rank destroys its own workspace -- memory that another
+ * process still has open must not be freed. */
+int emirwv_peer_disconnect(emirwv_peer *peer);
 void emirwv_peer_destroy(emirwv_peer *peer);
 int emirwv_peer_timed_out(emirwv_peer *peer);
 int emirwv_abba_mean_push(emirwv_peer *peer, const void *d_frames, const int8_t *d_labels,

@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "emirwv_prereduce", "emirwv_prereduce_ex", "emirwv_stack_sigmaclip",
     "emirwv_abba_sigmaclip", "emirwv_shift_rows", "emirwv_plan_set_calibration",
     "emirwv_run_host_raw", "emirwv_abba_host", "emirwv_gather", "emirwv_abba_reduce",
-    "emirwv_peer_create", "emirwv_peer_connect", "emirwv_peer_destroy", "emirwv_peer_timed_out",
+    "emirwv_peer_create", "emirwv_peer_connect", "emirwv_peer_disconnect", "emirwv_peer_destroy", "emirwv_peer_timed_out",
     "emirwv_abba_mean_push",
 )
 
@@ -211,6 +211,8 @@ def load():
     lib.emirwv_peer_create.argtypes = [ctypes.c_int64, i32, i32, ctypes.POINTER(vp), vp]
     lib.emirwv_peer_connect.restype = i32
     lib.emirwv_peer_connect.argtypes = [vp, vp]
+    lib.emirwv_peer_disconnect.restype = i32
+    lib.emirwv_peer_disconnect.argtypes = [vp]
     lib.emirwv_peer_destroy.restype = None
     lib.emirwv_peer_destroy.argtypes = [vp]
     lib.emirwv_peer_timed_out.restype = i32

@@ -1432,12 +1432,22 @@ int emirwv_peer_connect(emirwv_peer *p, const void *h_handles) {
     return EMIRWV_OK;
 }
 
+int emirwv_peer_disconnect(emirwv_peer *p) {
+    if (p == nullptr) return fail(EMIRWV_E_VALUE, "null argument");
+    DeviceGuard guard(p->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int r = 0; r < p->world; ++r) {
+        if (r != p->rank && p->peer[r] != nullptr) cudaIpcCloseMemHandle(p->peer[r]);
+        p->peer[r] = nullptr;
+    }
+    p->connected = false;
+    return EMIRWV_OK;
+}
+
 void emirwv_peer_destroy(emirwv_peer *p) {
     if (p == nullptr) return;
+    emirwv_peer_disconnect(p);
     DeviceGuard guard(p->device);
-    cudaDeviceSynchronize();
-    for (int r = 0; r < p->world; ++r)
-        if (r != p->rank && p->peer[r] != nullptr) cudaIpcCloseMemHandle(p->peer[r]);
     cudaFree(p->local);
     delete p;
 }

@@ -62,8 +62,12 @@ class PeerWorkspace:
     def close(self):
         if getattr(self, "_handle", None) and self._handle.value:
             import torch.distributed as dist
+            # nobody still writes into a workspace, nobody keeps one open that is about to be freed
             if self.world > 1 and dist.is_initialized():
-                dist.barrier()          # nobody still writes into a workspace that goes away
+                dist.barrier()
+            self._lib.emirwv_peer_disconnect(self._handle)
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier()
             self._lib.emirwv_peer_destroy(self._handle)
             self._handle = ctypes.c_void_p()
 
